@@ -1,0 +1,161 @@
+"""Host side of the Gram recursion: argument handling, plan cache, launches.
+
+Everything here enqueues work on torch's current CUDA stream through the C ABI of
+include/cnngp.h; torch is only used for device memory and streams.  There is no CPU route:
+CPU tensors raise.
+"""
+import ctypes
+
+import torch
+
+from . import _native as nat
+from . import program
+
+_DTYPE_CODE = {torch.float32: nat.F32, torch.float64: nat.F64}
+
+# "auto" | "generic" | "fused" -- tests and benchmarks pin a path through this knob
+_force_path = "auto"
+_PATH_CODE = {"auto": nat.PATH_AUTO, "generic": nat.PATH_GENERIC, "fused": nat.PATH_FUSED}
+
+
+def set_path(name):
+    """Select the kernel family: "auto" (fused when the program is covered), "generic", "fused"."""
+    global _force_path
+    if name not in _PATH_CODE:
+        raise ValueError(name)
+    prev, _force_path = _force_path, name
+    return prev
+
+
+def last_path():
+    return {0: "none", 1: "generic", 2: "fused"}[nat.lib().cnngp_last_path()]
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"cnn_gp (B200): {what} is on {t.device}; this implementation has no CPU path. "
+            "Move the model inputs to a CUDA device.")
+    if t.dtype not in _DTYPE_CODE:
+        raise TypeError(f"cnn_gp (B200): unsupported dtype {t.dtype}; use float32 or float64")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def plan_for(model, H, W, dtype):
+    """Compiled plan for ``model`` on H x W maps, cached on the module."""
+    cache = model.__dict__.setdefault("_cnngp_plans", {})
+    key = (H, W, dtype, model._mixture_signature())
+    plan = cache.get(key)
+    if plan is None:
+        ops, n_slots = program.compile_model(model)
+        plan = nat.Plan(ops, n_slots, H, W, _DTYPE_CODE[dtype])
+        cache[key] = plan
+    return plan
+
+
+def variances(plan, x, z=None):
+    """Per-image variance maps at every ReLU input and the diagonal kernel value.
+
+    -> (aux_x [N, aux_elems], aux_z or None, kdiag [N]).  With ``z`` given, evaluates the
+    literal same=True semantics for two different image sets (reference kernels.py:155-156).
+    """
+    N, C = x.shape[0], x.shape[1]
+    aux_x = torch.empty((N, max(1, plan.aux_elems)), dtype=x.dtype, device=x.device)
+    aux_z = torch.empty_like(aux_x) if z is not None else None
+    kdiag = torch.empty((N,), dtype=x.dtype, device=x.device)
+    nat.check(nat.lib().cnngp_variances(
+        plan.handle, x.data_ptr(), z.data_ptr() if z is not None else None, N, C,
+        aux_x.data_ptr(), aux_z.data_ptr() if aux_z is not None else None, kdiag.data_ptr(),
+        _stream()), "cnngp_variances")
+    return aux_x, aux_z, kdiag
+
+
+def gram_with_aux(plan, x, z, aux_x, aux_z, same, diag, symmetric, out=None):
+    """One cnngp_gram launch on prepared operands; ``out`` may be a (strided-row) view."""
+    N1, N2, C = x.shape[0], z.shape[0], x.shape[1]
+    if out is None:
+        out = torch.empty((N1,) if diag else (N1, N2), dtype=x.dtype, device=x.device)
+    ld = 1 if diag else out.stride(0)
+    if not diag:
+        assert out.stride(1) == 1 and out.shape == (N1, N2)
+    nat.check(nat.lib().cnngp_gram(
+        plan.handle, x.data_ptr(), N1, z.data_ptr(), N2, C, aux_x.data_ptr(), aux_z.data_ptr(),
+        int(same), int(diag), int(symmetric), out.data_ptr(), ld, _PATH_CODE[_force_path], _stream()),
+        "cnngp_gram")
+    return out
+
+
+@torch.no_grad()
+def gram(model, x, y, same, diag):
+    """model(x, y, same, diag) -- reference kernels.py:18-57."""
+    _require_cuda(x, "x")
+    _require_cuda(y, "y")
+    if x.dtype != y.dtype or x.device != y.device:
+        raise RuntimeError("x and y must share dtype and device")
+    identical = (y is x) or (y.data_ptr() == x.data_ptr() and y.shape == x.shape
+                             and y.stride() == x.stride())
+    x = x.detach().contiguous()
+    y = x if identical else y.detach().contiguous()
+    N1, N2 = x.shape[0], y.shape[0]
+    if same and not diag and N1 != N2:
+        # the reference fails broadcasting eye(N1) against [N1, N2, W, H] (kernels.py:161-162)
+        raise RuntimeError(f"same=True needs equally many images, got {N1} and {N2}")
+    with torch.cuda.device(x.device):
+        plan = plan_for(model, x.shape[2], x.shape[3], x.dtype)
+        if N1 == 0 or N2 == 0:
+            return torch.empty((N1,) if diag else (N1, N2), dtype=x.dtype, device=x.device)
+        symmetric = bool(same and identical)
+        if same and not identical:
+            aux_x, aux_z, _ = variances(plan, x, y)
+        else:
+            aux_x, _, _ = variances(plan, x)
+            aux_z = aux_x if identical else variances(plan, y)[0]
+        return gram_with_aux(plan, x, y, aux_x, aux_z, same, diag, symmetric)
+
+
+def _conv_op(mod):
+    import numpy as np
+    zf = bool(mod.kernel_has_row_of_zeros)
+    return nat.Op(opcode=nat.OP_CONV, src=0, dst=0, ke=int(mod.kernel_size) + int(zf), zero_first=int(zf),
+                  stride=int(mod.stride), pad=int(mod.padding), dil=int(mod.dilation),
+                  scale=float(np.float32(float(mod.var_weight) / int(mod.kernel_size) ** 2)),
+                  bias=float(mod.var_bias))
+
+
+@torch.no_grad()
+def conv_maps(mod, maps):
+    """F.conv2d(patch, box) + var_bias of reference kernels.py:94-97 on [M, 1, W, H] maps."""
+    _require_cuda(maps, "kernel patch")
+    maps = maps.contiguous()
+    M, _, Hi, Wi = maps.shape
+    op = _conv_op(mod)
+
+    def osz(n):
+        return (n + 2 * op.pad - op.dil * (op.ke - 1) - 1) // op.stride + 1
+    Ho, Wo = osz(Hi), osz(Wi)
+    if Ho < 1 or Wo < 1:
+        raise RuntimeError("conv output would be empty")
+    out = torch.empty((M, 1, Ho, Wo), dtype=maps.dtype, device=maps.device)
+    with torch.cuda.device(maps.device):
+        nat.check(nat.lib().cnngp_conv_maps(maps.data_ptr(), M, Hi, Wi, ctypes.byref(op),
+                                            _DTYPE_CODE[maps.dtype], out.data_ptr(), _stream()),
+                  "cnngp_conv_maps")
+    return out
+
+
+@torch.no_grad()
+def relu_maps(kp):
+    """xy' of reference kernels.py:146-162 for a NonlinKP."""
+    _require_cuda(kp.xy, "kernel patch")
+    if kp.same and not kp.diag and kp.Nx != kp.Ny:
+        raise RuntimeError("same=True needs Nx == Ny")
+    xy = kp.xy.contiguous().clone()
+    xx, yy = kp.xx.contiguous(), kp.yy.contiguous()
+    with torch.cuda.device(xy.device):
+        nat.check(nat.lib().cnngp_relu_maps(xy.data_ptr(), xx.data_ptr(), yy.data_ptr(), kp.Nx, kp.Ny,
+                                            kp.W * kp.H, int(bool(kp.same)), int(bool(kp.diag)),
+                                            _DTYPE_CODE[xy.dtype], _stream()), "cnngp_relu_maps")
+    return xy

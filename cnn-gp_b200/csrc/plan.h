@@ -1,0 +1,66 @@
+// plan.h -- host-side plan: the linearised layer program with inferred shapes.
+// Reference semantics: cnn_gp/kernels.py:18-57 (forward), :61-98 (Conv2d), :128-165 (ReLU),
+// :246-254 (Sum), :203-225 (Mixture).  See include/cnngp.h for the op encoding.
+#pragma once
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/cnngp.h"
+
+namespace cnngp {
+
+// One op with resolved geometry, laid out for the device interpreter.
+struct DevOp {
+    int32_t opcode, src, dst;
+    int32_t ke, t0, stride, pad, dil;  // t0 = first non-zero tap (1 when zero_first)
+    int32_t Hi, Wi, Ho, Wo;            // input / output map size of this op
+    int32_t aux_off;                   // RELU: offset of its variance map in the per-image aux row
+    int32_t relu_index;                // RELU: ordinal
+    float scale_f, bias_f;
+    double scale_d, bias_d;
+};
+
+struct FusedPlan;  // gram_fused.cu
+
+struct Plan {
+    int32_t n_ops = 0, n_slots = 0, H = 0, W = 0, dtype = 0;
+    std::vector<DevOp> ops;
+    int64_t aux_elems = 0;
+    int32_t n_relu = 0;
+    int32_t max_map = 0;      // largest map (or separable-conv intermediate) in elements
+    int32_t final_slot = 0;
+    // lazily uploaded device copy of `ops` (per device the plan was first used on)
+    mutable std::mutex mu;
+    mutable DevOp *d_ops = nullptr;
+    mutable int d_ops_device = -1;
+    // fused-kernel description (nullptr when the program is outside the fused kernel's set)
+    FusedPlan *fused = nullptr;
+};
+
+void set_error(const std::string &msg);
+int build_plan(const cnngp_op *ops, int32_t n_ops, int32_t n_slots, int32_t H, int32_t W,
+               int32_t dtype, Plan **out);
+const DevOp *plan_device_ops(const Plan *plan);  // uploads on first use; nullptr on CUDA error
+double plan_flops_per_pair(const Plan *plan, int32_t C);
+
+// gram_generic.cu
+int launch_generic_variances(const Plan *plan, const void *d_x, const void *d_z, int64_t N, int32_t C,
+                             void *d_aux_x, void *d_aux_z, void *d_kdiag, void *stream);
+int launch_generic_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2,
+                        int32_t C, const void *d_aux_x, const void *d_aux_z, int32_t same, int32_t diag,
+                        int32_t symmetric, void *d_out, int64_t ld_out, void *stream);
+int launch_conv_maps(const void *d_in, int64_t M, int32_t Hi, int32_t Wi, const cnngp_op *conv,
+                     int32_t dtype, void *d_out, void *stream);
+int launch_relu_maps(void *d_xy, const void *d_xx, const void *d_yy, int64_t Nx, int64_t Ny, int64_t P,
+                     int32_t same, int32_t diag, int32_t dtype, void *stream);
+
+// gram_fused.cu
+FusedPlan *fused_plan_create(const Plan *plan);  // nullptr if not covered
+void fused_plan_destroy(FusedPlan *fp);
+int launch_fused_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2,
+                      int32_t C, const void *d_aux_x, const void *d_aux_z, int32_t same, int32_t diag,
+                      int32_t symmetric, void *d_out, int64_t ld_out, void *stream);
+
+}  // namespace cnngp

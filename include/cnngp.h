@@ -1,0 +1,135 @@
+/*
+ * cnngp.h -- C ABI of the B200-native cnn-gp hot path (libcnngp.so, sm_100a).
+ *
+ * The reference (waleedbinkhalid74/cnn-gp) is pure Python on PyTorch and has no FFI of its
+ * own; its "operator interface" for this path is the Python call protocol
+ *     model(x, y=None, same=None, diag=False)                cnn_gp/kernels.py:18-57
+ *     module.propagate(kp)                                    cnn_gp/kernels.py:92-98,134-165,
+ *                                                             184-187,221-225,252-254
+ *     save_K(f, kern, name, X, X2, diag, batch_size, ...)     cnn_gp/kernel_save_tools.py:26-58
+ *     solve_system(Kxx, Y) / print_accuracy(A, Kxvx, Y, key)  exp_mnist_resnet/classify_gp.py:17-42
+ * The entry points below are what a binding for that path needs; every one cites the
+ * reference code it replaces.  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer named d_* is a DEVICE pointer owned by the caller
+ *     (PyTorch allocates; pass tensor.data_ptr()).  The library allocates nothing that
+ *     outlives a call except the small plan object.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), on the current
+ *     device; no hidden synchronisation.
+ *   - return value 0 = success, non-zero = error; cnngp_last_error() returns a thread-local
+ *     message.  Nothing throws or exits across the ABI.
+ *   - dtype: 0 = float32, 1 = float64 (a .double() model, parity 1e-10).
+ */
+#ifndef CNNGP_H
+#define CNNGP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNNGP_ABI_VERSION 1
+
+enum { CNNGP_F32 = 0, CNNGP_F64 = 1 };
+
+/* One step of the linearised layer program.  A program is the module tree
+ * (Sequential / Sum / Mixture of Conv2d and ReLU, kernels.py:178-254) flattened by the host
+ * into three-address ops over numbered map slots; slot 0 holds the initial per-pixel
+ * covariance map (kernels.py:43-49) and the last op's dst holds the final 1x1 map. */
+enum {
+    CNNGP_OP_CONV  = 1, /* dst = box_conv(src)*scale + bias          kernels.py:92-98   */
+    CNNGP_OP_RELU  = 2, /* dst = arccos expectation of src           kernels.py:134-165 */
+    CNNGP_OP_COPY  = 3, /* dst = src                 (Sum keeps its input alive)        */
+    CNNGP_OP_ADD   = 4, /* dst = dst + src           Sum.propagate, kernels.py:252-254  */
+    CNNGP_OP_SCALE = 5  /* dst = src * scale         Mixture.propagate, kernels.py:221-225 */
+};
+
+typedef struct cnngp_op {
+    int32_t opcode;
+    int32_t src, dst;   /* slot indices, 0 <= slot < n_slots */
+    int32_t ke;         /* CONV: kernel extent = kernel_size (+1 when zero_first)           */
+    int32_t zero_first; /* CONV: row 0 / col 0 of the kernel are zero (kernels.py:73-84)    */
+    int32_t stride;     /* CONV */
+    int32_t pad;        /* CONV: zero padding on every side                                 */
+    int32_t dil;        /* CONV: dilation                                                   */
+    double scale;       /* CONV: tap = float32(var_weight/kernel_size^2) (kernels.py:87-88);
+                           SCALE: mixture proportion                                        */
+    double bias;        /* CONV: var_bias                                                   */
+} cnngp_op;
+
+typedef struct cnngp_plan cnngp_plan; /* opaque, immutable after creation, thread-shareable */
+
+/* Which implementation cnngp_gram used for the last call on this thread. */
+enum { CNNGP_PATH_NONE = 0, CNNGP_PATH_GENERIC = 1, CNNGP_PATH_FUSED = 2 };
+
+int cnngp_abi_version(void);
+const char *cnngp_last_error(void);
+
+/* Build a plan for `ops` on H x W input maps.  Fails if any conv output would be empty, a
+ * slot is read before it is written, ADD shapes differ, or the final map is not 1x1 (the
+ * reference fails there with a view error, kernels.py:54-57). */
+int cnngp_plan_create(const cnngp_op *ops, int32_t n_ops, int32_t n_slots, int32_t H, int32_t W,
+                      int32_t dtype, cnngp_plan **out);
+void cnngp_plan_destroy(cnngp_plan *plan);
+
+/* Number of per-image variance-map elements (sum over RELU ops of their input map size):
+ * the `xx` / `yy` operands of every ReLU, kernels.py:146. */
+int64_t cnngp_plan_aux_elems(const cnngp_plan *plan);
+/* Algorithmic flop per image pair under SURVEY.md 8(d)'s counting convention. */
+double cnngp_plan_flops_per_pair(const cnngp_plan *plan, int32_t C);
+/* 1 if the register-resident fused kernel covers this program, else 0 (generic kernel). */
+int cnngp_plan_has_fused(const cnngp_plan *plan);
+
+/* Per-image variance recursion: the xx / yy maps of kernels.py:48-49 pushed through the
+ * program (Conv2d acts on them as on xy, kernels.py:98; ReLU halves them, kernels.py:154,164).
+ *   d_x        [N, C, H, W] images
+ *   d_z        NULL, or [N, C, H, W] partner images for the literal same=True-with-different-
+ *              data semantics (after each ReLU yy := xx, kernels.py:155-156)
+ *   d_aux_x    [N, aux_elems] out: xx at the input of every ReLU
+ *   d_aux_z    [N, aux_elems] out (only when d_z != NULL): yy at the input of every ReLU
+ *   d_kdiag    [N] out, may be NULL: the final 1x1 value of the xx recursion, i.e.
+ *              model(x, diag=True) (kernels.py:155-158) */
+int cnngp_variances(const cnngp_plan *plan, const void *d_x, const void *d_z, int64_t N, int32_t C,
+                    void *d_aux_x, void *d_aux_z, void *d_kdiag, void *stream);
+
+/* The Gram tile: model(x, z, same, diag) of kernels.py:18-57.
+ *   d_x [N1,C,H,W], d_z [N2,C,H,W]; d_aux_x / d_aux_z from cnngp_variances
+ *   same   != 0: entries with i == j follow the variance recursion (kernels.py:155-162)
+ *   diag   != 0: only pairs (n, n) are evaluated, out is [N1]  (requires N1 == N2)
+ *   symmetric != 0: caller asserts d_x and d_z hold the same images (model(X)): only
+ *                j >= i is computed and mirrored
+ *   d_out  [N1, ld_out] (row stride ld_out elements) or [N1] when diag
+ *   path   0 = auto (fused when available), 1 = force generic, 2 = force fused */
+int cnngp_gram(const cnngp_plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2,
+               int32_t C, const void *d_aux_x, const void *d_aux_z, int32_t same, int32_t diag,
+               int32_t symmetric, void *d_out, int64_t ld_out, int32_t path, void *stream);
+int cnngp_last_path(void);
+
+/* Map-level steps behind module.propagate(kp): a stack of M maps [M, Hi, Wi]. */
+int cnngp_conv_maps(const void *d_in, int64_t M, int32_t Hi, int32_t Wi, const cnngp_op *conv,
+                    int32_t dtype, void *d_out, void *stream);                 /* kernels.py:94-97 */
+int cnngp_relu_maps(void *d_xy, const void *d_xx, const void *d_yy, int64_t Nx, int64_t Ny,
+                    int64_t P, int32_t same, int32_t diag, int32_t dtype, void *stream); /* :146-162 */
+
+/* exp_mnist_resnet/classify_gp.py:17-27: scipy.linalg.solve(Kxx, Y, assume_a='pos',
+ * lower=False) == LAPACK dposv('U').  Column-major is not assumed: A is row-major [n, lda]
+ * and only its upper triangle (j >= i) is read, exactly the blocks save_K writes.
+ * potrf overwrites the upper triangle with U (A = U^T U); *d_info = 0 on success, k > 0 if
+ * the leading minor of order k is not positive definite.  potrs solves U^T U X = B in place,
+ * B row-major [n, ldb] with nrhs columns. */
+int cnngp_potrf_upper_f64(double *d_A, int64_t n, int64_t lda, int32_t *d_info, void *stream);
+int cnngp_potrs_upper_f64(const double *d_U, int64_t n, int64_t lda, double *d_B, int32_t nrhs,
+                          int64_t ldb, void *stream);
+/* classify_gp.py:39-41: pred[r] = argmax_c (K[r,:] . A[:,c]); K row-major float32 [R, ldk]
+ * (as stored by save_K), A row-major float64 [n, nrhs]; accumulates in float64. */
+int cnngp_predict_argmax(const float *d_K, int64_t R, int64_t n, int64_t ldk, const double *d_A,
+                         int32_t nrhs, int64_t *d_pred, double *d_scores, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNNGP_H */

@@ -1,0 +1,158 @@
+"""Parity of the CUDA Gram recursion (through the C ABI) against the golden vectors of the
+unmodified reference and against the CPU oracle on seeded inputs.  Needs a B200.
+
+Tolerances (BASELINE.json north_star): rel 1e-5 in float32, rel 1e-10 in float64 for kernel
+entries.  Entries are compared element-wise relative to the reference value; for degenerate
+entries (all-zero image, zero bias) whose reference value is ~1e-20 a floor of 1e-30 * scale
+keeps the ratio finite (`rel_err`)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from cnn_gp import engine
+from models import golden_models, readme_model, CONFIGS
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+MODELS = golden_models()
+RTOL = {"f32": 1e-5, "f64": 1e-10}
+DT = {"f32": torch.float32, "f64": torch.float64}
+
+
+def rel_err(got, want):
+    want = np.asarray(want, np.float64)
+    got = np.asarray(got, np.float64)
+    return float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300)))
+
+
+def _calls(model, X, Z):
+    n = min(len(X), len(Z))
+    return {
+        "Kxx": lambda: model(X),
+        "Kxz": lambda: model(X, Z),
+        "Kxx_diag": lambda: model(X, diag=True),
+        "Kxz_diag": lambda: model(X[:n], Z[:n], diag=True),
+        "Kxz_same": lambda: model(X[:n], Z[:n], same=True),
+        "Kxz_same_diag": lambda: model(X[:n], Z[:n], same=True, diag=True),
+    }
+
+
+@pytest.mark.parametrize("path", ["generic", "auto"])
+@pytest.mark.parametrize("name", sorted(MODELS))
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_golden_parity(name, tag, path):
+    g = np.load(os.path.join(GOLD, f"gram_{name}.npz"))
+    model = MODELS[name].to(DT[tag]).cuda()
+    X = torch.from_numpy(g["X"]).to(DT[tag]).cuda()
+    Z = torch.from_numpy(g["Z"]).to(DT[tag]).cuda()
+    prev = engine.set_path(path)
+    try:
+        for key, fn in _calls(model, X, Z).items():
+            got = fn()
+            want = g[f"{key}_{tag}"]
+            assert got.is_cuda and got.dtype == DT[tag] and tuple(got.shape) == want.shape
+            err = rel_err(got.cpu().numpy(), want)
+            assert err < RTOL[tag], (name, key, tag, path, err)
+    finally:
+        engine.set_path(prev)
+
+
+def test_readme_calls():
+    """The four calls of the reference README (README.md:33-46)."""
+    g = np.load(os.path.join(GOLD, "gram_readme.npz"))
+    model = readme_model().cuda()
+    X, Z = torch.from_numpy(g["X"]).cuda(), torch.from_numpy(g["Z"]).cuda()
+    Kxx = model(X)
+    Kxx2 = model(X, X, same=True)
+    Kxz = model(X, Z)
+    Kd = model(X, diag=True)
+    torch.testing.assert_close(Kxx, Kxx2, rtol=0, atol=0)
+    torch.testing.assert_close(Kxx, Kxx.T, rtol=0, atol=0)
+    torch.testing.assert_close(torch.diagonal(Kxx), Kd, rtol=1e-6, atol=0)
+    assert rel_err(Kxz.cpu().numpy(), g["Kxz_f32"]) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", CONFIGS)
+def test_tile_vs_oracle(cfg):
+    """A seeded 24 x 20 tile per shipped config against the CPU oracle (float32)."""
+    S, C = (32, 3) if cfg == "cifar10" else (28, 1)
+    gen = torch.Generator().manual_seed(7)
+    X = torch.rand(24, C, S, S, generator=gen)
+    Z = torch.rand(20, C, S, S, generator=gen)
+    model = MODELS[cfg].float()
+    want = oracle.gram(model, X.numpy(), Z.numpy())
+    got = model.cuda()(X.cuda(), Z.cuda()).cpu().numpy()
+    assert rel_err(got, want) < 1e-5
+    want = oracle.gram(model, X.numpy())
+    got = model(X.cuda()).cpu().numpy()
+    assert rel_err(got, want) < 1e-5
+    np.testing.assert_array_equal(got, got.T)
+
+
+def test_zero_image_and_near_duplicates():
+    model = readme_model().cuda()
+    gen = torch.Generator().manual_seed(3)
+    X = torch.rand(5, 3, 28, 28, generator=gen)
+    X[1] = 0.0
+    X[3] = X[2] * (1 + 1e-4)      # almost collinear: cos(theta) -> 1
+    X[4] = X[2]                   # exact duplicate in another slot
+    Z = X.flip(0).contiguous()
+    want = oracle.gram(readme_model(), X.numpy(), Z.numpy())
+    got = model(X.cuda(), Z.cuda()).cpu().numpy()
+    assert np.isfinite(got).all()
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-12 * scale)
+    # the zero image gives ~1.7e-20-sized entries, not 0 and not NaN
+    assert 0 < got[1, 3] < 1e-12
+
+
+def test_errors_and_edge_shapes():
+    model = readme_model().cuda()
+    X = torch.rand(3, 3, 28, 28, device="cuda")
+    with pytest.raises(RuntimeError):
+        model(X, X[:2].clone(), same=True)
+    with pytest.raises(RuntimeError, match="1x1"):
+        model(torch.rand(2, 3, 30, 30, device="cuda"))
+    out = model(X[:0], X)
+    assert tuple(out.shape) == (0, 3)
+    one = model(X[:1])
+    assert tuple(one.shape) == (1, 1)
+    # non-contiguous inputs and inputs that are views of each other
+    Xb = torch.rand(6, 3, 28, 28, device="cuda")
+    a = model(Xb[::2], Xb[1::2])
+    b = model(Xb[::2].contiguous(), Xb[1::2].contiguous())
+    torch.testing.assert_close(a, b, rtol=0, atol=0)
+
+
+def test_propagate_protocol_matches_forward():
+    """module.propagate(kp) driven by hand (reference kernels.py:51-53) equals forward."""
+    from cnn_gp.kernel_patch import ConvKP, NonlinKP
+    model = MODELS["edge_evenk_sum"].cuda()
+    g = np.load(os.path.join(GOLD, "gram_edge_evenk_sum.npz"))
+    X, Z = torch.from_numpy(g["X"]).cuda(), torch.from_numpy(g["Z"]).cuda()
+    N1, N2, C, W, H = X.shape[0], Z.shape[0], X.shape[1], X.shape[2], X.shape[3]
+    xy = (X.unsqueeze(1) * Z).mean(2).view(N1 * N2, 1, W, H)
+    xx = (X ** 2).mean(1, keepdim=True)
+    yy = (Z ** 2).mean(1, keepdim=True)
+    kp = model.propagate(ConvKP(False, False, xy, xx, yy))
+    r = NonlinKP(kp).xy.view(N1, N2)
+    assert rel_err(r.cpu().numpy(), g["Kxz_f32"]) < 1e-5
+
+
+def test_large_symmetric_properties():
+    """Full-size behaviour through size-independent properties: symmetry, diagonal equals the
+    diag path, and the Gram matrix is positive semi-definite."""
+    model = MODELS["mnist_paper_convnet_gp"].cuda()
+    gen = torch.Generator().manual_seed(11)
+    X = torch.rand(700, 1, 28, 28, generator=gen).cuda()
+    K = model(X)
+    torch.testing.assert_close(K, K.T, rtol=0, atol=0)
+    torch.testing.assert_close(torch.diagonal(K), model(X, diag=True), rtol=2e-6, atol=0)
+    # blocks computed as separate rectangular tiles agree with the symmetric run
+    Kb = model(X[:300], X[300:])
+    torch.testing.assert_close(Kb, K[:300, 300:], rtol=1e-5, atol=0)
+    ev = torch.linalg.eigvalsh(K.double())
+    assert ev.min() > -1e-6 * ev.max()

@@ -1,0 +1,247 @@
+"""Host-side logic that needs no GPU: the drop-in API surface, the program compiler, plan
+validation through the C ABI, tile enumeration, the block store and the exported symbols."""
+import ctypes
+import inspect
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import cnn_gp
+from cnn_gp import Conv2d, ReLU, Sequential, Sum, Mixture, resnet_block
+from cnn_gp import _native as nat
+from cnn_gp import program, data, block_store
+from models import golden_models, readme_model
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_public_api_matches_reference():
+    # reference cnn_gp/__init__.py:1-6 + kernels.py:9-10, data.py:7-8, kernel_save_tools.py:4
+    assert set(cnn_gp.__all__) == {
+        "NNGPKernel", "Conv2d", "ReLU", "Sequential", "Mixture", "MixtureModule", "Sum", "SumModule",
+        "resnet_block", "DatasetFromConfig", "ProductIterator", "DiagIterator", "print_timings",
+        "create_h5py_dataset", "save_K"}
+    sig = inspect.signature
+    assert list(sig(cnn_gp.NNGPKernel.forward).parameters) == ["self", "x", "y", "same", "diag"]
+    assert list(sig(Conv2d.__init__).parameters) == [
+        "self", "kernel_size", "stride", "padding", "dilation", "var_weight", "var_bias",
+        "in_channel_multiplier", "out_channel_multiplier"]
+    assert list(sig(cnn_gp.ProductIterator.__init__).parameters) == [
+        "self", "batch_size", "X", "X2", "worker_rank", "n_workers"]
+    assert list(sig(cnn_gp.save_K).parameters) == [
+        "f", "kern", "name", "X", "X2", "diag", "batch_size", "worker_rank", "n_workers", "print_interval"]
+    assert list(sig(resnet_block).parameters) == ["stride", "projection_shortcut", "multiplier"]
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "cnngp.h")).read()
+    declared = set(re.findall(r"\b(cnngp_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    L = ctypes.CDLL(nat.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/cnngp.h but not exported"
+    assert declared == set(nat.EXPORTS)
+    assert nat.lib().cnngp_abi_version() == 1
+
+
+def test_conv_module_attributes():
+    c = Conv2d(4, var_weight=3.2)
+    assert c.kernel_has_row_of_zeros and c.padding == 2 and tuple(c.kernel.shape) == (1, 1, 5, 5)
+    assert float(c.kernel[0, 0, 0, 3]) == 0.0 and float(c.kernel[0, 0, 2, 0]) == 0.0
+    assert float(c.kernel[0, 0, 1, 1]) == np.float32(3.2 / 16)
+    c = Conv2d(3, dilation=2)
+    assert c.padding == 2 and not c.kernel_has_row_of_zeros
+    c = Conv2d(14, padding=0)
+    assert c.padding == 0
+    # .double() widens the float32-rounded tap (part of the reference's semantics)
+    assert float(Conv2d(3).double().kernel[0, 0, 0, 0]) == float(np.float32(1 / 9))
+
+
+def test_nn_builds_matching_network():
+    m = readme_model()
+    net = m.nn(channels=16, in_channels=3, out_channels=10)
+    y = net(torch.randn(2, 3, 28, 28))
+    assert tuple(y.shape) == (2, 10, 1, 1)
+    assert m.layers() == 3
+    r = Sequential(Conv2d(3), resnet_block(1, True), resnet_block(), resnet_block(2, True, 2))
+    assert r.layers() == 1 + 2 + 2 + 2
+    y = r.nn(channels=4, in_channels=1)(torch.randn(1, 1, 28, 28))
+    assert tuple(y.shape) == (1, 8, 14, 14)
+    e = Conv2d(4, var_bias=0.5).nn(3)
+    assert e.kernel_size == (5, 5) and float(e.weight.detach()[0, 0, 0, 2]) == 0.0 and e.bias is not None
+
+
+def _simulate(ops, n_slots, shape):
+    """Interpret a program symbolically: every slot holds an expression string."""
+    slots = {0: "x"}
+    for o in ops:
+        s = slots[o.src]
+        if o.opcode == nat.OP_CONV:
+            slots[o.dst] = f"conv{o.ke - o.zero_first}s{o.stride}({s})"
+        elif o.opcode == nat.OP_RELU:
+            slots[o.dst] = f"relu({s})"
+        elif o.opcode == nat.OP_COPY:
+            slots[o.dst] = s
+        elif o.opcode == nat.OP_SCALE:
+            slots[o.dst] = f"{o.scale:.3f}*({s})"
+        elif o.opcode == nat.OP_ADD:
+            slots[o.dst] = f"({slots[o.dst]}+{s})"
+    return slots[ops[-1].dst] if ops else slots[0]
+
+
+def test_program_compiler_semantics():
+    m = Sequential(Conv2d(3), Sum([Sequential(), Sequential(ReLU(), Conv2d(3))]))
+    ops, ns = program.compile_model(m)
+    assert _simulate(ops, ns, None) in ("(conv3s1(relu(conv3s1(x)))+conv3s1(x))",)
+    assert ns == 2
+    # projection block: both branches read the post-ReLU map
+    m = resnet_block(2, True, 2)
+    ops, ns = program.compile_model(m)
+    assert _simulate(ops, ns, None) == "(conv1s2(relu(x))+conv3s1(relu(conv3s2(relu(x)))))"
+    # sum of two identities needs a copy
+    ops, ns = program.compile_model(Sum([Sequential(), Sequential()]))
+    assert _simulate(ops, ns, None) == "(x+x)"
+    # three branches keep left-to-right association up to commutativity of the first add
+    m = Sum([Conv2d(1), Sequential(), Conv2d(3)])
+    ops, ns = program.compile_model(m)
+    assert _simulate(ops, ns, None) == "((conv1s1(x)+x)+conv3s1(x))"
+    # mixture weights
+    m = Mixture([Sequential(), Conv2d(3)], logit_proportions=torch.tensor([0.0, 0.0]))
+    ops, ns = program.compile_model(m)
+    assert _simulate(ops, ns, None) == "(0.500*(x)+0.500*(conv3s1(x)))"
+
+
+def test_shipped_programs_need_two_slots_and_match_survey_flops():
+    # algorithmic flop per pair
+    want = {"readme": (3, 25873), "mnist_paper_convnet_gp": (1, 161505),
+            "mnist_paper_residual_cnn_gp": (1, 170913), "mnist_as_tf": (1, 241147), "mnist": (1, 241147),
+            "cifar10": (3, 319060)}
+    relu_px = {"readme": 980, "mnist_paper_convnet_gp": 5488, "mnist_paper_residual_cnn_gp": 7056,
+               "mnist_as_tf": 11026, "cifar10": 14401}
+    models = golden_models()
+    for name, (C, flops) in want.items():
+        ops, ns = program.compile_model(models[name])
+        S = 32 if name == "cifar10" else 28
+        plan = nat.Plan(ops, ns, S, S, nat.F32)
+        assert ns <= 2, name
+        assert plan.flops_per_pair(C) == flops, (name, plan.flops_per_pair(C))
+        if name in relu_px:
+            assert plan.aux_elems == relu_px[name]
+
+
+def test_plan_rejects_bad_programs():
+    ops, ns = program.compile_model(readme_model())
+    with pytest.raises(RuntimeError, match="not 1x1"):
+        nat.Plan(ops, ns, 30, 30, nat.F32)
+    with pytest.raises(RuntimeError, match="empty"):
+        nat.Plan(ops, ns, 4, 4, nat.F32)
+    bad = [nat.Op(opcode=nat.OP_ADD, src=1, dst=0)]
+    with pytest.raises(RuntimeError, match="before it is written"):
+        nat.Plan(bad, 2, 1, 1, nat.F32)
+
+
+def test_cpu_tensors_are_refused():
+    m = readme_model()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.randn(2, 3, 28, 28))
+    with pytest.raises(AssertionError):
+        m(torch.randn(2, 3, 28, 28), torch.randn(3, 3, 28, 28), diag=True)
+    with pytest.raises(AssertionError):
+        m(torch.randn(2, 3, 28, 28), torch.randn(2, 1, 28, 28))
+
+
+def test_tiles_match_reference_enumeration():
+    with open(os.path.join(GOLD, "tiles.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        got = data.worker_tiles(c["N"], c["N2"], c["bs"], c["rank"], c["n_workers"])
+        assert [list(map(int, t)) for t in got] == c["tiles"], c
+        start, count = data._this_worker_batch(data.tile_count(c["N"], c["N2"], c["bs"]), c["rank"], c["n_workers"])
+        assert (start, count) == (c["start"], c["count"])
+
+
+def test_product_iterator_serves_reference_batches():
+    X = data.ResidentDataset(torch.arange(10.).view(10, 1, 1, 1), torch.arange(10))
+    Z = data.ResidentDataset(torch.arange(7.).view(7, 1, 1, 1) + 100, torch.arange(7))
+    seen = []
+    it = cnn_gp.ProductIterator(4, X, None, worker_rank=1, n_workers=2)
+    assert len(it) == 3
+    for same, (i, (x, y)), (j, (x2, y2)) in it:
+        seen.append((same, i, j, x.flatten().tolist(), x2.flatten().tolist()))
+    assert seen == [(True, 4, 4, [4., 5., 6., 7.], [4., 5., 6., 7.]), (False, 4, 8, [4., 5., 6., 7.], [8., 9.]),
+                    (True, 8, 8, [8., 9.], [8., 9.])]
+    it = cnn_gp.ProductIterator(4, X, Z)
+    tiles = [(s, i, j, len(a[0]), len(b[0])) for s, (i, a), (j, b) in it]
+    assert tiles == [(False, 0, 0, 4, 4), (False, 0, 4, 4, 3), (False, 4, 0, 4, 4), (False, 4, 4, 4, 3),
+                     (False, 8, 0, 2, 4), (False, 8, 4, 2, 3)]
+    # generic map-style datasets go through default_collate
+    ds = torch.utils.data.TensorDataset(torch.arange(5.).view(5, 1, 1, 1), torch.arange(5))
+    (same, (i, (x, y)), (j, (x2, y2))), = list(cnn_gp.ProductIterator(8, ds))
+    assert same and i == 0 and j == 0 and x.shape == (5, 1, 1, 1) and y.tolist() == [0, 1, 2, 3, 4]
+    d = list(cnn_gp.DiagIterator(2, X, Z))
+    assert [(s, i, len(a[0]), len(b[0])) for s, (i, a), (j, b) in d] == [
+        (False, 0, 2, 2), (False, 2, 2, 2), (False, 4, 2, 2), (False, 6, 2, 1)]
+    assert len(cnn_gp.DiagIterator(3, X)) == 4
+
+
+def test_save_k_block_layout(tmp_path):
+    """save_K with a fake kernel: which blocks each worker writes (NaN elsewhere), chunking and
+    skip-if-present -- against the reference's own loop (tests/golden/save_k_layout.npz)."""
+    g = np.load(os.path.join(GOLD, "save_k_layout.npz"))
+    meta = json.loads(str(g["meta"]))
+    Xs = data.ResidentDataset(torch.from_numpy(g["Xs"]))
+    Xt = data.ResidentDataset(torch.from_numpy(g["Xt"]))
+
+    def kern(x, x2, same, diag):  # value = 1000*i + j, enough to check placement
+        if diag:
+            return np.ones(len(x), np.float32)
+        return np.ones((len(x), len(x2)), np.float32)
+
+    for nw in (1, 3):
+        for r in range(nw):
+            with block_store.open_store(str(tmp_path / f"s{nw}_{r}"), "w") as f:
+                cnn_gp.save_K(f, kern, "Kxx", Xs, None, diag=False, batch_size=4, worker_rank=r, n_workers=nw,
+                              print_interval=1e9)
+                cnn_gp.save_K(f, kern, "Kxtx", Xt, Xs, diag=False, batch_size=4, worker_rank=r, n_workers=nw,
+                              print_interval=1e9)
+                for name in ("Kxx", "Kxtx"):
+                    want = g[f"{name}_nw{nw}_r{r}"]
+                    got = f[name][...]
+                    assert got.shape == want.shape and got.dtype == np.float32
+                    np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+                    assert list(f[name].chunks) == meta[f"{name}_nw{nw}_r{r}"]["chunks"]
+                    assert list(f[name].maxshape) == meta[f"{name}_nw{nw}_r{r}"]["maxshape"]
+                # an existing dataset is skipped, not recomputed
+                cnn_gp.save_K(f, lambda *a: 1 / 0, "Kxx", Xs, None, diag=False, batch_size=4)
+    with block_store.open_store(str(tmp_path / "s1_0"), "a") as f:
+        cnn_gp.save_K(f, kern, "Kt_diag", Xt, None, diag=True, batch_size=4, print_interval=1e9)
+        assert f["Kt_diag"].shape == (1, 5) and list(f["Kt_diag"].chunks) == [1, 4]
+        A = np.empty((11, 11), np.float32)
+        f["Kxx"].read_direct(A, source_sel=np.s_[0, :, :])
+        assert np.isnan(A[4, 0]) and A[0, 4] == 1.0
+
+    def bad(x, x2, same, diag):
+        k = np.ones((len(x), len(x2)), np.float32)
+        k[0, 0] = np.inf
+        return k
+    with block_store.open_store(str(tmp_path / "bad"), "w") as f:
+        with pytest.raises(FloatingPointError):
+            cnn_gp.save_K(f, bad, "Kxx", Xs, None, diag=False, batch_size=4, print_interval=1e9)
+
+
+def test_merge_fills_only_nan(tmp_path):
+    a = block_store.open_store(str(tmp_path / "a"), "w")
+    b = block_store.open_store(str(tmp_path / "b"), "w")
+    da = a.create_dataset("K", shape=(1, 2, 2), dtype=np.float32, fillvalue=np.nan)
+    db = b.create_dataset("K", shape=(1, 2, 2), dtype=np.float32, fillvalue=np.nan)
+    b.create_dataset("only_b", shape=(1, 2), dtype=np.float32, fillvalue=np.nan)
+    da[0, 0, :] = [1, 2]
+    db[0, :, :] = [[9, 9], [3, 4]]
+    block_store.merge_into(a, b)
+    np.testing.assert_array_equal(a["K"][0], [[1, 2], [3, 4]])
+    assert "only_b" not in a
