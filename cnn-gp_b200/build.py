@@ -50,6 +50,10 @@ def build(force=False, verbose=False):
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _newer_than(LIB, objs):
         run([NVCC, "-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart"])
+    # measurement-only probes (roofline denominators for bench.py)
+    mb_src, mb_lib = os.path.join(CSRC, "microbench.cu"), os.path.join(HERE, "libcnngp_bench.so")
+    if force or _newer_than(mb_lib, [mb_src]):
+        run([NVCC] + FLAGS + ["-shared", mb_src, "-o", mb_lib, "-lcudart"])
     return LIB
 
 
