@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: image-pair kernel entries per second of the ConvNet-GP
+Gram recursion (BASELINE.json `metric`, quoted on configs[1]: mnist_paper_convnet_gp, full
+symmetric Gram of 10k synthetic 28x28x1 images).
+
+    python bench.py --gpus N --steps K --warmup W            our CUDA path
+    python bench.py --impl reference --steps K --warmup W    the CPU arm (oracle port, all threads)
+
+One "step" = one full pass of the hot path over the workload: per-image variance maps + every
+unique pair of the symmetric Gram, result written to HBM.  At N > 1 (torchrun, one rank per
+GPU) the workload grows with N (weak scaling: round(10000*sqrt(N)) images, N x the pairs), the
+reference's tile list (cnn_gp/data.py:11-29, tile `--tile`) is split contiguously over the
+ranks exactly like its `_this_worker_batch`, ranks compute with no communication, and the
+blocks are gathered on rank 0 (timed in `e2e`, not in `value`).
+
+JSON keys beyond the base contract:
+  roofline      dominant kernel (the Gram kernel) against the FP32 CUDA-core peak measured live
+                with an FFMA probe (MEASURED_PEAKS.json carries no FP32 figure); algorithmic
+                flop per pair from SURVEY.md 8(d) via cnngp_plan_flops_per_pair
+  cpu_baseline  the oracle port on the host cores, bounded sample (rank 0, N=1 only)
+  e2e           same metric through model(x) with HOST (pinned) inputs and outputs
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.join(ROOT, "cnn-gp_b200"), ROOT]
+
+CONFIG = "mnist_paper_convnet_gp"
+N_IMAGES = 10000
+C, S = 1, 28
+SEED = 1234
+METRIC = "image-pair kernel entries/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=CONFIG)
+    ap.add_argument("--n-images", type=int, default=N_IMAGES)
+    ap.add_argument("--tile", type=int, default=1000, help="tile edge for the multi-GPU tile list")
+    ap.add_argument("--path", default="auto", choices=["auto", "generic", "fused"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the baseline sample")
+    return ap.parse_args()
+
+
+def workload_dims(config):
+    return (3, 32) if config == "cifar10" else (C, S)
+
+
+def config_obj(args, world):
+    c, s = workload_dims(args.config)
+    n = int(round(args.n_images * world ** 0.5))
+    return {"workload": f"{args.config} full symmetric Gram, {n} synthetic {s}x{s}x{c} images "
+                        f"({n * (n + 1) // 2} unique pairs/step)",
+            "tile": "one launch" if world == 1 else args.tile, "parallelism": f"tiles/{world}",
+            "l2": "inputs+outputs per step exceed L2 (>=400 MB output, 220 MB variance maps)"}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_rate(model, config, seconds, repeats=1):
+    """pairs/s of the oracle port (all host threads) on a bounded tile of the same workload."""
+    import numpy as np
+    import torch
+    from oracle import oracle
+    c, s = workload_dims(config)
+    gen = torch.Generator().manual_seed(SEED)
+    X = torch.rand(512, c, s, s, generator=gen).numpy()
+    cores = oracle.num_threads()
+    t0 = time.perf_counter()
+    oracle.gram(model, X[:48], X[48:96])  # calibration
+    per_pair = (time.perf_counter() - t0) / (48 * 48)
+    edge = int(max(48, min(448, (seconds / max(per_pair, 1e-9)) ** 0.5)))
+    edge -= edge % 8
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        K = oracle.gram(model, X[:edge], X[512 - edge:])
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    assert np.isfinite(K).all()
+    return edge * edge / best, cores, f"{edge}x{edge} tile of {config}, same=False, float32, best of {repeats}"
+
+
+def run_reference(args):
+    """CPU arm: each step is one bounded tile of the workload through the oracle port."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model = importlib.import_module("configs." + args.config).initial_model
+    rates = []
+    cores = sample = None
+    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for k in range(args.warmup + args.steps):
+        r, cores, sample = cpu_rate(model, args.config, per_step)
+        if k >= args.warmup:
+            rates.append(r)
+    v = statistics.mean(rates)
+    edge = int(sample.split("x")[0])
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * edge * edge / v,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(config_obj(args, args.gpus), sample=sample),
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [f.strip() for f in line.split(",")]))
+
+    def summary(self, t0, t1):
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows if len(r) > 3 + k)]
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
+
+
+def fp32_peak_tflops():
+    L = ctypes.CDLL(os.path.join(ROOT, "cnn-gp_b200", "libcnngp_bench.so"))
+    L.mb_probe.restype = ctypes.c_double
+    L.mb_probe.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    return 2.0 * max(L.mb_probe(0, 8, 4000), L.mb_probe(0, 4, 4000)) / 1e12  # FMA = 2 flop
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cnn_gp import engine
+    from cnn_gp.tiles import GramJob, compute_worker_blocks, gather_blocks
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    engine.set_path(args.path)
+
+    c, s = workload_dims(args.config)
+    n = int(round(args.n_images * world ** 0.5))
+    model = importlib.import_module("configs." + args.config).initial_model.to(dev)
+    gen = torch.Generator().manual_seed(SEED)
+    X_host = torch.rand(n, c, s, s, generator=gen).pin_memory()
+    X = X_host.to(dev)
+    total_pairs = n * (n + 1) // 2
+    out = torch.empty((n, n), dtype=torch.float32, device=dev)
+
+    launches = [0]
+
+    def step_kernel():
+        """The hot path with inputs resident in HBM; returns (pairs, [events around gram launches])."""
+        job = GramJob(model, X)
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+        if world == 1:
+            job.block(out, 0, n, 0, n, symmetric=True)
+            pairs = total_pairs
+        else:
+            pairs = compute_worker_blocks(job, out, args.tile, rank, world)
+        ev[1].record()
+        launches[0] += job.launches
+        return pairs, ev, job.launches - 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step_kernel()
+    barrier()
+    # L2 (126 MB) is flushed between steps by the step itself: each step streams its n x n float32
+    # output (>= 400 MB) and ~220 MB of variance maps through L2.
+    sampler = ClockSampler(local)
+    time.sleep(0.3)
+    launches[0] = 0
+    gram_ms, gram_launches, my_pairs = 0.0, 0, 0
+    t_wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    evs = []
+    for _ in range(args.steps):
+        pairs, ev, nl = step_kernel()
+        my_pairs = pairs
+        evs.append(ev)
+        gram_launches += nl
+    e1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    gram_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.summary(t_wall0, t_wall1)
+    if world > 1:
+        t = torch.tensor([ms, gram_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, gram_ms_max = float(t[0]), float(t[1])
+    else:
+        gram_ms_max = gram_ms
+    ms_per_step = ms / args.steps
+    value = total_pairs / (ms_per_step * 1e-3)
+    n_launch = launches[0]
+
+    # ---- end to end through the public API with host buffers ----------------------------
+    K_host = torch.empty((n, n), dtype=torch.float32).pin_memory() if rank == 0 else None
+
+    def step_e2e():
+        x = X_host.to(dev, non_blocking=True)
+        if world == 1:
+            K = model(x)  # public call: plan lookup, variances, one fused launch
+        else:
+            K = torch.full((n, n), float("nan"), dtype=torch.float32, device=dev)
+            compute_worker_blocks(GramJob(model, x), K, args.tile, rank, world)
+            K = gather_blocks(K, dst=0)
+        if rank == 0:
+            K_host.copy_(K, non_blocking=True)
+        torch.cuda.synchronize()
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+
+    if rank == 0:
+        plan = engine.plan_for(model, s, s, torch.float32)
+        f_alg = plan.flops_per_pair(c)
+        peak = fp32_peak_tflops()
+        # dominant kernel = the Gram kernel; achieved = algorithmic flop of this rank's launches / their time
+        achieved = f_alg * my_pairs * args.steps / (gram_ms * 1e-3) / 1e12
+        roof = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None,
+                "note": "FP32 CUDA-core bound (SURVEY 8d); peak = FFMA probe measured in this run "
+                        "(MEASURED_PEAKS.json has no FP32 figure); achieved = F_alg x pairs / CUDA-event time of "
+                        "the Gram launches on torch's current stream",
+                "flops_per_pair": f_alg, "kernel": engine.last_path(),
+                "avg_launch_ms": gram_ms / max(1, gram_launches)}
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_obj(args, world),
+            "roofline": roof,
+            "e2e": {"value": total_pairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": X_host.numel() * 4,
+                    "d2h_bytes_per_step": n * n * 4, "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": n_launch,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample = cpu_rate(model.cpu(), args.config, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

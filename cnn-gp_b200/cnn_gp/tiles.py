@@ -1,0 +1,95 @@
+"""Gram matrices of GPU-resident datasets, tile list sharded over workers.
+
+The reference computes one 200 x 200 tile per Python iteration, copying both image batches to
+the device and the result back every time (exp_mnist_resnet/save_kernel.py:21-24,
+cnn_gp/kernel_save_tools.py:49-58).  Here the images stay in HBM, the per-image variance maps
+are computed once per dataset, and a worker's contiguous slice of the reference's tile list
+(cnn_gp/data.py:11-29) is evaluated with at most two launches per block row: the diagonal tile
+(symmetric: only j >= i is computed) and the rectangle to its right.
+
+Tiles are independent, so workers never talk to each other while computing; `gather_blocks`
+is the single exchange step (the reference does it through files, merge_h5_files.py).
+"""
+import torch
+
+from . import engine
+from .data import worker_tiles
+
+
+class GramJob:
+    """Variance maps + plan for one (model, X[, X2]) pair, ready to evaluate any tile."""
+
+    def __init__(self, model, X, X2=None):
+        self.model = model
+        self.X = X.contiguous()
+        self.same = X2 is None
+        self.X2 = self.X if self.same else X2.contiguous()
+        assert self.X.is_cuda and self.X2.is_cuda
+        with torch.cuda.device(self.X.device):
+            self.plan = engine.plan_for(model, X.shape[2], X.shape[3], X.dtype)
+            self.aux_x, _, self.kdiag = engine.variances(self.plan, self.X)
+            self.aux_x2 = self.aux_x if self.same else engine.variances(self.plan, self.X2)[0]
+        self.launches = 1 if self.same else 2
+
+    def block(self, out, i0, i1, j0, j1, symmetric):
+        """out[i0:i1, j0:j1] = K(X[i0:i1], X2[j0:j1]) (upper triangle mirrored when symmetric)."""
+        with torch.cuda.device(self.X.device):
+            engine.gram_with_aux(self.plan, self.X[i0:i1], self.X2[j0:j1], self.aux_x[i0:i1],
+                                 self.aux_x2[j0:j1], same=symmetric, diag=False, symmetric=symmetric,
+                                 out=out[i0:i1, j0:j1])
+        self.launches += 1
+
+
+def row_segments(tiles):
+    """Group a contiguous slice of the reference tile list by block row:
+    -> [(block_row, has_diag_tile, first_col, last_col_exclusive)], columns excluding the
+    diagonal tile (first_col is None when the row holds only its diagonal tile)."""
+    rows, order = {}, []
+    for same, i, j in tiles:
+        if i not in rows:
+            rows[i] = [False, None, None]
+            order.append(i)
+        seg = rows[i]
+        if same:
+            seg[0] = True
+        elif seg[1] is None:
+            seg[1], seg[2] = j, j + 1
+        else:
+            assert j == seg[2], "tile slice is not contiguous within a row"
+            seg[2] = j + 1
+    return [(i, rows[i][0], rows[i][1], rows[i][2]) for i in order]
+
+
+def compute_worker_blocks(job, out, batch_size, worker_rank=0, n_workers=1):
+    """Fill ``out`` ([N, N2], any float dtype matching the job) with this worker's tiles; entries
+    owned by other workers are left untouched.  Returns the number of unique pairs computed."""
+    N, N2 = job.X.shape[0], job.X2.shape[0]
+    tiles = worker_tiles(N, None if job.same else N2, batch_size, worker_rank, n_workers)
+    pairs = 0
+    for r, has_diag, c0, c1 in row_segments(tiles):
+        i0, i1 = r * batch_size, min(N, (r + 1) * batch_size)
+        if has_diag:
+            job.block(out, i0, i1, i0, i1, symmetric=True)
+            pairs += (i1 - i0) * (i1 - i0 + 1) // 2
+        if c0 is not None:
+            j0, j1 = c0 * batch_size, min(N2, c1 * batch_size)
+            job.block(out, i0, i1, j0, j1, symmetric=False)
+            pairs += (i1 - i0) * (j1 - j0)
+    return pairs
+
+
+def gather_blocks(out, dst=0, group=None):
+    """Combine the workers' partial matrices on rank ``dst``: every entry is NaN on all workers
+    but its owner (the NaN-fill / merge-where-NaN contract of kernel_save_tools.py:21-23 and
+    merge_h5_files.py:27-28), so a NaN-ignoring reduction reproduces the merge.  Uses a SUM of
+    NaN-zeroed matrices plus a SUM of ownership masks over NCCL (NVLink / NVSwitch)."""
+    import torch.distributed as dist
+    owned = ~torch.isnan(out)
+    vals = torch.where(owned, out, torch.zeros_like(out))
+    cnt = owned.to(out.dtype)
+    dist.reduce(vals, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    dist.reduce(cnt, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    if dist.get_rank(group) == dst:
+        vals[cnt == 0] = float("nan")
+        return vals
+    return None
