@@ -73,7 +73,7 @@ def variances(plan, x, z=None):
     return aux_x, aux_z, kdiag
 
 
-def gram_with_aux(plan, x, z, aux_x, aux_z, same, diag, symmetric, out=None):
+def gram_with_aux(plan, x, z, aux_x, aux_z, same, diag, symmetric, out=None, kdiag=None):
     """One cnngp_gram launch on prepared operands; ``out`` may be a (strided-row) view."""
     N1, N2, C = x.shape[0], z.shape[0], x.shape[1]
     if out is None:
@@ -83,6 +83,7 @@ def gram_with_aux(plan, x, z, aux_x, aux_z, same, diag, symmetric, out=None):
         assert out.stride(1) == 1 and out.shape == (N1, N2)
     nat.check(nat.lib().cnngp_gram(
         plan.handle, x.data_ptr(), N1, z.data_ptr(), N2, C, aux_x.data_ptr(), aux_z.data_ptr(),
+        kdiag.data_ptr() if kdiag is not None else None,
         int(same), int(diag), int(symmetric), out.data_ptr(), ld, _PATH_CODE[_force_path], _stream()),
         "cnngp_gram")
     return out
@@ -109,11 +110,12 @@ def gram(model, x, y, same, diag):
             return torch.empty((N1,) if diag else (N1, N2), dtype=x.dtype, device=x.device)
         symmetric = bool(same and identical)
         if same and not identical:
-            aux_x, aux_z, _ = variances(plan, x, y)
+            aux_x, aux_z, kdiag = variances(plan, x, y)
         else:
-            aux_x, _, _ = variances(plan, x)
+            aux_x, _, kdiag = variances(plan, x)
             aux_z = aux_x if identical else variances(plan, y)[0]
-        return gram_with_aux(plan, x, y, aux_x, aux_z, same, diag, symmetric)
+        return gram_with_aux(plan, x, y, aux_x, aux_z, same, diag, symmetric,
+                             kdiag=kdiag if symmetric else None)
 
 
 def _conv_op(mod):

@@ -36,7 +36,7 @@ class GramJob:
         with torch.cuda.device(self.X.device):
             engine.gram_with_aux(self.plan, self.X[i0:i1], self.X2[j0:j1], self.aux_x[i0:i1],
                                  self.aux_x2[j0:j1], same=symmetric, diag=False, symmetric=symmetric,
-                                 out=out[i0:i1, j0:j1])
+                                 out=out[i0:i1, j0:j1], kdiag=self.kdiag[i0:i1] if symmetric else None)
         self.launches += 1
 
 

@@ -1,17 +1,450 @@
-// gram_fused.cu -- register-resident fused Gram kernel (placeholder until the kernel lands).
+// gram_fused.cu -- register-resident fused Gram kernel for sm_100a.
+//
+// One warp owns a 2 x 2 block of image pairs and keeps their four covariance maps in
+// registers for the whole layer stack: lane = one coordinate of the map, register index = the
+// other.  A box convolution is a sliding-window sum along the register axis, a transposition
+// through the warp's private shared-memory tile, and a second sliding-window sum; every layer
+// therefore flips the map between "lane = column" and "lane = row" layout.  The ReLU step is
+// element-wise in registers and reads the per-image standard deviations (s, 1/s) of the eight
+// warps' twelve images from a double-buffered shared-memory stage that a producer warp fills
+// one layer ahead with bulk async copies (cp.async.bulk + mbarrier, SASS UBLKCP).  The dense
+// last layer is a register sum plus a warp-shuffle reduction.  Nothing but the final kernel
+// entry is written to HBM.
+//
+// Reference semantics (paths relative to /root/reference):
+//   init   cnn_gp/kernels.py:43-49     conv  cnn_gp/kernels.py:92-98
+//   relu   cnn_gp/kernels.py:146-152 rewritten as
+//            xy' = relu(c)/2 + s * e^1.5 * H(e),  s = sqrt(xx*yy), e = 1 - |c|/s
+//          where H is analytic on [0,1] (degree-6 minimax fit, error below float32 rounding);
+//          this needs one MUFU.SQRT per pixel instead of rsqrt + sqrt + acos + divide.
+//          The factor 1/2 is folded into the next convolution's tap (exact: power of two).
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
 #include "plan.h"
 
 namespace cnngp {
 
-struct FusedPlan { int unused; };
+namespace {
 
-FusedPlan *fused_plan_create(const Plan *) { return nullptr; }
+constexpr int kWarps = 8;                    // consumer warps per CTA
+constexpr int kTileI = 4, kTileJ = 8;        // images per CTA along i and j (2 x 4 warps of 2 x 2)
+constexpr int kImgs = kTileI + kTileJ;       // variance-map rows staged per layer
+constexpr int kThreads = (kWarps + 1) * 32;  // + producer warp
+constexpr int kMaxOps = 40;
+constexpr int kSuperJ = 64, kSuperI = 128;   // super-tile = 512 x 512 images (L2-resident variance maps)
+
+enum { F_CONV = 0, F_RELU = 1, F_DENSE = 2 };
+
+struct FOp {
+    int kind;
+    int lo, hi;     // F_CONV: window offsets [-lo, +hi] along each axis
+    float scale, bias;
+    int aux_off;    // F_RELU: offset (in pixels) of this layer inside the per-image fused row
+};
+
+struct FParams {
+    FOp ops[kMaxOps];
+    int n_ops, n_relu;
+    const float *x, *z;          // images [N, C, S, S]
+    const float *aux_x, *aux_z;  // per-image rows; fused (s, 1/s) maps start at aux_f_off floats
+    long long aux_stride;        // floats per image row
+    int aux_f_off;
+    int N1, N2, C;
+    float *out;
+    long long ld_out;
+    int symmetric;
+    const float *kdiag;
+    int nbi, nbj;      // CTA tiles along i / j
+    int sti, stj;      // super-tile size in CTA tiles
+    int nst_j;         // super-tiles along j (non-symmetric)
+    int nst;           // super-tiles per side (symmetric)
+};
+
+// ---- PTX helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n"
+            " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ float sqrt_approx(float v) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// 2*H(e) on [0,1]: out = relu(c) + (s-|c|) * sqrt(e) * H2(e) is twice the reference's ReLU output.
+__device__ __forceinline__ float h2_poly(float e) {
+    float h = 7.577116048e-05f;
+    h = fmaf(h, e, -5.945927478e-05f);
+    h = fmaf(h, e, 2.400144585e-04f);
+    h = fmaf(h, e, 5.259375321e-04f);
+    h = fmaf(h, e, 2.417275915e-03f);
+    h = fmaf(h, e, 1.500489842e-02f);
+    h = fmaf(h, e, 3.001054525e-01f);
+    return h;
+}
+
+// Sliding-window box sum along the register axis with zero padding: out[y] = sum_{t=-LO..HI} v[y+t].
+template <int S, int LO, int HI>
+__device__ __forceinline__ void box_pass(float (&v)[S]) {
+    if (LO == 0 && HI == 0) return;
+    float o[S];
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t <= HI && t < S; ++t) acc += v[t];
+    o[0] = acc;
+#pragma unroll
+    for (int y = 1; y < S; ++y) {
+        if (y + HI < S) acc += v[y + HI];
+        if (y - LO - 1 >= 0) acc -= v[y - LO - 1];
+        o[y] = acc;
+    }
+#pragma unroll
+    for (int y = 0; y < S; ++y) v[y] = o[y];
+}
+
+template <int S>
+__device__ __forceinline__ void box_pass_dyn(float (&v)[S], int lo, int hi) {
+    // the shipped programs: k7 (3,3), k3 (1,1), k4 "same" (1,2), k5 (2,2), k1 (0,0)
+    if (lo == 3 && hi == 3) box_pass<S, 3, 3>(v);
+    else if (lo == 1 && hi == 1) box_pass<S, 1, 1>(v);
+    else if (lo == 1 && hi == 2) box_pass<S, 1, 2>(v);
+    else if (lo == 2 && hi == 2) box_pass<S, 2, 2>(v);
+}
+
+// Transpose the four maps of this warp through its private smem tile, two maps at a time.
+template <int S>
+__device__ __forceinline__ void transpose4(float (&m)[4][S], float2 *tile, int lane, int lx) {
+    constexpr int PITCH = S + 1;  // odd: both the row-wise write and the column-wise read are conflict-free
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (lane < S) {
+#pragma unroll
+            for (int r = 0; r < S; ++r) tile[r * PITCH + lane] = make_float2(m[2 * h][r], m[2 * h + 1][r]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < S; ++r) {
+            const float2 t = tile[lx * PITCH + r];
+            m[2 * h][r] = t.x;
+            m[2 * h + 1][r] = t.y;
+        }
+        __syncwarp();
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constant__ FParams p) {
+    constexpr int P = S * S;
+    constexpr int PITCH = S + 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // [2][kImgs][P] float2 variance stage | [kWarps][S*PITCH] float2 transpose tiles | barriers
+    float2 *stage = reinterpret_cast<float2 *>(smem_raw);
+    float2 *tiles = stage + 2 * kImgs * P;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + kWarps * S * PITCH);
+    uint64_t *full = bars, *empty = bars + 2;
+
+    // ---- which CTA tile -------------------------------------------------------------------
+    const int per_st = p.sti * p.stj;
+    const int st = blockIdx.x / per_st, w_in = blockIdx.x - st * per_st;
+    int si, sj;
+    if (p.symmetric) {  // upper-triangular enumeration of square super-tiles
+        int r = 0, rem = st;
+        while (rem >= p.nst - r) { rem -= p.nst - r; ++r; }
+        si = r; sj = r + rem;
+    } else {
+        si = st / p.nst_j; sj = st - si * p.nst_j;
+    }
+    const int ib = si * p.sti + w_in / p.stj;
+    const int jb = sj * p.stj + w_in % p.stj;
+    if (ib >= p.nbi || jb >= p.nbj) return;
+    if (p.symmetric && jb * kTileJ + (kTileJ - 1) < ib * kTileI) return;  // entirely below the diagonal
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        mbar_init(&empty[0], kWarps); mbar_init(&empty[1], kWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int i_base = ib * kTileI, j_base = jb * kTileJ;
+
+    if (warp == kWarps) {
+        // ---- producer: stage layer l's (s, 1/s) maps of the 12 images, one layer ahead ----
+        if (lane == 0) {
+            for (int l = 0, k = 0; k < p.n_ops; ++k) {
+                if (p.ops[k].kind != F_RELU) continue;
+                const int buf = l & 1;
+                if (l >= 2) mbar_wait(&empty[buf], ((l >> 1) - 1) & 1);
+                mbar_arrive_expect_tx(&full[buf], kImgs * P * 8);
+                float2 *dst = stage + buf * kImgs * P;
+                const long long off = p.aux_f_off + 2LL * p.ops[k].aux_off;
+                for (int s = 0; s < kImgs; ++s) {
+                    const float *src;
+                    if (s < kTileI) src = p.aux_x + (long long)min(i_base + s, p.N1 - 1) * p.aux_stride + off;
+                    else src = p.aux_z + (long long)min(j_base + s - kTileI, p.N2 - 1) * p.aux_stride + off;
+                    bulk_g2s(dst + s * P, src, P * 8, &full[buf]);
+                }
+                ++l;
+            }
+        }
+        return;
+    }
+
+    // ---- consumers ------------------------------------------------------------------------
+    const int wi = warp >> 2, wj = warp & 3;
+    const int lx = lane < S ? lane : S - 1;  // clamped lane for loads
+    float2 *tile = tiles + warp * S * PITCH;
+    int gi[2], gj[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        gi[a] = min(i_base + wi * 2 + a, p.N1 - 1);
+        gj[a] = min(j_base + wj * 2 + a, p.N2 - 1);
+    }
+
+    float m[4][S];  // pair (a, b) -> m[2a + b]
+    {
+        // init, kernels.py:43-49: lane = column, register = row
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int r = 0; r < S; ++r) m[q][r] = 0.f;
+        for (int c = 0; c < p.C; ++c) {
+            const float *x0 = p.x + ((long long)gi[0] * p.C + c) * P + lx;
+            const float *x1 = p.x + ((long long)gi[1] * p.C + c) * P + lx;
+            const float *z0 = p.z + ((long long)gj[0] * p.C + c) * P + lx;
+            const float *z1 = p.z + ((long long)gj[1] * p.C + c) * P + lx;
+#pragma unroll
+            for (int r = 0; r < S; ++r) {
+                const float a0 = __ldg(x0 + r * S), a1 = __ldg(x1 + r * S);
+                const float b0 = __ldg(z0 + r * S), b1 = __ldg(z1 + r * S);
+                m[0][r] = fmaf(a0, b0, m[0][r]);
+                m[1][r] = fmaf(a0, b1, m[1][r]);
+                m[2][r] = fmaf(a1, b0, m[2][r]);
+                m[3][r] = fmaf(a1, b1, m[3][r]);
+            }
+        }
+        if (p.C > 1) {
+            const float cnt = (float)p.C;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int r = 0; r < S; ++r) m[q][r] = __fdiv_rn(m[q][r], cnt);
+        }
+    }
+
+    int relu_l = 0;
+    for (int k = 0; k < p.n_ops; ++k) {
+        const FOp o = p.ops[k];
+        if (o.kind == F_CONV) {
+            if (o.lo != 0 || o.hi != 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) box_pass_dyn<S>(m[q], o.lo, o.hi);
+                transpose4<S>(m, tile, lane, lx);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) box_pass_dyn<S>(m[q], o.lo, o.hi);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int r = 0; r < S; ++r) m[q][r] = fmaf(m[q][r], o.scale, o.bias);
+        } else if (o.kind == F_RELU) {
+            const int buf = relu_l & 1;
+            mbar_wait(&full[buf], (relu_l >> 1) & 1);
+            const float2 *sb = stage + buf * kImgs * P + lx;
+            const float2 *ai0 = sb + (wi * 2 + 0) * P, *ai1 = sb + (wi * 2 + 1) * P;
+            const float2 *bj0 = sb + (kTileI + wj * 2 + 0) * P, *bj1 = sb + (kTileI + wj * 2 + 1) * P;
+#pragma unroll
+            for (int r = 0; r < S; ++r) {
+                const float2 A0 = ai0[r * S], A1 = ai1[r * S], B0 = bj0[r * S], B1 = bj1[r * S];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 A = (q & 2) ? A1 : A0, B = (q & 1) ? B1 : B0;
+                    const float s = A.x * B.x, rr = A.y * B.y;
+                    const float c = m[q][r];
+                    const float d = s - fabsf(c);
+                    const float e = d * rr;
+                    const float w = d * sqrt_approx(fabsf(e));
+                    m[q][r] = fmaf(w, h2_poly(e), fmaxf(c, 0.f));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[buf]);
+            ++relu_l;
+        } else {  // F_DENSE: whole-map sum, scale, bias -> the kernel entry
+            float tot[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float a = 0.f;
+#pragma unroll
+                for (int r = 0; r < S; ++r) a += m[q][r];
+                if (lane >= S) a = 0.f;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+                tot[q] = fmaf(a, o.scale, o.bias);
+            }
+            if (lane < 4) {
+                const int a = lane >> 1, b = lane & 1;
+                const int i = i_base + wi * 2 + a, j = j_base + wj * 2 + b;
+                const float v = lane == 0 ? tot[0] : lane == 1 ? tot[1] : lane == 2 ? tot[2] : tot[3];
+                if (i < p.N1 && j < p.N2) {
+                    if (!p.symmetric) {
+                        p.out[(long long)i * p.ld_out + j] = v;
+                    } else if (j > i) {
+                        p.out[(long long)i * p.ld_out + j] = v;
+                        p.out[(long long)j * p.ld_out + i] = v;
+                    } else if (j == i) {
+                        // i == j follows the variance recursion (kernels.py:155-162)
+                        p.out[(long long)i * p.ld_out + i] = p.kdiag ? p.kdiag[i] : v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+struct FusedPlan {
+    int S = 0;
+    int n_ops = 0, n_relu = 0;
+    FOp ops[kMaxOps];
+    size_t smem = 0;
+};
+
+// Decide whether the program is in the fused kernel's set and, if so, translate it.  Also marks
+// which ReLU layers consume their variance maps in transposed (lane = row) layout.
+FusedPlan *fused_plan_create(const Plan *plan_const) {
+    Plan *plan = const_cast<Plan *>(plan_const);
+    if (plan->dtype != CNNGP_F32) return nullptr;
+    if (plan->H != plan->W || plan->H != 28) return nullptr;
+    if (plan->aux_elems % 4 != 0) return nullptr;
+    const int S = plan->H;
+    FusedPlan fp;
+    fp.S = S;
+    int cur = 0;             // the slot the straight-line program lives in
+    bool transposed = false;  // current register layout: lane = row?
+    float pending = 1.f;     // power-of-two factor owed by the ReLU's doubled output
+    bool done = false;
+    for (size_t k = 0; k < plan->ops.size(); ++k) {
+        DevOp &o = plan->ops[k];
+        if (done || fp.n_ops >= kMaxOps) return nullptr;
+        if (o.src != cur) return nullptr;
+        FOp f{};
+        if (o.opcode == CNNGP_OP_CONV) {
+            if (o.dil != 1 || o.stride != 1) return nullptr;
+            if (o.Hi != S || o.Wi != S) return nullptr;
+            const int lo = o.pad - o.t0, hi = o.ke - 1 - o.pad;
+            if (o.Ho == S && o.Wo == S) {
+                if (lo < 0 || hi < 0) return nullptr;
+                const bool known = (lo == 0 && hi == 0) || (lo == 3 && hi == 3) || (lo == 1 && hi == 1) ||
+                                   (lo == 1 && hi == 2) || (lo == 2 && hi == 2);
+                if (!known) return nullptr;
+                f.kind = F_CONV; f.lo = lo; f.hi = hi;
+                if (lo || hi) transposed = !transposed;
+            } else if (o.Ho == 1 && o.Wo == 1 && o.pad == 0 && o.t0 == 0 && o.ke == S) {
+                f.kind = F_DENSE;
+                done = true;
+            } else {
+                return nullptr;
+            }
+            f.scale = o.scale_f * pending;
+            f.bias = o.bias_f;
+            pending = 1.f;
+        } else if (o.opcode == CNNGP_OP_RELU) {
+            if (pending != 1.f) return nullptr;  // ReLU directly after ReLU: not in the set
+            if (o.Hi != S || o.Wi != S) return nullptr;
+            f.kind = F_RELU;
+            f.aux_off = o.aux_off;
+            o.aux_t = transposed ? 1 : 0;
+            pending = 0.5f;
+            ++fp.n_relu;
+        } else {
+            return nullptr;
+        }
+        cur = o.dst;
+        fp.ops[fp.n_ops++] = f;
+    }
+    if (!done) {
+        for (DevOp &o : plan->ops) o.aux_t = 0;
+        return nullptr;
+    }
+    fp.smem = (size_t)2 * kImgs * S * S * 8 + (size_t)kWarps * S * (S + 1) * 8 + 64;
+    return new FusedPlan(fp);
+}
+
 void fused_plan_destroy(FusedPlan *fp) { delete fp; }
 
-int launch_fused_gram(const Plan *, const void *, int64_t, const void *, int64_t, int32_t, const void *,
-                      const void *, int32_t, int32_t, int32_t, void *, int64_t, void *) {
-    set_error("fused kernel not built");
-    return 4;
+int launch_fused_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2,
+                      int32_t C, const void *d_aux_x, const void *d_aux_z, int32_t same, int32_t diag,
+                      int32_t symmetric, const void *d_kdiag, void *d_out, int64_t ld_out, void *stream) {
+    (void)same;
+    const FusedPlan *fp = plan->fused;
+    if (!fp || diag) { set_error("fused kernel: unsupported call"); return 4; }
+    if (N1 > 2000000000LL || N2 > 2000000000LL) { set_error("fused kernel: too many images"); return 8; }
+    FParams p{};
+    memcpy(p.ops, fp->ops, sizeof(FOp) * fp->n_ops);
+    p.n_ops = fp->n_ops; p.n_relu = fp->n_relu;
+    p.x = (const float *)d_x; p.z = (const float *)d_z;
+    p.aux_x = (const float *)d_aux_x; p.aux_z = (const float *)d_aux_z;
+    p.aux_stride = plan->aux_elems; p.aux_f_off = plan->aux_f_off;
+    p.N1 = (int)N1; p.N2 = (int)N2; p.C = C;
+    p.out = (float *)d_out; p.ld_out = ld_out;
+    p.symmetric = symmetric ? 1 : 0;
+    p.kdiag = (const float *)d_kdiag;
+    p.nbi = (int)((N1 + kTileI - 1) / kTileI);
+    p.nbj = (int)((N2 + kTileJ - 1) / kTileJ);
+    long long n_super;
+    if (p.nbi <= kSuperI && p.nbj <= kSuperJ) {  // one (possibly small) super-tile
+        p.sti = p.nbi; p.stj = p.nbj; p.nst_j = 1; p.nst = 1;
+        n_super = 1;
+    } else {
+        p.sti = kSuperI; p.stj = kSuperJ;
+        const int nsi = (p.nbi + kSuperI - 1) / kSuperI, nsj = (p.nbj + kSuperJ - 1) / kSuperJ;
+        p.nst_j = nsj;
+        p.nst = nsi > nsj ? nsi : nsj;
+        n_super = p.symmetric ? (long long)p.nst * (p.nst + 1) / 2 : (long long)nsi * nsj;
+    }
+    const long long blocks = n_super * p.sti * p.stj;
+    if (blocks > 2147483647LL) { set_error("fused kernel: grid too large for one launch"); return 8; }
+    auto kern = fused_kernel<28>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem);
+    if (e != cudaSuccess) { set_error(std::string("fused cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 7; }
+    kern<<<(unsigned)blocks, kThreads, fp->smem, (cudaStream_t)stream>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error(std::string("fused kernel launch: ") + cudaGetErrorString(e)); return 9; }
+    return 0;
 }
 
 }  // namespace cnngp

@@ -67,6 +67,7 @@ struct GenericParams {
     int64_t N1, N2, Q;  // Q = number of entries
     const T *aux_x, *aux_z;
     int64_t aux_elems;
+    int aux_f_off;  // variance mode: where the fused (s, 1/s) maps start in a row (0 = none)
     T *out;
     int64_t ld_out;
     int same, diag, sym, final_slot;
@@ -196,6 +197,16 @@ __global__ void __launch_bounds__(kThreads) generic_kernel(GenericParams<T> p) {
                         const size_t arow = (size_t)ei[g0] * p.aux_elems + o.aux_off + px;
                         const T v0 = slot(o.src, g0)[px];
                         p.aux_x_out[arow] = v0;
+                        if (p.aux_f_off > 0) {
+                            // operands of the fused kernel's ReLU: s = sqrt(xx) (+ sqrt(f32_tiny), the
+                            // separable stand-in for kernels.py:146's "+ f32_tiny") and 1/s, stored in the
+                            // register layout that kernel is in when it reaches this layer
+                            const int tp = o.aux_t ? (px % o.Wi) * o.Hi + px / o.Wi : px;
+                            const T sd = add_rn(sqrt_rn(v0), (T)1.0842021724855044e-19);
+                            T *f = p.aux_x_out + (size_t)ei[g0] * p.aux_elems + p.aux_f_off + 2 * (size_t)(o.aux_off + tp);
+                            f[0] = sd;
+                            f[1] = div_rn((T)1, sd);
+                        }
                         const T h0 = div_rn(v0, (T)2);  // kernels.py:154
                         if (p.NP == 2) {
                             p.aux_z_out[arow] = slot(o.src, g0 + 1)[px];
@@ -260,6 +271,7 @@ int launch(const Plan *plan, GenericParams<T> &gp, int NP, cudaStream_t st) {
     gp.H = plan->H; gp.W = plan->W;
     gp.final_slot = plan->final_slot;
     gp.aux_elems = plan->aux_elems;
+    gp.aux_f_off = plan->aux_f_off;
     gp.NP = NP;
     int dev = 0;
     cudaGetDevice(&dev);

@@ -49,7 +49,7 @@ int build_plan(const cnngp_op *ops, int32_t n_ops, int32_t n_slots, int32_t H, i
         DevOp d{};
         d.opcode = o.opcode; d.src = o.src; d.dst = o.dst;
         d.Hi = slot[o.src].h; d.Wi = slot[o.src].w; d.Ho = d.Hi; d.Wo = d.Wi;
-        d.aux_off = 0; d.relu_index = -1;
+        d.aux_off = 0; d.relu_index = -1; d.aux_t = 0;
         d.scale_d = o.scale; d.bias_d = o.bias; d.scale_f = (float)o.scale; d.bias_f = (float)o.bias;
         switch (o.opcode) {
             case CNNGP_OP_CONV: {
@@ -89,7 +89,12 @@ int build_plan(const cnngp_op *ops, int32_t n_ops, int32_t n_slots, int32_t H, i
         delete p;
         return 3;
     }
+    p->relu_elems = (int32_t)p->aux_elems;
     p->fused = fused_plan_create(p);
+    if (p->fused) {  // rows grow by the (s, 1/s) float2 maps the fused kernel stages
+        p->aux_f_off = p->relu_elems;
+        p->aux_elems = 3LL * p->relu_elems;
+    }
     *out = p;
     return 0;
 }
@@ -176,8 +181,8 @@ int cnngp_variances(const cnngp_plan *plan, const void *d_x, const void *d_z, in
 }
 
 int cnngp_gram(const cnngp_plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2,
-               int32_t C, const void *d_aux_x, const void *d_aux_z, int32_t same, int32_t diag,
-               int32_t symmetric, void *d_out, int64_t ld_out, int32_t path, void *stream) {
+               int32_t C, const void *d_aux_x, const void *d_aux_z, const void *d_kdiag, int32_t same,
+               int32_t diag, int32_t symmetric, void *d_out, int64_t ld_out, int32_t path, void *stream) {
     const Plan *p = reinterpret_cast<const Plan *>(plan);
     if (!p || !d_x || !d_z || !d_out || N1 < 0 || N2 < 0 || C < 1) { set_error("cnngp_gram: bad arguments"); return 1; }
     if (p->aux_elems > 0 && (!d_aux_x || !d_aux_z)) { set_error("cnngp_gram: variance maps missing"); return 1; }
@@ -201,7 +206,7 @@ int cnngp_gram(const cnngp_plan *plan, const void *d_x, int64_t N1, const void *
     if (use_fused && diag) use_fused = false;  // O(N) work: generic is enough
     g_last_path = use_fused ? CNNGP_PATH_FUSED : CNNGP_PATH_GENERIC;
     if (use_fused)
-        return launch_fused_gram(p, d_x, N1, d_z, N2, C, d_aux_x, d_aux_z, same, diag, symmetric, d_out, ld_out, stream);
+        return launch_fused_gram(p, d_x, N1, d_z, N2, C, d_aux_x, d_aux_z, same, diag, symmetric, d_kdiag, d_out, ld_out, stream);
     return launch_generic_gram(p, d_x, N1, d_z, N2, C, d_aux_x, d_aux_z, same, diag, symmetric, d_out, ld_out, stream);
 }
 

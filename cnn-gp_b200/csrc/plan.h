@@ -18,6 +18,7 @@ struct DevOp {
     int32_t Hi, Wi, Ho, Wo;            // input / output map size of this op
     int32_t aux_off;                   // RELU: offset of its variance map in the per-image aux row
     int32_t relu_index;                // RELU: ordinal
+    int32_t aux_t;                     // RELU: fused (s, 1/s) map stored transposed (lane = row layout)
     float scale_f, bias_f;
     double scale_d, bias_d;
 };
@@ -27,7 +28,9 @@ struct FusedPlan;  // gram_fused.cu
 struct Plan {
     int32_t n_ops = 0, n_slots = 0, H = 0, W = 0, dtype = 0;
     std::vector<DevOp> ops;
-    int64_t aux_elems = 0;
+    int64_t aux_elems = 0;    // floats per image row: xx maps [+ fused (s, 1/s) maps]
+    int32_t relu_elems = 0;   // sum of ReLU input map sizes
+    int32_t aux_f_off = 0;    // offset of the fused maps inside a row (0 = none)
     int32_t n_relu = 0;
     int32_t max_map = 0;      // largest map (or separable-conv intermediate) in elements
     int32_t final_slot = 0;
@@ -61,6 +64,6 @@ FusedPlan *fused_plan_create(const Plan *plan);  // nullptr if not covered
 void fused_plan_destroy(FusedPlan *fp);
 int launch_fused_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2,
                       int32_t C, const void *d_aux_x, const void *d_aux_z, int32_t same, int32_t diag,
-                      int32_t symmetric, void *d_out, int64_t ld_out, void *stream);
+                      int32_t symmetric, const void *d_kdiag, void *d_out, int64_t ld_out, void *stream);
 
 }  // namespace cnngp

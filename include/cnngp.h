@@ -76,8 +76,9 @@ int cnngp_plan_create(const cnngp_op *ops, int32_t n_ops, int32_t n_slots, int32
                       int32_t dtype, cnngp_plan **out);
 void cnngp_plan_destroy(cnngp_plan *plan);
 
-/* Number of per-image variance-map elements (sum over RELU ops of their input map size):
- * the `xx` / `yy` operands of every ReLU, kernels.py:146. */
+/* Elements per image row of the variance buffers cnngp_variances fills: the `xx` / `yy`
+ * operand of every ReLU (kernels.py:146), followed -- when the fused kernel covers the program
+ * -- by the same maps as (sqrt, 1/sqrt) pairs in the layout that kernel stages. */
 int64_t cnngp_plan_aux_elems(const cnngp_plan *plan);
 /* Algorithmic flop per image pair under SURVEY.md 8(d)'s counting convention. */
 double cnngp_plan_flops_per_pair(const cnngp_plan *plan, int32_t C);
@@ -98,6 +99,8 @@ int cnngp_variances(const cnngp_plan *plan, const void *d_x, const void *d_z, in
 
 /* The Gram tile: model(x, z, same, diag) of kernels.py:18-57.
  *   d_x [N1,C,H,W], d_z [N2,C,H,W]; d_aux_x / d_aux_z from cnngp_variances
+ *   d_kdiag  NULL, or [N1] from cnngp_variances: with `symmetric` the diagonal entries are
+ *            copied from it, so that diag(model(X)) == model(X, diag=True) bit for bit
  *   same   != 0: entries with i == j follow the variance recursion (kernels.py:155-162)
  *   diag   != 0: only pairs (n, n) are evaluated, out is [N1]  (requires N1 == N2)
  *   symmetric != 0: caller asserts d_x and d_z hold the same images (model(X)): only
@@ -105,8 +108,8 @@ int cnngp_variances(const cnngp_plan *plan, const void *d_x, const void *d_z, in
  *   d_out  [N1, ld_out] (row stride ld_out elements) or [N1] when diag
  *   path   0 = auto (fused when available), 1 = force generic, 2 = force fused */
 int cnngp_gram(const cnngp_plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2,
-               int32_t C, const void *d_aux_x, const void *d_aux_z, int32_t same, int32_t diag,
-               int32_t symmetric, void *d_out, int64_t ld_out, int32_t path, void *stream);
+               int32_t C, const void *d_aux_x, const void *d_aux_z, const void *d_kdiag, int32_t same,
+               int32_t diag, int32_t symmetric, void *d_out, int64_t ld_out, int32_t path, void *stream);
 int cnngp_last_path(void);
 
 /* Map-level steps behind module.propagate(kp): a stack of M maps [M, Hi, Wi]. */

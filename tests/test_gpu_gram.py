@@ -156,3 +156,62 @@ def test_large_symmetric_properties():
     torch.testing.assert_close(Kb, K[:300, 300:], rtol=1e-5, atol=0)
     ev = torch.linalg.eigvalsh(K.double())
     assert ev.min() > -1e-6 * ev.max()
+
+
+def _fused_model(k=7, layers=3, bias=0.3):
+    from cnn_gp import Conv2d, ReLU, Sequential
+    mods = []
+    for _ in range(layers):
+        mods += [Conv2d(k, var_weight=1.3, var_bias=bias), ReLU()]
+    return Sequential(*mods, Conv2d(28, padding=0, var_weight=0.7, var_bias=bias))
+
+
+@pytest.mark.parametrize("k", [1, 3, 4, 5, 7])
+def test_fused_matches_generic_and_oracle(k):
+    """The register-resident kernel against the generic kernel and the oracle on ragged tiles
+    (sizes that are not multiples of the 4 x 8 CTA tile), rectangular and symmetric."""
+    model = _fused_model(k).cuda()
+    gen = torch.Generator().manual_seed(100 + k)
+    X = torch.rand(37, 1, 28, 28, generator=gen)
+    Z = torch.randn(21, 1, 28, 28, generator=gen)   # negative correlations too
+    Xc, Zc = X.cuda(), Z.cuda()
+    engine.set_path("fused")
+    try:
+        Kf = model(Xc, Zc)
+        assert engine.last_path() == "fused"
+        Ks = model(Xc)
+        assert engine.last_path() == "fused"
+    finally:
+        engine.set_path("auto")
+    engine.set_path("generic")
+    try:
+        Kg = model(Xc, Zc)
+        Ksg = model(Xc)
+    finally:
+        engine.set_path("auto")
+    assert rel_err(Kf.cpu().numpy(), Kg.cpu().numpy()) < 5e-6
+    assert rel_err(Ks.cpu().numpy(), Ksg.cpu().numpy()) < 5e-6
+    torch.testing.assert_close(Ks, Ks.T, rtol=0, atol=0)
+    torch.testing.assert_close(torch.diagonal(Ks), model(Xc, diag=True), rtol=0, atol=0)
+    want = oracle.gram(_fused_model(k), X.numpy(), Z.numpy())
+    assert rel_err(Kf.cpu().numpy(), want) < 1e-5
+
+
+def test_fused_headline_program_large():
+    """mnist_paper_convnet_gp through the fused kernel on a tile spanning several super-tiles'
+    worth of CTA tiles; checked against the generic kernel on a sample of rows."""
+    model = MODELS["mnist_paper_convnet_gp"].float().cuda()
+    gen = torch.Generator().manual_seed(5)
+    X = torch.rand(1100, 1, 28, 28, generator=gen).cuda()
+    K = model(X)
+    assert engine.last_path() == "fused"
+    torch.testing.assert_close(K, K.T, rtol=0, atol=0)
+    rows = torch.tensor([0, 1, 255, 256, 511, 512, 513, 1023, 1024, 1099], device="cuda")
+    engine.set_path("generic")
+    try:
+        Kg = model(X[rows], X)
+    finally:
+        engine.set_path("auto")
+    assert rel_err(K[rows].cpu().numpy(), Kg.cpu().numpy()) < 5e-6
+    Kr = model(X[:600], X[500:])
+    assert rel_err(Kr.cpu().numpy(), K[:600, 500:].cpu().numpy()) < 5e-6

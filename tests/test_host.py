@@ -131,7 +131,8 @@ def test_shipped_programs_need_two_slots_and_match_survey_flops():
         assert ns <= 2, name
         assert plan.flops_per_pair(C) == flops, (name, plan.flops_per_pair(C))
         if name in relu_px:
-            assert plan.aux_elems == relu_px[name]
+            # rows also carry the fused kernel's (s, 1/s) pairs when it covers the program
+            assert plan.aux_elems == relu_px[name] * (3 if plan.has_fused else 1)
 
 
 def test_plan_rejects_bad_programs():
