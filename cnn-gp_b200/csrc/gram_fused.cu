@@ -63,6 +63,8 @@ struct FParams {
     int sti, stj;      // super-tile size in CTA tiles
     int nst_j;         // super-tiles along j (non-symmetric)
     int nst;           // super-tiles per side (symmetric)
+    long long n_tiles; // CTA tiles enumerated (super-tile padded)
+    float inv_c;       // 1 / C
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------
@@ -114,56 +116,70 @@ __device__ __forceinline__ float h2_poly(float e) {
     return h;
 }
 
-// Sliding-window box sum along the register axis with zero padding: out[y] = sum_{t=-LO..HI} v[y+t].
+// Box sum along the register axis with zero padding, out[y] = sum_{t=-LO..HI} v[y+t], as two
+// sliding windows that start at the two ends and meet in the middle: two independent
+// dependency chains per map (ILP) and half the rounding-error accumulation of one long slide.
 template <int S, int LO, int HI>
 __device__ __forceinline__ void box_pass(float (&v)[S]) {
     if (LO == 0 && HI == 0) return;
+    constexpr int MID = S / 2;
     float o[S];
-    float acc = 0.f;
+    float top = 0.f, bot = 0.f;
 #pragma unroll
-    for (int t = 0; t <= HI && t < S; ++t) acc += v[t];
-    o[0] = acc;
+    for (int t = 0; t <= HI && t < S; ++t) top += v[t];
 #pragma unroll
-    for (int y = 1; y < S; ++y) {
-        if (y + HI < S) acc += v[y + HI];
-        if (y - LO - 1 >= 0) acc -= v[y - LO - 1];
-        o[y] = acc;
+    for (int t = 0; t <= LO && t < S; ++t) bot += v[S - 1 - t];
+    o[0] = top;
+    o[S - 1] = bot;
+#pragma unroll
+    for (int y = 1; y < MID; ++y) {
+        if (y + HI < S) top += v[y + HI];
+        if (y - LO - 1 >= 0) top -= v[y - LO - 1];
+        o[y] = top;
+    }
+#pragma unroll
+    for (int y = S - 2; y >= MID; --y) {
+        if (y - LO >= 0) bot += v[y - LO];
+        if (y + HI + 1 < S) bot -= v[y + HI + 1];
+        o[y] = bot;
     }
 #pragma unroll
     for (int y = 0; y < S; ++y) v[y] = o[y];
 }
 
-template <int S>
-__device__ __forceinline__ void box_pass_dyn(float (&v)[S], int lo, int hi) {
-    // the shipped programs: k7 (3,3), k3 (1,1), k4 "same" (1,2), k5 (2,2), k1 (0,0)
-    if (lo == 3 && hi == 3) box_pass<S, 3, 3>(v);
-    else if (lo == 1 && hi == 1) box_pass<S, 1, 1>(v);
-    else if (lo == 1 && hi == 2) box_pass<S, 1, 2>(v);
-    else if (lo == 2 && hi == 2) box_pass<S, 2, 2>(v);
-}
-
-// Transpose the four maps of this warp through its private smem tile, two maps at a time.
-template <int S>
-__device__ __forceinline__ void transpose4(float (&m)[4][S], float2 *tile, int lane, int lx) {
-    constexpr int PITCH = S + 1;  // odd: both the row-wise write and the column-wise read are conflict-free
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        if (lane < S) {
-#pragma unroll
-            for (int r = 0; r < S; ++r) tile[r * PITCH + lane] = make_float2(m[2 * h][r], m[2 * h + 1][r]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int r = 0; r < S; ++r) {
-            const float2 t = tile[lx * PITCH + r];
-            m[2 * h][r] = t.x;
-            m[2 * h + 1][r] = t.y;
-        }
-        __syncwarp();
+// LO < 0 selects the window at run time (programs that mix window shapes).
+template <int S, int LO, int HI>
+__device__ __forceinline__ void box_any(float (&v)[S], int lo, int hi) {
+    if (LO >= 0) {
+        box_pass<S, (LO >= 0 ? LO : 0), HI>(v);
+    } else {
+        if (lo == 3 && hi == 3) box_pass<S, 3, 3>(v);
+        else if (lo == 1 && hi == 1) box_pass<S, 1, 1>(v);
+        else if (lo == 1 && hi == 2) box_pass<S, 1, 2>(v);
+        else if (lo == 2 && hi == 2) box_pass<S, 2, 2>(v);
     }
 }
 
 template <int S>
+__device__ __forceinline__ void tile_store(float2 *tile, const float (&a)[S], const float (&b)[S], int lane) {
+    constexpr int PITCH = S + 1;  // odd: row-wise writes and column-wise reads are both conflict-free
+    if (lane < S) {
+#pragma unroll
+        for (int r = 0; r < S; ++r) tile[r * PITCH + lane] = make_float2(a[r], b[r]);
+    }
+}
+template <int S>
+__device__ __forceinline__ void tile_load_t(const float2 *tile, float (&a)[S], float (&b)[S], int lx) {
+    constexpr int PITCH = S + 1;
+#pragma unroll
+    for (int r = 0; r < S; ++r) {
+        const float2 t = tile[lx * PITCH + r];
+        a[r] = t.x;
+        b[r] = t.y;
+    }
+}
+
+template <int S, int LO, int HI>
 __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constant__ FParams p) {
     constexpr int P = S * S;
     constexpr int PITCH = S + 1;
@@ -174,22 +190,6 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
     uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + kWarps * S * PITCH);
     uint64_t *full = bars, *empty = bars + 2;
 
-    // ---- which CTA tile -------------------------------------------------------------------
-    const int per_st = p.sti * p.stj;
-    const int st = blockIdx.x / per_st, w_in = blockIdx.x - st * per_st;
-    int si, sj;
-    if (p.symmetric) {  // upper-triangular enumeration of square super-tiles
-        int r = 0, rem = st;
-        while (rem >= p.nst - r) { rem -= p.nst - r; ++r; }
-        si = r; sj = r + rem;
-    } else {
-        si = st / p.nst_j; sj = st - si * p.nst_j;
-    }
-    const int ib = si * p.sti + w_in / p.stj;
-    const int jb = sj * p.stj + w_in % p.stj;
-    if (ib >= p.nbi || jb >= p.nbj) return;
-    if (p.symmetric && jb * kTileJ + (kTileJ - 1) < ib * kTileI) return;  // entirely below the diagonal
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(&full[0], 1); mbar_init(&full[1], 1);
@@ -198,25 +198,50 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
     }
     __syncthreads();
 
-    const int i_base = ib * kTileI, j_base = jb * kTileJ;
+    const int per_st = p.sti * p.stj;
+    // CTA tile t -> (ib, jb); false when the tile is outside the matrix or below the diagonal
+    auto decode = [&](long long t, int &ib, int &jb) -> bool {
+        const int st = (int)(t / per_st), w_in = (int)(t - (long long)st * per_st);
+        int si, sj;
+        if (p.symmetric) {  // upper-triangular enumeration of square super-tiles
+            int r = 0, rem = st;
+            while (rem >= p.nst - r) { rem -= p.nst - r; ++r; }
+            si = r; sj = r + rem;
+        } else {
+            si = st / p.nst_j; sj = st - si * p.nst_j;
+        }
+        ib = si * p.sti + w_in / p.stj;
+        jb = sj * p.stj + w_in % p.stj;
+        if (ib >= p.nbi || jb >= p.nbj) return false;
+        if (p.symmetric && jb * kTileJ + (kTileJ - 1) < ib * kTileI) return false;
+        return true;
+    };
 
     if (warp == kWarps) {
-        // ---- producer: stage layer l's (s, 1/s) maps of the 12 images, one layer ahead ----
+        // ---- producer: stages each ReLU layer's (s, 1/s) maps of the tile's 12 images one
+        // layer ahead; it runs on across tile boundaries, so the next tile's first layer is
+        // already in flight while the consumers finish the current tile.
         if (lane == 0) {
-            for (int l = 0, k = 0; k < p.n_ops; ++k) {
-                if (p.ops[k].kind != F_RELU) continue;
-                const int buf = l & 1;
-                if (l >= 2) mbar_wait(&empty[buf], ((l >> 1) - 1) & 1);
-                mbar_arrive_expect_tx(&full[buf], kImgs * P * 8);
-                float2 *dst = stage + buf * kImgs * P;
-                const long long off = p.aux_f_off + 2LL * p.ops[k].aux_off;
-                for (int s = 0; s < kImgs; ++s) {
-                    const float *src;
-                    if (s < kTileI) src = p.aux_x + (long long)min(i_base + s, p.N1 - 1) * p.aux_stride + off;
-                    else src = p.aux_z + (long long)min(j_base + s - kTileI, p.N2 - 1) * p.aux_stride + off;
-                    bulk_g2s(dst + s * P, src, P * 8, &full[buf]);
+            unsigned l = 0;  // running layer counter over all tiles of this CTA
+            for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+                int ib, jb;
+                if (!decode(t, ib, jb)) continue;
+                const int i_base = ib * kTileI, j_base = jb * kTileJ;
+                for (int k = 0; k < p.n_ops; ++k) {
+                    if (p.ops[k].kind != F_RELU) continue;
+                    const unsigned buf = l & 1;
+                    if (l >= 2) mbar_wait(&empty[buf], ((l >> 1) - 1) & 1);
+                    mbar_arrive_expect_tx(&full[buf], kImgs * P * 8);
+                    float2 *dst = stage + buf * kImgs * P;
+                    const long long off = p.aux_f_off + 2LL * p.ops[k].aux_off;
+                    for (int s = 0; s < kImgs; ++s) {
+                        const float *src;
+                        if (s < kTileI) src = p.aux_x + (long long)min(i_base + s, p.N1 - 1) * p.aux_stride + off;
+                        else src = p.aux_z + (long long)min(j_base + s - kTileI, p.N2 - 1) * p.aux_stride + off;
+                        bulk_g2s(dst + s * P, src, P * 8, &full[buf]);
+                    }
+                    ++l;
                 }
-                ++l;
             }
         }
         return;
@@ -226,107 +251,126 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
     const int wi = warp >> 2, wj = warp & 3;
     const int lx = lane < S ? lane : S - 1;  // clamped lane for loads
     float2 *tile = tiles + warp * S * PITCH;
-    int gi[2], gj[2];
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        gi[a] = min(i_base + wi * 2 + a, p.N1 - 1);
-        gj[a] = min(j_base + wj * 2 + a, p.N2 - 1);
-    }
+    unsigned relu_l = 0;  // running layer counter, in step with the producer's
 
-    float m[4][S];  // pair (a, b) -> m[2a + b]
-    {
-        // init, kernels.py:43-49: lane = column, register = row
+    for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        int ib, jb;
+        if (!decode(t, ib, jb)) continue;
+        const int i_base = ib * kTileI, j_base = jb * kTileJ;
+        int gi[2], gj[2];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int r = 0; r < S; ++r) m[q][r] = 0.f;
-        for (int c = 0; c < p.C; ++c) {
-            const float *x0 = p.x + ((long long)gi[0] * p.C + c) * P + lx;
-            const float *x1 = p.x + ((long long)gi[1] * p.C + c) * P + lx;
-            const float *z0 = p.z + ((long long)gj[0] * p.C + c) * P + lx;
-            const float *z1 = p.z + ((long long)gj[1] * p.C + c) * P + lx;
-#pragma unroll
-            for (int r = 0; r < S; ++r) {
-                const float a0 = __ldg(x0 + r * S), a1 = __ldg(x1 + r * S);
-                const float b0 = __ldg(z0 + r * S), b1 = __ldg(z1 + r * S);
-                m[0][r] = fmaf(a0, b0, m[0][r]);
-                m[1][r] = fmaf(a0, b1, m[1][r]);
-                m[2][r] = fmaf(a1, b0, m[2][r]);
-                m[3][r] = fmaf(a1, b1, m[3][r]);
-            }
+        for (int a = 0; a < 2; ++a) {
+            gi[a] = min(i_base + wi * 2 + a, p.N1 - 1);
+            gj[a] = min(j_base + wj * 2 + a, p.N2 - 1);
         }
-        if (p.C > 1) {
-            const float cnt = (float)p.C;
+
+        float m[4][S];  // pair (a, b) -> m[2a + b]; lane = column, register = row after init
+        {
+            // init, kernels.py:43-49
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int r = 0; r < S; ++r) m[q][r] = __fdiv_rn(m[q][r], cnt);
-        }
-    }
-
-    int relu_l = 0;
-    for (int k = 0; k < p.n_ops; ++k) {
-        const FOp o = p.ops[k];
-        if (o.kind == F_CONV) {
-            if (o.lo != 0 || o.hi != 0) {
+                for (int r = 0; r < S; ++r) m[q][r] = 0.f;
+            for (int c = 0; c < p.C; ++c) {
+                const float *x0 = p.x + ((long long)gi[0] * p.C + c) * P + lx;
+                const float *x1 = p.x + ((long long)gi[1] * p.C + c) * P + lx;
+                const float *z0 = p.z + ((long long)gj[0] * p.C + c) * P + lx;
+                const float *z1 = p.z + ((long long)gj[1] * p.C + c) * P + lx;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) box_pass_dyn<S>(m[q], o.lo, o.hi);
-                transpose4<S>(m, tile, lane, lx);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) box_pass_dyn<S>(m[q], o.lo, o.hi);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int r = 0; r < S; ++r) m[q][r] = fmaf(m[q][r], o.scale, o.bias);
-        } else if (o.kind == F_RELU) {
-            const int buf = relu_l & 1;
-            mbar_wait(&full[buf], (relu_l >> 1) & 1);
-            const float2 *sb = stage + buf * kImgs * P + lx;
-            const float2 *ai0 = sb + (wi * 2 + 0) * P, *ai1 = sb + (wi * 2 + 1) * P;
-            const float2 *bj0 = sb + (kTileI + wj * 2 + 0) * P, *bj1 = sb + (kTileI + wj * 2 + 1) * P;
-#pragma unroll
-            for (int r = 0; r < S; ++r) {
-                const float2 A0 = ai0[r * S], A1 = ai1[r * S], B0 = bj0[r * S], B1 = bj1[r * S];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float2 A = (q & 2) ? A1 : A0, B = (q & 1) ? B1 : B0;
-                    const float s = A.x * B.x, rr = A.y * B.y;
-                    const float c = m[q][r];
-                    const float d = s - fabsf(c);
-                    const float e = d * rr;
-                    const float w = d * sqrt_approx(fabsf(e));
-                    m[q][r] = fmaf(w, h2_poly(e), fmaxf(c, 0.f));
+                for (int r = 0; r < S; ++r) {
+                    const float a0 = __ldg(x0 + r * S), a1 = __ldg(x1 + r * S);
+                    const float b0 = __ldg(z0 + r * S), b1 = __ldg(z1 + r * S);
+                    m[0][r] = fmaf(a0, b0, m[0][r]);
+                    m[1][r] = fmaf(a0, b1, m[1][r]);
+                    m[2][r] = fmaf(a1, b0, m[2][r]);
+                    m[3][r] = fmaf(a1, b1, m[3][r]);
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[buf]);
-            ++relu_l;
-        } else {  // F_DENSE: whole-map sum, scale, bias -> the kernel entry
-            float tot[4];
+            if (p.C > 1) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float a = 0.f;
+                for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int r = 0; r < S; ++r) a += m[q][r];
-                if (lane >= S) a = 0.f;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
-                tot[q] = fmaf(a, o.scale, o.bias);
+                    for (int r = 0; r < S; ++r) m[q][r] *= p.inv_c;
             }
-            if (lane < 4) {
-                const int a = lane >> 1, b = lane & 1;
-                const int i = i_base + wi * 2 + a, j = j_base + wj * 2 + b;
-                const float v = lane == 0 ? tot[0] : lane == 1 ? tot[1] : lane == 2 ? tot[2] : tot[3];
-                if (i < p.N1 && j < p.N2) {
-                    if (!p.symmetric) {
-                        p.out[(long long)i * p.ld_out + j] = v;
-                    } else if (j > i) {
-                        p.out[(long long)i * p.ld_out + j] = v;
-                        p.out[(long long)j * p.ld_out + i] = v;
-                    } else if (j == i) {
-                        // i == j follows the variance recursion (kernels.py:155-162)
-                        p.out[(long long)i * p.ld_out + i] = p.kdiag ? p.kdiag[i] : v;
+        }
+
+        for (int k = 0; k < p.n_ops; ++k) {
+            const FOp o = p.ops[k];
+            if (o.kind == F_CONV) {
+                if (o.lo != 0 || o.hi != 0) {
+                    // pass 1, transposition, pass 2 -- software-pipelined over the two halves
+                    // (maps 0,1 and 2,3) so that the smem traffic of one half overlaps the
+                    // adds of the other
+                    box_any<S, LO, HI>(m[0], o.lo, o.hi);
+                    box_any<S, LO, HI>(m[1], o.lo, o.hi);
+                    tile_store<S>(tile, m[0], m[1], lane);
+                    __syncwarp();
+                    tile_load_t<S>(tile, m[0], m[1], lx);
+                    box_any<S, LO, HI>(m[2], o.lo, o.hi);
+                    box_any<S, LO, HI>(m[3], o.lo, o.hi);
+                    __syncwarp();
+                    tile_store<S>(tile, m[2], m[3], lane);
+                    box_any<S, LO, HI>(m[0], o.lo, o.hi);
+                    box_any<S, LO, HI>(m[1], o.lo, o.hi);
+                    __syncwarp();
+                    tile_load_t<S>(tile, m[2], m[3], lx);
+                    __syncwarp();
+                    box_any<S, LO, HI>(m[2], o.lo, o.hi);
+                    box_any<S, LO, HI>(m[3], o.lo, o.hi);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int r = 0; r < S; ++r) m[q][r] = fmaf(m[q][r], o.scale, o.bias);
+            } else if (o.kind == F_RELU) {
+                const unsigned buf = relu_l & 1;
+                mbar_wait(&full[buf], (relu_l >> 1) & 1);
+                const float2 *sb = stage + buf * kImgs * P + lx;
+                const float2 *ai0 = sb + (wi * 2 + 0) * P, *ai1 = sb + (wi * 2 + 1) * P;
+                const float2 *bj0 = sb + (kTileI + wj * 2 + 0) * P, *bj1 = sb + (kTileI + wj * 2 + 1) * P;
+#pragma unroll
+                for (int r = 0; r < S; ++r) {
+                    const float2 A0 = ai0[r * S], A1 = ai1[r * S], B0 = bj0[r * S], B1 = bj1[r * S];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 A = (q & 2) ? A1 : A0, B = (q & 1) ? B1 : B0;
+                        const float s = A.x * B.x, rr = A.y * B.y;
+                        const float c = m[q][r];
+                        const float d = s - fabsf(c);
+                        const float e = d * rr;
+                        const float w = d * sqrt_approx(fabsf(e));
+                        m[q][r] = fmaf(w, h2_poly(e), fmaxf(c, 0.f));
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[buf]);
+                ++relu_l;
+            } else {  // F_DENSE: whole-map sum, scale, bias -> the kernel entry
+                float tot[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int r = 0; r < S; ++r) a += m[q][r];
+                    if (lane >= S) a = 0.f;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+                    tot[q] = fmaf(a, o.scale, o.bias);
+                }
+                if (lane < 4) {
+                    const int a = lane >> 1, b = lane & 1;
+                    const int i = i_base + wi * 2 + a, j = j_base + wj * 2 + b;
+                    const float v = lane == 0 ? tot[0] : lane == 1 ? tot[1] : lane == 2 ? tot[2] : tot[3];
+                    if (i < p.N1 && j < p.N2) {
+                        if (!p.symmetric) {
+                            p.out[(long long)i * p.ld_out + j] = v;
+                        } else if (j > i) {
+                            p.out[(long long)i * p.ld_out + j] = v;
+                            p.out[(long long)j * p.ld_out + i] = v;
+                        } else if (j == i) {
+                            // i == j follows the variance recursion (kernels.py:155-162)
+                            p.out[(long long)i * p.ld_out + i] = p.kdiag ? p.kdiag[i] : v;
+                        }
                     }
                 }
             }
@@ -338,6 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
 
 struct FusedPlan {
     int S = 0;
+    int lo = -1, hi = -1;  // the single non-trivial window shape of the program, or -1 if mixed
     int n_ops = 0, n_relu = 0;
     FOp ops[kMaxOps];
     size_t smem = 0;
@@ -357,6 +402,7 @@ FusedPlan *fused_plan_create(const Plan *plan_const) {
     bool transposed = false;  // current register layout: lane = row?
     float pending = 1.f;     // power-of-two factor owed by the ReLU's doubled output
     bool done = false;
+    int n_windows = 0;
     for (size_t k = 0; k < plan->ops.size(); ++k) {
         DevOp &o = plan->ops[k];
         if (done || fp.n_ops >= kMaxOps) return nullptr;
@@ -372,7 +418,12 @@ FusedPlan *fused_plan_create(const Plan *plan_const) {
                                    (lo == 1 && hi == 2) || (lo == 2 && hi == 2);
                 if (!known) return nullptr;
                 f.kind = F_CONV; f.lo = lo; f.hi = hi;
-                if (lo || hi) transposed = !transposed;
+                if (lo || hi) {
+                    transposed = !transposed;
+                    if (n_windows == 0) { fp.lo = lo; fp.hi = hi; }
+                    else if (fp.lo != lo || fp.hi != hi) { fp.lo = -1; fp.hi = -1; }
+                    ++n_windows;
+                }
             } else if (o.Ho == 1 && o.Wo == 1 && o.pad == 0 && o.t0 == 0 && o.ke == S) {
                 f.kind = F_DENSE;
                 done = true;
@@ -436,12 +487,21 @@ int launch_fused_gram(const Plan *plan, const void *d_x, int64_t N1, const void 
         p.nst = nsi > nsj ? nsi : nsj;
         n_super = p.symmetric ? (long long)p.nst * (p.nst + 1) / 2 : (long long)nsi * nsj;
     }
-    const long long blocks = n_super * p.sti * p.stj;
-    if (blocks > 2147483647LL) { set_error("fused kernel: grid too large for one launch"); return 8; }
-    auto kern = fused_kernel<28>;
+    p.n_tiles = n_super * p.sti * p.stj;
+    p.inv_c = 1.0f / (float)C;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);  // persistent: one CTA per SM
+    void (*kern)(const FParams) = nullptr;
+    if (fp->lo == 3 && fp->hi == 3) kern = fused_kernel<28, 3, 3>;
+    else if (fp->lo == 1 && fp->hi == 1) kern = fused_kernel<28, 1, 1>;
+    else if (fp->lo == 1 && fp->hi == 2) kern = fused_kernel<28, 1, 2>;
+    else if (fp->lo == 2 && fp->hi == 2) kern = fused_kernel<28, 2, 2>;
+    else kern = fused_kernel<28, -1, -1>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem);
     if (e != cudaSuccess) { set_error(std::string("fused cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 7; }
-    kern<<<(unsigned)blocks, kThreads, fp->smem, (cudaStream_t)stream>>>(p);
+    kern<<<grid, kThreads, fp->smem, (cudaStream_t)stream>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) { set_error(std::string("fused kernel launch: ") + cudaGetErrorString(e)); return 9; }
     return 0;
