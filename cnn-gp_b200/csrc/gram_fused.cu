@@ -227,6 +227,20 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
                 int ib, jb;
                 if (!decode(t, ib, jb)) continue;
                 const int i_base = ib * kTileI, j_base = jb * kTileJ;
+                // stage 0..C-1 of a tile: channel c of the 12 images (the init step reads them)
+                for (int c = 0; c < p.C; ++c) {
+                    const unsigned buf = l & 1;
+                    if (l >= 2) mbar_wait(&empty[buf], ((l >> 1) - 1) & 1);
+                    mbar_arrive_expect_tx(&full[buf], kImgs * P * 4);
+                    float *dst = reinterpret_cast<float *>(stage + buf * kImgs * P);
+                    for (int s = 0; s < kImgs; ++s) {
+                        const float *src;
+                        if (s < kTileI) src = p.x + ((long long)min(i_base + s, p.N1 - 1) * p.C + c) * P;
+                        else src = p.z + ((long long)min(j_base + s - kTileI, p.N2 - 1) * p.C + c) * P;
+                        bulk_g2s(dst + s * P, src, P * 4, &full[buf]);
+                    }
+                    ++l;
+                }
                 for (int k = 0; k < p.n_ops; ++k) {
                     if (p.ops[k].kind != F_RELU) continue;
                     const unsigned buf = l & 1;
@@ -251,40 +265,36 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
     const int wi = warp >> 2, wj = warp & 3;
     const int lx = lane < S ? lane : S - 1;  // clamped lane for loads
     float2 *tile = tiles + warp * S * PITCH;
-    unsigned relu_l = 0;  // running layer counter, in step with the producer's
+    unsigned relu_l = 0;  // running stage counter (image channels + ReLU layers), in step with the producer's
 
     for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
         int ib, jb;
         if (!decode(t, ib, jb)) continue;
         const int i_base = ib * kTileI, j_base = jb * kTileJ;
-        int gi[2], gj[2];
-#pragma unroll
-        for (int a = 0; a < 2; ++a) {
-            gi[a] = min(i_base + wi * 2 + a, p.N1 - 1);
-            gj[a] = min(j_base + wj * 2 + a, p.N2 - 1);
-        }
-
         float m[4][S];  // pair (a, b) -> m[2a + b]; lane = column, register = row after init
         {
-            // init, kernels.py:43-49
+            // init, kernels.py:43-49: channel c of the tile's images arrives through the stage
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int r = 0; r < S; ++r) m[q][r] = 0.f;
             for (int c = 0; c < p.C; ++c) {
-                const float *x0 = p.x + ((long long)gi[0] * p.C + c) * P + lx;
-                const float *x1 = p.x + ((long long)gi[1] * p.C + c) * P + lx;
-                const float *z0 = p.z + ((long long)gj[0] * p.C + c) * P + lx;
-                const float *z1 = p.z + ((long long)gj[1] * p.C + c) * P + lx;
+                const unsigned buf = relu_l & 1;
+                mbar_wait(&full[buf], (relu_l >> 1) & 1);
+                const float *sb = reinterpret_cast<const float *>(stage + buf * kImgs * P) + lx;
+                const float *x0 = sb + (wi * 2 + 0) * P, *x1 = sb + (wi * 2 + 1) * P;
+                const float *z0 = sb + (kTileI + wj * 2 + 0) * P, *z1 = sb + (kTileI + wj * 2 + 1) * P;
 #pragma unroll
                 for (int r = 0; r < S; ++r) {
-                    const float a0 = __ldg(x0 + r * S), a1 = __ldg(x1 + r * S);
-                    const float b0 = __ldg(z0 + r * S), b1 = __ldg(z1 + r * S);
+                    const float a0 = x0[r * S], a1 = x1[r * S], b0 = z0[r * S], b1 = z1[r * S];
                     m[0][r] = fmaf(a0, b0, m[0][r]);
                     m[1][r] = fmaf(a0, b1, m[1][r]);
                     m[2][r] = fmaf(a1, b0, m[2][r]);
                     m[3][r] = fmaf(a1, b1, m[3][r]);
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[buf]);
+                ++relu_l;
             }
             if (p.C > 1) {
 #pragma unroll
