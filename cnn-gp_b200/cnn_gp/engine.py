@@ -63,7 +63,8 @@ def variances(plan, x, z=None):
     literal same=True semantics for two different image sets (reference kernels.py:155-156).
     """
     N, C = x.shape[0], x.shape[1]
-    aux_x = torch.empty((N, max(1, plan.aux_elems)), dtype=x.dtype, device=x.device)
+    # an even number of rows: the fused kernel's maps interleave images 2k and 2k+1 over both rows
+    aux_x = torch.empty((N + (N & 1), max(1, plan.aux_elems)), dtype=x.dtype, device=x.device)
     aux_z = torch.empty_like(aux_x) if z is not None else None
     kdiag = torch.empty((N,), dtype=x.dtype, device=x.device)
     nat.check(nat.lib().cnngp_variances(

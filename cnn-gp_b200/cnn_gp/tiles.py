@@ -32,7 +32,9 @@ class GramJob:
         self.launches = 1 if self.same else 2
 
     def block(self, out, i0, i1, j0, j1, symmetric):
-        """out[i0:i1, j0:j1] = K(X[i0:i1], X2[j0:j1]) (upper triangle mirrored when symmetric)."""
+        """out[i0:i1, j0:j1] = K(X[i0:i1], X2[j0:j1]) (upper triangle mirrored when symmetric).
+        Block origins must be even: the fused kernel's variance maps interleave images 2k, 2k+1."""
+        assert i0 % 2 == 0 and j0 % 2 == 0, "tile origins must be even (use an even batch_size)"
         with torch.cuda.device(self.X.device):
             engine.gram_with_aux(self.plan, self.X[i0:i1], self.X2[j0:j1], self.aux_x[i0:i1],
                                  self.aux_x2[j0:j1], same=symmetric, diag=False, symmetric=symmetric,

@@ -33,7 +33,8 @@ namespace {
 
 constexpr int kWarps = 8;                    // consumer warps per CTA
 constexpr int kTileI = 4, kTileJ = 8;        // images per CTA along i and j (2 x 4 warps of 2 x 2)
-constexpr int kImgs = kTileI + kTileJ;       // variance-map rows staged per layer
+constexpr int kImgs = kTileI + kTileJ;       // images per CTA tile
+constexpr int kPairs = kImgs / 2;            // image pairs whose interleaved variance maps are staged per layer
 constexpr int kThreads = (kWarps + 1) * 32;  // + producer warp
 constexpr int kMaxOps = 40;
 constexpr int kSuperJ = 64, kSuperI = 128;   // super-tile = 512 x 512 images (L2-resident variance maps)
@@ -51,7 +52,8 @@ struct FParams {
     FOp ops[kMaxOps];
     int n_ops, n_relu;
     const float *x, *z;          // images [N, C, S, S]
-    const float *aux_x, *aux_z;  // per-image rows; fused (s, 1/s) maps start at aux_f_off floats
+    const float *aux_x, *aux_z;  // per-image rows; the fused maps start at aux_f_off floats; rows 2k and
+                                 // 2k+1 together hold pair k's (s_2k, s_2k+1, 1/s_2k, 1/s_2k+1) maps
     long long aux_stride;        // floats per image row
     int aux_f_off;
     int N1, N2, C;
@@ -104,43 +106,64 @@ __device__ __forceinline__ float sqrt_approx(float v) {
     return r;
 }
 
-// 2*H(e) on [0,1]: out = relu(c) + (s-|c|) * sqrt(e) * H2(e) is twice the reference's ReLU output.
-__device__ __forceinline__ float h2_poly(float e) {
-    float h = 7.577116048e-05f;
-    h = fmaf(h, e, -5.945927478e-05f);
-    h = fmaf(h, e, 2.400144585e-04f);
-    h = fmaf(h, e, 5.259375321e-04f);
-    h = fmaf(h, e, 2.417275915e-03f);
-    h = fmaf(h, e, 1.500489842e-02f);
-    h = fmaf(h, e, 3.001054525e-01f);
-    return h;
+// ---- packed f32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2, one issue slot for two lanes-ops) --
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
 }
+__device__ __forceinline__ void upk(u64 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float neg_abs(float v) { return __int_as_float(__float_as_int(v) | 0x80000000); }
 
-// Box sum along the register axis with zero padding, out[y] = sum_{t=-LO..HI} v[y+t], as two
-// sliding windows that start at the two ends and meet in the middle: two independent
-// dependency chains per map (ILP) and half the rounding-error accumulation of one long slide.
+// Box sum along the register axis with zero padding, out[y] = sum_{t=-LO..HI} v[y+t], on two
+// maps at once (packed lanes), as two sliding windows that start at the two ends and meet in
+// the middle: independent dependency chains (ILP) and half the rounding-error accumulation of
+// one long slide.
 template <int S, int LO, int HI>
-__device__ __forceinline__ void box_pass(float (&v)[S]) {
+__device__ __forceinline__ void box_pass(u64 (&v)[S]) {
     if (LO == 0 && HI == 0) return;
     constexpr int MID = S / 2;
-    float o[S];
-    float top = 0.f, bot = 0.f;
+    u64 o[S];
+    u64 top = v[0], bot = v[S - 1];
 #pragma unroll
-    for (int t = 0; t <= HI && t < S; ++t) top += v[t];
+    for (int t = 1; t <= HI && t < S; ++t) top = add2(top, v[t]);
 #pragma unroll
-    for (int t = 0; t <= LO && t < S; ++t) bot += v[S - 1 - t];
+    for (int t = 1; t <= LO && t < S; ++t) bot = add2(bot, v[S - 1 - t]);
     o[0] = top;
     o[S - 1] = bot;
 #pragma unroll
     for (int y = 1; y < MID; ++y) {
-        if (y + HI < S) top += v[y + HI];
-        if (y - LO - 1 >= 0) top -= v[y - LO - 1];
+        if (y + HI < S) top = add2(top, v[y + HI]);
+        if (y - LO - 1 >= 0) top = sub2(top, v[y - LO - 1]);
         o[y] = top;
     }
 #pragma unroll
     for (int y = S - 2; y >= MID; --y) {
-        if (y - LO >= 0) bot += v[y - LO];
-        if (y + HI + 1 < S) bot -= v[y + HI + 1];
+        if (y - LO >= 0) bot = add2(bot, v[y - LO]);
+        if (y + HI + 1 < S) bot = sub2(bot, v[y + HI + 1]);
         o[y] = bot;
     }
 #pragma unroll
@@ -149,7 +172,7 @@ __device__ __forceinline__ void box_pass(float (&v)[S]) {
 
 // LO < 0 selects the window at run time (programs that mix window shapes).
 template <int S, int LO, int HI>
-__device__ __forceinline__ void box_any(float (&v)[S], int lo, int hi) {
+__device__ __forceinline__ void box_any(u64 (&v)[S], int lo, int hi) {
     if (LO >= 0) {
         box_pass<S, (LO >= 0 ? LO : 0), HI>(v);
     } else {
@@ -161,32 +184,32 @@ __device__ __forceinline__ void box_any(float (&v)[S], int lo, int hi) {
 }
 
 template <int S>
-__device__ __forceinline__ void tile_store(float2 *tile, const float (&a)[S], const float (&b)[S], int lane) {
+__device__ __forceinline__ void tile_store(u64 *tile, const u64 (&a)[S], int lane) {
     constexpr int PITCH = S + 1;  // odd: row-wise writes and column-wise reads are both conflict-free
     if (lane < S) {
 #pragma unroll
-        for (int r = 0; r < S; ++r) tile[r * PITCH + lane] = make_float2(a[r], b[r]);
+        for (int r = 0; r < S; ++r) tile[r * PITCH + lane] = a[r];
     }
 }
 template <int S>
-__device__ __forceinline__ void tile_load_t(const float2 *tile, float (&a)[S], float (&b)[S], int lx) {
+__device__ __forceinline__ void tile_load_t(const u64 *tile, u64 (&a)[S], int lx) {
     constexpr int PITCH = S + 1;
 #pragma unroll
-    for (int r = 0; r < S; ++r) {
-        const float2 t = tile[lx * PITCH + r];
-        a[r] = t.x;
-        b[r] = t.y;
-    }
+    for (int r = 0; r < S; ++r) a[r] = tile[lx * PITCH + r];
 }
 
+// Warp w of a CTA tile owns images i0 = 2*(2*ib + wi) + {0,1} and j0 = 2*(4*jb + wj) + {0,1}.
+// Its four maps live in two packed arrays:  M[0][r] = (i0j0, i1j1),  M[1][r] = (i0j1, i1j0),
+// so that every packed operation multiplies the (i0, i1) pair of one image pair with the
+// (j0, j1) pair -- or its swap -- of another: no broadcasts are needed.
 template <int S, int LO, int HI>
 __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constant__ FParams p) {
     constexpr int P = S * S;
     constexpr int PITCH = S + 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // [2][kImgs][P] float2 variance stage | [kWarps][S*PITCH] float2 transpose tiles | barriers
-    float2 *stage = reinterpret_cast<float2 *>(smem_raw);
-    float2 *tiles = stage + 2 * kImgs * P;
+    // [2][kPairs][P] float4 variance stage | [kWarps][S*PITCH] u64 transpose tiles | barriers
+    float4 *stage = reinterpret_cast<float4 *>(smem_raw);
+    u64 *tiles = reinterpret_cast<u64 *>(stage + 2 * kPairs * P);
     uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + kWarps * S * PITCH);
     uint64_t *full = bars, *empty = bars + 2;
 
@@ -218,21 +241,22 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
     };
 
     if (warp == kWarps) {
-        // ---- producer: stages each ReLU layer's (s, 1/s) maps of the tile's 12 images one
-        // layer ahead; it runs on across tile boundaries, so the next tile's first layer is
-        // already in flight while the consumers finish the current tile.
+        // ---- producer: one elected thread stages, one pipeline stage ahead, first the tile's
+        // images (one stage per channel) and then each ReLU layer's pair-interleaved
+        // (s_a, s_b, 1/s_a, 1/s_b) maps of the tile's six image pairs.  It runs on across tile
+        // boundaries, so the next tile's first stages are in flight while the consumers finish.
         if (lane == 0) {
-            unsigned l = 0;  // running layer counter over all tiles of this CTA
+            unsigned l = 0;  // running stage counter over all tiles of this CTA
+            const int last_pi = (p.N1 - 1) >> 1, last_pj = (p.N2 - 1) >> 1;
             for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
                 int ib, jb;
                 if (!decode(t, ib, jb)) continue;
                 const int i_base = ib * kTileI, j_base = jb * kTileJ;
-                // stage 0..C-1 of a tile: channel c of the 12 images (the init step reads them)
                 for (int c = 0; c < p.C; ++c) {
                     const unsigned buf = l & 1;
                     if (l >= 2) mbar_wait(&empty[buf], ((l >> 1) - 1) & 1);
                     mbar_arrive_expect_tx(&full[buf], kImgs * P * 4);
-                    float *dst = reinterpret_cast<float *>(stage + buf * kImgs * P);
+                    float *dst = reinterpret_cast<float *>(stage + buf * kPairs * P);
                     for (int s = 0; s < kImgs; ++s) {
                         const float *src;
                         if (s < kTileI) src = p.x + ((long long)min(i_base + s, p.N1 - 1) * p.C + c) * P;
@@ -245,14 +269,18 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
                     if (p.ops[k].kind != F_RELU) continue;
                     const unsigned buf = l & 1;
                     if (l >= 2) mbar_wait(&empty[buf], ((l >> 1) - 1) & 1);
-                    mbar_arrive_expect_tx(&full[buf], kImgs * P * 8);
-                    float2 *dst = stage + buf * kImgs * P;
+                    mbar_arrive_expect_tx(&full[buf], kPairs * P * 16);
+                    float4 *dst = stage + buf * kPairs * P;
                     const long long off = p.aux_f_off + 2LL * p.ops[k].aux_off;
-                    for (int s = 0; s < kImgs; ++s) {
-                        const float *src;
-                        if (s < kTileI) src = p.aux_x + (long long)min(i_base + s, p.N1 - 1) * p.aux_stride + off;
-                        else src = p.aux_z + (long long)min(j_base + s - kTileI, p.N2 - 1) * p.aux_stride + off;
+                    for (int s = 0; s < kPairs; ++s) {
+                        // pair s of the tile; its float4 map is split over the two images' rows
+                        const float *base;
+                        long long pr;
+                        if (s < kTileI / 2) { pr = min((i_base >> 1) + s, last_pi); base = p.aux_x; }
+                        else { pr = min((j_base >> 1) + s - kTileI / 2, last_pj); base = p.aux_z; }
+                        const float *src = base + 2 * pr * p.aux_stride + off;
                         bulk_g2s(dst + s * P, src, P * 8, &full[buf]);
+                        bulk_g2s(dst + s * P + P / 2, src + p.aux_stride, P * 8, &full[buf]);
                     }
                     ++l;
                 }
@@ -264,43 +292,48 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
     // ---- consumers ------------------------------------------------------------------------
     const int wi = warp >> 2, wj = warp & 3;
     const int lx = lane < S ? lane : S - 1;  // clamped lane for loads
-    float2 *tile = tiles + warp * S * PITCH;
-    unsigned relu_l = 0;  // running stage counter (image channels + ReLU layers), in step with the producer's
+    u64 *tile = tiles + warp * S * PITCH;
+    unsigned stage_l = 0;  // running stage counter, in step with the producer's
+    const u64 C6 = pk(7.577116048e-05f, 7.577116048e-05f), C5 = pk(-5.945927478e-05f, -5.945927478e-05f),
+              C4 = pk(2.400144585e-04f, 2.400144585e-04f), C3 = pk(5.259375321e-04f, 5.259375321e-04f),
+              C2 = pk(2.417275915e-03f, 2.417275915e-03f), C1 = pk(1.500489842e-02f, 1.500489842e-02f),
+              C0 = pk(3.001054525e-01f, 3.001054525e-01f);
 
     for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
         int ib, jb;
         if (!decode(t, ib, jb)) continue;
         const int i_base = ib * kTileI, j_base = jb * kTileJ;
-        float m[4][S];  // pair (a, b) -> m[2a + b]; lane = column, register = row after init
+
+        u64 M[2][S];  // lane = column, register = row after init
         {
             // init, kernels.py:43-49: channel c of the tile's images arrives through the stage
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int r = 0; r < S; ++r) m[q][r] = 0.f;
+                for (int r = 0; r < S; ++r) M[h][r] = 0ull;
             for (int c = 0; c < p.C; ++c) {
-                const unsigned buf = relu_l & 1;
-                mbar_wait(&full[buf], (relu_l >> 1) & 1);
-                const float *sb = reinterpret_cast<const float *>(stage + buf * kImgs * P) + lx;
+                const unsigned buf = stage_l & 1;
+                mbar_wait(&full[buf], (stage_l >> 1) & 1);
+                const float *sb = reinterpret_cast<const float *>(stage + buf * kPairs * P) + lx;
                 const float *x0 = sb + (wi * 2 + 0) * P, *x1 = sb + (wi * 2 + 1) * P;
                 const float *z0 = sb + (kTileI + wj * 2 + 0) * P, *z1 = sb + (kTileI + wj * 2 + 1) * P;
 #pragma unroll
                 for (int r = 0; r < S; ++r) {
                     const float a0 = x0[r * S], a1 = x1[r * S], b0 = z0[r * S], b1 = z1[r * S];
-                    m[0][r] = fmaf(a0, b0, m[0][r]);
-                    m[1][r] = fmaf(a0, b1, m[1][r]);
-                    m[2][r] = fmaf(a1, b0, m[2][r]);
-                    m[3][r] = fmaf(a1, b1, m[3][r]);
+                    const u64 A = pk(a0, a1);
+                    M[0][r] = fma2(A, pk(b0, b1), M[0][r]);
+                    M[1][r] = fma2(A, pk(b1, b0), M[1][r]);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[buf]);
-                ++relu_l;
+                ++stage_l;
             }
             if (p.C > 1) {
+                const u64 IC = pk(p.inv_c, p.inv_c);
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int r = 0; r < S; ++r) m[q][r] *= p.inv_c;
+                    for (int r = 0; r < S; ++r) M[h][r] = mul2(M[h][r], IC);
             }
         }
 
@@ -308,64 +341,76 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
             const FOp o = p.ops[k];
             if (o.kind == F_CONV) {
                 if (o.lo != 0 || o.hi != 0) {
-                    // pass 1, transposition, pass 2 -- software-pipelined over the two halves
-                    // (maps 0,1 and 2,3) so that the smem traffic of one half overlaps the
-                    // adds of the other
-                    box_any<S, LO, HI>(m[0], o.lo, o.hi);
-                    box_any<S, LO, HI>(m[1], o.lo, o.hi);
-                    tile_store<S>(tile, m[0], m[1], lane);
+                    // pass 1, transposition, pass 2 -- software-pipelined over the two packed
+                    // arrays so that the smem traffic of one overlaps the adds of the other
+                    box_any<S, LO, HI>(M[0], o.lo, o.hi);
+                    tile_store<S>(tile, M[0], lane);
                     __syncwarp();
-                    tile_load_t<S>(tile, m[0], m[1], lx);
-                    box_any<S, LO, HI>(m[2], o.lo, o.hi);
-                    box_any<S, LO, HI>(m[3], o.lo, o.hi);
+                    tile_load_t<S>(tile, M[0], lx);
+                    box_any<S, LO, HI>(M[1], o.lo, o.hi);
                     __syncwarp();
-                    tile_store<S>(tile, m[2], m[3], lane);
-                    box_any<S, LO, HI>(m[0], o.lo, o.hi);
-                    box_any<S, LO, HI>(m[1], o.lo, o.hi);
+                    tile_store<S>(tile, M[1], lane);
+                    box_any<S, LO, HI>(M[0], o.lo, o.hi);
                     __syncwarp();
-                    tile_load_t<S>(tile, m[2], m[3], lx);
+                    tile_load_t<S>(tile, M[1], lx);
                     __syncwarp();
-                    box_any<S, LO, HI>(m[2], o.lo, o.hi);
-                    box_any<S, LO, HI>(m[3], o.lo, o.hi);
+                    box_any<S, LO, HI>(M[1], o.lo, o.hi);
                 }
+                const u64 SC = pk(o.scale, o.scale), BI = pk(o.bias, o.bias);
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int r = 0; r < S; ++r) m[q][r] = fmaf(m[q][r], o.scale, o.bias);
+                    for (int r = 0; r < S; ++r) M[h][r] = fma2(M[h][r], SC, BI);
             } else if (o.kind == F_RELU) {
-                const unsigned buf = relu_l & 1;
-                mbar_wait(&full[buf], (relu_l >> 1) & 1);
-                const float2 *sb = stage + buf * kImgs * P + lx;
-                const float2 *ai0 = sb + (wi * 2 + 0) * P, *ai1 = sb + (wi * 2 + 1) * P;
-                const float2 *bj0 = sb + (kTileI + wj * 2 + 0) * P, *bj1 = sb + (kTileI + wj * 2 + 1) * P;
+                const unsigned buf = stage_l & 1;
+                mbar_wait(&full[buf], (stage_l >> 1) & 1);
+                const float4 *sb = stage + buf * kPairs * P + lx;
+                const float4 *ai = sb + wi * P, *bj = sb + (kTileI / 2 + wj) * P;
 #pragma unroll
                 for (int r = 0; r < S; ++r) {
-                    const float2 A0 = ai0[r * S], A1 = ai1[r * S], B0 = bj0[r * S], B1 = bj1[r * S];
+                    const float4 A = ai[r * S], B = bj[r * S];
+                    const u64 SA = pk(A.x, A.y), RA = pk(A.z, A.w);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float2 A = (q & 2) ? A1 : A0, B = (q & 1) ? B1 : B0;
-                        const float s = A.x * B.x, rr = A.y * B.y;
-                        const float c = m[q][r];
-                        const float d = s - fabsf(c);
-                        const float e = d * rr;
-                        const float w = d * sqrt_approx(fabsf(e));
-                        m[q][r] = fmaf(w, h2_poly(e), fmaxf(c, 0.f));
+                    for (int h = 0; h < 2; ++h) {
+                        const u64 SB = h ? pk(B.y, B.x) : pk(B.x, B.y);
+                        const u64 RB = h ? pk(B.w, B.z) : pk(B.z, B.w);
+                        float c0, c1;
+                        upk(M[h][r], c0, c1);
+                        const u64 D = fma2(SA, SB, pk(neg_abs(c0), neg_abs(c1)));  // s - |c|
+                        const u64 E = mul2(D, mul2(RA, RB));                       // e = 1 - |c|/s
+                        float e0, e1;
+                        upk(E, e0, e1);
+                        const u64 W = mul2(D, pk(sqrt_approx(fabsf(e0)), sqrt_approx(fabsf(e1))));
+                        u64 H = fma2(C6, E, C5);
+                        H = fma2(H, E, C4);
+                        H = fma2(H, E, C3);
+                        H = fma2(H, E, C2);
+                        H = fma2(H, E, C1);
+                        H = fma2(H, E, C0);
+                        M[h][r] = fma2(W, H, pk(fmaxf(c0, 0.f), fmaxf(c1, 0.f)));
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[buf]);
-                ++relu_l;
+                ++stage_l;
             } else {  // F_DENSE: whole-map sum, scale, bias -> the kernel entry
                 float tot[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float a = 0.f;
+                for (int h = 0; h < 2; ++h) {
+                    u64 acc = M[h][0];
 #pragma unroll
-                    for (int r = 0; r < S; ++r) a += m[q][r];
-                    if (lane >= S) a = 0.f;
+                    for (int r = 1; r < S; ++r) acc = add2(acc, M[h][r]);
+                    float a0, a1;
+                    upk(acc, a0, a1);
+                    if (lane >= S) { a0 = 0.f; a1 = 0.f; }
 #pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
-                    tot[q] = fmaf(a, o.scale, o.bias);
+                    for (int d = 16; d > 0; d >>= 1) {
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, d);
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, d);
+                    }
+                    // M[0] = (i0j0, i1j1), M[1] = (i0j1, i1j0); tot index = 2a + b
+                    tot[h == 0 ? 0 : 1] = fmaf(a0, o.scale, o.bias);
+                    tot[h == 0 ? 3 : 2] = fmaf(a1, o.scale, o.bias);
                 }
                 if (lane < 4) {
                     const int a = lane >> 1, b = lane & 1;

@@ -199,13 +199,18 @@ __global__ void __launch_bounds__(kThreads) generic_kernel(GenericParams<T> p) {
                         p.aux_x_out[arow] = v0;
                         if (p.aux_f_off > 0) {
                             // operands of the fused kernel's ReLU: s = sqrt(xx) (+ sqrt(f32_tiny), the
-                            // separable stand-in for kernels.py:146's "+ f32_tiny") and 1/s, stored in the
-                            // register layout that kernel is in when it reaches this layer
+                            // separable stand-in for kernels.py:146's "+ f32_tiny") and 1/s, in the
+                            // register layout that kernel is in at this layer, interleaved with the
+                            // partner image of the pair (2k, 2k+1): float4 (s_2k, s_2k+1, 1/s_2k, 1/s_2k+1)
+                            // per pixel, first half of the pixels in row 2k, second half in row 2k+1
                             const int tp = o.aux_t ? (px % o.Wi) * o.Hi + px / o.Wi : px;
+                            const int half = P / 2;
+                            const int64_t n = ei[g0];
                             const T sd = add_rn(sqrt_rn(v0), (T)1.0842021724855044e-19);
-                            T *f = p.aux_x_out + (size_t)ei[g0] * p.aux_elems + p.aux_f_off + 2 * (size_t)(o.aux_off + tp);
+                            T *f = p.aux_x_out + (size_t)((n & ~(int64_t)1) + (tp >= half ? 1 : 0)) * p.aux_elems +
+                                   p.aux_f_off + 2 * (size_t)o.aux_off + 4 * (size_t)(tp % half) + (n & 1);
                             f[0] = sd;
-                            f[1] = div_rn((T)1, sd);
+                            f[2] = div_rn((T)1, sd);
                         }
                         const T h0 = div_rn(v0, (T)2);  // kernels.py:154
                         if (p.NP == 2) {

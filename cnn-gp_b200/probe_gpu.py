@@ -46,7 +46,17 @@ def gram_rate(cfg, n, path, C=1, S=28, reps=3):
         engine.set_path(prev)
 
 
+def relu_probes():
+    L = ctypes.CDLL(os.path.join(ROOT, "cnn-gp_b200", "libcnngp_bench.so"))
+    L.mb_relu.restype = ctypes.c_double
+    L.mb_relu.argtypes = [ctypes.c_int, ctypes.c_int]
+    return {f"relu_v{v}_Gpp_per_s": L.mb_relu(v, 2000) / 1e9 for v in (0, 1)}
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["relu"]:
+        print(json.dumps(relu_probes(), indent=1))
+        sys.exit(0)
     res = {"probes_Tops": probes()}
     for cfg, C, S in (("mnist_paper_convnet_gp", 1, 28), ("mnist_as_tf", 1, 28), ("cifar10", 3, 32)):
         for path in sys.argv[1:] or ["generic"]:

@@ -98,7 +98,10 @@ int cnngp_variances(const cnngp_plan *plan, const void *d_x, const void *d_z, in
                     void *d_aux_x, void *d_aux_z, void *d_kdiag, void *stream);
 
 /* The Gram tile: model(x, z, same, diag) of kernels.py:18-57.
- *   d_x [N1,C,H,W], d_z [N2,C,H,W]; d_aux_x / d_aux_z from cnngp_variances
+ *   d_x [N1,C,H,W], d_z [N2,C,H,W]; d_aux_x / d_aux_z from cnngp_variances.  Sub-blocks of a
+ *            larger array may be passed (offset image / row pointers) as long as they start at an
+ *            EVEN image index: the fused maps interleave images 2k and 2k+1 over rows 2k, 2k+1,
+ *            and the variance buffers must hold an even number of rows
  *   d_kdiag  NULL, or [N1] from cnngp_variances: with `symmetric` the diagonal entries are
  *            copied from it, so that diag(model(X)) == model(X, diag=True) bit for bit
  *   same   != 0: entries with i == j follow the variance recursion (kernels.py:155-162)
