@@ -35,7 +35,9 @@ constexpr int kWarps = 8;                    // consumer warps per CTA
 constexpr int kTileI = 4, kTileJ = 8;        // images per CTA along i and j (2 x 4 warps of 2 x 2)
 constexpr int kImgs = kTileI + kTileJ;       // images per CTA tile
 constexpr int kPairs = kImgs / 2;            // image pairs whose interleaved variance maps are staged per layer
-constexpr int kThreads = (kWarps + 1) * 32;  // + producer warp
+constexpr int kThreads = (kWarps + 4) * 32;  // + a third warpgroup: the producer warp and three warps that
+                                             // only donate their registers (setmaxnreg)
+constexpr int kRegsProducer = 24, kRegsConsumer = 240;
 constexpr int kMaxOps = 40;
 constexpr int kSuperJ = 64, kSuperI = 128;   // super-tile = 512 x 512 images (L2-resident variance maps)
 
@@ -240,7 +242,10 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
         return true;
     };
 
-    if (warp == kWarps) {
+    if (warp >= kWarps) {
+        // third warpgroup: hand its registers to the consumers; only its first warp works
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
+        if (warp != kWarps) return;
         // ---- producer: one elected thread stages, one pipeline stage ahead, first the tile's
         // images (one stage per channel) and then each ReLU layer's pair-interleaved
         // (s_a, s_b, 1/s_a, 1/s_b) maps of the tile's six image pairs.  It runs on across tile
@@ -290,6 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
     }
 
     // ---- consumers ------------------------------------------------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsConsumer));
     const int wi = warp >> 2, wj = warp & 3;
     const int lx = lane < S ? lane : S - 1;  // clamped lane for loads
     u64 *tile = tiles + warp * S * PITCH;
