@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
     const u64 C6 = pk(7.577116048e-05f, 7.577116048e-05f), C5 = pk(-5.945927478e-05f, -5.945927478e-05f),
               C4 = pk(2.400144585e-04f, 2.400144585e-04f), C3 = pk(5.259375321e-04f, 5.259375321e-04f),
               C2 = pk(2.417275915e-03f, 2.417275915e-03f), C1 = pk(1.500489842e-02f, 1.500489842e-02f),
-              C0 = pk(3.001054525e-01f, 3.001054525e-01f);
+              C0 = pk(3.001054525e-01f, 3.001054525e-01f), ONE = pk(1.f, 1.f);
 
     for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
         int ib, jb;
@@ -382,8 +382,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
                         const u64 RB = h ? pk(B.w, B.z) : pk(B.z, B.w);
                         float c0, c1;
                         upk(M[h][r], c0, c1);
-                        const u64 D = fma2(SA, SB, pk(neg_abs(c0), neg_abs(c1)));  // s - |c|
-                        const u64 E = mul2(D, mul2(RA, RB));                       // e = 1 - |c|/s
+                        const u64 NC = pk(neg_abs(c0), neg_abs(c1));
+                        const u64 D = fma2(SA, SB, NC);               // s - |c|
+                        const u64 E = fma2(NC, mul2(RA, RB), ONE);    // e = 1 - |c|/s, independent of D
                         float e0, e1;
                         upk(E, e0, e1);
                         const u64 W = mul2(D, pk(sqrt_approx(fabsf(e0)), sqrt_approx(fabsf(e1))));
