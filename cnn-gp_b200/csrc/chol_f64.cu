@@ -1,19 +1,544 @@
-// chol_f64.cu -- blocked fp64 Cholesky / triangular solves / prediction (placeholder).
+// chol_f64.cu -- blocked fp64 Cholesky (upper, row-major), triangular solves and the
+// prediction step of the GP classifier, for sm_100a.
+//
+// Reference (paths relative to /root/reference):
+//   exp_mnist_resnet/classify_gp.py:17-27   scipy.linalg.solve(Kxx, Y, assume_a='pos', lower=False)
+//                                           == LAPACK dposv('U'): A = U^T U, then two triangular solves
+//   exp_mnist_resnet/classify_gp.py:39-41   (Kxvx @ A).argmax(dim=1)
+//
+// Layout.  A is row-major [n, lda]; only j >= i is ever read or written (save_K never writes the
+// strictly lower block triangle of Kxx, it stays NaN: cnn_gp/kernel_save_tools.py:21-23,
+// cnn_gp/data.py:22-29).  U overwrites the upper triangle.
+//
+// potrf, right-looking with block size NB = 128, per block column k:
+//   potf2_inv   one CTA: U_kk = chol(A_kk) in shared memory, then W = U_kk^{-1} (workspace)
+//   tn_kernel<1>  row panel X = W^T A[k, k+1:]            (the triangular solve as a DMMA GEMM)
+//   tn_kernel<0>  trailing update A22 -= X^T X, j >= i     (SYRK, the one dense contraction:
+//                 mma.sync.m8n8k4.f64 = SASS DMMA, the FP64 tensor pipe of sm_100a)
+// with one block column of look-ahead: the SYRK tiles of the next block row run first, then the
+// next potf2_inv runs on a second stream underneath the rest of the trailing update.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <string>
+
 #include "plan.h"
+
+namespace cnngp {
+namespace {
+
+constexpr int NB = 128;        // block column width
+constexpr int TI = 128, TJ = 64;  // CTA tile of the DMMA kernel (rows i x columns j)
+constexpr int KC = 16;         // k-chunk per pipeline stage
+constexpr int STAGES = 3;
+constexpr int PP = TI + 8, PQ = TJ + 8;  // smem pitches (doubles), == 8 mod 16: fragment loads hit the
+                                         // two-wavefront minimum
+constexpr int TN_THREADS = 256;
+
+__device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async8(void *dst, const void *src, bool valid) {
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s_u32(dst)), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, int valid_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s_u32(dst)), "l"(src), "r"(valid_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+struct TnParams {
+    const double *P;  // [K, ldp]: operand giving the rows of C (C row i <- column i of P)
+    const double *Q;  // [K, ldq]: operand giving the columns of C
+    double *C;        // [M, ldc]
+    long long ldp, ldq, ldc;
+    int M, N, K;
+    int Tj;            // column tiles
+    int ib_lo;         // first row tile of this launch
+    long long t_off;   // linear index of tile (ib_lo, first column) in the triangular enumeration
+    int vec_ok;        // every row of P, Q, C is 16-byte aligned at even columns
+};
+
+// C (op)= P^T Q on TI x TJ tiles.  MODE 0: C -= P^T Q restricted to j >= i (SYRK; tiles are
+// enumerated over the upper block triangle only).  MODE 1: C = P^T Q, a single row tile
+// (M <= TI); Q and C may alias because a CTA owns whole columns.
+template <int MODE>
+__global__ void __launch_bounds__(TN_THREADS, 2) tn_kernel(const TnParams g) {
+    extern __shared__ __align__(16) double tn_smem[];
+    double *Ps = tn_smem;                       // [STAGES][KC][PP]
+    double *Qs = tn_smem + STAGES * KC * PP;    // [STAGES][KC][PQ]
+
+    int ib, jb;
+    if (MODE == 0) {
+        // row tile ib holds column tiles jb >= 2 ib: prefix(ib) = ib*Tj - ib*(ib-1)
+        const long long t = g.t_off + blockIdx.x;
+        const double b = (double)g.Tj + 1.0;
+        long long r = (long long)floor((b - sqrt(fmax(b * b - 4.0 * (double)t, 0.0))) * 0.5);
+        if (r < 0) r = 0;
+        while (r > 0 && r * g.Tj - r * (r - 1) > t) --r;
+        while ((r + 1) * g.Tj - (r + 1) * r <= t) ++r;
+        ib = (int)r;
+        jb = 2 * ib + (int)(t - (r * g.Tj - r * (r - 1)));
+    } else {
+        ib = 0;
+        jb = blockIdx.x;
+    }
+    const int i0 = ib * TI, j0 = jb * TJ;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wi = warp >> 1, wj = warp & 1;  // 4 x 2 warps of 32 x 32
+    const int nchunks = (g.K + KC - 1) / KC;
+
+    auto load_chunk = [&](int chunk, int stage) {
+        const int k0 = chunk * KC;
+        double *ps = Ps + stage * KC * PP, *qs = Qs + stage * KC * PQ;
+        if (g.vec_ok) {
+            // P: KC rows x TI/2 16-byte pieces; Q: KC rows x TJ/2
+            for (int e = tid; e < KC * (TI / 2); e += TN_THREADS) {
+                const int t = e / (TI / 2), c = (e % (TI / 2)) * 2;
+                const int col = i0 + c;
+                int bytes = (k0 + t < g.K) ? 8 * max(0, min(2, g.M - col)) : 0;
+                const double *src = g.P + (long long)(bytes ? k0 + t : 0) * g.ldp + (bytes ? col : 0);
+                cp_async16(ps + t * PP + c, src, bytes);
+            }
+            for (int e = tid; e < KC * (TJ / 2); e += TN_THREADS) {
+                const int t = e / (TJ / 2), c = (e % (TJ / 2)) * 2;
+                const int col = j0 + c;
+                int bytes = (k0 + t < g.K) ? 8 * max(0, min(2, g.N - col)) : 0;
+                const double *src = g.Q + (long long)(bytes ? k0 + t : 0) * g.ldq + (bytes ? col : 0);
+                cp_async16(qs + t * PQ + c, src, bytes);
+            }
+        } else {
+            for (int e = tid; e < KC * TI; e += TN_THREADS) {
+                const int t = e / TI, c = e % TI;
+                const bool ok = (k0 + t < g.K) && (i0 + c < g.M);
+                cp_async8(ps + t * PP + c, g.P + (ok ? (long long)(k0 + t) * g.ldp + i0 + c : 0), ok);
+            }
+            for (int e = tid; e < KC * TJ; e += TN_THREADS) {
+                const int t = e / TJ, c = e % TJ;
+                const bool ok = (k0 + t < g.K) && (j0 + c < g.N);
+                cp_async8(qs + t * PQ + c, g.Q + (ok ? (long long)(k0 + t) * g.ldq + j0 + c : 0), ok);
+            }
+        }
+    };
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nchunks) load_chunk(s, s);
+        cp_commit();
+    }
+    const int lr = lane >> 2, lk = lane & 3;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        cp_wait<STAGES - 2>();
+        __syncthreads();
+        if (ch + STAGES - 1 < nchunks) load_chunk(ch + STAGES - 1, (ch + STAGES - 1) % STAGES);
+        cp_commit();
+        const double *ps = Ps + (ch % STAGES) * KC * PP + wi * 32 + lr;
+        const double *qs = Qs + (ch % STAGES) * KC * PQ + wj * 32 + lr;
+#pragma unroll
+        for (int k4 = 0; k4 < KC / 4; ++k4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                a[f] = ps[(k4 * 4 + lk) * PP + f * 8];
+                b[f] = qs[(k4 * 4 + lk) * PQ + f * 8];
+            }
+#pragma unroll
+            for (int fi = 0; fi < 4; ++fi)
+#pragma unroll
+                for (int fj = 0; fj < 4; ++fj) dmma(acc[fi][fj][0], acc[fi][fj][1], a[fi], b[fj]);
+        }
+    }
+    cp_wait<0>();
+
+    // epilogue: fragment (fi, fj) holds C[i][j], C[i][j+1] with i = i0 + wi*32 + fi*8 + lane/4,
+    // j = j0 + wj*32 + fj*8 + 2*(lane%4)
+#pragma unroll
+    for (int fi = 0; fi < 4; ++fi) {
+        const int i = i0 + wi * 32 + fi * 8 + lr;
+        if (i >= g.M) continue;
+        double *crow = g.C + (long long)i * g.ldc;
+#pragma unroll
+        for (int fj = 0; fj < 4; ++fj) {
+            const int j = j0 + wj * 32 + fj * 8 + 2 * lk;
+            if (MODE == 0) {
+                if (j + 1 < g.N && j >= i && g.vec_ok) {
+                    double2 c = *reinterpret_cast<double2 *>(crow + j);
+                    c.x -= acc[fi][fj][0];
+                    c.y -= acc[fi][fj][1];
+                    *reinterpret_cast<double2 *>(crow + j) = c;
+                } else {
+                    if (j < g.N && j >= i) crow[j] -= acc[fi][fj][0];
+                    if (j + 1 < g.N && j + 1 >= i) crow[j + 1] -= acc[fi][fj][1];
+                }
+            } else {
+                if (j + 1 < g.N && g.vec_ok) {
+                    *reinterpret_cast<double2 *>(crow + j) = make_double2(acc[fi][fj][0], acc[fi][fj][1]);
+                } else {
+                    if (j < g.N) crow[j] = acc[fi][fj][0];
+                    if (j + 1 < g.N) crow[j + 1] = acc[fi][fj][1];
+                }
+            }
+        }
+    }
+}
+
+constexpr size_t kTnSmem = (size_t)STAGES * KC * (PP + PQ) * sizeof(double);
+
+// ---- diagonal block: unblocked Cholesky + triangular inverse in shared memory ---------------
+constexpr int DP = NB + 1;  // pitch
+constexpr int POTF2_THREADS = 512;
+
+// D = A[kb:kb+nb, kb:kb+nb] (upper).  Writes U_kk back over D and W = U_kk^{-1} (upper, zero
+// elsewhere, full NB x NB) to the workspace.  *info = kb + c + 1 for the first non-positive
+// pivot (LAPACK dpotrf convention).
+__global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_inv_kernel(double *A, long long lda, int kb, int nb,
+                                                                     double *W, int *info) {
+    extern __shared__ __align__(16) double ps_smem[];
+    double *s = ps_smem;            // [NB][DP]
+    double *row = ps_smem + NB * DP;  // [NB]
+    const int tid = threadIdx.x;
+    double *D = A + (long long)kb * lda + kb;
+    for (int e = tid; e < NB * NB; e += POTF2_THREADS) {
+        const int i = e / NB, j = e % NB;
+        s[i * DP + j] = (i < nb && j < nb && j >= i) ? D[(long long)i * lda + j] : (i == j ? 1.0 : 0.0);
+    }
+    const int ty = tid >> 5, tx = tid & 31;  // 16 x 32
+    for (int c = 0; c < nb; ++c) {
+        __syncthreads();
+        const double d = s[c * DP + c];
+        const bool bad = !(d > 0.0);
+        const double r = bad ? nan("") : sqrt(d);
+        if (bad && tid == 0 && *info == 0) *info = kb + c + 1;
+        if (tid >= c && tid < nb) row[tid] = tid == c ? r : s[c * DP + tid] / r;
+        __syncthreads();
+        if (tid >= c && tid < nb) s[c * DP + tid] = row[tid];
+        for (int i = c + 1 + ty; i < nb; i += 16) {
+            const double ri = row[i];
+            for (int j = tx + ((i - tx + 31) & ~31); j < nb; j += 32)  // first j >= i congruent to tx
+                s[i * DP + j] -= ri * row[j];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < nb * nb; e += POTF2_THREADS) {
+        const int i = e / nb, j = e % nb;
+        if (j >= i) D[(long long)i * lda + j] = s[i * DP + j];
+    }
+    __syncthreads();
+    // in-place inverse of the upper triangle, column by column (LAPACK dtrti2 order): with
+    // T = inv(U[0:j,0:j]) already in place, column j becomes -T U[0:j,j] / U[j][j].
+    const int ri = tid >> 2, rq = tid & 3;  // row i, quarter q of its dot product
+    for (int j = 0; j < nb; ++j) {
+        const double inv = 1.0 / s[j * DP + j];
+        double part = 0.0;
+        if (ri < j)
+            for (int t = ri + rq; t < j; t += 4) part += s[ri * DP + t] * s[t * DP + j];
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        __syncthreads();
+        if (rq == 0) {
+            if (ri < j) s[ri * DP + j] = -part * inv;
+            else if (ri == j) s[j * DP + j] = inv;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < NB * NB; e += POTF2_THREADS) {
+        const int i = e / NB, j = e % NB;
+        W[e] = (i < nb && j < nb && j >= i) ? s[i * DP + j] : 0.0;
+    }
+}
+
+constexpr size_t kPotf2Smem = (size_t)(NB * DP + NB) * sizeof(double);
+
+// ---- triangular solves with a few right-hand sides ------------------------------------------
+constexpr int NR = 16;  // right-hand sides per pass
+
+// One CTA: solve with the diagonal block.  FWD: U_kk^T y = b (forward);  else U_kk x = y (backward).
+template <bool FWD>
+__global__ void __launch_bounds__(512, 1) trsv_block_kernel(const double *U, long long lda, int kb, int nb,
+                                                           double *B, long long ldb, int c0, int nr) {
+    extern __shared__ __align__(16) double tr_smem[];
+    double *s = tr_smem;             // [NB][DP]
+    double *bs = tr_smem + NB * DP;  // [NB][NR]
+    const int tid = threadIdx.x;
+    const double *D = U + (long long)kb * lda + kb;
+    for (int e = tid; e < nb * nb; e += 512) {
+        const int i = e / nb, j = e % nb;
+        if (j >= i) s[i * DP + j] = D[(long long)i * lda + j];
+    }
+    for (int e = tid; e < nb * nr; e += 512) {
+        const int r = e / nr, c = e % nr;
+        bs[r * NR + c] = B[(long long)(kb + r) * ldb + c0 + c];
+    }
+    const int r = tid & (NB - 1), cg = tid >> 7;  // 4 column groups
+    if (FWD) {
+        for (int t = 0; t < nb; ++t) {
+            __syncthreads();
+            if (r > t && r < nb) {
+                const double f = s[t * DP + r] / s[t * DP + t];
+                for (int c = cg; c < nr; c += 4) bs[r * NR + c] -= f * bs[t * NR + c];
+            }
+        }
+    } else {
+        for (int t = nb - 1; t >= 0; --t) {
+            __syncthreads();
+            if (r < t) {
+                const double f = s[r * DP + t] / s[t * DP + t];
+                for (int c = cg; c < nr; c += 4) bs[r * NR + c] -= f * bs[t * NR + c];
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < nb * nr; e += 512) {
+        const int rr = e / nr, c = e % nr;
+        B[(long long)(kb + rr) * ldb + c0 + c] = bs[rr * NR + c] / s[rr * DP + rr];
+    }
+}
+
+constexpr size_t kTrsvSmem = (size_t)(NB * DP + NB * NR) * sizeof(double);
+
+// forward update: B[j] -= sum_t U[kb+t][j] * Y[t]  for j >= kb + nb   (thread per row j of B)
+__global__ void __launch_bounds__(256) fwd_update_kernel(const double *U, long long lda, int kb, int nb, int n,
+                                                         double *B, long long ldb, int c0, int nr) {
+    __shared__ double ys[NB * NR];
+    for (int e = threadIdx.x; e < nb * NR; e += 256) {
+        const int t = e / NR, c = e % NR;
+        ys[e] = c < nr ? B[(long long)(kb + t) * ldb + c0 + c] : 0.0;
+    }
+    __syncthreads();
+    const long long j = (long long)kb + nb + (long long)blockIdx.x * 256 + threadIdx.x;
+    if (j >= n) return;
+    double acc[NR];
+#pragma unroll
+    for (int c = 0; c < NR; ++c) acc[c] = 0.0;
+    const double *u = U + (long long)kb * lda + j;
+    for (int t = 0; t < nb; ++t) {
+        const double v = u[(long long)t * lda];
+#pragma unroll
+        for (int c = 0; c < NR; ++c) acc[c] += v * ys[t * NR + c];
+    }
+    double *b = B + j * ldb + c0;
+#pragma unroll
+    for (int c = 0; c < NR; ++c)
+        if (c < nr) b[c] -= acc[c];
+}
+
+// backward update: Y[i] -= sum_t U[i][kb+t] * X[t]  for i < kb   (64 rows per CTA, staged)
+__global__ void __launch_bounds__(256) bwd_update_kernel(const double *U, long long lda, int kb, int nb, double *B,
+                                                         long long ldb, int c0, int nr) {
+    extern __shared__ __align__(16) double bw_smem[];
+    double *us = bw_smem;             // [64][DP]
+    double *xs = bw_smem + 64 * DP;   // [NB][NR]
+    const int i0 = blockIdx.x * 64;
+    for (int e = threadIdx.x; e < 64 * nb; e += 256) {
+        const int i = e / nb, t = e % nb;
+        us[i * DP + t] = (i0 + i < kb) ? U[(long long)(i0 + i) * lda + kb + t] : 0.0;
+    }
+    for (int e = threadIdx.x; e < nb * NR; e += 256) {
+        const int t = e / NR, c = e % NR;
+        xs[e] = c < nr ? B[(long long)(kb + t) * ldb + c0 + c] : 0.0;
+    }
+    __syncthreads();
+    const int i = threadIdx.x & 63, cg = threadIdx.x >> 6;  // columns cg, cg+4, cg+8, cg+12
+    if (i0 + i >= kb) return;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int t = 0; t < nb; ++t) {
+        const double v = us[i * DP + t];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] += v * xs[t * NR + cg + 4 * q];
+    }
+    double *b = B + (long long)(i0 + i) * ldb + c0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (cg + 4 * q < nr) b[cg + 4 * q] -= acc[q];
+}
+
+constexpr size_t kBwdSmem = (size_t)(64 * DP + NB * NR) * sizeof(double);
+
+// ---- prediction: scores = K A (float32 K widened to float64), pred = argmax ------------------
+// One warp per row of K; lanes stride over the n training points.
+template <int NC>
+__global__ void __launch_bounds__(256) predict_kernel(const float *K, long long R, long long n, long long ldk,
+                                                      const double *A, int nrhs, int c0, long long *pred,
+                                                      double *scores, double *best_val) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * 8 + warp;
+    if (r >= R) return;
+    const int nc = min(NC, nrhs - c0);
+    double acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+    const float *k = K + r * ldk;
+    for (long long t = lane; t < n; t += 32) {
+        const double kv = (double)k[t];
+        const double *a = A + t * nrhs + c0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            if (c < nc) acc[c] += kv * a[c];
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], d);
+    if (lane == 0) {
+        double bv = c0 == 0 ? -INFINITY : best_val[r];
+        long long bi = c0 == 0 ? 0 : pred[r];
+        bool any = c0 != 0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            if (c >= nc) break;
+            if (scores) scores[r * nrhs + c0 + c] = acc[c];
+            // first maximum wins, NaN propagates like torch.argmax (a NaN score is the maximum)
+            if (!any || acc[c] > bv || (acc[c] != acc[c] && bv == bv)) { bv = acc[c]; bi = c0 + c; any = true; }
+        }
+        pred[r] = bi;
+        if (best_val) best_val[r] = bv;
+    }
+}
+
+bool check(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return false;
+}
+
+bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
+// Tj column tiles; row tile ib holds jb in [2 ib, Tj)
+long long tri_prefix(long long ib, long long Tj) { return ib * Tj - ib * (ib - 1); }
+
+}  // namespace
+}  // namespace cnngp
+
+using namespace cnngp;
 
 extern "C" {
 
-int cnngp_potrf_upper_f64(double *, int64_t, int64_t, int32_t *, void *) {
-    cnngp::set_error("cnngp_potrf_upper_f64: not implemented yet");
-    return 100;
+int cnngp_potrf_upper_f64(double *d_A, int64_t n, int64_t lda, int32_t *d_info, void *stream_) {
+    if (!d_A || n < 0 || lda < n || !d_info) { set_error("cnngp_potrf_upper_f64: bad arguments"); return 1; }
+    if (n > 2000000000LL) { set_error("cnngp_potrf_upper_f64: n too large"); return 1; }
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (!check(cudaMemsetAsync(d_info, 0, sizeof(int32_t), s), "potrf memset")) return 5;
+    if (n == 0) return 0;
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_done[dev]) {
+        if (!check(cudaFuncSetAttribute(tn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTnSmem), "attr") ||
+            !check(cudaFuncSetAttribute(tn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTnSmem), "attr") ||
+            !check(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotf2Smem), "attr"))
+            return 7;
+        attr_done[dev] = true;
+    }
+    double *W = nullptr;
+    if (!check(cudaMallocAsync((void **)&W, sizeof(double) * NB * NB, s), "potrf workspace")) return 6;
+    cudaStream_t s2 = nullptr;
+    cudaEvent_t ev_head = nullptr, ev_diag = nullptr;
+    if (!check(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking), "potrf stream") ||
+        !check(cudaEventCreateWithFlags(&ev_head, cudaEventDisableTiming), "potrf event") ||
+        !check(cudaEventCreateWithFlags(&ev_diag, cudaEventDisableTiming), "potrf event"))
+        return 6;
+    const int vec_ok = (lda % 2 == 0) && aligned16(d_A);
+
+    potf2_inv_kernel<<<1, POTF2_THREADS, kPotf2Smem, s>>>(d_A, lda, 0, (int)(n < NB ? n : NB), W, d_info);
+    for (int64_t kb = 0; kb < n; kb += NB) {
+        const int nb = (int)(n - kb < NB ? n - kb : NB);
+        const int64_t m = n - kb - nb;  // trailing size
+        if (m <= 0) break;
+        double *panel = d_A + kb * lda + kb + nb;
+        const int Tj = (int)((m + TJ - 1) / TJ), Ti = (int)((m + TI - 1) / TI);
+        {   // X = W^T A[k, k+1:]  (in place)
+            TnParams g{};
+            g.P = W; g.ldp = NB; g.Q = panel; g.ldq = lda; g.C = panel; g.ldc = lda;
+            g.M = nb; g.N = (int)m; g.K = nb; g.Tj = Tj; g.ib_lo = 0; g.t_off = 0; g.vec_ok = vec_ok;
+            tn_kernel<1><<<Tj, TN_THREADS, kTnSmem, s>>>(g);
+        }
+        TnParams g{};
+        g.P = panel; g.ldp = lda; g.Q = panel; g.ldq = lda;
+        g.C = d_A + (kb + nb) * lda + kb + nb; g.ldc = lda;
+        g.M = (int)m; g.N = (int)m; g.K = nb; g.Tj = Tj; g.vec_ok = vec_ok;
+        // look-ahead: the next block row first, then its diagonal block on the side stream
+        g.ib_lo = 0; g.t_off = 0;
+        tn_kernel<0><<<Tj, TN_THREADS, kTnSmem, s>>>(g);
+        cudaEventRecord(ev_head, s);
+        cudaStreamWaitEvent(s2, ev_head, 0);
+        const int nb2 = (int)(m < NB ? m : NB);
+        potf2_inv_kernel<<<1, POTF2_THREADS, kPotf2Smem, s2>>>(d_A, lda, (int)(kb + nb), nb2, W, d_info);
+        cudaEventRecord(ev_diag, s2);
+        if (Ti > 1) {
+            g.ib_lo = 1; g.t_off = tri_prefix(1, Tj);
+            const long long tiles = tri_prefix(Ti, Tj) - g.t_off;
+            tn_kernel<0><<<(unsigned)tiles, TN_THREADS, kTnSmem, s>>>(g);
+        }
+        cudaStreamWaitEvent(s, ev_diag, 0);
+    }
+    cudaFreeAsync(W, s);
+    cudaEventDestroy(ev_head);
+    cudaEventDestroy(ev_diag);
+    cudaStreamDestroy(s2);
+    return check(cudaGetLastError(), "cnngp_potrf_upper_f64") ? 0 : 9;
 }
-int cnngp_potrs_upper_f64(const double *, int64_t, int64_t, double *, int32_t, int64_t, void *) {
-    cnngp::set_error("cnngp_potrs_upper_f64: not implemented yet");
-    return 100;
+
+int cnngp_potrs_upper_f64(const double *d_U, int64_t n, int64_t lda, double *d_B, int32_t nrhs, int64_t ldb,
+                          void *stream_) {
+    if (!d_U || !d_B || n < 0 || lda < n || nrhs < 0 || ldb < nrhs) { set_error("cnngp_potrs_upper_f64: bad arguments"); return 1; }
+    if (n == 0 || nrhs == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream_;
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_done[dev]) {
+        if (!check(cudaFuncSetAttribute(trsv_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsvSmem), "attr") ||
+            !check(cudaFuncSetAttribute(trsv_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsvSmem), "attr") ||
+            !check(cudaFuncSetAttribute(bwd_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem), "attr"))
+            return 7;
+        attr_done[dev] = true;
+    }
+    for (int c0 = 0; c0 < nrhs; c0 += NR) {
+        const int nr = nrhs - c0 < NR ? nrhs - c0 : NR;
+        for (int64_t kb = 0; kb < n; kb += NB) {  // U^T y = b
+            const int nb = (int)(n - kb < NB ? n - kb : NB);
+            trsv_block_kernel<true><<<1, 512, kTrsvSmem, s>>>(d_U, lda, (int)kb, nb, d_B, ldb, c0, nr);
+            const int64_t m = n - kb - nb;
+            if (m > 0)
+                fwd_update_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(d_U, lda, (int)kb, nb, (int)n, d_B, ldb, c0, nr);
+        }
+        const int64_t last = ((n - 1) / NB) * NB;
+        for (int64_t kb = last; kb >= 0; kb -= NB) {  // U x = y
+            const int nb = (int)(n - kb < NB ? n - kb : NB);
+            trsv_block_kernel<false><<<1, 512, kTrsvSmem, s>>>(d_U, lda, (int)kb, nb, d_B, ldb, c0, nr);
+            if (kb > 0)
+                bwd_update_kernel<<<(unsigned)((kb + 63) / 64), 256, kBwdSmem, s>>>(d_U, lda, (int)kb, nb, d_B, ldb, c0, nr);
+        }
+    }
+    return check(cudaGetLastError(), "cnngp_potrs_upper_f64") ? 0 : 9;
 }
-int cnngp_predict_argmax(const float *, int64_t, int64_t, int64_t, const double *, int32_t, int64_t *, double *,
-                         void *) {
-    cnngp::set_error("cnngp_predict_argmax: not implemented yet");
-    return 100;
+
+int cnngp_predict_argmax(const float *d_K, int64_t R, int64_t n, int64_t ldk, const double *d_A, int32_t nrhs,
+                         int64_t *d_pred, double *d_scores, void *stream_) {
+    if (!d_K || !d_A || !d_pred || R < 0 || n < 0 || ldk < n || nrhs < 1) { set_error("cnngp_predict_argmax: bad arguments"); return 1; }
+    if (R == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream_;
+    double *best = nullptr;
+    if (nrhs > NR && !check(cudaMallocAsync((void **)&best, sizeof(double) * R, s), "predict workspace")) return 6;
+    for (int c0 = 0; c0 < nrhs; c0 += NR)
+        predict_kernel<NR><<<(unsigned)((R + 7) / 8), 256, 0, s>>>(d_K, R, n, ldk, d_A, nrhs, c0, (long long *)d_pred,
+                                                                   d_scores, best);
+    if (best) cudaFreeAsync(best, s);
+    return check(cudaGetLastError(), "cnngp_predict_argmax") ? 0 : 9;
 }
-}
+
+}  // extern "C"

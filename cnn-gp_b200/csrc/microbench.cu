@@ -91,6 +91,44 @@ __global__ void __launch_bounds__(256) probe_lds(float *out, int iters) {
     if (acc == 123.456f) out[0] = acc;
 }
 
+// FP64 tensor pipe: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4), CH independent accumulator chains per warp
+template <int CH>
+__global__ void __launch_bounds__(256) probe_dmma(float *out, int iters) {
+    double acc[CH][2];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) acc[k][0] = acc[k][1] = threadIdx.x * 1e-3 + k;
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < CH; ++k)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(acc[k][0]), "+d"(acc[k][1])
+                             : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < CH; ++k) s += acc[k][0] + acc[k][1];
+    if (s == 123.456) out[0] = (float)s;
+}
+
+// DFMA, 8 independent chains
+__global__ void __launch_bounds__(256) probe_dfma(float *out, int iters, double a, double b) {
+    double r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = threadIdx.x * 1e-3 + k;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = fma(r[k], a, b);
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += r[k];
+    if (s == 123.456) out[0] = (float)s;
+}
+
 }  // namespace
 
 // returns ops-per-second of the probed instruction (lane-ops, i.e. 32 x warp instructions),
@@ -116,6 +154,8 @@ extern "C" double mb_probe(int kind, int blocks_per_sm, int iters) {
             case 6: probe<6><<<grid, 256>>>(d, n, 1.0001f, 1e-3f); break;
             case 10: probe_lds<1><<<grid, 256>>>(d, n); break;
             case 11: probe_lds<4><<<grid, 256>>>(d, n); break;
+            case 20: probe_dmma<8><<<grid, 256>>>(d, n); break;
+            case 21: probe_dfma<<<grid, 256>>>(d, n, 1.0000001, 1e-9); break;
         }
     };
     run(iters / 4 + 1);
@@ -134,6 +174,9 @@ extern "C" double mb_probe(int kind, int blocks_per_sm, int iters) {
     cudaEventDestroy(e1);
     cudaFree(d);
     if (cudaGetLastError() != cudaSuccess) return -1.0;
+    // kind 20: FMA-equivalents of the DMMA chain (8 x 4 mma per iteration per warp, 256 FMA each);
+    // kind 21: DFMA lane-ops
+    if (kind == 20) return 8.0 * 4 * iters * 256.0 * (256 / 32) * grid / (best * 1e-3);
     double per_thread = (kind >= 10) ? 8.0 * iters * (kind == 11 ? 4 : 1) : 8.0 * 4 * iters * (kind == 1 ? 2 : 1);
     return per_thread * 256.0 * grid / (best * 1e-3);
 }

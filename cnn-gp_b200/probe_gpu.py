@@ -17,7 +17,7 @@ def probes():
     L.mb_probe.restype = ctypes.c_double
     L.mb_probe.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
     names = {0: "ffma", 1: "ffma2(x2)", 2: "mufu.sqrt", 3: "mufu.rcp", 4: "7ffma+1mufu", 5: "fadd",
-             6: "6ffma+2fmnmx", 10: "lds32", 11: "lds128(words)"}
+             6: "6ffma+2fmnmx", 10: "lds32", 11: "lds128(words)", 20: "dmma(fma-equiv)", 21: "dfma"}
     out = {}
     for k, n in names.items():
         for bps in (4, 8):
