@@ -145,24 +145,65 @@ class DiagIterator(object):
         return (self.same, (ib, xy), (ib, xy2))
 
 
+def _as_tensors(ds):
+    """(images [N,C,H,W] float32 in [0,1], labels [N]) of a whole torchvision-style dataset without
+    going through per-item PIL decoding, or None when the dataset offers no array view.  Equals
+    what ``ToTensor`` yields item by item: uint8 HW / HWC -> float CHW / 255."""
+    if hasattr(ds, "images") and hasattr(ds, "labels") and torch.is_tensor(ds.images):
+        return ds.images, torch.as_tensor(ds.labels)
+    data, targets = getattr(ds, "data", None), getattr(ds, "targets", None)
+    if data is None or targets is None:
+        return None
+    data = torch.as_tensor(data)
+    if data.dtype != torch.uint8 or data.dim() not in (3, 4):
+        return None
+    if data.dim() == 3:
+        data = data[:, None]            # MNIST: [N, H, W]
+    else:
+        data = data.permute(0, 3, 1, 2)  # CIFAR: [N, H, W, C]
+    return data.to(torch.float32).div(255), torch.as_tensor(targets, dtype=torch.long)
+
+
 class DatasetFromConfig(object):
     """train / validation / test subsets described by a config module
     (``dataset``, ``dataset_name``, ``transforms``, ``train_range``, ``validation_range``,
-    ``test_range``), as the reference's data.py:129-162."""
+    ``test_range``), as the reference's data.py:129-162.
 
-    def __init__(self, datasets_path, config):
-        import torchvision
+    When the config adds no transforms and the dataset exposes its pixels as one array
+    (torchvision MNIST / CIFAR ``.data``, ``SyntheticImages.images``), the three subsets are
+    ``ResidentDataset`` tensors -- bit-identical to per-item ``ToTensor`` output -- that the tile
+    iterators slice without any per-item work; ``resident()`` moves one to the GPU."""
+
+    def __init__(self, datasets_path, config, download=True):
         self.config = config
-        trans = torchvision.transforms.ToTensor()
-        if len(config.transforms) > 0:
-            trans = torchvision.transforms.Compose([trans] + config.transforms)
         root = os.path.join(datasets_path, config.dataset_name)
-        train_full = config.dataset(root, train=True, download=True, transform=trans)
+        trans = None
+        try:
+            import torchvision
+            trans = torchvision.transforms.ToTensor()
+            if len(config.transforms) > 0:
+                trans = torchvision.transforms.Compose([trans] + list(config.transforms))
+        except ImportError:  # synthetic datasets do not need torchvision
+            if len(config.transforms) > 0:
+                raise
+        train_full = config.dataset(root, train=True, download=download, transform=trans)
         test_full = config.dataset(root, train=False, transform=trans)
         self.data_full = ConcatDataset([train_full, test_full])
-        self.train = Subset(self.data_full, config.train_range)
-        self.validation = Subset(self.data_full, config.validation_range)
-        self.test = Subset(self.data_full, config.test_range)
+        arrays = None
+        if len(config.transforms) == 0:
+            a, b = _as_tensors(train_full), _as_tensors(test_full)
+            if a is not None and b is not None:
+                arrays = torch.cat([a[0], b[0]]), torch.cat([a[1], b[1]])
+        if arrays is not None:
+            def pick(rng):
+                idx = torch.as_tensor(list(rng), dtype=torch.long)
+                return ResidentDataset(arrays[0][idx].contiguous(), arrays[1][idx].contiguous())
+        else:
+            def pick(rng):
+                return Subset(self.data_full, rng)
+        self.train = pick(config.train_range)
+        self.validation = pick(config.validation_range)
+        self.test = pick(config.test_range)
 
     @staticmethod
     def load_full(dataset):

@@ -53,3 +53,81 @@ def save_K(f, kern, name, X, X2, diag, batch_size, worker_rank=0, n_workers=1,
             out[0, i:i + len(x)] = k
         else:
             out[0, i:i + len(x), j:j + len(x2)] = k
+
+
+def _images_of(dataset, device):
+    import torch
+    from .data import _batch
+    x = dataset.images if hasattr(dataset, "images") and torch.is_tensor(dataset.images) else \
+        _batch(dataset, 0, len(dataset))[0]
+    return x.to(device, non_blocking=True).contiguous()
+
+
+def save_K_resident(f, model, name, X, X2, diag, batch_size, worker_rank=0, n_workers=1,
+                    print_interval=2., device=None):
+    """``save_K`` with the datasets resident in HBM: same dataset layout, same tile ownership
+    (the reference's contiguous slice of its tile list, cnn_gp/data.py:11-29, 54-60) and the same
+    values, but the images are uploaded once, the per-image variance maps are computed once per
+    dataset, every block row is at most two kernel launches, and finished rows stream to the
+    store through double-buffered pinned memory while the next row is being computed.
+
+    Replaces the per-tile H2D / D2H round trips of exp_mnist_resnet/save_kernel.py:21-24."""
+    import torch
+    from .tiles import GramJob, row_segments
+    from .data import worker_tiles
+    if name in f.keys():
+        print("Skipping {} (group exists)".format(name))
+        return
+    if device is None:
+        bufs = list(model.buffers())
+        device = bufs[0].device if bufs else torch.device("cuda")
+    N = len(X)
+    N2 = N if X2 is None else len(X2)
+    out = create_h5py_dataset(f, batch_size, name, diag, N, N2)
+    with torch.cuda.device(device):
+        x = _images_of(X, device)
+        if diag:
+            # DiagIterator semantics (data.py:99-126): index-aligned, truncated to the shorter set
+            n = N if X2 is None else min(N, N2)
+            x2 = x if X2 is None else _images_of(X2, device)
+            k = model(x[:n], x2[:n], same=(X2 is None), diag=True)
+            if not bool(torch.isfinite(k).all()):
+                raise FloatingPointError(f"nan or inf in kernel diagonal {name}")
+            out[0, 0:n] = k.cpu().numpy()
+            return
+        job = GramJob(model, x, None if X2 is None else _images_of(X2, device))
+        tiles = worker_tiles(N, None if X2 is None else N2, batch_size, worker_rank, n_workers)
+        segs = row_segments(tiles)
+        copy_stream = torch.cuda.Stream()
+        pending = []  # (event, host buffer, i0, i1, j0, j1)
+
+        def drain(keep):
+            while len(pending) > keep:
+                ev, host, i0, i1, j0, j1 = pending.pop(0)
+                ev.synchronize()
+                out[0, i0:i1, j0:j1] = host.numpy()
+
+        segs = print_timings(segs, desc=f"{name} rows (worker {worker_rank}/{n_workers})",
+                             print_interval=print_interval)
+        for r, has_diag, c0, c1 in segs:
+            i0, i1 = r * batch_size, min(N, (r + 1) * batch_size)
+            j0 = i0 if has_diag else c0 * batch_size
+            j1 = min(N2, c1 * batch_size) if c0 is not None else i1
+            buf = torch.empty((i1 - i0, j1 - j0), dtype=torch.float32, device=device)
+            if has_diag:
+                job.block_into(buf[:, :i1 - i0], i0, i1, i0, i1, symmetric=True)
+            if c0 is not None:
+                js = c0 * batch_size
+                job.block_into(buf[:, js - j0:], i0, i1, js, j1, symmetric=False)
+            if not bool(torch.isfinite(buf).all()):
+                raise FloatingPointError(f"nan or inf in kernel block row {name}[{i0}:{i1}]")
+            host = torch.empty(buf.shape, dtype=torch.float32).pin_memory()
+            copy_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(copy_stream):
+                host.copy_(buf, non_blocking=True)
+                buf.record_stream(copy_stream)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            pending.append((ev, host, i0, i1, j0, j1))
+            drain(keep=1)
+        drain(keep=0)

@@ -34,11 +34,16 @@ class GramJob:
     def block(self, out, i0, i1, j0, j1, symmetric):
         """out[i0:i1, j0:j1] = K(X[i0:i1], X2[j0:j1]) (upper triangle mirrored when symmetric).
         Block origins must be even: the fused kernel's variance maps interleave images 2k, 2k+1."""
+        self.block_into(out[i0:i1, j0:j1], i0, i1, j0, j1, symmetric)
+
+    def block_into(self, view, i0, i1, j0, j1, symmetric):
+        """view[...] = K(X[i0:i1], X2[j0:j1]); ``view`` is any [i1-i0, j1-j0] tensor with unit
+        column stride (e.g. a slice of a row buffer)."""
         assert i0 % 2 == 0 and j0 % 2 == 0, "tile origins must be even (use an even batch_size)"
         with torch.cuda.device(self.X.device):
             engine.gram_with_aux(self.plan, self.X[i0:i1], self.X2[j0:j1], self.aux_x[i0:i1],
                                  self.aux_x2[j0:j1], same=symmetric, diag=False, symmetric=symmetric,
-                                 out=out[i0:i1, j0:j1], kdiag=self.kdiag[i0:i1] if symmetric else None)
+                                 out=view, kdiag=self.kdiag[i0:i1] if symmetric else None)
         self.launches += 1
 
 

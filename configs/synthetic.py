@@ -1,0 +1,25 @@
+"""A machine-checkable stand-in for the MNIST configs when no dataset files exist: the paper's
+7-layer ConvNet GP (configs/mnist_paper_convnet_gp.py) on synthetic 28x28x1 class-template
+images (cnn_gp/synthetic.py).  Sizes follow the environment variables CNNGP_SYNTH_TRAIN /
+CNNGP_SYNTH_VAL / CNNGP_SYNTH_TEST (defaults 1000 / 200 / 300) so that the same
+save_kernel -> merge -> classify_gp pipeline runs from a unit test up to 60k images."""
+import os
+
+from cnn_gp.synthetic import synthetic_dataset
+from .mnist_paper_convnet_gp import initial_model  # noqa: F401
+
+_n_train = int(os.environ.get("CNNGP_SYNTH_TRAIN", "1000"))
+_n_val = int(os.environ.get("CNNGP_SYNTH_VAL", "200"))
+_n_test = int(os.environ.get("CNNGP_SYNTH_TEST", "300"))
+
+train_range = range(0, _n_train)
+validation_range = range(_n_train, _n_train + _n_val)
+test_range = range(_n_train + _n_val, _n_train + _n_val + _n_test)
+
+dataset_name = "SYNTHETIC"
+model_name = "ConvNet"
+transforms = []
+epochs = 0
+in_channels = 1
+out_channels = 10
+dataset = synthetic_dataset(_n_train + _n_val, _n_test)

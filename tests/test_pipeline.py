@@ -1,0 +1,242 @@
+"""The experiment pipeline around the Gram kernel: datasets, the multi-worker exchange, and
+save_kernel -> merge -> classify_gp (reference exp_mnist_resnet/*.py, cnn_gp/data.py:129-162)."""
+import importlib
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _synthetic_config(train=120, val=40, test=60):
+    os.environ.update(CNNGP_SYNTH_TRAIN=str(train), CNNGP_SYNTH_VAL=str(val), CNNGP_SYNTH_TEST=str(test))
+    import configs.synthetic as cfg
+    return importlib.reload(cfg)
+
+
+# ------------------------------------------------------------------------------- datasets (CPU)
+def test_synthetic_dataset_splits_are_disjoint_and_deterministic():
+    from cnn_gp import DatasetFromConfig
+    cfg = _synthetic_config()
+    a = DatasetFromConfig("/nonexistent", cfg)
+    b = DatasetFromConfig("/nonexistent", cfg)
+    assert (len(a.train), len(a.validation), len(a.test)) == (120, 40, 60)
+    xa, ya = a.load_full(a.train)
+    xb, yb = b.load_full(b.train)
+    assert xa.shape == (120, 1, 28, 28) and xa.dtype == torch.float32
+    assert torch.equal(xa, xb) and torch.equal(ya, yb)
+    assert 0.0 <= float(xa.min()) and float(xa.max()) < 1.0
+    xt, _ = a.load_full(a.test)
+    xv, _ = a.load_full(a.validation)
+    allx = torch.cat([xa, xv, xt]).flatten(1)
+    assert len(torch.unique(allx, dim=0)) == 220, "no image may appear in two splits"
+
+
+class _FakeMNIST(torch.utils.data.Dataset):
+    """uint8 ``.data`` / ``.targets`` like torchvision.datasets.MNIST, items through ``transform``."""
+
+    def __init__(self, root, train=True, download=False, transform=None):
+        g = torch.Generator().manual_seed(7 if train else 8)
+        n = 50 if train else 20
+        self.data = torch.randint(0, 256, (n, 28, 28), generator=g, dtype=torch.uint8)
+        self.targets = torch.randint(0, 10, (n,), generator=g)
+        self.transform = transform
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, i):
+        from PIL import Image
+        img = Image.fromarray(self.data[i].numpy(), mode="L")
+        return self.transform(img), int(self.targets[i])
+
+
+class _FakeCIFAR(_FakeMNIST):
+    def __init__(self, root, train=True, download=False, transform=None):
+        g = np.random.default_rng(3 if train else 4)
+        n = 30 if train else 10
+        self.data = g.integers(0, 256, (n, 32, 32, 3), dtype=np.uint8)
+        self.targets = list(g.integers(0, 10, n))
+        self.transform = transform
+
+    def __getitem__(self, i):
+        from PIL import Image
+        return self.transform(Image.fromarray(self.data[i])), int(self.targets[i])
+
+
+@pytest.mark.parametrize("cls,shape", [(_FakeMNIST, (1, 28, 28)), (_FakeCIFAR, (3, 32, 32))])
+def test_resident_fast_path_equals_per_item_totensor(cls, shape):
+    """The array view of a torchvision dataset must give the bytes ToTensor gives item by item
+    (reference data.py:143-151), in the config's index order."""
+    pytest.importorskip("torchvision")
+    pytest.importorskip("PIL")
+    from types import SimpleNamespace
+    from cnn_gp import DatasetFromConfig
+    n_tr = 50 if cls is _FakeMNIST else 30
+    cfg = SimpleNamespace(dataset=cls, dataset_name="FAKE", transforms=[], train_range=range(5, n_tr - 5),
+                          validation_range=list(range(n_tr - 5, n_tr)) + list(range(0, 5)),
+                          test_range=range(n_tr, n_tr + 10))
+    ds = DatasetFromConfig("/nonexistent", cfg)
+    from cnn_gp.data import ResidentDataset
+    assert isinstance(ds.train, ResidentDataset)
+    for name in ("train", "validation", "test"):
+        sub = getattr(ds, name)
+        rng = getattr(cfg, name + "_range")
+        assert sub.images.shape == (len(rng),) + shape
+        for k in (0, len(rng) // 2, len(rng) - 1):
+            x, y = ds.data_full[list(rng)[k]]
+            assert torch.equal(sub.images[k], x) and int(sub.labels[k]) == y
+
+
+# --------------------------------------------------------------- multi-worker exchange (gloo, CPU)
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gather_worker(rank, world, port, N, N2, bs, same, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path[:0] = [os.path.join(ROOT, "cnn-gp_b200"), ROOT]
+    import torch.distributed as dist
+    from cnn_gp.data import worker_tiles
+    from cnn_gp.tiles import gather_blocks, row_segments
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    truth = torch.arange(N * N2, dtype=torch.float32).reshape(N, N2) + 1.0
+    K = torch.full((N, N2), float("nan"))
+    pairs = 0
+    for r, has_diag, c0, c1 in row_segments(worker_tiles(N, None if same else N2, bs, rank, world)):
+        i0, i1 = r * bs, min(N, (r + 1) * bs)
+        if has_diag:
+            K[i0:i1, i0:i1] = truth[i0:i1, i0:i1]
+            pairs += (i1 - i0) ** 2
+        if c0 is not None:
+            j0, j1 = c0 * bs, min(N2, c1 * bs)
+            K[i0:i1, j0:j1] = truth[i0:i1, j0:j1]
+            pairs += (i1 - i0) * (j1 - j0)
+    counts = torch.tensor([pairs], dtype=torch.int64)
+    dist.all_reduce(counts)
+    merged = gather_blocks(K, dst=0)
+    if rank == 0:
+        ret["merged"] = merged.numpy()
+        ret["pairs"] = int(counts[0])
+    else:
+        assert merged is None
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("N,N2,bs,same", [(50, 50, 8, True), (37, 53, 10, False)])
+def test_two_workers_cover_the_matrix_and_gather_like_merge(N, N2, bs, same):
+    """world_size 2 over gloo: the reference's contiguous tile split (data.py:11-19) gives every
+    tile to exactly one worker, and gather_blocks reproduces merge_h5_files' NaN-fill semantics:
+    for Kxx the strictly lower block triangle stays NaN."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, N, N2, bs, same, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    merged = ret["merged"]
+    truth = np.arange(N * N2, dtype=np.float32).reshape(N, N2) + 1.0
+    bi, bj = np.arange(N)[:, None] // bs, np.arange(N2)[None, :] // bs
+    owned = (bj >= bi) if same else np.ones((N, N2), bool)
+    assert ret["pairs"] == owned.sum(), "tiles must be disjoint and complete"
+    np.testing.assert_array_equal(merged[owned], truth[owned])
+    assert np.isnan(merged[~owned]).all()
+
+
+def test_merge_script_fills_only_nan(tmp_path):
+    from cnn_gp.block_store import open_store
+    from exp_mnist_resnet.merge_h5_files import merge
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    with open_store(a, "w") as f:
+        d = f.create_dataset("Kxx", shape=(1, 4, 4), dtype=np.float32, fillvalue=np.nan)
+        d[0, :2, :] = 1.0
+        f.create_dataset("only_a", shape=(1, 2), dtype=np.float32, fillvalue=np.nan)
+    with open_store(b, "w") as f:
+        d = f.create_dataset("Kxx", shape=(1, 4, 4), dtype=np.float32, fillvalue=np.nan)
+        d[0, 1:3, :] = 2.0
+    merge(a, [b])
+    with open_store(a, "r") as f:
+        got = f["Kxx"][0]
+        assert np.isnan(f["only_a"][0]).all()
+    assert (got[:2] == 1.0).all() and (got[2] == 2.0).all() and np.isnan(got[3]).all()
+
+
+# ------------------------------------------------------------------------ whole pipeline (GPU)
+@pytest.mark.gpu
+def test_save_kernel_resident_equals_reference_loop_and_classify_matches_scipy(tmp_path):
+    """Two workers, both save paths, merge, classify.  The resident path must write the very
+    bytes of the literal save_K loop; decisions must equal the oracle's scipy solve on the same
+    Kxx bytes (reference classify_gp.py:17-42)."""
+    from cnn_gp import DatasetFromConfig
+    from cnn_gp.block_store import open_store
+    from exp_mnist_resnet import classify_gp, merge_h5_files, save_kernel
+    from oracle import oracle
+    cfg = _synthetic_config(300, 80, 100)
+    ds = DatasetFromConfig("/nonexistent", cfg)
+    paths = {}
+    for resident in (True, False):
+        for rank in range(2):
+            p = str(tmp_path / f"{'res' if resident else 'ref'}_{rank}")
+            save_kernel.compute_all(cfg, ds, p, batch_size=64, n_workers=2, worker_rank=rank, resident=resident)
+            paths[resident, rank] = p
+    for rank in range(2):
+        with open_store(paths[True, rank], "r") as a, open_store(paths[False, rank], "r") as b:
+            assert sorted(a.keys()) == sorted(b.keys())
+            assert ("Kv_diag" in a.keys()) == (rank == 0)
+            for k in a.keys():
+                x, y = a[k][...], b[k][...]
+                assert x.shape == y.shape and x.dtype == np.float32
+                np.testing.assert_array_equal(np.isnan(x), np.isnan(y))
+                np.testing.assert_array_equal(x[~np.isnan(x)], y[~np.isnan(y)])
+    merge_h5_files.merge(paths[True, 0], [paths[True, 1]])
+    with open_store(paths[True, 0], "r") as f:
+        Kxx, Kxtx, Kxvx = f["Kxx"][0], f["Kxtx"][0], f["Kxvx"][0]
+        kt = f["Kt_diag"][0]
+    bi = np.arange(300) // 64
+    assert np.isnan(Kxx[bi[:, None] > bi[None, :]]).all() and np.isfinite(Kxx[bi[:, None] <= bi[None, :]]).all()
+    assert np.isfinite(Kxtx).all() and np.isfinite(Kxvx).all() and np.isfinite(kt).all()
+    # kernel values against the oracle on a corner
+    xtr, ytr = ds.load_full(ds.train)
+    want = oracle.gram(cfg.initial_model, xtr[:24].numpy(), xtr[:24].numpy(), same=True)
+    np.testing.assert_allclose(Kxx[:24, :24], want, rtol=1e-5)
+    res = classify_gp.classify(cfg, ds, paths[True, 0])
+    Y = -np.ones((300, 10))
+    Y[np.arange(300), ytr.numpy()] = 1.0
+    A = oracle.solve_system(np.triu(Kxx.astype(np.float64)), Y)
+    np.testing.assert_allclose(res["A"].cpu().numpy(), A, rtol=0, atol=1e-8 * np.abs(A).max())
+    for key, K, sub in (("validation", Kxvx, ds.validation), ("test", Kxtx, ds.test)):
+        pred = oracle.predict(K.astype(np.float64), A)
+        _, ys = ds.load_full(sub)
+        assert res[key] == pytest.approx(float((pred == ys.numpy()).mean()))
+        got = classify_gp.predict(res["A"], torch.from_numpy(K))
+        np.testing.assert_array_equal(got.numpy(), pred)
+    assert res["test"] > 0.9, "class-template images are separable"
+
+
+@pytest.mark.gpu
+def test_classify_api_matches_reference_functions():
+    """solve_system / diag_add / print_accuracy keep the reference's signatures and semantics."""
+    from exp_mnist_resnet import classify_gp
+    g = np.load(os.path.join(ROOT, "tests", "golden", "solve.npz"))
+    K = torch.from_numpy(np.triu(g["Kxx"].astype(np.float64)))
+    classify_gp.diag_add(K, 0.0)
+    with pytest.raises(AssertionError):
+        classify_gp.solve_system(K.float(), torch.from_numpy(g["Y"]))
+    A = classify_gp.solve_system(K, torch.from_numpy(g["Y"]))
+    assert A.device.type == "cpu" and A.dtype == torch.float64
+    np.testing.assert_allclose(A.numpy(), g["A"], rtol=0, atol=1e-9 * np.abs(g["A"]).max())
+    acc = classify_gp.print_accuracy(A, torch.from_numpy(g["Kxtx"]).to(torch.float64), g["yte"], "test")
+    assert acc == pytest.approx(float((g["pred"] == g["yte"]).mean()))
+    K2 = np.eye(3)
+    classify_gp.diag_add(K2, 0.5)
+    assert (np.diag(K2) == 1.5).all()
