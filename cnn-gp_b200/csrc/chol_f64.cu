@@ -10,13 +10,16 @@
 // strictly lower block triangle of Kxx, it stays NaN: cnn_gp/kernel_save_tools.py:21-23,
 // cnn_gp/data.py:22-29).  U overwrites the upper triangle.
 //
-// potrf, right-looking with block size NB = 128, per block column k:
-//   potf2_inv   one CTA: U_kk = chol(A_kk) in shared memory, then W = U_kk^{-1} (workspace)
-//   tn_kernel<1>  row panel X = W^T A[k, k+1:]            (the triangular solve as a DMMA GEMM)
-//   tn_kernel<0>  trailing update A22 -= X^T X, j >= i     (SYRK, the one dense contraction:
-//                 mma.sync.m8n8k4.f64 = SASS DMMA, the FP64 tensor pipe of sm_100a)
-// with one block column of look-ahead: the SYRK tiles of the next block row run first, then the
-// next potf2_inv runs on a second stream underneath the rest of the trailing update.
+// potrf, right-looking, two levels.  A block row of 2 NB = 256 rows is factorised as a panel:
+//   potf2_inv     one CTA: U_kk = chol(A_kk) in shared memory, then W = U_kk^{-1} (workspace)
+//   tn_kernel<1>  X = W^T A[k, k+1:]                       (the triangular solve as a DMMA GEMM)
+//   tn_kernel<0>  rank-128 update of the panel's second half, then potf2_inv / tn_kernel<1> again
+// and the trailing matrix takes one rank-256 update per panel,
+//   tn_kernel<0>  A22 -= X^T X, j >= i    (SYRK, the one dense contraction: mma.sync.m8n8k4.f64 =
+//                 SASS DMMA.8x8x4, the FP64 tensor pipe of sm_100a),
+// which halves the read-modify-write traffic of A22 against rank-128 updates.  Look-ahead: the
+// update's first 256 rows run first; the next panel is then factorised on a high-priority side
+// stream underneath the rest of the update (it touches only those 256 rows).
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -32,8 +35,8 @@ constexpr int NB = 128;        // block column width
 constexpr int TI = 128, TJ = 64;  // CTA tile of the DMMA kernel (rows i x columns j)
 constexpr int KC = 16;         // k-chunk per pipeline stage
 constexpr int STAGES = 3;
-constexpr int PP = TI + 8, PQ = TJ + 8;  // smem pitches (doubles), == 8 mod 16: fragment loads hit the
-                                         // two-wavefront minimum
+constexpr int PP = TI + 4, PQ = TJ + 4;  // smem pitches (doubles), == 4 mod 16: a half-warp's fragment load
+                                         // (k = lane%4, row = lane/4) covers 16 distinct 8-byte banks
 constexpr int TN_THREADS = 256;
 
 __device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -446,48 +449,72 @@ int cnngp_potrf_upper_f64(double *d_A, int64_t n, int64_t lda, int32_t *d_info, 
     double *W = nullptr;
     if (!check(cudaMallocAsync((void **)&W, sizeof(double) * NB * NB, s), "potrf workspace")) return 6;
     cudaStream_t s2 = nullptr;
-    cudaEvent_t ev_head = nullptr, ev_diag = nullptr;
-    if (!check(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking), "potrf stream") ||
+    cudaEvent_t ev_head = nullptr, ev_panel = nullptr;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (!check(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, prio_hi), "potrf stream") ||
         !check(cudaEventCreateWithFlags(&ev_head, cudaEventDisableTiming), "potrf event") ||
-        !check(cudaEventCreateWithFlags(&ev_diag, cudaEventDisableTiming), "potrf event"))
+        !check(cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming), "potrf event")) {
+        if (s2) cudaStreamDestroy(s2);
+        if (ev_head) cudaEventDestroy(ev_head);
+        cudaFreeAsync(W, s);
         return 6;
+    }
     const int vec_ok = (lda % 2 == 0) && aligned16(d_A);
+    constexpr int NBO = 2 * NB;
 
-    potf2_inv_kernel<<<1, POTF2_THREADS, kPotf2Smem, s>>>(d_A, lda, 0, (int)(n < NB ? n : NB), W, d_info);
-    for (int64_t kb = 0; kb < n; kb += NB) {
-        const int nb = (int)(n - kb < NB ? n - kb : NB);
-        const int64_t m = n - kb - nb;  // trailing size
-        if (m <= 0) break;
-        double *panel = d_A + kb * lda + kb + nb;
-        const int Tj = (int)((m + TJ - 1) / TJ), Ti = (int)((m + TI - 1) / TI);
-        {   // X = W^T A[k, k+1:]  (in place)
-            TnParams g{};
-            g.P = W; g.ldp = NB; g.Q = panel; g.ldq = lda; g.C = panel; g.ldc = lda;
-            g.M = nb; g.N = (int)m; g.K = nb; g.Tj = Tj; g.ib_lo = 0; g.t_off = 0; g.vec_ok = vec_ok;
-            tn_kernel<1><<<Tj, TN_THREADS, kTnSmem, s>>>(g);
-        }
+    // SYRK launch: C = A[r0:, r0:] (size m) -= X^T X with X = A[k0:k0+K, r0:], row tiles [ib_lo, ib_hi)
+    auto syrk = [&](int64_t k0, int K, int64_t r0, int ib_lo, int ib_hi, cudaStream_t st) {
+        const int64_t m = n - r0;
+        if (m <= 0) return;
         TnParams g{};
-        g.P = panel; g.ldp = lda; g.Q = panel; g.ldq = lda;
-        g.C = d_A + (kb + nb) * lda + kb + nb; g.ldc = lda;
-        g.M = (int)m; g.N = (int)m; g.K = nb; g.Tj = Tj; g.vec_ok = vec_ok;
-        // look-ahead: the next block row first, then its diagonal block on the side stream
-        g.ib_lo = 0; g.t_off = 0;
-        tn_kernel<0><<<Tj, TN_THREADS, kTnSmem, s>>>(g);
+        g.P = d_A + k0 * lda + r0; g.ldp = lda; g.Q = g.P; g.ldq = lda;
+        g.C = d_A + r0 * lda + r0; g.ldc = lda;
+        g.M = (int)m; g.N = (int)m; g.K = K; g.vec_ok = vec_ok;
+        g.Tj = (int)((m + TJ - 1) / TJ);
+        const int Ti = (int)((m + TI - 1) / TI);
+        if (ib_hi > Ti) ib_hi = Ti;
+        if (ib_lo >= ib_hi) return;
+        g.ib_lo = ib_lo; g.t_off = tri_prefix(ib_lo, g.Tj);
+        const long long tiles = tri_prefix(ib_hi, g.Tj) - g.t_off;
+        tn_kernel<0><<<(unsigned)tiles, TN_THREADS, kTnSmem, st>>>(g);
+    };
+    // X = W^T A[k0:k0+nb, c0:n] in place
+    auto trsm = [&](int64_t k0, int nb, int64_t c0, cudaStream_t st) {
+        const int64_t m = n - c0;
+        if (m <= 0) return;
+        TnParams g{};
+        g.P = W; g.ldp = NB; g.Q = d_A + k0 * lda + c0; g.ldq = lda; g.C = d_A + k0 * lda + c0; g.ldc = lda;
+        g.M = nb; g.N = (int)m; g.K = nb; g.vec_ok = vec_ok;
+        g.Tj = (int)((m + TJ - 1) / TJ);
+        tn_kernel<1><<<(unsigned)g.Tj, TN_THREADS, kTnSmem, st>>>(g);
+    };
+    // factorise the block row starting at kb (up to 2 NB rows): diagonal blocks and row panels
+    auto panel = [&](int64_t kb, cudaStream_t st) {
+        const int nb1 = (int)(n - kb < NB ? n - kb : NB);
+        potf2_inv_kernel<<<1, POTF2_THREADS, kPotf2Smem, st>>>(d_A, lda, (int)kb, nb1, W, d_info);
+        if (n - kb <= NB) return;
+        trsm(kb, nb1, kb + NB, st);
+        syrk(kb, nb1, kb + NB, 0, 1, st);  // only the panel's second half needs the rank-128 update now
+        const int nb2 = (int)(n - kb - NB < NB ? n - kb - NB : NB);
+        potf2_inv_kernel<<<1, POTF2_THREADS, kPotf2Smem, st>>>(d_A, lda, (int)(kb + NB), nb2, W, d_info);
+        trsm(kb + NB, nb2, kb + NBO, st);
+    };
+
+    panel(0, s);
+    for (int64_t kb = 0; kb + NBO < n; kb += NBO) {
+        const int64_t r0 = kb + NBO;  // trailing matrix origin
+        syrk(kb, NBO, r0, 0, NBO / TI, s);  // look-ahead: the next panel's rows first
         cudaEventRecord(ev_head, s);
         cudaStreamWaitEvent(s2, ev_head, 0);
-        const int nb2 = (int)(m < NB ? m : NB);
-        potf2_inv_kernel<<<1, POTF2_THREADS, kPotf2Smem, s2>>>(d_A, lda, (int)(kb + nb), nb2, W, d_info);
-        cudaEventRecord(ev_diag, s2);
-        if (Ti > 1) {
-            g.ib_lo = 1; g.t_off = tri_prefix(1, Tj);
-            const long long tiles = tri_prefix(Ti, Tj) - g.t_off;
-            tn_kernel<0><<<(unsigned)tiles, TN_THREADS, kTnSmem, s>>>(g);
-        }
-        cudaStreamWaitEvent(s, ev_diag, 0);
+        panel(r0, s2);
+        cudaEventRecord(ev_panel, s2);
+        syrk(kb, NBO, r0, NBO / TI, 1 << 30, s);
+        cudaStreamWaitEvent(s, ev_panel, 0);
     }
     cudaFreeAsync(W, s);
     cudaEventDestroy(ev_head);
-    cudaEventDestroy(ev_diag);
+    cudaEventDestroy(ev_panel);
     cudaStreamDestroy(s2);
     return check(cudaGetLastError(), "cnngp_potrf_upper_f64") ? 0 : 9;
 }
