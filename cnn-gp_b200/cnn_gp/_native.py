@@ -96,7 +96,8 @@ class Plan:
             raise RuntimeError(msg)
         self.handle = handle
         self.aux_elems = int(L.cnngp_plan_aux_elems(handle))
-        self.has_fused = bool(L.cnngp_plan_has_fused(handle))
+        self.fused_kind = int(L.cnngp_plan_has_fused(handle))  # 0 none, 2 straight-line, 3 net
+        self.has_fused = self.fused_kind != 0
         self.H, self.W, self.dtype_code = H, W, dtype_code
         self.n_ops, self.n_slots = len(ops), n_slots
 

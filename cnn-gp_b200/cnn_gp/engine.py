@@ -28,7 +28,7 @@ def set_path(name):
 
 
 def last_path():
-    return {0: "none", 1: "generic", 2: "fused"}[nat.lib().cnngp_last_path()]
+    return {0: "none", 1: "generic", 2: "fused", 3: "fused_net"}[nat.lib().cnngp_last_path()]
 
 
 def _require_cuda(t, what):

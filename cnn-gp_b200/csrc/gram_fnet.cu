@@ -1,0 +1,928 @@
+// gram_fnet.cu -- register-resident fused Gram kernel for layer programs with Sum (residual)
+// branches, strided convolutions and several map sizes: the ResNet GPs of configs/mnist.py,
+// mnist_as_tf.py, cifar10.py, the residual CNN GP and the README model.
+//
+// Same execution model as gram_fused.cu: a persistent CTA per SM, eight consumer warps that each
+// keep the four covariance maps of a 2 x 2 block of image pairs in registers (lane = one map
+// coordinate, register index = the other, two maps per packed f32x2 register), a producer warp
+// that stages images and per-layer (s, 1/s) variance maps with bulk async copies, box
+// convolutions as sliding sums along the register axis + a shared-memory transposition.
+//
+// What is new here:
+//   * a two-slot program needs a second live map per pair (the skip connection of a Sum,
+//     reference cnn_gp/kernels.py:246-254).  It does not fit the register file next to the
+//     working map, and shared memory is taken by the staging ring -- so it is stashed in TENSOR
+//     MEMORY: each warp owns 2 x 128 columns of its 32-lane TMEM quadrant and moves a whole map
+//     set with tcgen05.st / tcgen05.ld (SASS STTM / LDTM), off the shared-memory port.
+//   * stride-2 convolutions (kernels.py:92-98 with stride 2) subsample along the register axis
+//     in both passes; maps shrink to S/2 and S/4 with lane = column < S'.
+//   * every windowed convolution flips the register layout (lane = column <-> lane = row); the
+//     translator tracks the layout of every slot and inserts a transposition where a Sum would
+//     add maps of different layouts, and records for every ReLU the layout its variance maps
+//     must be stored in.
+//   * ReLU outputs are kept doubled (see gram_fused.cu); the power-of-two factor owed by each
+//     slot is tracked and folded into the next convolution tap or into the Sum (exact).
+//   * the tail after the global pooling convolution (1 x 1 maps: kernels.py:134-165 on one
+//     pixel, 1 x 1 convolutions) runs on the four scalars of the warp.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fused_common.cuh"
+#include "plan.h"
+
+namespace cnngp {
+
+namespace {
+using namespace fusedk;
+
+constexpr int kWarps = 8;
+constexpr int kTileI = 4, kTileJ = 8;
+constexpr int kImgs = kTileI + kTileJ;
+constexpr int kPairs = kImgs / 2;
+constexpr int kThreads = (kWarps + 4) * 32;
+constexpr int kRegsProducer = 24, kRegsConsumer = 240;
+constexpr int kMaxNOps = 192;
+constexpr int kTmemCols = 512;
+
+enum { N_CONV = 0, N_AFFINE, N_RELU, N_STASH, N_UNSTASH, N_ADD, N_TRANSPOSE, N_DENSE, T_RELU, T_AFFINE };
+
+struct NOp {
+    int kind;
+    short si, so;       // map edge before / after the op
+    short lo, hi, st;   // N_CONV: window offsets [-lo, +hi] and stride
+    short slot;         // N_STASH / N_UNSTASH / N_ADD: tensor-memory slot (0 or 1)
+    float scale, bias;  // N_CONV / N_AFFINE / N_DENSE / T_AFFINE; N_ADD: factor applied to the stashed map
+    int aux;            // N_RELU: float offset inside the fused section; T_RELU: float offset of xx in the row
+    int half;           // N_RELU: pixels held by the first row of the pair
+};
+
+struct NParams {
+    NOp ops[kMaxNOps];
+    int n_ops;
+    const float *x, *z;
+    const float *aux_x, *aux_z;
+    long long aux_stride;
+    int aux_f_off;
+    int N1, N2, C;
+    float *out;
+    long long ld_out;
+    int symmetric;
+    const float *kdiag;
+    int nbi, nbj, sti, stj, nst_j, nst;
+    long long n_tiles;
+    float inv_c;
+};
+
+// ---- tensor memory ---------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, u64 a0, u64 a1, u64 a2, u64 a3, u64 a4, u64 a5, u64 a6,
+                                         u64 a7) {
+    asm volatile(
+        "{\n .reg .b32 t<16>;\n"
+        " mov.b64 {t0, t1}, %1;\n mov.b64 {t2, t3}, %2;\n mov.b64 {t4, t5}, %3;\n mov.b64 {t6, t7}, %4;\n"
+        " mov.b64 {t8, t9}, %5;\n mov.b64 {t10, t11}, %6;\n mov.b64 {t12, t13}, %7;\n mov.b64 {t14, t15}, %8;\n"
+        " tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, t11, t12, t13, "
+        "t14, t15};\n}"
+        ::"r"(taddr), "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(a4), "l"(a5), "l"(a6), "l"(a7)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, u64 a0, u64 a1, u64 a2, u64 a3) {
+    asm volatile(
+        "{\n .reg .b32 t<8>;\n"
+        " mov.b64 {t0, t1}, %1;\n mov.b64 {t2, t3}, %2;\n mov.b64 {t4, t5}, %3;\n mov.b64 {t6, t7}, %4;\n"
+        " tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {t0, t1, t2, t3, t4, t5, t6, t7};\n}"
+        ::"r"(taddr), "l"(a0), "l"(a1), "l"(a2), "l"(a3)
+        : "memory");
+}
+// the wait sits inside the block: the b32 registers may only be read once the load has landed
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, u64 &a0, u64 &a1, u64 &a2, u64 &a3, u64 &a4, u64 &a5,
+                                         u64 &a6, u64 &a7) {
+    asm volatile(
+        "{\n .reg .b32 t<16>;\n"
+        " tcgen05.ld.sync.aligned.32x32b.x16.b32 {t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, t11, t12, t13, t14, "
+        "t15}, [%8];\n"
+        " tcgen05.wait::ld.sync.aligned;\n"
+        " mov.b64 %0, {t0, t1};\n mov.b64 %1, {t2, t3};\n mov.b64 %2, {t4, t5};\n mov.b64 %3, {t6, t7};\n"
+        " mov.b64 %4, {t8, t9};\n mov.b64 %5, {t10, t11};\n mov.b64 %6, {t12, t13};\n mov.b64 %7, {t14, t15};\n}"
+        : "=l"(a0), "=l"(a1), "=l"(a2), "=l"(a3), "=l"(a4), "=l"(a5), "=l"(a6), "=l"(a7)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, u64 &a0, u64 &a1, u64 &a2, u64 &a3) {
+    asm volatile(
+        "{\n .reg .b32 t<8>;\n"
+        " tcgen05.ld.sync.aligned.32x32b.x8.b32 {t0, t1, t2, t3, t4, t5, t6, t7}, [%4];\n"
+        " tcgen05.wait::ld.sync.aligned;\n"
+        " mov.b64 %0, {t0, t1};\n mov.b64 %1, {t2, t3};\n mov.b64 %2, {t4, t5};\n mov.b64 %3, {t6, t7};\n}"
+        : "=l"(a0), "=l"(a1), "=l"(a2), "=l"(a3)
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// whole map set (two packed arrays, first S entries each) -> tensor memory; an array takes 64 columns
+template <int S0, int S>
+__device__ __forceinline__ void stash_store(uint32_t tbase, const u64 (&M)[2][S0]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        constexpr int FULL = S / 8, REM = S % 8;
+#pragma unroll
+        for (int c = 0; c < FULL; ++c)
+            tmem_st8(tbase + h * 64 + c * 16, M[h][c * 8 + 0], M[h][c * 8 + 1], M[h][c * 8 + 2], M[h][c * 8 + 3],
+                     M[h][c * 8 + 4], M[h][c * 8 + 5], M[h][c * 8 + 6], M[h][c * 8 + 7]);
+        if (REM > 4) {  // round up to eight entries (the array has at least S0 >= FULL*8+8 of them)
+            constexpr int b = FULL * 8;
+            tmem_st8(tbase + h * 64 + FULL * 16, M[h][b + 0], M[h][b + 1], M[h][b + 2], M[h][b + 3],
+                     M[h][(b + 4) % S0], M[h][(b + 5) % S0], M[h][(b + 6) % S0], M[h][(b + 7) % S0]);
+        } else if (REM > 0) {
+            constexpr int b = FULL * 8;
+            tmem_st4(tbase + h * 64 + FULL * 16, M[h][b + 0], M[h][(b + 1) % S0], M[h][(b + 2) % S0], M[h][(b + 3) % S0]);
+        }
+    }
+    tmem_wait_st();
+}
+
+// M = stash (ADD == false) or M = stash * alpha + M (ADD == true)
+template <int S0, int S, bool ADD>
+__device__ __forceinline__ void stash_load(uint32_t tbase, u64 (&M)[2][S0], u64 alpha) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        constexpr int FULL = S / 8, REM = S % 8;
+#pragma unroll
+        for (int c = 0; c < FULL; ++c) {
+            u64 t[8];
+            tmem_ld8(tbase + h * 64 + c * 16, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) M[h][c * 8 + q] = ADD ? fma2(t[q], alpha, M[h][c * 8 + q]) : t[q];
+        }
+        if (REM > 4) {
+            u64 t[8];
+            tmem_ld8(tbase + h * 64 + FULL * 16, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
+#pragma unroll
+            for (int q = 0; q < REM; ++q) M[h][FULL * 8 + q] = ADD ? fma2(t[q], alpha, M[h][FULL * 8 + q]) : t[q];
+        } else if (REM > 0) {
+            u64 t[4];
+            tmem_ld4(tbase + h * 64 + FULL * 16, t[0], t[1], t[2], t[3]);
+#pragma unroll
+            for (int q = 0; q < REM; ++q) M[h][FULL * 8 + q] = ADD ? fma2(t[q], alpha, M[h][FULL * 8 + q]) : t[q];
+        }
+    }
+}
+
+// ---- box sums along the register axis --------------------------------------------------------
+// stride 1, zero padding: out[y] = sum_{t=-LO..HI} v[y+t] on the first S entries, two sliding
+// windows from both ends (as gram_fused.cu)
+template <int S0, int S, int LO, int HI>
+__device__ __forceinline__ void box_s1(u64 (&v)[S0]) {
+    if (LO == 0 && HI == 0) return;
+    constexpr int MID = S / 2;
+    u64 o[S];
+    u64 top = v[0], bot = v[S - 1];
+#pragma unroll
+    for (int t = 1; t <= HI && t < S; ++t) top = add2(top, v[t]);
+#pragma unroll
+    for (int t = 1; t <= LO && t < S; ++t) bot = add2(bot, v[S - 1 - t]);
+    o[0] = top;
+    o[S - 1] = bot;
+#pragma unroll
+    for (int y = 1; y < MID; ++y) {
+        if (y + HI < S) top = add2(top, v[y + HI]);
+        if (y - LO - 1 >= 0) top = sub2(top, v[y - LO - 1]);
+        o[y] = top;
+    }
+#pragma unroll
+    for (int y = S - 2; y >= MID; --y) {
+        if (y - LO >= 0) bot = add2(bot, v[y - LO]);
+        if (y + HI + 1 < S) bot = sub2(bot, v[y + HI + 1]);
+        o[y] = bot;
+    }
+#pragma unroll
+    for (int y = 0; y < S; ++y) v[y] = o[y];
+}
+
+// stride 2: out[y] = sum_{t=-LO..HI} v[2y+t], SI entries -> SO entries
+template <int S0, int SI, int SO, int LO, int HI>
+__device__ __forceinline__ void box_s2(u64 (&v)[S0]) {
+    u64 o[SO];
+#pragma unroll
+    for (int y = 0; y < SO; ++y) {
+        bool first = true;
+#pragma unroll
+        for (int t = -LO; t <= HI; ++t) {
+            const int idx = 2 * y + t;
+            if (idx >= 0 && idx < SI) {
+                o[y] = first ? v[idx] : add2(o[y], v[idx]);
+                first = false;
+            }
+        }
+    }
+#pragma unroll
+    for (int y = 0; y < SO; ++y) v[y] = o[y];
+}
+
+template <int S0, int R, int L>
+__device__ __forceinline__ void tstore(u64 *tile, const u64 (&a)[S0], int lane) {
+    constexpr int PITCH = S0 + 1;  // odd: row-wise writes and column-wise reads are both conflict-free
+    if (lane < L) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) tile[r * PITCH + lane] = a[r];
+    }
+}
+template <int S0, int R>
+__device__ __forceinline__ void tload(const u64 *tile, u64 (&a)[S0], int lx) {
+    constexpr int PITCH = S0 + 1;
+#pragma unroll
+    for (int r = 0; r < R; ++r) a[r] = tile[lx * PITCH + r];
+}
+
+// box convolution SI x SI -> SO x SO: pass, transposition, pass (flips the register layout),
+// software-pipelined over the two packed arrays, then tap * sum + bias
+template <int S0, int SI, int SO, int LO, int HI, int ST>
+__device__ __forceinline__ void conv_op(u64 (&M)[2][S0], u64 *tile, int lane, float scale, float bias) {
+    static_assert(ST == 1 ? SI == SO : SI == 2 * SO, "conv geometry");
+    auto pass = [](u64 (&v)[S0]) {
+        if (ST == 1) box_s1<S0, SI, LO, HI>(v);
+        else box_s2<S0, SI, SO, LO, HI>(v);
+    };
+    const int lx = lane < SO ? lane : SO - 1;
+    pass(M[0]);
+    tstore<S0, SO, SI>(tile, M[0], lane);
+    __syncwarp();
+    tload<S0, SI>(tile, M[0], lx);
+    pass(M[1]);
+    __syncwarp();
+    tstore<S0, SO, SI>(tile, M[1], lane);
+    pass(M[0]);
+    __syncwarp();
+    tload<S0, SI>(tile, M[1], lx);
+    __syncwarp();
+    pass(M[1]);
+    const u64 SC = pk(scale, scale), BI = pk(bias, bias);
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int r = 0; r < SO; ++r) M[h][r] = fma2(M[h][r], SC, BI);
+}
+
+template <int S0, int S>
+__device__ __forceinline__ void transpose_op(u64 (&M)[2][S0], u64 *tile, int lane) {
+    const int lx = lane < S ? lane : S - 1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        tstore<S0, S, S>(tile, M[h], lane);
+        __syncwarp();
+        tload<S0, S>(tile, M[h], lx);
+        __syncwarp();
+    }
+}
+
+template <int S0, int S>
+__device__ __forceinline__ void affine_op(u64 (&M)[2][S0], float scale, float bias) {
+    const u64 SC = pk(scale, scale), BI = pk(bias, bias);
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int r = 0; r < S; ++r) M[h][r] = fma2(M[h][r], SC, BI);
+}
+
+// 2 * H(e), degree-5 minimax fit on [0,1] (gram_fused.cu)
+#define FNET_C5 1.678542030e-04f
+#define FNET_C4 -1.571319990e-05f
+#define FNET_C3 6.585370866e-04f
+#define FNET_C2 2.386197913e-03f
+#define FNET_C1 1.500756294e-02f
+#define FNET_C0 3.001053929e-01f
+
+// rows [R0, R1) of the ReLU step; ai / bj point at this lane's pixel of row 0 of the staged
+// (s_a, s_b, 1/s_a, 1/s_b) maps of the warp's i-pair and j-pair
+template <int S0, int S, int R0, int R1>
+__device__ __forceinline__ void relu_rows(u64 (&M)[2][S0], const float4 *ai, const float4 *bj) {
+    const u64 C5 = pk(FNET_C5, FNET_C5), C4 = pk(FNET_C4, FNET_C4), C3 = pk(FNET_C3, FNET_C3),
+              C2 = pk(FNET_C2, FNET_C2), C1 = pk(FNET_C1, FNET_C1), C0 = pk(FNET_C0, FNET_C0), ONE = pk(1.f, 1.f);
+#pragma unroll
+    for (int r = R0; r < R1; ++r) {
+        const float4 A = ai[r * S], B = bj[r * S];
+        const u64 SA = pk(A.x, A.y), RA = pk(A.z, A.w);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const u64 SB = h ? pk(B.y, B.x) : pk(B.x, B.y);
+            const u64 RB = h ? pk(B.w, B.z) : pk(B.z, B.w);
+            float c0, c1;
+            upk(M[h][r], c0, c1);
+            const u64 NC = pk(neg_abs(c0), neg_abs(c1));
+            const u64 D = fma2(SA, SB, NC);             // s - |c|
+            const u64 E = fma2(NC, mul2(RA, RB), ONE);  // e = 1 - |c|/s
+            float e0, e1;
+            upk(E, e0, e1);
+            const u64 W = mul2(D, pk(sqrt_approx(fabsf(e0)), sqrt_approx(fabsf(e1))));
+            u64 H = fma2(C5, E, C4);
+            H = fma2(H, E, C3);
+            H = fma2(H, E, C2);
+            H = fma2(H, E, C1);
+            H = fma2(H, E, C0);
+            M[h][r] = fma2(W, H, pk(fmaxf(c0, 0.f), fmaxf(c1, 0.f)));
+        }
+    }
+}
+
+// the same step on one pixel in scalar code (1 x 1 maps after the pooling convolution); returns
+// the doubled value like the packed version
+__device__ __forceinline__ float relu_scalar(float c, float vx, float vy) {
+    const float tiny = 1.0842021724855044e-19f;  // sqrt(f32_tiny), as cnngp_variances stores it
+    const float sx = sqrtf(vx) + tiny, sy = sqrtf(vy) + tiny;
+    const float s = sx * sy;
+    const float nc = -fabsf(c);
+    const float d = s + nc;
+    const float e = fmaf(nc, (1.0f / sx) * (1.0f / sy), 1.0f);
+    const float w = d * sqrtf(fabsf(e));
+    float h = fmaf(FNET_C5, e, FNET_C4);
+    h = fmaf(h, e, FNET_C3);
+    h = fmaf(h, e, FNET_C2);
+    h = fmaf(h, e, FNET_C1);
+    h = fmaf(h, e, FNET_C0);
+    return fmaf(w, h, fmaxf(c, 0.f));
+}
+
+template <int S0, int S>
+__device__ __forceinline__ void dense_op(const u64 (&M)[2][S0], int lane, float scale, float bias, float (&tot)[4]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        u64 acc = M[h][0];
+#pragma unroll
+        for (int r = 1; r < S; ++r) acc = add2(acc, M[h][r]);
+        float a0, a1;
+        upk(acc, a0, a1);
+        if (lane >= S) { a0 = 0.f; a1 = 0.f; }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, d);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, d);
+        }
+        // M[0] = (i0j0, i1j1), M[1] = (i0j1, i1j0); tot index = 2a + b
+        tot[h == 0 ? 0 : 1] = fmaf(a0, scale, bias);
+        tot[h == 0 ? 3 : 2] = fmaf(a1, scale, bias);
+    }
+}
+
+// dispatch on the map edge: S0, S0/2 or S0/4
+#define FNET_BY_SIZE(sz, CALL)                  \
+    do {                                        \
+        if ((sz) == S0) { constexpr int S = S0; CALL; }            \
+        else if ((sz) == S0 / 2) { constexpr int S = S0 / 2; CALL; } \
+        else { constexpr int S = S0 / 4; CALL; }                   \
+    } while (0)
+
+template <int S0, int NST>
+__global__ void __launch_bounds__(kThreads, 1) fnet_kernel(const __grid_constant__ NParams p) {
+    constexpr int P0 = S0 * S0;
+    constexpr int PITCH = S0 + 1;
+    constexpr int STAGE = 48 * P0;  // bytes: kImgs images of one channel == kPairs half maps of float4
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *stage = smem_raw;
+    u64 *tiles = reinterpret_cast<u64 *>(smem_raw + (size_t)NST * STAGE);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + kWarps * S0 * PITCH);
+    uint64_t *full = bars, *empty = bars + NST;
+    uint32_t *tmem_word = reinterpret_cast<uint32_t *>(bars + 2 * NST);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {  // one warp allocates all of this SM's tensor memory (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_word)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_word;
+
+    const int per_st = p.sti * p.stj;
+    auto decode = [&](long long t, int &ib, int &jb) -> bool {
+        const int st = (int)(t / per_st), w_in = (int)(t - (long long)st * per_st);
+        int si, sj;
+        if (p.symmetric) {
+            int r = 0, rem = st;
+            while (rem >= p.nst - r) { rem -= p.nst - r; ++r; }
+            si = r; sj = r + rem;
+        } else {
+            si = st / p.nst_j; sj = st - si * p.nst_j;
+        }
+        ib = si * p.sti + w_in / p.stj;
+        jb = sj * p.stj + w_in % p.stj;
+        if (ib >= p.nbi || jb >= p.nbj) return false;
+        if (p.symmetric && jb * kTileJ + (kTileJ - 1) < ib * kTileI) return false;
+        return true;
+    };
+
+    if (warp >= kWarps) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
+        if (warp != kWarps) return;
+        // ---- producer --------------------------------------------------------------------
+        if (lane == 0) {
+            unsigned l = 0;
+            const int last_pi = (p.N1 - 1) >> 1, last_pj = (p.N2 - 1) >> 1;
+            auto acquire = [&](unsigned bytes) -> unsigned char * {
+                const unsigned buf = l % NST;
+                if (l >= NST) mbar_wait(&empty[buf], ((l / NST) - 1) & 1);
+                mbar_arrive_expect_tx(&full[buf], bytes);
+                return stage + (size_t)buf * STAGE;
+            };
+            for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+                int ib, jb;
+                if (!decode(t, ib, jb)) continue;
+                const int i_base = ib * kTileI, j_base = jb * kTileJ;
+                for (int c = 0; c < p.C; ++c) {
+                    float *dst = reinterpret_cast<float *>(acquire(kImgs * P0 * 4));
+                    uint64_t *bar = &full[l % NST];
+                    for (int s = 0; s < kImgs; ++s) {
+                        const float *src;
+                        if (s < kTileI) src = p.x + ((long long)min(i_base + s, p.N1 - 1) * p.C + c) * P0;
+                        else src = p.z + ((long long)min(j_base + s - kTileI, p.N2 - 1) * p.C + c) * P0;
+                        bulk_g2s(dst + s * P0, src, P0 * 4, bar);
+                    }
+                    ++l;
+                }
+                for (int k = 0; k < p.n_ops; ++k) {
+                    if (p.ops[k].kind != N_RELU) continue;
+                    const int half = p.ops[k].half;
+                    const long long off = p.aux_f_off + (long long)p.ops[k].aux;
+                    const bool split = p.ops[k].si == S0;  // full-size layers: one stage per row of the pair
+                    for (int part = 0; part < (split ? 2 : 1); ++part) {
+                        const unsigned bytes = (unsigned)(kPairs * half * 16 * (split ? 1 : 2));
+                        float4 *dst = reinterpret_cast<float4 *>(acquire(bytes));
+                        uint64_t *bar = &full[l % NST];
+                        for (int s = 0; s < kPairs; ++s) {
+                            const float *base;
+                            long long pr;
+                            if (s < kTileI / 2) { pr = min((i_base >> 1) + s, last_pi); base = p.aux_x; }
+                            else { pr = min((j_base >> 1) + s - kTileI / 2, last_pj); base = p.aux_z; }
+                            const float *src = base + 2 * pr * p.aux_stride + off;
+                            if (split) {
+                                bulk_g2s(dst + s * half, src + part * p.aux_stride, half * 16, bar);
+                            } else {
+                                bulk_g2s(dst + s * 2 * half, src, half * 16, bar);
+                                bulk_g2s(dst + s * 2 * half + half, src + p.aux_stride, half * 16, bar);
+                            }
+                        }
+                        ++l;
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers ------------------------------------------------------------------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsConsumer));
+    const int wi = warp >> 2, wj = warp & 3;
+    u64 *tile = tiles + warp * S0 * PITCH;
+    // this warp's tensor-memory window: lanes of quadrant warp % 4, 256 columns, two slots of 128
+    const uint32_t tm_warp = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
+    unsigned stage_l = 0;
+
+    for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        int ib, jb;
+        if (!decode(t, ib, jb)) continue;
+        const int i_base = ib * kTileI, j_base = jb * kTileJ;
+
+        u64 M[2][S0];
+        float tot[4] = {0.f, 0.f, 0.f, 0.f};
+        {   // init, kernels.py:43-49
+            const int lx = lane < S0 ? lane : S0 - 1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int r = 0; r < S0; ++r) M[h][r] = 0ull;
+            for (int c = 0; c < p.C; ++c) {
+                const unsigned buf = stage_l % NST;
+                mbar_wait(&full[buf], (stage_l / NST) & 1);
+                const float *sb = reinterpret_cast<const float *>(stage + (size_t)buf * STAGE) + lx;
+                const float *x0 = sb + (wi * 2 + 0) * P0, *x1 = sb + (wi * 2 + 1) * P0;
+                const float *z0 = sb + (kTileI + wj * 2 + 0) * P0, *z1 = sb + (kTileI + wj * 2 + 1) * P0;
+#pragma unroll
+                for (int r = 0; r < S0; ++r) {
+                    const float a0 = x0[r * S0], a1 = x1[r * S0], b0 = z0[r * S0], b1 = z1[r * S0];
+                    const u64 A = pk(a0, a1);
+                    M[0][r] = fma2(A, pk(b0, b1), M[0][r]);
+                    M[1][r] = fma2(A, pk(b1, b0), M[1][r]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[buf]);
+                ++stage_l;
+            }
+            if (p.C > 1) affine_op<S0, S0>(M, p.inv_c, 0.f);
+        }
+
+        for (int k = 0; k < p.n_ops; ++k) {
+            const NOp o = p.ops[k];
+            switch (o.kind) {
+                case N_CONV: {
+                    const int key = (o.si == S0 ? 0 : (o.si == S0 / 2 ? 1 : 2)) * 100 + o.st * 10 + o.lo * 3 + o.hi;
+                    // key = size class * 100 + stride * 10 + lo * 3 + hi
+                    switch (key) {
+                        case 0 * 100 + 10 + 1 * 3 + 1: conv_op<S0, S0, S0, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
+                        case 0 * 100 + 10 + 1 * 3 + 2: conv_op<S0, S0, S0, 1, 2, 1>(M, tile, lane, o.scale, o.bias); break;
+                        case 0 * 100 + 10 + 2 * 3 + 2: conv_op<S0, S0, S0, 2, 2, 1>(M, tile, lane, o.scale, o.bias); break;
+                        case 0 * 100 + 10 + 3 * 3 + 3: conv_op<S0, S0, S0, 3, 3, 1>(M, tile, lane, o.scale, o.bias); break;
+                        case 0 * 100 + 20 + 1 * 3 + 1: conv_op<S0, S0, S0 / 2, 1, 1, 2>(M, tile, lane, o.scale, o.bias); break;
+                        case 0 * 100 + 20 + 0: conv_op<S0, S0, S0 / 2, 0, 0, 2>(M, tile, lane, o.scale, o.bias); break;
+                        case 1 * 100 + 10 + 1 * 3 + 1: conv_op<S0, S0 / 2, S0 / 2, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
+                        case 1 * 100 + 20 + 1 * 3 + 1: conv_op<S0, S0 / 2, S0 / 4, 1, 1, 2>(M, tile, lane, o.scale, o.bias); break;
+                        case 1 * 100 + 20 + 0: conv_op<S0, S0 / 2, S0 / 4, 0, 0, 2>(M, tile, lane, o.scale, o.bias); break;
+                        case 2 * 100 + 10 + 1 * 3 + 1: conv_op<S0, S0 / 4, S0 / 4, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
+                        default: break;  // the translator only emits the cases above
+                    }
+                    break;
+                }
+                case N_AFFINE:
+                    FNET_BY_SIZE(o.si, (affine_op<S0, S>(M, o.scale, o.bias)));
+                    break;
+                case N_TRANSPOSE:
+                    FNET_BY_SIZE(o.si, (transpose_op<S0, S>(M, tile, lane)));
+                    break;
+                case N_STASH:
+                    FNET_BY_SIZE(o.si, (stash_store<S0, S>(tm_warp + o.slot * 128, M)));
+                    break;
+                case N_UNSTASH:
+                    FNET_BY_SIZE(o.si, (stash_load<S0, S, false>(tm_warp + o.slot * 128, M, 0ull)));
+                    break;
+                case N_ADD:
+                    FNET_BY_SIZE(o.si, (stash_load<S0, S, true>(tm_warp + o.slot * 128, M, pk(o.scale, o.scale))));
+                    break;
+                case N_RELU: {
+                    if (o.si == S0) {  // two stages: rows [0, S0/2) from the pair's first row, the rest from the second
+                        const int lx = lane < S0 ? lane : S0 - 1;
+                        {
+                            const unsigned buf = stage_l % NST;
+                            mbar_wait(&full[buf], (stage_l / NST) & 1);
+                            const float4 *sb = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE) + lx;
+                            relu_rows<S0, S0, 0, S0 / 2>(M, sb + wi * o.half, sb + (kTileI / 2 + wj) * o.half);
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&empty[buf]);
+                            ++stage_l;
+                        }
+                        {
+                            const unsigned buf = stage_l % NST;
+                            mbar_wait(&full[buf], (stage_l / NST) & 1);
+                            const float4 *sb = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE) + lx - o.half;
+                            relu_rows<S0, S0, S0 / 2, S0>(M, sb + wi * o.half, sb + (kTileI / 2 + wj) * o.half);
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&empty[buf]);
+                            ++stage_l;
+                        }
+                    } else {
+                        const unsigned buf = stage_l % NST;
+                        mbar_wait(&full[buf], (stage_l / NST) & 1);
+                        const float4 *st4 = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE);
+                        if (o.si == S0 / 2) {
+                            constexpr int S = S0 / 2;
+                            const float4 *sb = st4 + (lane < S ? lane : S - 1);
+                            relu_rows<S0, S, 0, S>(M, sb + wi * 2 * o.half, sb + (kTileI / 2 + wj) * 2 * o.half);
+                        } else {
+                            constexpr int S = S0 / 4;
+                            const float4 *sb = st4 + (lane < S ? lane : S - 1);
+                            relu_rows<S0, S, 0, S>(M, sb + wi * 2 * o.half, sb + (kTileI / 2 + wj) * 2 * o.half);
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[buf]);
+                        ++stage_l;
+                    }
+                    break;
+                }
+                case N_DENSE:
+                    FNET_BY_SIZE(o.si, (dense_op<S0, S>(M, lane, o.scale, o.bias, tot)));
+                    break;
+                case T_AFFINE:
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) tot[q] = fmaf(tot[q], o.scale, o.bias);
+                    break;
+                case T_RELU: {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = min(i_base + wi * 2 + (q >> 1), p.N1 - 1), j = min(j_base + wj * 2 + (q & 1), p.N2 - 1);
+                        const float vx = __ldg(p.aux_x + (long long)i * p.aux_stride + o.aux);
+                        const float vy = __ldg(p.aux_z + (long long)j * p.aux_stride + o.aux);
+                        tot[q] = relu_scalar(tot[q], vx, vy);
+                    }
+                    break;
+                }
+                default: break;
+            }
+        }
+
+        if (lane < 4) {
+            const int a = lane >> 1, b = lane & 1;
+            const int i = i_base + wi * 2 + a, j = j_base + wj * 2 + b;
+            const float v = lane == 0 ? tot[0] : lane == 1 ? tot[1] : lane == 2 ? tot[2] : tot[3];
+            if (i < p.N1 && j < p.N2) {
+                if (!p.symmetric) {
+                    p.out[(long long)i * p.ld_out + j] = v;
+                } else if (j > i) {
+                    p.out[(long long)i * p.ld_out + j] = v;
+                    p.out[(long long)j * p.ld_out + i] = v;
+                } else if (j == i) {
+                    // i == j follows the variance recursion (kernels.py:155-162)
+                    p.out[(long long)i * p.ld_out + i] = p.kdiag ? p.kdiag[i] : v;
+                }
+            }
+        }
+    }
+
+    // all consumers are done with tensor memory before the allocating warp frees it
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kWarps * 32) : "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+}  // namespace
+
+// ---- host: translate the two-slot plan into the kernel's op list --------------------------------
+struct FNetPlan {
+    int S0 = 0;
+    int n_ops = 0;
+    NOp ops[kMaxNOps];
+    size_t smem = 0;
+    int nst = 0;
+    int fused_row_floats = 0;  // floats per image the Gram kernel reads (super-tile sizing)
+};
+
+namespace {
+
+bool conv_supported(int S0, int si, int lo, int hi, int st) {
+    if (si == S0) {
+        if (st == 1) return (lo == 1 && hi == 1) || (lo == 1 && hi == 2) || (lo == 2 && hi == 2) || (lo == 3 && hi == 3);
+        return (lo == 1 && hi == 1) || (lo == 0 && hi == 0);
+    }
+    if (si == S0 / 2) {
+        if (st == 1) return lo == 1 && hi == 1;
+        return (lo == 1 && hi == 1) || (lo == 0 && hi == 0);
+    }
+    if (si == S0 / 4) return st == 1 && lo == 1 && hi == 1;
+    return false;
+}
+
+struct Translator {
+    const std::vector<DevOp> &ops;
+    int S0;
+    std::vector<NOp> out;
+    bool ok = true;
+    // per program slot
+    struct Slot { bool valid = false; int size = 0; int orient = 0; float pend = 1.f; bool in_regs = false; int tm = -1; };
+    std::vector<Slot> slot;
+    int tm_owner[2] = {-1, -1};
+
+    Translator(const std::vector<DevOp> &o, int n_slots, int s0) : ops(o), S0(s0), slot(n_slots) {}
+
+    bool reads(const DevOp &o, int s) const { return o.src == s || (o.opcode == CNNGP_OP_ADD && o.dst == s); }
+    // is the value now in slot s needed by an op after index k?
+    bool live_after(int k, int s) const {
+        for (size_t q = k + 1; q < ops.size(); ++q) {
+            if (reads(ops[q], s)) return true;
+            if (ops[q].dst == s) return false;  // overwritten without being read
+        }
+        return false;
+    }
+    int reg_slot() const {
+        for (size_t s = 0; s < slot.size(); ++s)
+            if (slot[s].valid && slot[s].in_regs) return (int)s;
+        return -1;
+    }
+    void emit(NOp n) { out.push_back(n); }
+    void free_tm(int s) {
+        if (slot[s].tm >= 0) { tm_owner[slot[s].tm] = -1; slot[s].tm = -1; }
+    }
+    bool stash(int s) {  // copy the register-resident slot s to a free tensor-memory slot
+        if (slot[s].tm >= 0) return true;
+        if (slot[s].size == 1) return false;  // 1 x 1 maps live in scalars: no stash
+        for (int t = 0; t < 2; ++t)
+            if (tm_owner[t] < 0) {
+                NOp n{}; n.kind = N_STASH; n.si = n.so = (short)slot[s].size; n.slot = (short)t;
+                emit(n);
+                tm_owner[t] = s; slot[s].tm = t;
+                return true;
+            }
+        return false;
+    }
+    // make slot s the register-resident one; k = index of the op about to run
+    bool to_regs(int s, int k) {
+        if (slot[s].in_regs) return true;
+        if (slot[s].tm < 0) return false;
+        const int r = reg_slot();
+        if (r >= 0) {
+            // the op at k still counts as a reader of r
+            const bool needed = reads(ops[k], r) || (ops[k].dst != r && live_after(k, r));
+            if (needed && !stash(r)) return false;
+            slot[r].in_regs = false;
+            if (!needed) { slot[r].valid = false; free_tm(r); }
+        }
+        NOp n{}; n.kind = N_UNSTASH; n.si = n.so = (short)slot[s].size; n.slot = (short)slot[s].tm;
+        emit(n);
+        slot[s].in_regs = true;
+        return true;
+    }
+    void affine(int size, float scale, float bias) {
+        NOp n{}; n.kind = size == 1 ? T_AFFINE : N_AFFINE; n.si = n.so = (short)size; n.scale = scale; n.bias = bias;
+        emit(n);
+    }
+
+    bool run(std::vector<DevOp> &mutable_ops, int final_slot) {
+        slot[0].valid = true; slot[0].size = S0; slot[0].in_regs = true;
+        for (size_t k = 0; k < ops.size(); ++k) {
+            const DevOp &o = ops[k];
+            if (!slot[o.src].valid) return false;
+            if (o.opcode == CNNGP_OP_ADD) {  // dst += src
+                if (!slot[o.dst].valid || slot[o.dst].size != slot[o.src].size || o.src == o.dst) return false;
+                if (slot[o.dst].size == 1) return false;  // Sum on 1 x 1 maps: not in the set
+                // registers must hold one operand, tensor memory the other
+                if (!slot[o.dst].in_regs && !slot[o.src].in_regs && !to_regs(o.dst, (int)k)) return false;
+                const bool src_live = live_after((int)k, o.src);
+                const int r = slot[o.dst].in_regs ? o.dst : o.src, other = r == o.dst ? o.src : o.dst;
+                if (r == o.src && src_live && !stash(o.src)) return false;
+                if (slot[other].tm < 0) return false;
+                if (slot[r].orient != slot[other].orient) {
+                    NOp n{}; n.kind = N_TRANSPOSE; n.si = n.so = (short)slot[r].size;
+                    emit(n);
+                }
+                NOp n{}; n.kind = N_ADD; n.si = n.so = (short)slot[r].size; n.slot = (short)slot[other].tm;
+                n.scale = slot[r].pend / slot[other].pend;
+                emit(n);
+                Slot d = slot[r];
+                d.orient = slot[other].orient; d.in_regs = true; d.tm = -1; d.valid = true;
+                // the sum lives in registers and belongs to dst; stale copies of dst go
+                free_tm(o.dst);
+                slot[o.src].in_regs = false;
+                if (!src_live) { free_tm(o.src); slot[o.src].valid = false; }
+                slot[o.dst] = d;
+                continue;
+            }
+            // unary ops: CONV, RELU, COPY, SCALE
+            if (!to_regs(o.src, (int)k)) return false;
+            if (o.dst != o.src && live_after((int)k, o.src)) {
+                if (!stash(o.src)) return false;
+            }
+            Slot src = slot[o.src];
+            if (o.dst != o.src) {
+                slot[o.src].in_regs = false;
+                if (!live_after((int)k, o.src)) { free_tm(o.src); slot[o.src].valid = false; }
+                free_tm(o.dst);
+            } else {
+                free_tm(o.src);  // in-place update: a stashed copy would be stale
+            }
+            Slot dst = src;
+            dst.in_regs = true; dst.tm = -1; dst.valid = true;
+            switch (o.opcode) {
+                case CNNGP_OP_COPY: break;
+                case CNNGP_OP_SCALE: affine(src.size, o.scale_f, 0.f); break;
+                case CNNGP_OP_RELU: {
+                    if (src.pend != 1.f) { affine(src.size, 1.f / src.pend, 0.f); }
+                    if (o.Hi != o.Wi || o.Hi != src.size) return false;
+                    NOp n{};
+                    n.si = n.so = (short)src.size;
+                    if (src.size == 1) { n.kind = T_RELU; n.aux = o.aux_off; }
+                    else {
+                        n.kind = N_RELU; n.aux = o.aux_foff; n.half = o.aux_half;
+                        mutable_ops[k].aux_t = src.orient;
+                    }
+                    emit(n);
+                    dst.pend = 2.f;
+                    break;
+                }
+                case CNNGP_OP_CONV: {
+                    if (o.dil != 1 || o.Hi != o.Wi || o.Ho != o.Wo || o.Hi != src.size) return false;
+                    const int lo = o.pad - o.t0, hi = o.ke - 1 - o.pad;
+                    if (lo < 0 || hi < 0) return false;
+                    const float scale = o.scale_f / src.pend;
+                    NOp n{};
+                    n.si = (short)src.size; n.so = (short)o.Ho; n.scale = scale; n.bias = o.bias_f;
+                    if (src.size == 1) {
+                        if (lo != 0 || hi != 0 || o.Ho != 1) return false;
+                        n.kind = T_AFFINE;
+                    } else if (o.Ho == 1 && lo == 0 && hi == src.size - 1) {
+                        n.kind = N_DENSE;
+                    } else if (lo == 0 && hi == 0 && o.stride == 1) {
+                        n.kind = N_AFFINE;
+                    } else {
+                        if (o.stride != 1 && o.stride != 2) return false;
+                        if (!conv_supported(S0, src.size, lo, hi, o.stride)) return false;
+                        if (o.Ho != (o.stride == 1 ? src.size : src.size / 2)) return false;
+                        n.kind = N_CONV; n.lo = (short)lo; n.hi = (short)hi; n.st = (short)o.stride;
+                        dst.orient = src.orient ^ 1;
+                    }
+                    emit(n);
+                    dst.size = o.Ho;
+                    dst.pend = 1.f;
+                    break;
+                }
+                default: return false;
+            }
+            slot[o.dst] = dst;
+            if ((int)out.size() > kMaxNOps - 8) return false;
+        }
+        Slot &f = slot[final_slot];
+        if (!f.valid || !f.in_regs || f.size != 1) return false;
+        if (f.pend != 1.f) affine(1, 1.f / f.pend, 0.f);
+        return (int)out.size() <= kMaxNOps;
+    }
+};
+
+template <int S0, int NST>
+constexpr size_t fnet_smem() {
+    return (size_t)NST * 48 * S0 * S0 + (size_t)kWarps * S0 * (S0 + 1) * 8 + (size_t)2 * NST * 8 + 16;
+}
+
+}  // namespace
+
+FNetPlan *fnet_plan_create(const Plan *plan_const) {
+    Plan *plan = const_cast<Plan *>(plan_const);
+    if (plan->dtype != CNNGP_F32) return nullptr;
+    if (plan->H != plan->W || (plan->H != 28 && plan->H != 32)) return nullptr;
+    if (plan->n_slots > 2) return nullptr;
+    const int S0 = plan->H;
+    std::vector<DevOp> saved = plan->ops;
+    Translator tr(saved, plan->n_slots, S0);
+    if (!tr.run(plan->ops, plan->final_slot)) {
+        plan->ops = saved;
+        return nullptr;
+    }
+    // the scalar tail needs the pooled value: exactly one N_DENSE, and nothing map-shaped after it
+    int n_dense = 0;
+    for (const NOp &n : tr.out) n_dense += n.kind == N_DENSE;
+    if (n_dense != 1) { plan->ops = saved; return nullptr; }
+    FNetPlan *fp = new FNetPlan();
+    fp->S0 = S0;
+    fp->n_ops = (int)tr.out.size();
+    for (int k = 0; k < fp->n_ops; ++k) fp->ops[k] = tr.out[k];
+    if (S0 == 28) { fp->nst = 4; fp->smem = fnet_smem<28, 4>(); }
+    else { fp->nst = 3; fp->smem = fnet_smem<32, 3>(); }
+    for (const DevOp &o : plan->ops)
+        if (o.opcode == CNNGP_OP_RELU) fp->fused_row_floats += 4 * o.aux_half;
+    return fp;
+}
+
+void fnet_plan_destroy(FNetPlan *fp) { delete fp; }
+
+int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2, int32_t C,
+                     const void *d_aux_x, const void *d_aux_z, int32_t symmetric, const void *d_kdiag,
+                     void *d_out, int64_t ld_out, void *stream) {
+    const FNetPlan *fp = plan->fnet;
+    if (!fp) { set_error("fused-net kernel: unsupported call"); return 4; }
+    if (N1 > 2000000000LL || N2 > 2000000000LL) { set_error("fused-net kernel: too many images"); return 8; }
+    static NParams p;  // 6 KB of ops: filled per call under a lock, passed by value at launch
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    memset(&p, 0, sizeof p);
+    memcpy(p.ops, fp->ops, sizeof(NOp) * fp->n_ops);
+    p.n_ops = fp->n_ops;
+    p.x = (const float *)d_x; p.z = (const float *)d_z;
+    p.aux_x = (const float *)d_aux_x; p.aux_z = (const float *)d_aux_z;
+    p.aux_stride = plan->aux_elems; p.aux_f_off = plan->aux_f_off;
+    p.N1 = (int)N1; p.N2 = (int)N2; p.C = C;
+    p.out = (float *)d_out; p.ld_out = ld_out;
+    p.symmetric = symmetric ? 1 : 0;
+    p.kdiag = (const float *)d_kdiag;
+    p.nbi = (int)((N1 + kTileI - 1) / kTileI);
+    p.nbj = (int)((N2 + kTileJ - 1) / kTileJ);
+    // super-tiles of side `edge` images: the 2 * edge variance rows a wave of CTAs shares stay in L2
+    int edge = 512;
+    while (edge > 64 && (size_t)2 * edge * fp->fused_row_floats * 4 > ((size_t)72 << 20)) edge /= 2;
+    const int super_i = edge / kTileI, super_j = edge / kTileJ;
+    long long n_super;
+    if (p.nbi <= super_i && p.nbj <= super_j) {
+        p.sti = p.nbi; p.stj = p.nbj; p.nst_j = 1; p.nst = 1;
+        n_super = 1;
+    } else {
+        p.sti = super_i; p.stj = super_j;
+        const int nsi = (p.nbi + super_i - 1) / super_i, nsj = (p.nbj + super_j - 1) / super_j;
+        p.nst_j = nsj;
+        p.nst = nsi > nsj ? nsi : nsj;
+        n_super = p.symmetric ? (long long)p.nst * (p.nst + 1) / 2 : (long long)nsi * nsj;
+    }
+    p.n_tiles = n_super * p.sti * p.stj;
+    p.inv_c = 1.0f / (float)C;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);
+    void (*kern)(const NParams) = fp->S0 == 28 ? fnet_kernel<28, 4> : fnet_kernel<32, 3>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem);
+    if (e != cudaSuccess) { set_error(std::string("fused-net cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 7; }
+    kern<<<grid, kThreads, fp->smem, (cudaStream_t)stream>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error(std::string("fused-net kernel launch: ") + cudaGetErrorString(e)); return 9; }
+    return 0;
+}
+
+}  // namespace cnngp

@@ -25,6 +25,7 @@
 #include <cstring>
 #include <string>
 
+#include "fused_common.cuh"
 #include "plan.h"
 
 namespace cnngp {
@@ -47,7 +48,7 @@ struct FOp {
     int kind;
     int lo, hi;     // F_CONV: window offsets [-lo, +hi] along each axis
     float scale, bias;
-    int aux_off;    // F_RELU: offset (in pixels) of this layer inside the per-image fused row
+    int aux_off;    // F_RELU: offset (floats) of this layer inside the fused section of a row
 };
 
 struct FParams {
@@ -71,74 +72,7 @@ struct FParams {
     float inv_c;       // 1 / C
 };
 
-// ---- PTX helpers ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok = 0;
-    const uint32_t addr = smem_u32(bar);
-    do {
-        asm volatile(
-            "{\n .reg .pred p;\n"
-            " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            " selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ float sqrt_approx(float v) {
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-
-// ---- packed f32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2, one issue slot for two lanes-ops) --
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pk(float lo, float hi) {
-    u64 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void upk(u64 v, float &lo, float &hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-    u64 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
-    u64 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ u64 add2(u64 a, u64 b) {
-    u64 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
-    u64 r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ float neg_abs(float v) { return __int_as_float(__float_as_int(v) | 0x80000000); }
+using namespace fusedk;
 
 // Box sum along the register axis with zero padding, out[y] = sum_{t=-LO..HI} v[y+t], on two
 // maps at once (packed lanes), as two sliding windows that start at the two ends and meet in
@@ -276,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
                     if (l >= 2) mbar_wait(&empty[buf], ((l >> 1) - 1) & 1);
                     mbar_arrive_expect_tx(&full[buf], kPairs * P * 16);
                     float4 *dst = stage + buf * kPairs * P;
-                    const long long off = p.aux_f_off + 2LL * p.ops[k].aux_off;
+                    const long long off = p.aux_f_off + (long long)p.ops[k].aux_off;
                     for (int s = 0; s < kPairs; ++s) {
                         // pair s of the tile; its float4 map is split over the two images' rows
                         const float *base;
@@ -456,7 +390,6 @@ FusedPlan *fused_plan_create(const Plan *plan_const) {
     Plan *plan = const_cast<Plan *>(plan_const);
     if (plan->dtype != CNNGP_F32) return nullptr;
     if (plan->H != plan->W || plan->H != 28) return nullptr;
-    if (plan->aux_elems % 4 != 0) return nullptr;
     const int S = plan->H;
     FusedPlan fp;
     fp.S = S;
@@ -499,7 +432,7 @@ FusedPlan *fused_plan_create(const Plan *plan_const) {
             if (pending != 1.f) return nullptr;  // ReLU directly after ReLU: not in the set
             if (o.Hi != S || o.Wi != S) return nullptr;
             f.kind = F_RELU;
-            f.aux_off = o.aux_off;
+            f.aux_off = o.aux_foff;
             o.aux_t = transposed ? 1 : 0;
             pending = 0.5f;
             ++fp.n_relu;

@@ -204,11 +204,12 @@ __global__ void __launch_bounds__(kThreads) generic_kernel(GenericParams<T> p) {
                             // partner image of the pair (2k, 2k+1): float4 (s_2k, s_2k+1, 1/s_2k, 1/s_2k+1)
                             // per pixel, first half of the pixels in row 2k, second half in row 2k+1
                             const int tp = o.aux_t ? (px % o.Wi) * o.Hi + px / o.Wi : px;
-                            const int half = P / 2;
+                            const int half = o.aux_half;
+                            const int hi = tp >= half ? 1 : 0;
                             const int64_t n = ei[g0];
                             const T sd = add_rn(sqrt_rn(v0), (T)1.0842021724855044e-19);
-                            T *f = p.aux_x_out + (size_t)((n & ~(int64_t)1) + (tp >= half ? 1 : 0)) * p.aux_elems +
-                                   p.aux_f_off + 2 * (size_t)o.aux_off + 4 * (size_t)(tp % half) + (n & 1);
+                            T *f = p.aux_x_out + (size_t)((n & ~(int64_t)1) + hi) * p.aux_elems + p.aux_f_off +
+                                   (size_t)o.aux_foff + 4 * (size_t)(tp - hi * half) + (n & 1);
                             f[0] = sd;
                             f[2] = div_rn((T)1, sd);
                         }

@@ -49,7 +49,7 @@ int build_plan(const cnngp_op *ops, int32_t n_ops, int32_t n_slots, int32_t H, i
         DevOp d{};
         d.opcode = o.opcode; d.src = o.src; d.dst = o.dst;
         d.Hi = slot[o.src].h; d.Wi = slot[o.src].w; d.Ho = d.Hi; d.Wo = d.Wi;
-        d.aux_off = 0; d.relu_index = -1; d.aux_t = 0;
+        d.aux_off = 0; d.relu_index = -1; d.aux_t = 0; d.aux_foff = 0; d.aux_half = 0;
         d.scale_d = o.scale; d.bias_d = o.bias; d.scale_f = (float)o.scale; d.bias_f = (float)o.bias;
         switch (o.opcode) {
             case CNNGP_OP_CONV: {
@@ -90,10 +90,20 @@ int build_plan(const cnngp_op *ops, int32_t n_ops, int32_t n_slots, int32_t H, i
         return 3;
     }
     p->relu_elems = (int32_t)p->aux_elems;
-    p->fused = fused_plan_create(p);
-    if (p->fused) {  // rows grow by the (s, 1/s) float2 maps the fused kernel stages
-        p->aux_f_off = p->relu_elems;
-        p->aux_elems = 3LL * p->relu_elems;
+    {   // layout of the fused kernels' (s, 1/s) section: per ReLU 4 * ceil(pixels / 2) floats per row
+        int32_t foff = 0;
+        for (DevOp &d : p->ops) {
+            if (d.opcode != CNNGP_OP_RELU) continue;
+            d.aux_half = (d.Hi * d.Wi + 1) / 2;
+            d.aux_foff = foff;
+            foff += 4 * d.aux_half;
+        }
+        p->fused = fused_plan_create(p);
+        if (!p->fused) p->fnet = fnet_plan_create(p);
+        if (p->fused || p->fnet) {  // rows grow by the pair-interleaved maps, 16-byte aligned
+            p->aux_f_off = (p->relu_elems + 3) / 4 * 4;
+            p->aux_elems = (int64_t)p->aux_f_off + foff;
+        }
     }
     *out = p;
     return 0;
@@ -161,6 +171,7 @@ void cnngp_plan_destroy(cnngp_plan *plan) {
     if (!p) return;
     if (p->d_ops) cudaFree(p->d_ops);
     if (p->fused) fused_plan_destroy(p->fused);
+    if (p->fnet) fnet_plan_destroy(p->fnet);
     delete p;
 }
 
@@ -168,7 +179,10 @@ int64_t cnngp_plan_aux_elems(const cnngp_plan *plan) { return reinterpret_cast<c
 double cnngp_plan_flops_per_pair(const cnngp_plan *plan, int32_t C) {
     return plan_flops_per_pair(reinterpret_cast<const Plan *>(plan), C);
 }
-int cnngp_plan_has_fused(const cnngp_plan *plan) { return reinterpret_cast<const Plan *>(plan)->fused != nullptr; }
+int cnngp_plan_has_fused(const cnngp_plan *plan) {
+    const Plan *p = reinterpret_cast<const Plan *>(plan);
+    return p->fused ? CNNGP_PATH_FUSED : (p->fnet ? CNNGP_PATH_FUSED_NET : 0);
+}
 
 int cnngp_variances(const cnngp_plan *plan, const void *d_x, const void *d_z, int64_t N, int32_t C,
                     void *d_aux_x, void *d_aux_z, void *d_kdiag, void *stream) {
@@ -190,23 +204,26 @@ int cnngp_gram(const cnngp_plan *plan, const void *d_x, int64_t N1, const void *
     if ((same || symmetric) && !diag && N1 != N2) { set_error("cnngp_gram: same needs N1 == N2 (kernels.py:161)"); return 1; }
     if (!diag && ld_out < N2) { set_error("cnngp_gram: ld_out < N2"); return 1; }
     if (N1 == 0 || N2 == 0) return 0;
+    const bool have = p->fused || p->fnet;
     bool use_fused = false;
     if (path == CNNGP_PATH_FUSED) {
-        if (!p->fused) { set_error("cnngp_gram: fused kernel does not cover this program"); return 4; }
+        if (!have) { set_error("cnngp_gram: no fused kernel covers this program"); return 4; }
         use_fused = true;
     } else if (path == CNNGP_PATH_NONE) {
-        use_fused = p->fused != nullptr;
+        use_fused = have;
     }
-    // the fused kernel assumes i == j entries equal the variance recursion, which the literal
+    // the fused kernels assume i == j entries equal the variance recursion, which the literal
     // reference only guarantees when x and z hold the same images
     if (use_fused && same && !symmetric) {
         if (path == CNNGP_PATH_FUSED) { set_error("cnngp_gram: fused path needs symmetric when same"); return 4; }
         use_fused = false;
     }
     if (use_fused && diag) use_fused = false;  // O(N) work: generic is enough
-    g_last_path = use_fused ? CNNGP_PATH_FUSED : CNNGP_PATH_GENERIC;
-    if (use_fused)
+    g_last_path = !use_fused ? CNNGP_PATH_GENERIC : (p->fused ? CNNGP_PATH_FUSED : CNNGP_PATH_FUSED_NET);
+    if (use_fused && p->fused)
         return launch_fused_gram(p, d_x, N1, d_z, N2, C, d_aux_x, d_aux_z, same, diag, symmetric, d_kdiag, d_out, ld_out, stream);
+    if (use_fused)
+        return launch_fnet_gram(p, d_x, N1, d_z, N2, C, d_aux_x, d_aux_z, symmetric, d_kdiag, d_out, ld_out, stream);
     return launch_generic_gram(p, d_x, N1, d_z, N2, C, d_aux_x, d_aux_z, same, diag, symmetric, d_out, ld_out, stream);
 }
 

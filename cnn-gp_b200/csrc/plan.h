@@ -19,11 +19,15 @@ struct DevOp {
     int32_t aux_off;                   // RELU: offset of its variance map in the per-image aux row
     int32_t relu_index;                // RELU: ordinal
     int32_t aux_t;                     // RELU: fused (s, 1/s) map stored transposed (lane = row layout)
+    int32_t aux_foff;                  // RELU: offset (floats) of its pair-interleaved (s, 1/s) maps inside the
+                                       // fused section of a row; the section of this layer is 4*aux_half floats
+    int32_t aux_half;                  // RELU: ceil(pixels / 2): pixels [0, half) live in row 2k, the rest in 2k+1
     float scale_f, bias_f;
     double scale_d, bias_d;
 };
 
 struct FusedPlan;  // gram_fused.cu
+struct FNetPlan;   // gram_fnet.cu
 
 struct Plan {
     int32_t n_ops = 0, n_slots = 0, H = 0, W = 0, dtype = 0;
@@ -40,6 +44,8 @@ struct Plan {
     mutable int d_ops_device = -1;
     // fused-kernel description (nullptr when the program is outside the fused kernel's set)
     FusedPlan *fused = nullptr;
+    // fused kernel for programs with Sum / stride / several map sizes (nullptr when not covered)
+    FNetPlan *fnet = nullptr;
 };
 
 void set_error(const std::string &msg);
@@ -65,5 +71,12 @@ void fused_plan_destroy(FusedPlan *fp);
 int launch_fused_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2,
                       int32_t C, const void *d_aux_x, const void *d_aux_z, int32_t same, int32_t diag,
                       int32_t symmetric, const void *d_kdiag, void *d_out, int64_t ld_out, void *stream);
+
+// gram_fnet.cu
+FNetPlan *fnet_plan_create(const Plan *plan);  // nullptr if not covered
+void fnet_plan_destroy(FNetPlan *fp);
+int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2, int32_t C,
+                     const void *d_aux_x, const void *d_aux_z, int32_t symmetric, const void *d_kdiag,
+                     void *d_out, int64_t ld_out, void *stream);
 
 }  // namespace cnngp

@@ -64,7 +64,7 @@ typedef struct cnngp_op {
 typedef struct cnngp_plan cnngp_plan; /* opaque, immutable after creation, thread-shareable */
 
 /* Which implementation cnngp_gram used for the last call on this thread. */
-enum { CNNGP_PATH_NONE = 0, CNNGP_PATH_GENERIC = 1, CNNGP_PATH_FUSED = 2 };
+enum { CNNGP_PATH_NONE = 0, CNNGP_PATH_GENERIC = 1, CNNGP_PATH_FUSED = 2, CNNGP_PATH_FUSED_NET = 3 };
 
 int cnngp_abi_version(void);
 const char *cnngp_last_error(void);
@@ -82,7 +82,9 @@ void cnngp_plan_destroy(cnngp_plan *plan);
 int64_t cnngp_plan_aux_elems(const cnngp_plan *plan);
 /* Algorithmic flop per image pair under SURVEY.md 8(d)'s counting convention. */
 double cnngp_plan_flops_per_pair(const cnngp_plan *plan, int32_t C);
-/* 1 if the register-resident fused kernel covers this program, else 0 (generic kernel). */
+/* Which register-resident fused kernel covers this program: CNNGP_PATH_FUSED (straight-line 28x28
+ * programs), CNNGP_PATH_FUSED_NET (Sum / stride / several map sizes, skip maps stashed in tensor
+ * memory), or 0 (generic kernel only). */
 int cnngp_plan_has_fused(const cnngp_plan *plan);
 
 /* Per-image variance recursion: the xx / yy maps of kernels.py:48-49 pushed through the
@@ -109,7 +111,8 @@ int cnngp_variances(const cnngp_plan *plan, const void *d_x, const void *d_z, in
  *   symmetric != 0: caller asserts d_x and d_z hold the same images (model(X)): only
  *                j >= i is computed and mirrored
  *   d_out  [N1, ld_out] (row stride ld_out elements) or [N1] when diag
- *   path   0 = auto (fused when available), 1 = force generic, 2 = force fused */
+ *   path   0 = auto (a fused kernel when one covers the program), 1 = force generic,
+ *          2 = force fused (fails if neither fused kernel covers the program) */
 int cnngp_gram(const cnngp_plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2,
                int32_t C, const void *d_aux_x, const void *d_aux_z, const void *d_kdiag, int32_t same,
                int32_t diag, int32_t symmetric, void *d_out, int64_t ld_out, int32_t path, void *stream);

@@ -93,6 +93,12 @@ def test_tile_vs_oracle(cfg):
 
 
 def test_zero_image_and_near_duplicates():
+    """Degenerate inputs.  For an image paired with (almost) itself in a same=False call the
+    reference's float32 formula cancels in `xx*yy - xy**2` (kernels.py:150) and its own answer is
+    off by up to ~1e-4 relative to its float64 answer.  The generic kernel reproduces the float32
+    reference literally (rel 1e-5 against the float32 oracle); the fused kernels use the
+    cancellation-free form and are held to the float64 oracle instead."""
+    from cnn_gp import engine
     model = readme_model().cuda()
     gen = torch.Generator().manual_seed(3)
     X = torch.rand(5, 3, 28, 28, generator=gen)
@@ -100,12 +106,22 @@ def test_zero_image_and_near_duplicates():
     X[3] = X[2] * (1 + 1e-4)      # almost collinear: cos(theta) -> 1
     X[4] = X[2]                   # exact duplicate in another slot
     Z = X.flip(0).contiguous()
-    want = oracle.gram(readme_model(), X.numpy(), Z.numpy())
-    got = model(X.cuda(), Z.cuda()).cpu().numpy()
+    want32 = oracle.gram(readme_model(), X.numpy(), Z.numpy())
+    want64 = oracle.gram(readme_model().double(), X.double().numpy(), Z.double().numpy())
+    scale = np.abs(want64).max()
+    prev = engine.set_path("generic")
+    try:
+        got = model(X.cuda(), Z.cuda()).cpu().numpy()
+        assert engine.last_path() == "generic"
+    finally:
+        engine.set_path(prev)
     assert np.isfinite(got).all()
-    scale = np.abs(want).max()
-    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-12 * scale)
-    # the zero image gives ~1.7e-20-sized entries, not 0 and not NaN
+    np.testing.assert_allclose(got, want32, rtol=1e-5, atol=1e-12 * scale)
+    assert 0 < got[1, 3] < 1e-12  # the zero image gives ~1.7e-20-sized entries, not 0 and not NaN
+    got = model(X.cuda(), Z.cuda()).cpu().numpy()
+    assert engine.last_path() == "fused_net"
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got, want64, rtol=1e-5, atol=1e-12 * scale)
     assert 0 < got[1, 3] < 1e-12
 
 
@@ -225,3 +241,88 @@ def test_fused_headline_program_large():
     idx = np.arange(500, 600)
     off[idx, idx - 500] = False
     assert rel_err(Kr[off], Kq[off]) < 5e-6
+
+
+# ---- fused-net kernel: Sum / stride / several map sizes, skip maps in tensor memory ------------
+def _net_models():
+    from cnn_gp import Conv2d, ReLU, Sequential, Sum, Mixture, resnet_block
+    return {
+        "readme": (readme_model(), 3, 28),
+        "mnist_paper_residual_cnn_gp": (MODELS["mnist_paper_residual_cnn_gp"], 1, 28),
+        "mnist_as_tf": (MODELS["mnist_as_tf"], 1, 28),
+        "cifar10": (MODELS["cifar10"], 3, 32),
+        # projection block straight after the stem, mixture of identity and a conv branch, 5x5 and 7x7 windows
+        "custom_mix": (Sequential(
+            Conv2d(5, var_bias=0.1), resnet_block(stride=2, projection_shortcut=True),
+            Mixture([Sequential(), Sequential(ReLU(), Conv2d(3, var_weight=1.7))],
+                    logit_proportions=torch.tensor([0.2, -0.4])),
+            ReLU(), Conv2d(14, padding=0, var_bias=0.2)), 2, 28),
+        # post-activation residual with an even window (layout flips once per block -> transposes)
+        "custom_evenk": (Sequential(
+            Conv2d(7, var_weight=2.0, var_bias=0.5), ReLU(),
+            Sum([Sequential(), Sequential(Conv2d(4, var_weight=3.0, var_bias=0.3), ReLU())]),
+            Sum([Sequential(), Sequential(Conv2d(4, var_weight=3.0, var_bias=0.3), ReLU())]),
+            Conv2d(32, padding=0)), 1, 32),
+    }
+
+
+@pytest.mark.parametrize("name", ["readme", "mnist_paper_residual_cnn_gp", "mnist_as_tf", "cifar10",
+                                  "custom_mix", "custom_evenk"])
+def test_fused_net_matches_generic_and_oracles(name):
+    """Ragged rectangular and symmetric tiles through the fused-net kernel against the generic
+    kernel, the float32 oracle (rel 1e-5) and the float64 oracle."""
+    model, C, S = _net_models()[name]
+    gen = torch.Generator().manual_seed(sum(map(ord, name)))
+    X = torch.rand(27, C, S, S, generator=gen)
+    Z = torch.randn(13, C, S, S, generator=gen)   # negative correlations too
+    m = model.float().cuda()
+    Xc, Zc = X.cuda(), Z.cuda()
+    Kf = m(Xc, Zc)
+    assert engine.last_path() == "fused_net"
+    Ks = m(Xc)
+    assert engine.last_path() == "fused_net"
+    engine.set_path("generic")
+    try:
+        Kg, Ksg = m(Xc, Zc), m(Xc)
+        assert engine.last_path() == "generic"
+    finally:
+        engine.set_path("auto")
+    assert rel_err(Kf.cpu().numpy(), Kg.cpu().numpy()) < 5e-6
+    assert rel_err(Ks.cpu().numpy(), Ksg.cpu().numpy()) < 5e-6
+    torch.testing.assert_close(Ks, Ks.T, rtol=0, atol=0)
+    torch.testing.assert_close(torch.diagonal(Ks), m(Xc, diag=True), rtol=0, atol=0)
+    Kf = Kf.cpu().numpy()
+    want32 = oracle.gram(model.float().cpu(), X.numpy(), Z.numpy())
+    assert rel_err(Kf, want32) < 1e-5
+    want64 = oracle.gram(model.double().cpu(), X.double().numpy(), Z.double().numpy())
+    model.float()
+    assert rel_err(Kf, want64) < 5e-6
+
+
+@pytest.mark.parametrize("name,n", [("mnist_as_tf", 700), ("cifar10", 300)])
+def test_fused_net_large(name, n):
+    """Several super-tiles and many tiles per CTA (stage ring and tensor-memory reuse across
+    tiles): symmetric run against rectangular blocks and against generic rows."""
+    model, C, S = _net_models()[name]
+    m = model.float().cuda()
+    gen = torch.Generator().manual_seed(17)
+    X = torch.rand(n, C, S, S, generator=gen).cuda()
+    K = m(X)
+    assert engine.last_path() == "fused_net"
+    torch.testing.assert_close(K, K.T, rtol=0, atol=0)
+    Kb = m(X[:n // 3 + 1], X[n // 3 + 1:])
+    # 2-aligned split: the same warp arithmetic either way
+    rows = torch.tensor([0, 1, 2, n // 2, n - 2, n - 1], device="cuda")
+    engine.set_path("generic")
+    try:
+        Kg = m(X[rows], X)
+    finally:
+        engine.set_path("auto")
+    Ks, Kg = K[rows].cpu().numpy(), Kg.cpu().numpy()
+    off = np.ones_like(Ks, dtype=bool)
+    off[np.arange(len(rows)), rows.cpu().numpy()] = False
+    assert rel_err(Ks[off], Kg[off]) < 5e-6
+    a, b = Kb.cpu().numpy(), K[:n // 3 + 1, n // 3 + 1:].cpu().numpy()
+    assert rel_err(a, b) < 2e-6
+    ev = torch.linalg.eigvalsh(K.double())
+    assert ev.min() > -1e-6 * ev.max()
