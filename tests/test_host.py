@@ -132,7 +132,10 @@ def test_shipped_programs_need_two_slots_and_match_survey_flops():
         assert plan.flops_per_pair(C) == flops, (name, plan.flops_per_pair(C))
         if name in relu_px:
             # rows also carry the fused kernel's (s, 1/s) pairs when it covers the program
-            assert plan.aux_elems == relu_px[name] * (3 if plan.has_fused else 1)
+            # (cnngp.h: xx maps, padded to 16 bytes, then 4 * ceil(pixels / 2) floats per ReLU)
+            n_relu = sum(1 for o in ops if o.opcode == nat.OP_RELU)
+            assert plan.has_fused and plan.aux_elems % 4 == 0
+            assert 3 * relu_px[name] <= plan.aux_elems <= 3 * relu_px[name] + 3 + 2 * n_relu
 
 
 def test_plan_rejects_bad_programs():
