@@ -278,8 +278,27 @@ def run_ours(args):
         peak = fp32_peak_tflops()
         # dominant kernel = the Gram kernel; achieved = algorithmic flop of this rank's launches / their time
         achieved = f_alg * my_pairs * args.steps / (gram_ms * 1e-3) / 1e12
+        traffic = None
+        try:  # DRAM bytes of one launch from the committed ncu --set full capture of this very workload
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                traffic = json.load(fh).get(f"{args.config}@{n}", {}).get("dram_bytes_per_launch") if world == 1 else None
+        except OSError:
+            pass
+        # algorithmic HBM bytes of one launch: the n x n float32 result + images + staged variance maps, once
+        alg_bytes = 4.0 * n * n + 4.0 * n * (c * s * s) + 4.0 * n * (plan.aux_elems - plan.aux_elems // 3)
+        hbm_peak = 6551.0
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                hbm_peak = float(json.load(fh).get("hbm_gbs", hbm_peak))
+        except (OSError, ValueError):
+            pass
         roof = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None,
+                "traffic": traffic,
+                "hbm": {"algorithmic_bytes_per_launch": alg_bytes,
+                        "achieved_gbs": alg_bytes * gram_launches / (gram_ms * 1e-3) / 1e9 if world == 1 else None,
+                        "measured_dram_gbs": (traffic * gram_launches / (gram_ms * 1e-3) / 1e9) if traffic else None,
+                        "peak_gbs": hbm_peak,
+                        "note": "the path is FP32-pipe bound (arithmetic intensity ~1e4 flop/B); HBM shown for completeness"},
                 "note": "FP32 CUDA-core bound (SURVEY 8d); peak = FFMA probe measured in this run "
                         "(MEASURED_PEAKS.json has no FP32 figure); achieved = F_alg x pairs / CUDA-event time of "
                         "the Gram launches on torch's current stream",

@@ -28,6 +28,7 @@
 
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -898,6 +899,7 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
     // super-tiles of side `edge` images: the 2 * edge variance rows a wave of CTAs shares stay in L2
     int edge = 512;
     while (edge > 64 && (size_t)2 * edge * fp->fused_row_floats * 4 > ((size_t)72 << 20)) edge /= 2;
+    if (const char *e = getenv("CNNGP_SUPER_EDGE")) { const int v = atoi(e); if (v >= 32 && v % 32 == 0) edge = v; }
     const int super_i = edge / kTileI, super_j = edge / kTileJ;
     long long n_super;
     if (p.nbi <= super_i && p.nbj <= super_j) {

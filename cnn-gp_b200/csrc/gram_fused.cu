@@ -22,6 +22,7 @@
 
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -40,7 +41,7 @@ constexpr int kThreads = (kWarps + 4) * 32;  // + a third warpgroup: the produce
                                              // only donate their registers (setmaxnreg)
 constexpr int kRegsProducer = 24, kRegsConsumer = 240;
 constexpr int kMaxOps = 40;
-constexpr int kSuperJ = 64, kSuperI = 128;   // super-tile = 512 x 512 images (L2-resident variance maps)
+constexpr int kSuperEdge = 512;              // default super-tile edge in images (L2-resident variance maps)
 
 enum { F_CONV = 0, F_RELU = 1, F_DENSE = 2 };
 
@@ -472,12 +473,15 @@ int launch_fused_gram(const Plan *plan, const void *d_x, int64_t N1, const void 
     p.nbi = (int)((N1 + kTileI - 1) / kTileI);
     p.nbj = (int)((N2 + kTileJ - 1) / kTileJ);
     long long n_super;
-    if (p.nbi <= kSuperI && p.nbj <= kSuperJ) {  // one (possibly small) super-tile
+    int edge = kSuperEdge;
+    if (const char *e = getenv("CNNGP_SUPER_EDGE")) { const int v = atoi(e); if (v >= 32 && v % 32 == 0) edge = v; }
+    const int super_i = edge / kTileI, super_j = edge / kTileJ;
+    if (p.nbi <= super_i && p.nbj <= super_j) {  // one (possibly small) super-tile
         p.sti = p.nbi; p.stj = p.nbj; p.nst_j = 1; p.nst = 1;
         n_super = 1;
     } else {
-        p.sti = kSuperI; p.stj = kSuperJ;
-        const int nsi = (p.nbi + kSuperI - 1) / kSuperI, nsj = (p.nbj + kSuperJ - 1) / kSuperJ;
+        p.sti = super_i; p.stj = super_j;
+        const int nsi = (p.nbi + super_i - 1) / super_i, nsj = (p.nbj + super_j - 1) / super_j;
         p.nst_j = nsj;
         p.nst = nsi > nsj ? nsi : nsj;
         n_super = p.symmetric ? (long long)p.nst * (p.nst + 1) / 2 : (long long)nsi * nsj;
