@@ -3,10 +3,14 @@
 images (cnn_gp/synthetic.py).  Sizes follow the environment variables CNNGP_SYNTH_TRAIN /
 CNNGP_SYNTH_VAL / CNNGP_SYNTH_TEST (defaults 1000 / 200 / 300) so that the same
 save_kernel -> merge -> classify_gp pipeline runs from a unit test up to 60k images."""
+import importlib
 import os
 
 from cnn_gp.synthetic import synthetic_dataset
-from .mnist_paper_convnet_gp import initial_model  # noqa: F401
+
+# CNNGP_SYNTH_MODEL names the config whose architecture is used (default: the 7-layer ConvNet GP)
+initial_model = importlib.import_module(
+    "configs." + os.environ.get("CNNGP_SYNTH_MODEL", "mnist_paper_convnet_gp")).initial_model
 
 _n_train = int(os.environ.get("CNNGP_SYNTH_TRAIN", "1000"))
 _n_val = int(os.environ.get("CNNGP_SYNTH_VAL", "200"))
