@@ -10,8 +10,9 @@ One "step" = one full pass of the hot path over the workload: per-image variance
 unique pair of the symmetric Gram, result written to HBM.  At N > 1 (torchrun, one rank per
 GPU) the workload grows with N (weak scaling: round(10000*sqrt(N)) images, N x the pairs), the
 reference's tile list (cnn_gp/data.py:11-29, tile `--tile`) is split contiguously over the
-ranks exactly like its `_this_worker_batch`, ranks compute with no communication, and the
-blocks are gathered on rank 0 (timed in `e2e`, not in `value`).
+ranks like its `_this_worker_batch` but with the cut points balanced by pair count
+(cnn_gp.data.worker_tiles_balanced), ranks compute with no communication, and the blocks are
+gathered on rank 0 (timed in `e2e`, not in `value`).
 
 JSON keys beyond the base contract:
   roofline      dominant kernel (the Gram kernel) against the FP32 CUDA-core peak measured live
@@ -49,7 +50,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=CONFIG)
     ap.add_argument("--n-images", type=int, default=N_IMAGES)
-    ap.add_argument("--tile", type=int, default=1000, help="tile edge for the multi-GPU tile list")
+    ap.add_argument("--tile", type=int, default=500, help="tile edge for the multi-GPU tile list")
     ap.add_argument("--path", default="auto", choices=["auto", "generic", "fused"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the baseline sample")
@@ -200,7 +201,7 @@ def run_ours(args):
             job.block(out, 0, n, 0, n, symmetric=True)
             pairs = total_pairs
         else:
-            pairs = compute_worker_blocks(job, out, args.tile, rank, world)
+            pairs = compute_worker_blocks(job, out, args.tile, rank, world, balanced=True)
         ev[1].record()
         launches[0] += job.launches
         return pairs, ev, job.launches - 1
@@ -253,7 +254,7 @@ def run_ours(args):
             K = model(x)  # public call: plan lookup, variances, one fused launch
         else:
             K = torch.full((n, n), float("nan"), dtype=torch.float32, device=dev)
-            compute_worker_blocks(GramJob(model, x), K, args.tile, rank, world)
+            compute_worker_blocks(GramJob(model, x), K, args.tile, rank, world, balanced=True)
             K = gather_blocks(K, dst=0)
         if rank == 0:
             K_host.copy_(K, non_blocking=True)

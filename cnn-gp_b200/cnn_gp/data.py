@@ -60,6 +60,49 @@ def worker_tiles(N, N2, batch_size, worker_rank=0, n_workers=1):
     return list(itertools.islice(_product_generator(nbx, nb2, same), start, start + count))
 
 
+def tile_pairs(same, i, j, N, N2, batch_size):
+    """Unique pair entries of tile (i, j): a diagonal tile of a symmetric Gram only computes j >= i."""
+    n = min(batch_size, N - i * batch_size)
+    if same:
+        return n * (n + 1) // 2
+    return n * min(batch_size, N2 - j * batch_size)
+
+
+def worker_tiles_balanced(N, N2, batch_size, worker_rank=0, n_workers=1):
+    """Like ``worker_tiles`` -- a contiguous slice of the reference's tile list -- but the cut
+    points equalise the number of PAIR ENTRIES per worker instead of the number of tiles
+    (the reference's count split, data.py:11-19, gives the ranks that own many diagonal and edge
+    tiles up to ~8 % less work).  A pure function of (N, N2, batch_size, n_workers), so block
+    ownership is reproducible and the NaN-fill / merge contract holds unchanged."""
+    nbx = _round_up_div(N, batch_size)
+    same = N2 is None
+    nb2 = nbx if same else _round_up_div(N2, batch_size)
+    tiles = list(_product_generator(nbx, nb2, same))
+    cost, acc = [], 0
+    for s, i, j in tiles:
+        acc += tile_pairs(s, i, j, N, N if same else N2, batch_size)
+        cost.append(acc)
+    total = acc
+
+    def cut(r):  # first tile of worker r: the first tile whose preceding cost reaches r/n of the total
+        if r <= 0:
+            return 0
+        if r >= n_workers:
+            return len(tiles)
+        target = total * r / n_workers
+        lo, hi = 0, len(tiles)
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if cost[mid] < target:
+                lo = mid + 1
+            else:
+                hi = mid
+        # tile `lo` straddles the target: give it to the side that leaves the smaller error
+        before = cost[lo - 1] if lo > 0 else 0
+        return lo + 1 if (cost[lo] - target) < (target - before) else lo
+    return tiles[cut(worker_rank):cut(worker_rank + 1)]
+
+
 class ResidentDataset(Dataset):
     """Images and labels held as two tensors (on any device).  Slicing a batch is a view, so a
     dataset kept in HBM feeds tiles with no host work at all."""

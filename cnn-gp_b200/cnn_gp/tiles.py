@@ -13,7 +13,7 @@ is the single exchange step (the reference does it through files, merge_h5_files
 import torch
 
 from . import engine
-from .data import worker_tiles
+from .data import worker_tiles, worker_tiles_balanced
 
 
 class GramJob:
@@ -67,11 +67,13 @@ def row_segments(tiles):
     return [(i, rows[i][0], rows[i][1], rows[i][2]) for i in order]
 
 
-def compute_worker_blocks(job, out, batch_size, worker_rank=0, n_workers=1):
+def compute_worker_blocks(job, out, batch_size, worker_rank=0, n_workers=1, balanced=False):
     """Fill ``out`` ([N, N2], any float dtype matching the job) with this worker's tiles; entries
-    owned by other workers are left untouched.  Returns the number of unique pairs computed."""
+    owned by other workers are left untouched.  Returns the number of unique pairs computed.
+    ``balanced`` cuts the reference's tile list by pair count instead of tile count."""
     N, N2 = job.X.shape[0], job.X2.shape[0]
-    tiles = worker_tiles(N, None if job.same else N2, batch_size, worker_rank, n_workers)
+    split = worker_tiles_balanced if balanced else worker_tiles
+    tiles = split(N, None if job.same else N2, batch_size, worker_rank, n_workers)
     pairs = 0
     for r, has_diag, c0, c1 in row_segments(tiles):
         i0, i1 = r * batch_size, min(N, (r + 1) * batch_size)

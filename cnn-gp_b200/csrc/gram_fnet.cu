@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) fnet_kernel(const __grid_constant
             const int last_pi = (p.N1 - 1) >> 1, last_pj = (p.N2 - 1) >> 1;
             auto acquire = [&](unsigned bytes) -> unsigned char * {
                 const unsigned buf = l % NST;
-                if (l >= NST) mbar_wait(&empty[buf], ((l / NST) - 1) & 1);
+                if (l >= NST) mbar_wait_relaxed(&empty[buf], ((l / NST) - 1) & 1);
                 mbar_arrive_expect_tx(&full[buf], bytes);
                 return stage + (size_t)buf * STAGE;
             };

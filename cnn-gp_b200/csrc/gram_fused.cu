@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
                 const int i_base = ib * kTileI, j_base = jb * kTileJ;
                 for (int c = 0; c < p.C; ++c) {
                     const unsigned buf = l & 1;
-                    if (l >= 2) mbar_wait(&empty[buf], ((l >> 1) - 1) & 1);
+                    if (l >= 2) mbar_wait_relaxed(&empty[buf], ((l >> 1) - 1) & 1);
                     mbar_arrive_expect_tx(&full[buf], kImgs * P * 4);
                     float *dst = reinterpret_cast<float *>(stage + buf * kPairs * P);
                     for (int s = 0; s < kImgs; ++s) {
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
                 for (int k = 0; k < p.n_ops; ++k) {
                     if (p.ops[k].kind != F_RELU) continue;
                     const unsigned buf = l & 1;
-                    if (l >= 2) mbar_wait(&empty[buf], ((l >> 1) - 1) & 1);
+                    if (l >= 2) mbar_wait_relaxed(&empty[buf], ((l >> 1) - 1) & 1);
                     mbar_arrive_expect_tx(&full[buf], kPairs * P * 16);
                     float4 *dst = stage + buf * kPairs * P;
                     const long long off = p.aux_f_off + (long long)p.ops[k].aux_off;

@@ -34,7 +34,7 @@ def gram_sharded(model, X, X2, batch_size, rank, world):
     """This rank's tiles of K(X, X2) gathered on rank 0 (None elsewhere)."""
     N, N2 = X.shape[0], (X if X2 is None else X2).shape[0]
     K = torch.full((N, N2), float("nan"), dtype=torch.float32, device=X.device)
-    compute_worker_blocks(GramJob(model, X, X2), K, batch_size, rank, world)
+    compute_worker_blocks(GramJob(model, X, X2), K, batch_size, rank, world, balanced=True)
     if world == 1:
         return K
     return gather_blocks(K, dst=0)

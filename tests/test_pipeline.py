@@ -240,3 +240,19 @@ def test_classify_api_matches_reference_functions():
     K2 = np.eye(3)
     classify_gp.diag_add(K2, 0.5)
     assert (np.diag(K2) == 1.5).all()
+
+
+@pytest.mark.parametrize("N,N2,bs,n", [(1000, None, 64, 8), (333, None, 50, 3), (120, 77, 16, 5), (64, None, 64, 4)])
+def test_balanced_split_is_a_contiguous_partition_with_even_pair_counts(N, N2, bs, n):
+    """worker_tiles_balanced: same tile order as the reference, every tile owned exactly once,
+    pair counts per worker within one tile of the mean (the reference's count split is not)."""
+    from cnn_gp.data import worker_tiles, worker_tiles_balanced, tile_pairs
+    full = worker_tiles(N, N2, bs, 0, 1)
+    parts = [worker_tiles_balanced(N, N2, bs, r, n) for r in range(n)]
+    assert sum(parts, []) == full
+    same = N2 is None
+    cost = [sum(tile_pairs(s, i, j, N, N if same else N2, bs) for s, i, j in p) for p in parts]
+    total = N * (N + 1) // 2 if same and N <= bs else sum(cost)
+    assert sum(cost) == total
+    biggest = max(tile_pairs(s, i, j, N, N if same else N2, bs) for s, i, j in full)
+    assert max(cost) - sum(cost) / n <= biggest
