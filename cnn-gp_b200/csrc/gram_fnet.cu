@@ -53,8 +53,13 @@ constexpr int kTmemCols = 512;
 
 enum { N_CONV = 0, N_AFFINE, N_RELU, N_STASH, N_UNSTASH, N_ADD, N_TRANSPOSE, N_DENSE, T_RELU, T_AFFINE };
 
+// dense dispatch codes: kind x size class (0: S0, 1: S0/2, 2: S0/4), convolutions by variant
+enum { C_CONV = 0, C_AFFINE = 10, C_TRANSPOSE = 13, C_STASH = 16, C_UNSTASH = 19, C_ADD = 22, C_DENSE = 25,
+       C_RELU = 28, C_TAFFINE = 31, C_TRELU = 32 };
+
 struct NOp {
     int kind;
+    int code;           // filled by assign_codes()
     short si, so;       // map edge before / after the op
     short lo, hi, st;   // N_CONV: window offsets [-lo, +hi] and stride
     short slot;         // N_STASH / N_UNSTASH / N_ADD: tensor-memory slot (0 or 1)
@@ -81,96 +86,117 @@ struct NParams {
 };
 
 // ---- tensor memory ---------------------------------------------------------------------------
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, u64 a0, u64 a1, u64 a2, u64 a3, u64 a4, u64 a5, u64 a6,
-                                         u64 a7) {
+// tcgen05.st / tcgen05.ld move N consecutive 32-bit registers of every thread to / from N
+// consecutive columns of the thread's own TMEM lane.  The b32 halves of the packed maps are passed
+// as the instruction's own operands (no staging copies); a load is only complete after
+// tcgen05.wait::ld, which is tied to the loaded registers through "+r" operands so that the
+// compiler cannot move their first use above it.
+__device__ __forceinline__ void split64(u64 v, uint32_t &lo, uint32_t &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 join64(uint32_t lo, uint32_t hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
-        "{\n .reg .b32 t<16>;\n"
-        " mov.b64 {t0, t1}, %1;\n mov.b64 {t2, t3}, %2;\n mov.b64 {t4, t5}, %3;\n mov.b64 {t6, t7}, %4;\n"
-        " mov.b64 {t8, t9}, %5;\n mov.b64 {t10, t11}, %6;\n mov.b64 {t12, t13}, %7;\n mov.b64 {t14, t15}, %8;\n"
-        " tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, t11, t12, t13, "
-        "t14, t15};\n}"
-        ::"r"(taddr), "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(a4), "l"(a5), "l"(a6), "l"(a7)
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+        "%15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, u64 a0, u64 a1, u64 a2, u64 a3) {
-    asm volatile(
-        "{\n .reg .b32 t<8>;\n"
-        " mov.b64 {t0, t1}, %1;\n mov.b64 {t2, t3}, %2;\n mov.b64 {t4, t5}, %3;\n mov.b64 {t6, t7}, %4;\n"
-        " tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {t0, t1, t2, t3, t4, t5, t6, t7};\n}"
-        ::"r"(taddr), "l"(a0), "l"(a1), "l"(a2), "l"(a3)
-        : "memory");
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
 }
-// the wait sits inside the block: the b32 registers may only be read once the load has landed
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, u64 &a0, u64 &a1, u64 &a2, u64 &a3, u64 &a4, u64 &a5,
-                                         u64 &a6, u64 &a7) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
-        "{\n .reg .b32 t<16>;\n"
-        " tcgen05.ld.sync.aligned.32x32b.x16.b32 {t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, t11, t12, t13, t14, "
-        "t15}, [%8];\n"
-        " tcgen05.wait::ld.sync.aligned;\n"
-        " mov.b64 %0, {t0, t1};\n mov.b64 %1, {t2, t3};\n mov.b64 %2, {t4, t5};\n mov.b64 %3, {t6, t7};\n"
-        " mov.b64 %4, {t8, t9};\n mov.b64 %5, {t10, t11};\n mov.b64 %6, {t12, t13};\n mov.b64 %7, {t14, t15};\n}"
-        : "=l"(a0), "=l"(a1), "=l"(a2), "=l"(a3), "=l"(a4), "=l"(a5), "=l"(a6), "=l"(a7)
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+        "%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, u64 &a0, u64 &a1, u64 &a2, u64 &a3) {
-    asm volatile(
-        "{\n .reg .b32 t<8>;\n"
-        " tcgen05.ld.sync.aligned.32x32b.x8.b32 {t0, t1, t2, t3, t4, t5, t6, t7}, [%4];\n"
-        " tcgen05.wait::ld.sync.aligned;\n"
-        " mov.b64 %0, {t0, t1};\n mov.b64 %1, {t2, t3};\n mov.b64 %2, {t4, t5};\n mov.b64 %3, {t6, t7};\n}"
-        : "=l"(a0), "=l"(a1), "=l"(a2), "=l"(a3)
-        : "r"(taddr)
-        : "memory");
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_landed16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_landed8(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// whole map set (two packed arrays, first S entries each) -> tensor memory; an array takes 64 columns
+// whole map set (two packed arrays, first S entries each) -> tensor memory; an array takes 64
+// columns.  Entries are moved in groups of 8 (x16); a remainder of up to 4 entries as x8, a
+// larger one as a full group (the array always has the registers, S0 >= 8 * ceil(S / 8)).
 template <int S0, int S>
 __device__ __forceinline__ void stash_store(uint32_t tbase, const u64 (&M)[2][S0]) {
+    constexpr int FULL = S / 8, REM = S % 8, G16 = FULL + (REM > 4 ? 1 : 0);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        constexpr int FULL = S / 8, REM = S % 8;
 #pragma unroll
-        for (int c = 0; c < FULL; ++c)
-            tmem_st8(tbase + h * 64 + c * 16, M[h][c * 8 + 0], M[h][c * 8 + 1], M[h][c * 8 + 2], M[h][c * 8 + 3],
-                     M[h][c * 8 + 4], M[h][c * 8 + 5], M[h][c * 8 + 6], M[h][c * 8 + 7]);
-        if (REM > 4) {  // round up to eight entries (the array has at least S0 >= FULL*8+8 of them)
-            constexpr int b = FULL * 8;
-            tmem_st8(tbase + h * 64 + FULL * 16, M[h][b + 0], M[h][b + 1], M[h][b + 2], M[h][b + 3],
-                     M[h][(b + 4) % S0], M[h][(b + 5) % S0], M[h][(b + 6) % S0], M[h][(b + 7) % S0]);
-        } else if (REM > 0) {
-            constexpr int b = FULL * 8;
-            tmem_st4(tbase + h * 64 + FULL * 16, M[h][b + 0], M[h][(b + 1) % S0], M[h][(b + 2) % S0], M[h][(b + 3) % S0]);
+        for (int c = 0; c < G16; ++c) {
+            uint32_t r[16];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) split64(M[h][(c * 8 + q) % S0], r[2 * q], r[2 * q + 1]);
+            tmem_st16(tbase + h * 64 + c * 16, r);
+        }
+        if (REM > 0 && REM <= 4) {
+            uint32_t r[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) split64(M[h][(FULL * 8 + q) % S0], r[2 * q], r[2 * q + 1]);
+            tmem_st8(tbase + h * 64 + FULL * 16, r);
         }
     }
     tmem_wait_st();
 }
 
-// M = stash (ADD == false) or M = stash * alpha + M (ADD == true)
+// M = stash (ADD == false) or M = stash * alpha + M (ADD == true); all loads of one array are
+// in flight together
 template <int S0, int S, bool ADD>
 __device__ __forceinline__ void stash_load(uint32_t tbase, u64 (&M)[2][S0], u64 alpha) {
+    constexpr int FULL = S / 8, REM = S % 8, G16 = FULL + (REM > 4 ? 1 : 0);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        constexpr int FULL = S / 8, REM = S % 8;
+        uint32_t t[G16 > 0 ? G16 : 1][16];
+        uint32_t t8[8];
 #pragma unroll
-        for (int c = 0; c < FULL; ++c) {
-            u64 t[8];
-            tmem_ld8(tbase + h * 64 + c * 16, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
+        for (int c = 0; c < G16; ++c) tmem_ld16(tbase + h * 64 + c * 16, t[c]);
+        if (REM > 0 && REM <= 4) tmem_ld8(tbase + h * 64 + FULL * 16, t8);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) M[h][c * 8 + q] = ADD ? fma2(t[q], alpha, M[h][c * 8 + q]) : t[q];
+        for (int c = 0; c < G16; ++c) {
+            tmem_landed16(t[c]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (c * 8 + q < S) {
+                    const u64 v = join64(t[c][2 * q], t[c][2 * q + 1]);
+                    M[h][c * 8 + q] = ADD ? fma2(v, alpha, M[h][c * 8 + q]) : v;
+                }
+            }
         }
-        if (REM > 4) {
-            u64 t[8];
-            tmem_ld8(tbase + h * 64 + FULL * 16, t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
+        if (REM > 0 && REM <= 4) {
+            tmem_landed8(t8);
 #pragma unroll
-            for (int q = 0; q < REM; ++q) M[h][FULL * 8 + q] = ADD ? fma2(t[q], alpha, M[h][FULL * 8 + q]) : t[q];
-        } else if (REM > 0) {
-            u64 t[4];
-            tmem_ld4(tbase + h * 64 + FULL * 16, t[0], t[1], t[2], t[3]);
-#pragma unroll
-            for (int q = 0; q < REM; ++q) M[h][FULL * 8 + q] = ADD ? fma2(t[q], alpha, M[h][FULL * 8 + q]) : t[q];
+            for (int q = 0; q < REM; ++q) {
+                const u64 v = join64(t8[2 * q], t8[2 * q + 1]);
+                M[h][FULL * 8 + q] = ADD ? fma2(v, alpha, M[h][FULL * 8 + q]) : v;
+            }
         }
     }
 }
@@ -370,14 +396,6 @@ __device__ __forceinline__ void dense_op(const u64 (&M)[2][S0], int lane, float 
     }
 }
 
-// dispatch on the map edge: S0, S0/2 or S0/4
-#define FNET_BY_SIZE(sz, CALL)                  \
-    do {                                        \
-        if ((sz) == S0) { constexpr int S = S0; CALL; }            \
-        else if ((sz) == S0 / 2) { constexpr int S = S0 / 2; CALL; } \
-        else { constexpr int S = S0 / 4; CALL; }                   \
-    } while (0)
-
 template <int S0, int NST>
 __global__ void __launch_bounds__(kThreads, 1) fnet_kernel(const __grid_constant__ NParams p) {
     constexpr int P0 = S0 * S0;
@@ -524,90 +542,77 @@ __global__ void __launch_bounds__(kThreads, 1) fnet_kernel(const __grid_constant
             if (p.C > 1) affine_op<S0, S0>(M, p.inv_c, 0.f);
         }
 
+        // one jump per op: the translator precomputes a dense code = kind x size class (x window)
+        NOp o = p.ops[0];
         for (int k = 0; k < p.n_ops; ++k) {
-            const NOp o = p.ops[k];
-            switch (o.kind) {
-                case N_CONV: {
-                    const int key = (o.si == S0 ? 0 : (o.si == S0 / 2 ? 1 : 2)) * 100 + o.st * 10 + o.lo * 3 + o.hi;
-                    // key = size class * 100 + stride * 10 + lo * 3 + hi
-                    switch (key) {
-                        case 0 * 100 + 10 + 1 * 3 + 1: conv_op<S0, S0, S0, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
-                        case 0 * 100 + 10 + 1 * 3 + 2: conv_op<S0, S0, S0, 1, 2, 1>(M, tile, lane, o.scale, o.bias); break;
-                        case 0 * 100 + 10 + 2 * 3 + 2: conv_op<S0, S0, S0, 2, 2, 1>(M, tile, lane, o.scale, o.bias); break;
-                        case 0 * 100 + 10 + 3 * 3 + 3: conv_op<S0, S0, S0, 3, 3, 1>(M, tile, lane, o.scale, o.bias); break;
-                        case 0 * 100 + 20 + 1 * 3 + 1: conv_op<S0, S0, S0 / 2, 1, 1, 2>(M, tile, lane, o.scale, o.bias); break;
-                        case 0 * 100 + 20 + 0: conv_op<S0, S0, S0 / 2, 0, 0, 2>(M, tile, lane, o.scale, o.bias); break;
-                        case 1 * 100 + 10 + 1 * 3 + 1: conv_op<S0, S0 / 2, S0 / 2, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
-                        case 1 * 100 + 20 + 1 * 3 + 1: conv_op<S0, S0 / 2, S0 / 4, 1, 1, 2>(M, tile, lane, o.scale, o.bias); break;
-                        case 1 * 100 + 20 + 0: conv_op<S0, S0 / 2, S0 / 4, 0, 0, 2>(M, tile, lane, o.scale, o.bias); break;
-                        case 2 * 100 + 10 + 1 * 3 + 1: conv_op<S0, S0 / 4, S0 / 4, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
-                        default: break;  // the translator only emits the cases above
-                    }
-                    break;
-                }
-                case N_AFFINE:
-                    FNET_BY_SIZE(o.si, (affine_op<S0, S>(M, o.scale, o.bias)));
-                    break;
-                case N_TRANSPOSE:
-                    FNET_BY_SIZE(o.si, (transpose_op<S0, S>(M, tile, lane)));
-                    break;
-                case N_STASH:
-                    FNET_BY_SIZE(o.si, (stash_store<S0, S>(tm_warp + o.slot * 128, M)));
-                    break;
-                case N_UNSTASH:
-                    FNET_BY_SIZE(o.si, (stash_load<S0, S, false>(tm_warp + o.slot * 128, M, 0ull)));
-                    break;
-                case N_ADD:
-                    FNET_BY_SIZE(o.si, (stash_load<S0, S, true>(tm_warp + o.slot * 128, M, pk(o.scale, o.scale))));
-                    break;
-                case N_RELU: {
-                    if (o.si == S0) {  // two stages: rows [0, S0/2) from the pair's first row, the rest from the second
-                        const int lx = lane < S0 ? lane : S0 - 1;
-                        {
-                            const unsigned buf = stage_l % NST;
-                            mbar_wait(&full[buf], (stage_l / NST) & 1);
-                            const float4 *sb = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE) + lx;
-                            relu_rows<S0, S0, 0, S0 / 2>(M, sb + wi * o.half, sb + (kTileI / 2 + wj) * o.half);
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&empty[buf]);
-                            ++stage_l;
-                        }
-                        {
-                            const unsigned buf = stage_l % NST;
-                            mbar_wait(&full[buf], (stage_l / NST) & 1);
-                            const float4 *sb = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE) + lx - o.half;
-                            relu_rows<S0, S0, S0 / 2, S0>(M, sb + wi * o.half, sb + (kTileI / 2 + wj) * o.half);
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&empty[buf]);
-                            ++stage_l;
-                        }
-                    } else {
+            const NOp nxt = p.ops[k + 1 < p.n_ops ? k + 1 : k];  // descriptor of the next op: fetched under this op's work
+#define FNET_3(CODE, CALL)                                              \
+    case CODE + 0: { constexpr int S = S0; CALL; break; }               \
+    case CODE + 1: { constexpr int S = S0 / 2; CALL; break; }           \
+    case CODE + 2: { constexpr int S = S0 / 4; CALL; break; }
+            switch (o.code) {
+                case C_CONV + 0: conv_op<S0, S0, S0, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
+                case C_CONV + 1: conv_op<S0, S0, S0, 1, 2, 1>(M, tile, lane, o.scale, o.bias); break;
+                case C_CONV + 2: conv_op<S0, S0, S0, 2, 2, 1>(M, tile, lane, o.scale, o.bias); break;
+                case C_CONV + 3: conv_op<S0, S0, S0, 3, 3, 1>(M, tile, lane, o.scale, o.bias); break;
+                case C_CONV + 4: conv_op<S0, S0, S0 / 2, 1, 1, 2>(M, tile, lane, o.scale, o.bias); break;
+                case C_CONV + 5: conv_op<S0, S0, S0 / 2, 0, 0, 2>(M, tile, lane, o.scale, o.bias); break;
+                case C_CONV + 6: conv_op<S0, S0 / 2, S0 / 2, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
+                case C_CONV + 7: conv_op<S0, S0 / 2, S0 / 4, 1, 1, 2>(M, tile, lane, o.scale, o.bias); break;
+                case C_CONV + 8: conv_op<S0, S0 / 2, S0 / 4, 0, 0, 2>(M, tile, lane, o.scale, o.bias); break;
+                case C_CONV + 9: conv_op<S0, S0 / 4, S0 / 4, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
+                FNET_3(C_AFFINE, (affine_op<S0, S>(M, o.scale, o.bias)))
+                FNET_3(C_TRANSPOSE, (transpose_op<S0, S>(M, tile, lane)))
+                FNET_3(C_STASH, (stash_store<S0, S>(tm_warp + o.slot * 128, M)))
+                FNET_3(C_UNSTASH, (stash_load<S0, S, false>(tm_warp + o.slot * 128, M, 0ull)))
+                FNET_3(C_ADD, (stash_load<S0, S, true>(tm_warp + o.slot * 128, M, pk(o.scale, o.scale))))
+                FNET_3(C_DENSE, (dense_op<S0, S>(M, lane, o.scale, o.bias, tot)))
+                case C_RELU + 0: {  // two stages: rows [0, S0/2) from the pair's first row, the rest from the second
+                    const int lx = lane < S0 ? lane : S0 - 1;
+                    {
                         const unsigned buf = stage_l % NST;
                         mbar_wait(&full[buf], (stage_l / NST) & 1);
-                        const float4 *st4 = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE);
-                        if (o.si == S0 / 2) {
-                            constexpr int S = S0 / 2;
-                            const float4 *sb = st4 + (lane < S ? lane : S - 1);
-                            relu_rows<S0, S, 0, S>(M, sb + wi * 2 * o.half, sb + (kTileI / 2 + wj) * 2 * o.half);
-                        } else {
-                            constexpr int S = S0 / 4;
-                            const float4 *sb = st4 + (lane < S ? lane : S - 1);
-                            relu_rows<S0, S, 0, S>(M, sb + wi * 2 * o.half, sb + (kTileI / 2 + wj) * 2 * o.half);
-                        }
+                        const float4 *sb = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE) + lx;
+                        relu_rows<S0, S0, 0, S0 / 2>(M, sb + wi * o.half, sb + (kTileI / 2 + wj) * o.half);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[buf]);
+                        ++stage_l;
+                    }
+                    {
+                        const unsigned buf = stage_l % NST;
+                        mbar_wait(&full[buf], (stage_l / NST) & 1);
+                        const float4 *sb = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE) + lx - o.half;
+                        relu_rows<S0, S0, S0 / 2, S0>(M, sb + wi * o.half, sb + (kTileI / 2 + wj) * o.half);
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&empty[buf]);
                         ++stage_l;
                     }
                     break;
                 }
-                case N_DENSE:
-                    FNET_BY_SIZE(o.si, (dense_op<S0, S>(M, lane, o.scale, o.bias, tot)));
+                case C_RELU + 1:
+                case C_RELU + 2: {
+                    const unsigned buf = stage_l % NST;
+                    mbar_wait(&full[buf], (stage_l / NST) & 1);
+                    const float4 *st4 = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE);
+                    if (o.code == C_RELU + 1) {
+                        constexpr int S = S0 / 2;
+                        const float4 *sb = st4 + (lane < S ? lane : S - 1);
+                        relu_rows<S0, S, 0, S>(M, sb + wi * 2 * o.half, sb + (kTileI / 2 + wj) * 2 * o.half);
+                    } else {
+                        constexpr int S = S0 / 4;
+                        const float4 *sb = st4 + (lane < S ? lane : S - 1);
+                        relu_rows<S0, S, 0, S>(M, sb + wi * 2 * o.half, sb + (kTileI / 2 + wj) * 2 * o.half);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[buf]);
+                    ++stage_l;
                     break;
-                case T_AFFINE:
+                }
+                case C_TAFFINE:
 #pragma unroll
                     for (int q = 0; q < 4; ++q) tot[q] = fmaf(tot[q], o.scale, o.bias);
                     break;
-                case T_RELU: {
+                case C_TRELU: {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int i = min(i_base + wi * 2 + (q >> 1), p.N1 - 1), j = min(j_base + wj * 2 + (q & 1), p.N2 - 1);
@@ -619,6 +624,8 @@ __global__ void __launch_bounds__(kThreads, 1) fnet_kernel(const __grid_constant
                 }
                 default: break;
             }
+#undef FNET_3
+            o = nxt;
         }
 
         if (lane < 4) {
@@ -865,7 +872,28 @@ FNetPlan *fnet_plan_create(const Plan *plan_const) {
     FNetPlan *fp = new FNetPlan();
     fp->S0 = S0;
     fp->n_ops = (int)tr.out.size();
-    for (int k = 0; k < fp->n_ops; ++k) fp->ops[k] = tr.out[k];
+    for (int k = 0; k < fp->n_ops; ++k) {
+        NOp n = tr.out[k];
+        const int sc = n.si == S0 ? 0 : (n.si == S0 / 2 ? 1 : 2);  // size class of the op's input
+        switch (n.kind) {
+            case N_CONV: {
+                const int v = n.st == 1 ? (n.lo == 1 && n.hi == 1 ? 0 : n.lo == 1 && n.hi == 2 ? 1 : n.lo == 2 ? 2 : 3)
+                                        : (n.lo == 1 ? 4 : 5);
+                n.code = C_CONV + (sc == 0 ? v : sc == 1 ? (n.st == 1 ? 6 : (n.lo == 1 ? 7 : 8)) : 9);
+                break;
+            }
+            case N_AFFINE: n.code = C_AFFINE + sc; break;
+            case N_TRANSPOSE: n.code = C_TRANSPOSE + sc; break;
+            case N_STASH: n.code = C_STASH + sc; break;
+            case N_UNSTASH: n.code = C_UNSTASH + sc; break;
+            case N_ADD: n.code = C_ADD + sc; break;
+            case N_DENSE: n.code = C_DENSE + sc; break;
+            case N_RELU: n.code = C_RELU + sc; break;
+            case T_AFFINE: n.code = C_TAFFINE; break;
+            default: n.code = C_TRELU; break;
+        }
+        fp->ops[k] = n;
+    }
     if (S0 == 28) { fp->nst = 4; fp->smem = fnet_smem<28, 4>(); }
     else { fp->nst = 3; fp->smem = fnet_smem<32, 3>(); }
     for (const DevOp &o : plan->ops)
