@@ -1,7 +1,7 @@
 // gram_fused.cu -- register-resident fused Gram kernel for sm_100a.
 //
-// One warp owns a 2 x 2 block of image pairs and keeps their four covariance maps in
-// registers for the whole layer stack: lane = one coordinate of the map, register index = the
+// One warp owns a 2 x 2 block of image pairs (twelve consumer warps per CTA, one CTA per SM, a
+// 4 x 12-image tile) and keeps their four covariance maps in registers for the whole layer stack: lane = one coordinate of the map, register index = the
 // other.  A box convolution is a sliding-window sum along the register axis, a transposition
 // through the warp's private shared-memory tile, and a second sliding-window sum; every layer
 // therefore flips the map between "lane = column" and "lane = row" layout.  The ReLU step is
@@ -33,15 +33,20 @@ namespace cnngp {
 
 namespace {
 
-constexpr int kWarps = 8;                    // consumer warps per CTA
-constexpr int kTileI = 4, kTileJ = 8;        // images per CTA along i and j (2 x 4 warps of 2 x 2)
-constexpr int kImgs = kTileI + kTileJ;       // images per CTA tile
-constexpr int kPairs = kImgs / 2;            // image pairs whose interleaved variance maps are staged per layer
-constexpr int kThreads = (kWarps + 4) * 32;  // + a third warpgroup: the producer warp and three warps that
-                                             // only donate their registers (setmaxnreg)
-constexpr int kRegsProducer = 24, kRegsConsumer = 240;
+// Geometry of one kernel variant: NW consumer warps as 2 x NW/2 warps of 2 x 2 image pairs,
+// plus a fourth/third warpgroup that holds the producer warp and donates registers (setmaxnreg).
+template <int NW>
+struct Geo {
+    static constexpr int kWarps = NW;
+    static constexpr int kTileI = 4, kTileJ = NW;        // images per CTA tile along i and j
+    static constexpr int kImgs = kTileI + kTileJ;
+    static constexpr int kPairs = kImgs / 2;              // image pairs whose interleaved variance maps are staged
+    static constexpr int kThreads = (NW + 4) * 32;
+    static constexpr int kRegsProducer = 24;
+    static constexpr int kRegsConsumer = NW == 8 ? 240 : 160;  // 8*32*240 + 4*32*24 = 12*32*160 + 4*32*24 = 64512
+};
 constexpr int kMaxOps = 40;
-constexpr int kSuperEdge = 512;              // default super-tile edge in images (L2-resident variance maps)
+constexpr int kSuperEdge = 504;              // super-tile edge in images (L2-resident variance maps); 4 | 504, 8 | 504, 12 | 504
 
 enum { F_CONV = 0, F_RELU = 1, F_DENSE = 2 };
 
@@ -135,25 +140,36 @@ __device__ __forceinline__ void tile_load_t(const u64 *tile, u64 (&a)[S], int lx
     for (int r = 0; r < S; ++r) a[r] = tile[lx * PITCH + r];
 }
 
-// Warp w of a CTA tile owns images i0 = 2*(2*ib + wi) + {0,1} and j0 = 2*(4*jb + wj) + {0,1}.
+// Warp w of a CTA tile owns images i0 = 2*(2*ib + wi) + {0,1} and j0 = 2*((NW/2)*jb + wj) + {0,1}.
 // Its four maps live in two packed arrays:  M[0][r] = (i0j0, i1j1),  M[1][r] = (i0j1, i1j0),
 // so that every packed operation multiplies the (i0, i1) pair of one image pair with the
 // (j0, j1) pair -- or its swap -- of another: no broadcasts are needed.
-template <int S, int LO, int HI>
-__global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constant__ FParams p) {
+//
+// Staging: a ring of NST stages.  A ReLU layer's pair-interleaved variance maps arrive in NSPLIT
+// row bands (one stage each), a channel of the tile's images in IMG_PARTS bands.
+template <int S, int LO, int HI, int NW, int NSPLIT, int NST>
+__global__ void __launch_bounds__(Geo<NW>::kThreads, 1) fused_kernel(const __grid_constant__ FParams p) {
+    using G = Geo<NW>;
+    constexpr int kWarps = G::kWarps, kTileI = G::kTileI, kTileJ = G::kTileJ, kImgs = G::kImgs, kPairs = G::kPairs;
     constexpr int P = S * S;
     constexpr int PITCH = S + 1;
+    constexpr int IMG_PARTS = NSPLIT == 4 ? 2 : 1;
+    constexpr int BAND = P / NSPLIT;                  // pixels of one ReLU band
+    constexpr int STAGE_F4 = kPairs * BAND;           // float4 per stage
+    constexpr int IBAND = P / IMG_PARTS;              // pixels of one image band
+    static_assert(S % NSPLIT == 0 && (NSPLIT == 1 || NSPLIT == 2 || NSPLIT == 4), "band split");
+    static_assert(kImgs * IBAND * 4 <= STAGE_F4 * 16, "an image band must fit a stage");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // [2][kPairs][P] float4 variance stage | [kWarps][S*PITCH] u64 transpose tiles | barriers
+    // [NST][kPairs][BAND] float4 stages | [kWarps][S*PITCH] u64 transpose tiles | barriers
     float4 *stage = reinterpret_cast<float4 *>(smem_raw);
-    u64 *tiles = reinterpret_cast<u64 *>(stage + 2 * kPairs * P);
+    u64 *tiles = reinterpret_cast<u64 *>(stage + NST * STAGE_F4);
     uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + kWarps * S * PITCH);
-    uint64_t *full = bars, *empty = bars + 2;
+    uint64_t *full = bars, *empty = bars + NST;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-        mbar_init(&empty[0], kWarps); mbar_init(&empty[1], kWarps);
+#pragma unroll
+        for (int b = 0; b < NST; ++b) { mbar_init(&full[b], 1); mbar_init(&empty[b], kWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -178,51 +194,63 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
     };
 
     if (warp >= kWarps) {
-        // third warpgroup: hand its registers to the consumers; only its first warp works
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
+        // last warpgroup: hand its registers to the consumers; only its first warp works
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::kRegsProducer));
         if (warp != kWarps) return;
-        // ---- producer: one elected thread stages, one pipeline stage ahead, first the tile's
-        // images (one stage per channel) and then each ReLU layer's pair-interleaved
-        // (s_a, s_b, 1/s_a, 1/s_b) maps of the tile's six image pairs.  It runs on across tile
+        // ---- producer: one elected thread stages, up to NST - 1 stages ahead, first the tile's
+        // images (per channel) and then each ReLU layer's pair-interleaved
+        // (s_a, s_b, 1/s_a, 1/s_b) maps of the tile's image pairs.  It runs on across tile
         // boundaries, so the next tile's first stages are in flight while the consumers finish.
         if (lane == 0) {
             unsigned l = 0;  // running stage counter over all tiles of this CTA
             const int last_pi = (p.N1 - 1) >> 1, last_pj = (p.N2 - 1) >> 1;
+            auto acquire = [&](unsigned bytes) -> float4 * {
+                const unsigned buf = l % NST;
+                if (l >= NST) mbar_wait_relaxed(&empty[buf], ((l / NST) - 1) & 1);
+                mbar_arrive_expect_tx(&full[buf], bytes);
+                return stage + buf * STAGE_F4;
+            };
             for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
                 int ib, jb;
                 if (!decode(t, ib, jb)) continue;
                 const int i_base = ib * kTileI, j_base = jb * kTileJ;
                 for (int c = 0; c < p.C; ++c) {
-                    const unsigned buf = l & 1;
-                    if (l >= 2) mbar_wait_relaxed(&empty[buf], ((l >> 1) - 1) & 1);
-                    mbar_arrive_expect_tx(&full[buf], kImgs * P * 4);
-                    float *dst = reinterpret_cast<float *>(stage + buf * kPairs * P);
-                    for (int s = 0; s < kImgs; ++s) {
-                        const float *src;
-                        if (s < kTileI) src = p.x + ((long long)min(i_base + s, p.N1 - 1) * p.C + c) * P;
-                        else src = p.z + ((long long)min(j_base + s - kTileI, p.N2 - 1) * p.C + c) * P;
-                        bulk_g2s(dst + s * P, src, P * 4, &full[buf]);
+                    for (int ip = 0; ip < IMG_PARTS; ++ip) {
+                        float *dst = reinterpret_cast<float *>(acquire(kImgs * IBAND * 4));
+                        uint64_t *bar = &full[l % NST];
+                        for (int s = 0; s < kImgs; ++s) {
+                            const float *src;
+                            if (s < kTileI) src = p.x + ((long long)min(i_base + s, p.N1 - 1) * p.C + c) * P;
+                            else src = p.z + ((long long)min(j_base + s - kTileI, p.N2 - 1) * p.C + c) * P;
+                            bulk_g2s(dst + s * IBAND, src + ip * IBAND, IBAND * 4, bar);
+                        }
+                        ++l;
                     }
-                    ++l;
                 }
                 for (int k = 0; k < p.n_ops; ++k) {
                     if (p.ops[k].kind != F_RELU) continue;
-                    const unsigned buf = l & 1;
-                    if (l >= 2) mbar_wait_relaxed(&empty[buf], ((l >> 1) - 1) & 1);
-                    mbar_arrive_expect_tx(&full[buf], kPairs * P * 16);
-                    float4 *dst = stage + buf * kPairs * P;
                     const long long off = p.aux_f_off + (long long)p.ops[k].aux_off;
-                    for (int s = 0; s < kPairs; ++s) {
-                        // pair s of the tile; its float4 map is split over the two images' rows
-                        const float *base;
-                        long long pr;
-                        if (s < kTileI / 2) { pr = min((i_base >> 1) + s, last_pi); base = p.aux_x; }
-                        else { pr = min((j_base >> 1) + s - kTileI / 2, last_pj); base = p.aux_z; }
-                        const float *src = base + 2 * pr * p.aux_stride + off;
-                        bulk_g2s(dst + s * P, src, P * 8, &full[buf]);
-                        bulk_g2s(dst + s * P + P / 2, src + p.aux_stride, P * 8, &full[buf]);
+                    for (int q = 0; q < NSPLIT; ++q) {
+                        float4 *dst = acquire(STAGE_F4 * 16);
+                        uint64_t *bar = &full[l % NST];
+                        for (int s = 0; s < kPairs; ++s) {
+                            // pair s of the tile; its float4 map is split over the two images' rows
+                            const float *base;
+                            long long pr;
+                            if (s < kTileI / 2) { pr = min((i_base >> 1) + s, last_pi); base = p.aux_x; }
+                            else { pr = min((j_base >> 1) + s - kTileI / 2, last_pj); base = p.aux_z; }
+                            const float *src = base + 2 * pr * p.aux_stride + off;
+                            if (NSPLIT == 1) {
+                                bulk_g2s(dst + s * P, src, P * 8, bar);
+                                bulk_g2s(dst + s * P + P / 2, src + p.aux_stride, P * 8, bar);
+                            } else if (NSPLIT == 2) {
+                                bulk_g2s(dst + s * BAND, src + q * p.aux_stride, BAND * 16, bar);
+                            } else {
+                                bulk_g2s(dst + s * BAND, src + (q >> 1) * p.aux_stride + (q & 1) * BAND * 4, BAND * 16, bar);
+                            }
+                        }
+                        ++l;
                     }
-                    ++l;
                 }
             }
         }
@@ -230,8 +258,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
     }
 
     // ---- consumers ------------------------------------------------------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsConsumer));
-    const int wi = warp >> 2, wj = warp & 3;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(G::kRegsConsumer));
+    const int wi = warp / (NW / 2), wj = warp % (NW / 2);
     const int lx = lane < S ? lane : S - 1;  // clamped lane for loads
     u64 *tile = tiles + warp * S * PITCH;
     unsigned stage_l = 0;  // running stage counter, in step with the producer's
@@ -254,21 +282,26 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
 #pragma unroll
                 for (int r = 0; r < S; ++r) M[h][r] = 0ull;
             for (int c = 0; c < p.C; ++c) {
-                const unsigned buf = stage_l & 1;
-                mbar_wait(&full[buf], (stage_l >> 1) & 1);
-                const float *sb = reinterpret_cast<const float *>(stage + buf * kPairs * P) + lx;
-                const float *x0 = sb + (wi * 2 + 0) * P, *x1 = sb + (wi * 2 + 1) * P;
-                const float *z0 = sb + (kTileI + wj * 2 + 0) * P, *z1 = sb + (kTileI + wj * 2 + 1) * P;
 #pragma unroll
-                for (int r = 0; r < S; ++r) {
-                    const float a0 = x0[r * S], a1 = x1[r * S], b0 = z0[r * S], b1 = z1[r * S];
-                    const u64 A = pk(a0, a1);
-                    M[0][r] = fma2(A, pk(b0, b1), M[0][r]);
-                    M[1][r] = fma2(A, pk(b1, b0), M[1][r]);
+                for (int ip = 0; ip < IMG_PARTS; ++ip) {
+                    const unsigned buf = stage_l % NST;
+                    mbar_wait(&full[buf], (stage_l / NST) & 1);
+                    const float *sb = reinterpret_cast<const float *>(stage + buf * STAGE_F4) + lx;
+                    const float *x0 = sb + (wi * 2 + 0) * IBAND, *x1 = sb + (wi * 2 + 1) * IBAND;
+                    const float *z0 = sb + (kTileI + wj * 2 + 0) * IBAND, *z1 = sb + (kTileI + wj * 2 + 1) * IBAND;
+                    constexpr int R = S / IMG_PARTS;
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr) {
+                        const int r = ip * R + rr;
+                        const float a0 = x0[rr * S], a1 = x1[rr * S], b0 = z0[rr * S], b1 = z1[rr * S];
+                        const u64 A = pk(a0, a1);
+                        M[0][r] = fma2(A, pk(b0, b1), M[0][r]);
+                        M[1][r] = fma2(A, pk(b1, b0), M[1][r]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[buf]);
+                    ++stage_l;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[buf]);
-                ++stage_l;
             }
             if (p.C > 1) {
                 const u64 IC = pk(p.inv_c, p.inv_c);
@@ -304,37 +337,42 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
 #pragma unroll
                     for (int r = 0; r < S; ++r) M[h][r] = fma2(M[h][r], SC, BI);
             } else if (o.kind == F_RELU) {
-                const unsigned buf = stage_l & 1;
-                mbar_wait(&full[buf], (stage_l >> 1) & 1);
-                const float4 *sb = stage + buf * kPairs * P + lx;
-                const float4 *ai = sb + wi * P, *bj = sb + (kTileI / 2 + wj) * P;
 #pragma unroll
-                for (int r = 0; r < S; ++r) {
-                    const float4 A = ai[r * S], B = bj[r * S];
-                    const u64 SA = pk(A.x, A.y), RA = pk(A.z, A.w);
+                for (int q = 0; q < NSPLIT; ++q) {
+                    const unsigned buf = stage_l % NST;
+                    mbar_wait(&full[buf], (stage_l / NST) & 1);
+                    const float4 *sb = stage + buf * STAGE_F4 + lx;
+                    const float4 *ai = sb + wi * BAND, *bj = sb + (kTileI / 2 + wj) * BAND;
+                    constexpr int R = S / NSPLIT;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const u64 SB = h ? pk(B.y, B.x) : pk(B.x, B.y);
-                        const u64 RB = h ? pk(B.w, B.z) : pk(B.z, B.w);
-                        float c0, c1;
-                        upk(M[h][r], c0, c1);
-                        const u64 NC = pk(neg_abs(c0), neg_abs(c1));
-                        const u64 D = fma2(SA, SB, NC);               // s - |c|
-                        const u64 E = fma2(NC, mul2(RA, RB), ONE);    // e = 1 - |c|/s, independent of D
-                        float e0, e1;
-                        upk(E, e0, e1);
-                        const u64 W = mul2(D, pk(sqrt_approx(fabsf(e0)), sqrt_approx(fabsf(e1))));
-                        u64 H = fma2(C5, E, C4);
-                        H = fma2(H, E, C3);
-                        H = fma2(H, E, C2);
-                        H = fma2(H, E, C1);
-                        H = fma2(H, E, C0);
-                        M[h][r] = fma2(W, H, pk(fmaxf(c0, 0.f), fmaxf(c1, 0.f)));
+                    for (int rr = 0; rr < R; ++rr) {
+                        const int r = q * R + rr;
+                        const float4 A = ai[rr * S], B = bj[rr * S];
+                        const u64 SA = pk(A.x, A.y), RA = pk(A.z, A.w);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const u64 SB = h ? pk(B.y, B.x) : pk(B.x, B.y);
+                            const u64 RB = h ? pk(B.w, B.z) : pk(B.z, B.w);
+                            float c0, c1;
+                            upk(M[h][r], c0, c1);
+                            const u64 NC = pk(neg_abs(c0), neg_abs(c1));
+                            const u64 D = fma2(SA, SB, NC);               // s - |c|
+                            const u64 E = fma2(NC, mul2(RA, RB), ONE);    // e = 1 - |c|/s, independent of D
+                            float e0, e1;
+                            upk(E, e0, e1);
+                            const u64 W = mul2(D, pk(sqrt_approx(fabsf(e0)), sqrt_approx(fabsf(e1))));
+                            u64 H = fma2(C5, E, C4);
+                            H = fma2(H, E, C3);
+                            H = fma2(H, E, C2);
+                            H = fma2(H, E, C1);
+                            H = fma2(H, E, C0);
+                            M[h][r] = fma2(W, H, pk(fmaxf(c0, 0.f), fmaxf(c1, 0.f)));
+                        }
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[buf]);
+                    ++stage_l;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[buf]);
-                ++stage_l;
             } else {  // F_DENSE: whole-map sum, scale, bias -> the kernel entry
                 float tot[4];
 #pragma unroll
@@ -373,6 +411,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const __grid_constan
             }
         }
     }
+}
+
+template <int NW, int NSPLIT, int NST>
+constexpr size_t fused_smem(int S) {
+    return (size_t)NST * (Geo<NW>::kPairs * S * S / NSPLIT) * 16 + (size_t)NW * S * (S + 1) * 8 + 2 * NST * 8;
 }
 
 }  // namespace
@@ -447,11 +490,57 @@ FusedPlan *fused_plan_create(const Plan *plan_const) {
         for (DevOp &o : plan->ops) o.aux_t = 0;
         return nullptr;
     }
-    fp.smem = (size_t)2 * kImgs * S * S * 8 + (size_t)kWarps * S * (S + 1) * 8 + 64;
     return new FusedPlan(fp);
 }
 
 void fused_plan_destroy(FusedPlan *fp) { delete fp; }
+
+namespace {
+
+struct Variant { int nw, nsplit, nst; };
+
+template <int NW, int NSPLIT, int NST>
+int launch_variant(const FusedPlan *fp, FParams &p, int64_t N1, int64_t N2, cudaStream_t stream) {
+    using G = Geo<NW>;
+    p.nbi = (int)((N1 + G::kTileI - 1) / G::kTileI);
+    p.nbj = (int)((N2 + G::kTileJ - 1) / G::kTileJ);
+    long long n_super;
+    int edge = kSuperEdge;
+    if (const char *e = getenv("CNNGP_SUPER_EDGE")) { const int v = atoi(e); if (v >= 24 && v % 24 == 0) edge = v; }
+    const int super_i = edge / G::kTileI, super_j = edge / G::kTileJ;
+    if (p.nbi <= super_i && p.nbj <= super_j) {  // one (possibly small) super-tile
+        p.sti = p.nbi; p.stj = p.nbj; p.nst_j = 1; p.nst = 1;
+        n_super = 1;
+    } else {
+        p.sti = super_i; p.stj = super_j;
+        const int nsi = (p.nbi + super_i - 1) / super_i, nsj = (p.nbj + super_j - 1) / super_j;
+        p.nst_j = nsj;
+        p.nst = nsi > nsj ? nsi : nsj;
+        n_super = p.symmetric ? (long long)p.nst * (p.nst + 1) / 2 : (long long)nsi * nsj;
+    }
+    p.n_tiles = n_super * p.sti * p.stj;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);  // persistent: one CTA per SM
+    void (*kern)(const FParams) = nullptr;
+    constexpr bool kDefault = NW == 12 && NSPLIT == 2 && NST == 2;
+    if (fp->lo == 3 && fp->hi == 3) kern = fused_kernel<28, 3, 3, NW, NSPLIT, NST>;
+    else if (kDefault && fp->lo == 1 && fp->hi == 1) kern = fused_kernel<28, 1, 1, 12, 2, 2>;
+    else if (kDefault && fp->lo == 1 && fp->hi == 2) kern = fused_kernel<28, 1, 2, 12, 2, 2>;
+    else if (kDefault && fp->lo == 2 && fp->hi == 2) kern = fused_kernel<28, 2, 2, 12, 2, 2>;
+    else if (kDefault) kern = fused_kernel<28, -1, -1, 12, 2, 2>;
+    else return -1;  // experimental variants exist for the 7x7 window only: caller falls back to the default
+    const size_t smem = fused_smem<NW, NSPLIT, NST>(28);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error(std::string("fused cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 7; }
+    kern<<<grid, G::kThreads, smem, stream>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error(std::string("fused kernel launch: ") + cudaGetErrorString(e)); return 9; }
+    return 0;
+}
+
+}  // namespace
 
 int launch_fused_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2,
                       int32_t C, const void *d_aux_x, const void *d_aux_z, int32_t same, int32_t diag,
@@ -470,40 +559,20 @@ int launch_fused_gram(const Plan *plan, const void *d_x, int64_t N1, const void 
     p.out = (float *)d_out; p.ld_out = ld_out;
     p.symmetric = symmetric ? 1 : 0;
     p.kdiag = (const float *)d_kdiag;
-    p.nbi = (int)((N1 + kTileI - 1) / kTileI);
-    p.nbj = (int)((N2 + kTileJ - 1) / kTileJ);
-    long long n_super;
-    int edge = kSuperEdge;
-    if (const char *e = getenv("CNNGP_SUPER_EDGE")) { const int v = atoi(e); if (v >= 32 && v % 32 == 0) edge = v; }
-    const int super_i = edge / kTileI, super_j = edge / kTileJ;
-    if (p.nbi <= super_i && p.nbj <= super_j) {  // one (possibly small) super-tile
-        p.sti = p.nbi; p.stj = p.nbj; p.nst_j = 1; p.nst = 1;
-        n_super = 1;
-    } else {
-        p.sti = super_i; p.stj = super_j;
-        const int nsi = (p.nbi + super_i - 1) / super_i, nsj = (p.nbj + super_j - 1) / super_j;
-        p.nst_j = nsj;
-        p.nst = nsi > nsj ? nsi : nsj;
-        n_super = p.symmetric ? (long long)p.nst * (p.nst + 1) / 2 : (long long)nsi * nsj;
-    }
-    p.n_tiles = n_super * p.sti * p.stj;
     p.inv_c = 1.0f / (float)C;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);  // persistent: one CTA per SM
-    void (*kern)(const FParams) = nullptr;
-    if (fp->lo == 3 && fp->hi == 3) kern = fused_kernel<28, 3, 3>;
-    else if (fp->lo == 1 && fp->hi == 1) kern = fused_kernel<28, 1, 1>;
-    else if (fp->lo == 1 && fp->hi == 2) kern = fused_kernel<28, 1, 2>;
-    else if (fp->lo == 2 && fp->hi == 2) kern = fused_kernel<28, 2, 2>;
-    else kern = fused_kernel<28, -1, -1>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem);
-    if (e != cudaSuccess) { set_error(std::string("fused cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 7; }
-    kern<<<grid, kThreads, fp->smem, (cudaStream_t)stream>>>(p);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) { set_error(std::string("fused kernel launch: ") + cudaGetErrorString(e)); return 9; }
-    return 0;
+    // kernel variant: consumer warps, ReLU bands per layer, ring depth.  Default 12 warps (three
+    // per SM sub-partition at 160 registers), two bands per layer, two stages: measured 247 M
+    // pairs/s on the 10k x 10k headline job against 228 M for the 8-warp / 240-register variant.
+    // CNNGP_FUSED_VARIANT=nw,nsplit,nst selects the others (7x7 window only) for comparison.
+    Variant v{12, 2, 2};
+    if (const char *e = getenv("CNNGP_FUSED_VARIANT")) sscanf(e, "%d,%d,%d", &v.nw, &v.nsplit, &v.nst);
+    int rc = -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (v.nw == 12 && v.nsplit == 4 && v.nst == 4) rc = launch_variant<12, 4, 4>(fp, p, N1, N2, st);
+    else if (v.nw == 8 && v.nsplit == 1 && v.nst == 2) rc = launch_variant<8, 1, 2>(fp, p, N1, N2, st);
+    else if (v.nw == 8 && v.nsplit == 2 && v.nst == 4) rc = launch_variant<8, 2, 4>(fp, p, N1, N2, st);
+    if (rc < 0) rc = launch_variant<12, 2, 2>(fp, p, N1, N2, st);
+    return rc;
 }
 
 }  // namespace cnngp
