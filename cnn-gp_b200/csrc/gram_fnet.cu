@@ -42,12 +42,17 @@ namespace cnngp {
 namespace {
 using namespace fusedk;
 
-constexpr int kWarps = 8;
-constexpr int kTileI = 4, kTileJ = 8;
-constexpr int kImgs = kTileI + kTileJ;
-constexpr int kPairs = kImgs / 2;
-constexpr int kThreads = (kWarps + 4) * 32;
-constexpr int kRegsProducer = 24, kRegsConsumer = 240;
+// NW consumer warps as 2 x NW/2 warps of 2 x 2 image pairs, plus a warpgroup holding the producer
+template <int NW>
+struct NGeo {
+    static constexpr int kWarps = NW;
+    static constexpr int kTileI = 4, kTileJ = NW;
+    static constexpr int kImgs = kTileI + kTileJ;
+    static constexpr int kPairs = kImgs / 2;
+    static constexpr int kThreads = (NW + 4) * 32;
+    static constexpr int kRegsProducer = 24;
+    static constexpr int kRegsConsumer = NW == 8 ? 240 : 160;
+};
 constexpr int kMaxNOps = 192;
 constexpr int kTmemCols = 512;
 
@@ -127,6 +132,26 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                  : "r"(taddr)
                  : "memory");
 }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, const uint32_t (&r)[2]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t (&r)[2]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_landed4(uint32_t (&r)[4]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]) : : "memory");
+}
+__device__ __forceinline__ void tmem_landed2(uint32_t (&r)[2]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]) : : "memory");
+}
 __device__ __forceinline__ void tmem_landed16(uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
@@ -142,62 +167,96 @@ __device__ __forceinline__ void tmem_landed8(uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// whole map set (two packed arrays, first S entries each) -> tensor memory; an array takes 64
-// columns.  Entries are moved in groups of 8 (x16); a remainder of up to 4 entries as x8, a
-// larger one as a full group (the array always has the registers, S0 >= 8 * ceil(S / 8)).
+// whole map set (two packed arrays, first S entries each) -> tensor memory.  Array h starts at
+// column h * astride and takes exactly 2 S columns: entries move in groups of 8 (x16), then 4
+// (x8), 2 (x4), 1 (x2).
 template <int S0, int S>
-__device__ __forceinline__ void stash_store(uint32_t tbase, const u64 (&M)[2][S0]) {
-    constexpr int FULL = S / 8, REM = S % 8, G16 = FULL + (REM > 4 ? 1 : 0);
+__device__ __forceinline__ void stash_store(uint32_t tbase, int astride, const u64 (&M)[2][S0]) {
+    constexpr int G8 = S / 8, R8 = S % 8, B4 = G8 * 8, B2 = B4 + (R8 & 4), B1 = B2 + (R8 & 2);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
+        const uint32_t ta = tbase + h * astride;
 #pragma unroll
-        for (int c = 0; c < G16; ++c) {
+        for (int c = 0; c < G8; ++c) {
             uint32_t r[16];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) split64(M[h][(c * 8 + q) % S0], r[2 * q], r[2 * q + 1]);
-            tmem_st16(tbase + h * 64 + c * 16, r);
+            for (int q = 0; q < 8; ++q) split64(M[h][c * 8 + q], r[2 * q], r[2 * q + 1]);
+            tmem_st16(ta + c * 16, r);
         }
-        if (REM > 0 && REM <= 4) {
+        if (R8 & 4) {
             uint32_t r[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) split64(M[h][(FULL * 8 + q) % S0], r[2 * q], r[2 * q + 1]);
-            tmem_st8(tbase + h * 64 + FULL * 16, r);
+            for (int q = 0; q < 4; ++q) split64(M[h][(B4 + q) % S0], r[2 * q], r[2 * q + 1]);
+            tmem_st8(ta + 2 * B4, r);
+        }
+        if (R8 & 2) {
+            uint32_t r[4];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) split64(M[h][(B2 + q) % S0], r[2 * q], r[2 * q + 1]);
+            tmem_st4(ta + 2 * B2, r);
+        }
+        if (R8 & 1) {
+            uint32_t r[2];
+            split64(M[h][B1 % S0], r[0], r[1]);
+            tmem_st2(ta + 2 * B1, r);
         }
     }
     tmem_wait_st();
 }
 
-// M = stash (ADD == false) or M = stash * alpha + M (ADD == true); all loads of one array are
-// in flight together
+// M = stash (ADD == false) or M = stash * alpha + M + beta (ADD == true); all loads of one array
+// are in flight together
 template <int S0, int S, bool ADD>
-__device__ __forceinline__ void stash_load(uint32_t tbase, u64 (&M)[2][S0], u64 alpha) {
-    constexpr int FULL = S / 8, REM = S % 8, G16 = FULL + (REM > 4 ? 1 : 0);
+__device__ __forceinline__ void stash_load(uint32_t tbase, int astride, u64 (&M)[2][S0], float alpha_f, float beta_f) {
+    constexpr int G8 = S / 8, R8 = S % 8, B4 = G8 * 8, B2 = B4 + (R8 & 4), B1 = B2 + (R8 & 2);
+    const u64 alpha = pk(alpha_f, alpha_f);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        uint32_t t[G16 > 0 ? G16 : 1][16];
-        uint32_t t8[8];
+        const uint32_t ta = tbase + h * astride;
+        uint32_t t[G8 > 0 ? G8 : 1][16];
+        uint32_t t8[8], t4[4], t2[2];
 #pragma unroll
-        for (int c = 0; c < G16; ++c) tmem_ld16(tbase + h * 64 + c * 16, t[c]);
-        if (REM > 0 && REM <= 4) tmem_ld8(tbase + h * 64 + FULL * 16, t8);
+        for (int c = 0; c < G8; ++c) tmem_ld16(ta + c * 16, t[c]);
+        if (R8 & 4) tmem_ld8(ta + 2 * B4, t8);
+        if (R8 & 2) tmem_ld4(ta + 2 * B2, t4);
+        if (R8 & 1) tmem_ld2(ta + 2 * B1, t2);
 #pragma unroll
-        for (int c = 0; c < G16; ++c) {
+        for (int c = 0; c < G8; ++c) {
             tmem_landed16(t[c]);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                if (c * 8 + q < S) {
-                    const u64 v = join64(t[c][2 * q], t[c][2 * q + 1]);
-                    M[h][c * 8 + q] = ADD ? fma2(v, alpha, M[h][c * 8 + q]) : v;
-                }
+                const u64 v = join64(t[c][2 * q], t[c][2 * q + 1]);
+                M[h][c * 8 + q] = ADD ? fma2(v, alpha, M[h][c * 8 + q]) : v;
             }
         }
-        if (REM > 0 && REM <= 4) {
+        if (R8 & 4) {
             tmem_landed8(t8);
 #pragma unroll
-            for (int q = 0; q < REM; ++q) {
+            for (int q = 0; q < 4; ++q) {
                 const u64 v = join64(t8[2 * q], t8[2 * q + 1]);
-                M[h][FULL * 8 + q] = ADD ? fma2(v, alpha, M[h][FULL * 8 + q]) : v;
+                M[h][(B4 + q) % S0] = ADD ? fma2(v, alpha, M[h][(B4 + q) % S0]) : v;
             }
         }
+        if (R8 & 2) {
+            tmem_landed4(t4);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const u64 v = join64(t4[2 * q], t4[2 * q + 1]);
+                M[h][(B2 + q) % S0] = ADD ? fma2(v, alpha, M[h][(B2 + q) % S0]) : v;
+            }
+        }
+        if (R8 & 1) {
+            tmem_landed2(t2);
+            const u64 v = join64(t2[0], t2[1]);
+            M[h][B1 % S0] = ADD ? fma2(v, alpha, M[h][B1 % S0]) : v;
+        }
+    }
+    if (ADD && beta_f != 0.f) {  // aliased 1 x 1 convolution with a bias (uniform branch)
+        const u64 beta = pk(beta_f, beta_f);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int r = 0; r < S; ++r) M[h][r] = add2(M[h][r], beta);
     }
 }
 
@@ -396,11 +455,19 @@ __device__ __forceinline__ void dense_op(const u64 (&M)[2][S0], int lane, float 
     }
 }
 
-template <int S0, int NST>
-__global__ void __launch_bounds__(kThreads, 1) fnet_kernel(const __grid_constant__ NParams p) {
+template <int S0, int NW, int NST>
+__global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __grid_constant__ NParams p) {
+    using G = NGeo<NW>;
+    constexpr int kWarps = G::kWarps, kTileI = G::kTileI, kTileJ = G::kTileJ, kImgs = G::kImgs, kPairs = G::kPairs;
     constexpr int P0 = S0 * S0;
     constexpr int PITCH = S0 + 1;
-    constexpr int STAGE = 48 * P0;  // bytes: kImgs images of one channel == kPairs half maps of float4
+    constexpr int STAGE = kImgs * P0 * 4;  // bytes: kImgs images of one channel == kPairs half maps of float4
+    // tensor-memory window of a warp: 8 warps: 256 columns, slots at 0 / 128 with 64 columns per
+    // array; 12 warps (three per lane quadrant): 6 S0 columns, slot 0 (full size) at 0 with 2 S0
+    // per array, slot 1 (at most half size) at 4 S0 with S0 per array
+    constexpr int TM_WARP = NW == 8 ? 256 : 6 * S0, TM_SLOT1 = NW == 8 ? 128 : 4 * S0;
+    constexpr int TM_A0 = NW == 8 ? 64 : 2 * S0, TM_A1 = NW == 8 ? 64 : S0;
+    static_assert((NW / 4) * TM_WARP <= kTmemCols, "tensor-memory budget");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *stage = smem_raw;
     u64 *tiles = reinterpret_cast<u64 *>(smem_raw + (size_t)NST * STAGE);
@@ -444,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, 1) fnet_kernel(const __grid_constant
     };
 
     if (warp >= kWarps) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsProducer));
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::kRegsProducer));
         if (warp != kWarps) return;
         // ---- producer --------------------------------------------------------------------
         if (lane == 0) {
@@ -502,11 +569,11 @@ __global__ void __launch_bounds__(kThreads, 1) fnet_kernel(const __grid_constant
     }
 
     // ---- consumers ------------------------------------------------------------------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsConsumer));
-    const int wi = warp >> 2, wj = warp & 3;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(G::kRegsConsumer));
+    const int wi = warp / (NW / 2), wj = warp % (NW / 2);
     u64 *tile = tiles + warp * S0 * PITCH;
-    // this warp's tensor-memory window: lanes of quadrant warp % 4, 256 columns, two slots of 128
-    const uint32_t tm_warp = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 256);
+    // this warp's tensor-memory window: lanes of quadrant warp % 4
+    const uint32_t tm_warp = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TM_WARP);
     unsigned stage_l = 0;
 
     for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
@@ -563,9 +630,9 @@ __global__ void __launch_bounds__(kThreads, 1) fnet_kernel(const __grid_constant
                 case C_CONV + 9: conv_op<S0, S0 / 4, S0 / 4, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
                 FNET_3(C_AFFINE, (affine_op<S0, S>(M, o.scale, o.bias)))
                 FNET_3(C_TRANSPOSE, (transpose_op<S0, S>(M, tile, lane)))
-                FNET_3(C_STASH, (stash_store<S0, S>(tm_warp + o.slot * 128, M)))
-                FNET_3(C_UNSTASH, (stash_load<S0, S, false>(tm_warp + o.slot * 128, M, 0ull)))
-                FNET_3(C_ADD, (stash_load<S0, S, true>(tm_warp + o.slot * 128, M, pk(o.scale, o.scale))))
+                FNET_3(C_STASH, (stash_store<S0, S>(tm_warp + o.slot * TM_SLOT1, o.slot ? TM_A1 : TM_A0, M)))
+                FNET_3(C_UNSTASH, (stash_load<S0, S, false>(tm_warp + o.slot * TM_SLOT1, o.slot ? TM_A1 : TM_A0, M, 1.f, 0.f)))
+                FNET_3(C_ADD, (stash_load<S0, S, true>(tm_warp + o.slot * TM_SLOT1, o.slot ? TM_A1 : TM_A0, M, o.scale, o.bias)))
                 FNET_3(C_DENSE, (dense_op<S0, S>(M, lane, o.scale, o.bias, tot)))
                 case C_RELU + 0: {  // two stages: rows [0, S0/2) from the pair's first row, the rest from the second
                     const int lx = lane < S0 ? lane : S0 - 1;
@@ -648,7 +715,7 @@ __global__ void __launch_bounds__(kThreads, 1) fnet_kernel(const __grid_constant
 
     // all consumers are done with tensor memory before the allocating warp frees it
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    asm volatile("bar.sync 1, %0;" ::"n"(kWarps * 32) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -665,6 +732,7 @@ struct FNetPlan {
     size_t smem = 0;
     int nst = 0;
     int fused_row_floats = 0;  // floats per image the Gram kernel reads (super-tile sizing)
+    int nw = 8;                // consumer warps of the kernel variant
 };
 
 namespace {
@@ -688,9 +756,16 @@ struct Translator {
     std::vector<NOp> out;
     bool ok = true;
     // per program slot
-    struct Slot { bool valid = false; int size = 0; int orient = 0; float pend = 1.f; bool in_regs = false; int tm = -1; };
+    // `pend`: the stored values are pend x the true ones.  A slot may be an ALIAS of a stashed map:
+    // true(slot) = a_scale * true(stash) + a_bias, where the stash holds a_pend x its true values
+    // (a 1 x 1 convolution, Mixture scaling or copy of a map that stays live is never materialised).
+    struct Slot {
+        bool valid = false; int size = 0; int orient = 0; float pend = 1.f; bool in_regs = false; int tm = -1;
+        bool alias = false; float a_scale = 1.f, a_bias = 0.f;
+    };
     std::vector<Slot> slot;
     int tm_owner[2] = {-1, -1};
+    int slot1_max = 0;  // largest map edge ever stashed in tensor-memory slot 1
 
     Translator(const std::vector<DevOp> &o, int n_slots, int s0) : ops(o), S0(s0), slot(n_slots) {}
 
@@ -709,19 +784,29 @@ struct Translator {
         return -1;
     }
     void emit(NOp n) { out.push_back(n); }
+    void affine(int size, float scale, float bias) {
+        NOp n{}; n.kind = size == 1 ? T_AFFINE : N_AFFINE; n.si = n.so = (short)size; n.scale = scale; n.bias = bias;
+        emit(n);
+    }
+
     void free_tm(int s) {
         if (slot[s].tm >= 0) { tm_owner[slot[s].tm] = -1; slot[s].tm = -1; }
     }
     bool stash(int s) {  // copy the register-resident slot s to a free tensor-memory slot
         if (slot[s].tm >= 0) return true;
         if (slot[s].size == 1) return false;  // 1 x 1 maps live in scalars: no stash
-        for (int t = 0; t < 2; ++t)
+        // full-size maps prefer slot 0, smaller ones slot 1 (the 12-warp kernel's slot 1 is half size)
+        const int first = slot[s].size == S0 ? 0 : 1;
+        for (int q = 0; q < 2; ++q) {
+            const int t = first ^ q;
             if (tm_owner[t] < 0) {
                 NOp n{}; n.kind = N_STASH; n.si = n.so = (short)slot[s].size; n.slot = (short)t;
                 emit(n);
                 tm_owner[t] = s; slot[s].tm = t;
+                if (t == 1 && slot[s].size > slot1_max) slot1_max = slot[s].size;
                 return true;
             }
+        }
         return false;
     }
     // make slot s the register-resident one; k = index of the op about to run
@@ -739,13 +824,13 @@ struct Translator {
         NOp n{}; n.kind = N_UNSTASH; n.si = n.so = (short)slot[s].size; n.slot = (short)slot[s].tm;
         emit(n);
         slot[s].in_regs = true;
+        if (slot[s].alias) {  // materialise: registers hold pend x true(stash); keep that factor
+            if (slot[s].a_scale != 1.f || slot[s].a_bias != 0.f) affine(slot[s].size, slot[s].a_scale, slot[s].a_bias * slot[s].pend);
+            slot[s].alias = false;
+            free_tm(s);  // the stash holds the un-aliased map, not this slot's value
+        }
         return true;
     }
-    void affine(int size, float scale, float bias) {
-        NOp n{}; n.kind = size == 1 ? T_AFFINE : N_AFFINE; n.si = n.so = (short)size; n.scale = scale; n.bias = bias;
-        emit(n);
-    }
-
     bool run(std::vector<DevOp> &mutable_ops, int final_slot) {
         slot[0].valid = true; slot[0].size = S0; slot[0].in_regs = true;
         for (size_t k = 0; k < ops.size(); ++k) {
@@ -758,6 +843,7 @@ struct Translator {
                 if (!slot[o.dst].in_regs && !slot[o.src].in_regs && !to_regs(o.dst, (int)k)) return false;
                 const bool src_live = live_after((int)k, o.src);
                 const int r = slot[o.dst].in_regs ? o.dst : o.src, other = r == o.dst ? o.src : o.dst;
+                if (slot[r].alias) return false;  // cannot happen: aliases are never register-resident
                 if (r == o.src && src_live && !stash(o.src)) return false;
                 if (slot[other].tm < 0) return false;
                 if (slot[r].orient != slot[other].orient) {
@@ -765,10 +851,12 @@ struct Translator {
                     emit(n);
                 }
                 NOp n{}; n.kind = N_ADD; n.si = n.so = (short)slot[r].size; n.slot = (short)slot[other].tm;
-                n.scale = slot[r].pend / slot[other].pend;
+                // registers (pend_r x true) += pend_r x true(other); the stash holds pend_o x true(stash)
+                n.scale = slot[r].pend / slot[other].pend * (slot[other].alias ? slot[other].a_scale : 1.f);
+                n.bias = slot[other].alias ? slot[r].pend * slot[other].a_bias : 0.f;
                 emit(n);
                 Slot d = slot[r];
-                d.orient = slot[other].orient; d.in_regs = true; d.tm = -1; d.valid = true;
+                d.orient = slot[other].orient; d.in_regs = true; d.tm = -1; d.valid = true; d.alias = false;
                 // the sum lives in registers and belongs to dst; stale copies of dst go
                 free_tm(o.dst);
                 slot[o.src].in_regs = false;
@@ -777,6 +865,29 @@ struct Translator {
                 continue;
             }
             // unary ops: CONV, RELU, COPY, SCALE
+            {   // a pointwise op (1 x 1 stride-1 convolution, scaling, copy) whose input stays live is
+                // not materialised: dst becomes an alias of the stashed input
+                bool pointwise = o.opcode == CNNGP_OP_COPY || o.opcode == CNNGP_OP_SCALE;
+                float a_scale = o.opcode == CNNGP_OP_SCALE ? o.scale_f : 1.f, a_bias = 0.f;
+                if (o.opcode == CNNGP_OP_CONV && o.dil == 1 && o.stride == 1 && o.pad == o.t0 && o.ke - 1 == o.pad &&
+                    o.Ho == o.Hi && o.Wo == o.Wi) {
+                    pointwise = true; a_scale = o.scale_f; a_bias = o.bias_f;
+                }
+                Slot &src = slot[o.src];
+                if (pointwise && o.dst != o.src && src.size > 1 && !src.alias && live_after((int)k, o.src) &&
+                    (src.in_regs || src.tm >= 0)) {
+                    if (src.tm < 0 && !stash(o.src)) return false;
+                    if (src.in_regs) {  // the stash moves to dst; src keeps living in registers
+                        free_tm(o.dst);
+                        Slot d = src;
+                        d.in_regs = false; d.alias = true; d.a_scale = a_scale; d.a_bias = a_bias;
+                        tm_owner[src.tm] = o.dst;
+                        src.tm = -1;
+                        slot[o.dst] = d;
+                        continue;
+                    }
+                }
+            }
             if (!to_regs(o.src, (int)k)) return false;
             if (o.dst != o.src && live_after((int)k, o.src)) {
                 if (!stash(o.src)) return false;
@@ -846,9 +957,9 @@ struct Translator {
     }
 };
 
-template <int S0, int NST>
+template <int S0, int NW, int NST>
 constexpr size_t fnet_smem() {
-    return (size_t)NST * 48 * S0 * S0 + (size_t)kWarps * S0 * (S0 + 1) * 8 + (size_t)2 * NST * 8 + 16;
+    return (size_t)NST * NGeo<NW>::kImgs * S0 * S0 * 4 + (size_t)NW * S0 * (S0 + 1) * 8 + (size_t)2 * NST * 8 + 16;
 }
 
 }  // namespace
@@ -894,8 +1005,11 @@ FNetPlan *fnet_plan_create(const Plan *plan_const) {
         }
         fp->ops[k] = n;
     }
-    if (S0 == 28) { fp->nst = 4; fp->smem = fnet_smem<28, 4>(); }
-    else { fp->nst = 3; fp->smem = fnet_smem<32, 3>(); }
+    // 28 x 28: twelve consumer warps when the second tensor-memory slot only ever holds maps of at
+    // most half the edge (3 warps share a 512-column lane quadrant: 3 x (112 + 56) columns)
+    if (S0 == 28 && tr.slot1_max <= S0 / 2 && !getenv("CNNGP_FNET_8WARPS")) { fp->nw = 12; fp->nst = 2; fp->smem = fnet_smem<28, 12, 2>(); }
+    else if (S0 == 28) { fp->nw = 8; fp->nst = 4; fp->smem = fnet_smem<28, 8, 4>(); }
+    else { fp->nw = 8; fp->nst = 3; fp->smem = fnet_smem<32, 8, 3>(); }
     for (const DevOp &o : plan->ops)
         if (o.opcode == CNNGP_OP_RELU) fp->fused_row_floats += 4 * o.aux_half;
     return fp;
@@ -922,12 +1036,13 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
     p.out = (float *)d_out; p.ld_out = ld_out;
     p.symmetric = symmetric ? 1 : 0;
     p.kdiag = (const float *)d_kdiag;
+    const int kTileI = 4, kTileJ = fp->nw;
     p.nbi = (int)((N1 + kTileI - 1) / kTileI);
     p.nbj = (int)((N2 + kTileJ - 1) / kTileJ);
     // super-tiles of side `edge` images: the 2 * edge variance rows a wave of CTAs shares stay in L2
-    int edge = 512;
-    while (edge > 64 && (size_t)2 * edge * fp->fused_row_floats * 4 > ((size_t)72 << 20)) edge /= 2;
-    if (const char *e = getenv("CNNGP_SUPER_EDGE")) { const int v = atoi(e); if (v >= 32 && v % 32 == 0) edge = v; }
+    int edge = 504;  // divisible by 4, 8 and 12
+    while (edge > 72 && (size_t)2 * edge * fp->fused_row_floats * 4 > ((size_t)72 << 20)) edge = edge / 2 / 24 * 24;
+    if (const char *e = getenv("CNNGP_SUPER_EDGE")) { const int v = atoi(e); if (v >= 24 && v % 24 == 0) edge = v; }
     const int super_i = edge / kTileI, super_j = edge / kTileJ;
     long long n_super;
     if (p.nbi <= super_i && p.nbj <= super_j) {
@@ -946,10 +1061,10 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);
-    void (*kern)(const NParams) = fp->S0 == 28 ? fnet_kernel<28, 4> : fnet_kernel<32, 3>;
+    void (*kern)(const NParams) = fp->S0 == 32 ? fnet_kernel<32, 8, 3> : (fp->nw == 12 ? fnet_kernel<28, 12, 2> : fnet_kernel<28, 8, 4>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem);
     if (e != cudaSuccess) { set_error(std::string("fused-net cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 7; }
-    kern<<<grid, kThreads, fp->smem, (cudaStream_t)stream>>>(p);
+    kern<<<grid, (fp->nw + 4) * 32, fp->smem, (cudaStream_t)stream>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) { set_error(std::string("fused-net kernel launch: ") + cudaGetErrorString(e)); return 9; }
     return 0;
