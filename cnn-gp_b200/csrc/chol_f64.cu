@@ -132,6 +132,16 @@ __global__ void __launch_bounds__(TN_THREADS, 2) tn_kernel(const TnParams g) {
         }
     };
 
+    if (MODE == 0) {
+        // the epilogue reads the C tile (128 rows x 512 bytes) after the last chunk: pull it into L2
+        // now so that those loads do not pay HBM latency with the tensor pipe idle
+        const int row = i0 + (tid >> 1);
+        if (row < g.M) {
+            const double *c = g.C + (long long)row * g.ldc + j0 + (tid & 1) * 32;
+            if (j0 + (tid & 1) * 32 < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(c));
+            if (j0 + (tid & 1) * 32 + 16 < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + 16));
+        }
+    }
     double acc[4][4][2];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -286,12 +296,17 @@ __global__ void __launch_bounds__(512, 1) trsv_block_kernel(const double *U, lon
         const int r = e / nr, c = e % nr;
         bs[r * NR + c] = B[(long long)(kb + r) * ldb + c0 + c];
     }
+    // reciprocals of the diagonal once (LAPACK's dtrsm scales by the reciprocal too), so that the
+    // 128 dependent steps below carry a multiply instead of a division
+    double *invd = bs + NB * NR;
+    __syncthreads();
+    if (tid < nb) invd[tid] = 1.0 / s[tid * DP + tid];
     const int r = tid & (NB - 1), cg = tid >> 7;  // 4 column groups
     if (FWD) {
         for (int t = 0; t < nb; ++t) {
             __syncthreads();
             if (r > t && r < nb) {
-                const double f = s[t * DP + r] / s[t * DP + t];
+                const double f = s[t * DP + r] * invd[t];
                 for (int c = cg; c < nr; c += 4) bs[r * NR + c] -= f * bs[t * NR + c];
             }
         }
@@ -299,7 +314,7 @@ __global__ void __launch_bounds__(512, 1) trsv_block_kernel(const double *U, lon
         for (int t = nb - 1; t >= 0; --t) {
             __syncthreads();
             if (r < t) {
-                const double f = s[r * DP + t] / s[t * DP + t];
+                const double f = s[r * DP + t] * invd[t];
                 for (int c = cg; c < nr; c += 4) bs[r * NR + c] -= f * bs[t * NR + c];
             }
         }
@@ -307,11 +322,11 @@ __global__ void __launch_bounds__(512, 1) trsv_block_kernel(const double *U, lon
     __syncthreads();
     for (int e = tid; e < nb * nr; e += 512) {
         const int rr = e / nr, c = e % nr;
-        B[(long long)(kb + rr) * ldb + c0 + c] = bs[rr * NR + c] / s[rr * DP + rr];
+        B[(long long)(kb + rr) * ldb + c0 + c] = bs[rr * NR + c] * invd[rr];
     }
 }
 
-constexpr size_t kTrsvSmem = (size_t)(NB * DP + NB * NR) * sizeof(double);
+constexpr size_t kTrsvSmem = (size_t)(NB * DP + NB * NR + NB) * sizeof(double);
 
 // forward update: B[j] -= sum_t U[kb+t][j] * Y[t]  for j >= kb + nb   (thread per row j of B)
 __global__ void __launch_bounds__(256) fwd_update_kernel(const double *U, long long lda, int kb, int nb, int n,
@@ -372,43 +387,67 @@ __global__ void __launch_bounds__(256) bwd_update_kernel(const double *U, long l
 constexpr size_t kBwdSmem = (size_t)(64 * DP + NB * NR) * sizeof(double);
 
 // ---- prediction: scores = K A (float32 K widened to float64), pred = argmax ------------------
-// One warp per row of K; lanes stride over the n training points.
+// A warp owns PR_ROWS rows of K; its lanes stride over the n training points, so K is read from
+// HBM exactly once, coalesced, and every weight row A[t, :] fetched (L1 / L2 resident: n x nrhs
+// doubles) serves PR_ROWS rows.  No shared memory, no block barriers: many warps in flight hide
+// the load latency.
+constexpr int PR_ROWS = 4;
+
 template <int NC>
-__global__ void __launch_bounds__(256) predict_kernel(const float *K, long long R, long long n, long long ldk,
+__global__ void __launch_bounds__(128) predict_kernel(const float *K, long long R, long long n, long long ldk,
                                                       const double *A, int nrhs, int c0, long long *pred,
                                                       double *scores, double *best_val) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long r = (long long)blockIdx.x * 8 + warp;
-    if (r >= R) return;
+    const long long r0 = ((long long)blockIdx.x * 4 + warp) * PR_ROWS;
+    if (r0 >= R) return;
     const int nc = min(NC, nrhs - c0);
-    double acc[NC];
+    double acc[PR_ROWS][NC];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) acc[c] = 0.0;
-    const float *k = K + r * ldk;
+    for (int q = 0; q < PR_ROWS; ++q)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[q][c] = 0.0;
+    const float *k[PR_ROWS];
+#pragma unroll
+    for (int q = 0; q < PR_ROWS; ++q) k[q] = K + min(r0 + q, R - 1) * ldk;
+#pragma unroll 2
     for (long long t = lane; t < n; t += 32) {
-        const double kv = (double)k[t];
+        double kv[PR_ROWS];
+#pragma unroll
+        for (int q = 0; q < PR_ROWS; ++q) kv[q] = (double)__ldg(k[q] + t);
         const double *a = A + t * nrhs + c0;
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
-            if (c < nc) acc[c] += kv * a[c];
+        for (int c = 0; c < NC; ++c) {
+            if (c < nc) {
+                const double av = __ldg(a + c);
+#pragma unroll
+                for (int q = 0; q < PR_ROWS; ++q) acc[q][c] += kv[q] * av;
+            }
+        }
     }
 #pragma unroll
-    for (int c = 0; c < NC; ++c)
+    for (int q = 0; q < PR_ROWS; ++q)
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], d);
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) acc[q][c] += __shfl_xor_sync(0xffffffffu, acc[q][c], d);
     if (lane == 0) {
-        double bv = c0 == 0 ? -INFINITY : best_val[r];
-        long long bi = c0 == 0 ? 0 : pred[r];
-        bool any = c0 != 0;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            if (c >= nc) break;
-            if (scores) scores[r * nrhs + c0 + c] = acc[c];
-            // first maximum wins, NaN propagates like torch.argmax (a NaN score is the maximum)
-            if (!any || acc[c] > bv || (acc[c] != acc[c] && bv == bv)) { bv = acc[c]; bi = c0 + c; any = true; }
+        for (int q = 0; q < PR_ROWS; ++q) {
+            const long long r = r0 + q;
+            if (r >= R) break;
+            double bv = c0 == 0 ? -INFINITY : best_val[r];
+            long long bi = c0 == 0 ? 0 : pred[r];
+            bool any = c0 != 0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                if (c >= nc) break;
+                if (scores) scores[r * nrhs + c0 + c] = acc[q][c];
+                // first maximum wins, NaN propagates like torch.argmax (a NaN score is the maximum)
+                if (!any || acc[q][c] > bv || (acc[q][c] != acc[q][c] && bv == bv)) { bv = acc[q][c]; bi = c0 + c; any = true; }
+            }
+            pred[r] = bi;
+            if (best_val) best_val[r] = bv;
         }
-        pred[r] = bi;
-        if (best_val) best_val[r] = bv;
     }
 }
 
@@ -560,10 +599,11 @@ int cnngp_predict_argmax(const float *d_K, int64_t R, int64_t n, int64_t ldk, co
     if (R == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream_;
     double *best = nullptr;
-    if (nrhs > NR && !check(cudaMallocAsync((void **)&best, sizeof(double) * R, s), "predict workspace")) return 6;
-    for (int c0 = 0; c0 < nrhs; c0 += NR)
-        predict_kernel<NR><<<(unsigned)((R + 7) / 8), 256, 0, s>>>(d_K, R, n, ldk, d_A, nrhs, c0, (long long *)d_pred,
-                                                                   d_scores, best);
+    if (nrhs > 10 && !check(cudaMallocAsync((void **)&best, sizeof(double) * R, s), "predict workspace")) return 6;
+    constexpr int PC = 10;  // right-hand sides per pass: the ten classes of the shipped configs
+    const unsigned grid = (unsigned)((R + 4 * PR_ROWS - 1) / (4 * PR_ROWS));
+    for (int c0 = 0; c0 < nrhs; c0 += PC)
+        predict_kernel<PC><<<grid, 128, 0, s>>>(d_K, R, n, ldk, d_A, nrhs, c0, (long long *)d_pred, d_scores, best);
     if (best) cudaFreeAsync(best, s);
     return check(cudaGetLastError(), "cnngp_predict_argmax") ? 0 : 9;
 }
