@@ -99,7 +99,12 @@ def save_K_resident(f, model, name, X, X2, diag, batch_size, worker_rank=0, n_wo
         tiles = worker_tiles(N, None if X2 is None else N2, batch_size, worker_rank, n_workers)
         segs = row_segments(tiles)
         copy_stream = torch.cuda.Stream()
-        pending = []  # (event, host buffer, i0, i1, j0, j1)
+        # two device row buffers and two pinned host buffers, allocated once and used alternately:
+        # row k is copied out and written to the store while row k + 1 is being computed
+        width = N2
+        dev_bufs = [torch.empty((batch_size, width), dtype=torch.float32, device=device) for _ in range(2)]
+        host_bufs = [torch.empty((batch_size, width), dtype=torch.float32).pin_memory() for _ in range(2)]
+        pending = []  # (event, host view, i0, i1, j0, j1)
 
         def drain(keep):
             while len(pending) > keep:
@@ -109,11 +114,12 @@ def save_K_resident(f, model, name, X, X2, diag, batch_size, worker_rank=0, n_wo
 
         segs = print_timings(segs, desc=f"{name} rows (worker {worker_rank}/{n_workers})",
                              print_interval=print_interval)
-        for r, has_diag, c0, c1 in segs:
+        for k, (r, has_diag, c0, c1) in enumerate(segs):
             i0, i1 = r * batch_size, min(N, (r + 1) * batch_size)
             j0 = i0 if has_diag else c0 * batch_size
             j1 = min(N2, c1 * batch_size) if c0 is not None else i1
-            buf = torch.empty((i1 - i0, j1 - j0), dtype=torch.float32, device=device)
+            drain(keep=1)  # buffer k % 2 was last used by row k - 2
+            buf = dev_bufs[k % 2][:i1 - i0, :j1 - j0]
             if has_diag:
                 job.block_into(buf[:, :i1 - i0], i0, i1, i0, i1, symmetric=True)
             if c0 is not None:
@@ -121,13 +127,12 @@ def save_K_resident(f, model, name, X, X2, diag, batch_size, worker_rank=0, n_wo
                 job.block_into(buf[:, js - j0:], i0, i1, js, j1, symmetric=False)
             if not bool(torch.isfinite(buf).all()):
                 raise FloatingPointError(f"nan or inf in kernel block row {name}[{i0}:{i1}]")
-            host = torch.empty(buf.shape, dtype=torch.float32).pin_memory()
+            host = host_bufs[k % 2][:i1 - i0, :j1 - j0]
             copy_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(copy_stream):
                 host.copy_(buf, non_blocking=True)
-                buf.record_stream(copy_stream)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
+            # (drain(keep=1) above waits for this event before the device buffer is reused)
             pending.append((ev, host, i0, i1, j0, j1))
-            drain(keep=1)
         drain(keep=0)
