@@ -218,55 +218,136 @@ constexpr int POTF2_THREADS = 512;
 // D = A[kb:kb+nb, kb:kb+nb] (upper).  Writes U_kk back over D and W = U_kk^{-1} (upper, zero
 // elsewhere, full NB x NB) to the workspace.  *info = kb + c + 1 for the first non-positive
 // pivot (LAPACK dpotrf convention).
+//
+// Blocked in shared memory with 32-wide panels so that the 128 dependent pivot steps need no
+// block-wide barrier: the 32 x 32 diagonal blocks are factorised / inverted by single warps
+// (__syncwarp only), the row-panel solves keep a column in registers, and the block updates
+// are small products spread over all 512 threads.
+constexpr int QB = 32;
+
 __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_inv_kernel(double *A, long long lda, int kb, int nb,
                                                                      double *W, int *info) {
     extern __shared__ __align__(16) double ps_smem[];
-    double *s = ps_smem;            // [NB][DP]
-    double *row = ps_smem + NB * DP;  // [NB]
-    const int tid = threadIdx.x;
+    double *s = ps_smem;                 // [NB][DP]
+    double *rinv = ps_smem + NB * DP;    // [NB] reciprocals of the diagonal of U
+    double *tmp = rinv + NB;             // [QB][QB + 1]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     double *D = A + (long long)kb * lda + kb;
+#pragma unroll 8
     for (int e = tid; e < NB * NB; e += POTF2_THREADS) {
         const int i = e / NB, j = e % NB;
         s[i * DP + j] = (i < nb && j < nb && j >= i) ? D[(long long)i * lda + j] : (i == j ? 1.0 : 0.0);
     }
-    const int ty = tid >> 5, tx = tid & 31;  // 16 x 32
-    for (int c = 0; c < nb; ++c) {
-        __syncthreads();
-        const double d = s[c * DP + c];
-        const bool bad = !(d > 0.0);
-        const double r = bad ? nan("") : sqrt(d);
-        if (bad && tid == 0 && *info == 0) *info = kb + c + 1;
-        if (tid >= c && tid < nb) row[tid] = tid == c ? r : s[c * DP + tid] / r;
-        __syncthreads();
-        if (tid >= c && tid < nb) s[c * DP + tid] = row[tid];
-        for (int i = c + 1 + ty; i < nb; i += 16) {
-            const double ri = row[i];
-            for (int j = tx + ((i - tx + 31) & ~31); j < nb; j += 32)  // first j >= i congruent to tx
-                s[i * DP + j] -= ri * row[j];
-        }
-    }
     __syncthreads();
+
+    // ---- U = chol(D), right-looking over 32-wide panels -------------------------------------
+    for (int o = 0; o < NB; o += QB) {
+        if (warp == 0) {  // diagonal block in registers: lane j holds column j, pivots travel by shuffle
+            double a[QB];
+#pragma unroll
+            for (int i = 0; i < QB; ++i) a[i] = s[(o + i) * DP + o + lane];
+#pragma unroll
+            for (int c = 0; c < QB; ++c) {
+                const double d = __shfl_sync(0xffffffffu, a[c], c);
+                const bool bad = !(d > 0.0);
+                if (bad && lane == 0 && *info == 0) *info = kb + o + c + 1;
+                const double r = bad ? nan("") : sqrt(d), ri = 1.0 / r;
+                const double u = lane == c ? r : a[c] * ri;  // row c of U at this lane's column (valid for lane >= c)
+                a[c] = u;
+                if (lane == c) rinv[o + c] = ri;
+#pragma unroll
+                for (int i = c + 1; i < QB; ++i) {
+                    const double ui = __shfl_sync(0xffffffffu, u, i);
+                    a[i] -= ui * u;  // only entries with lane >= i are ever used
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < QB; ++i)
+                if (lane >= i) s[(o + i) * DP + o + lane] = a[i];
+        }
+        __syncthreads();
+        const int ncol = NB - o - QB;  // columns right of the panel
+        if (tid < ncol) {  // row panel: X = U_oo^{-T} A[o:o+32, j], one column per thread, in registers
+            const int j = o + QB + tid;
+            double x[QB];
+#pragma unroll
+            for (int c = 0; c < QB; ++c) x[c] = s[(o + c) * DP + j];
+#pragma unroll
+            for (int c = 0; c < QB; ++c) {
+                x[c] *= rinv[o + c];
+#pragma unroll
+                for (int c2 = c + 1; c2 < QB; ++c2) x[c2] -= s[(o + c) * DP + o + c2] * x[c];
+            }
+#pragma unroll
+            for (int c = 0; c < QB; ++c) s[(o + c) * DP + j] = x[c];
+        }
+        __syncthreads();
+        for (int e = tid; e < ncol * ncol; e += POTF2_THREADS) {  // trailing block -= X^T X (j >= i)
+            const int ii = e / ncol, jj = e % ncol;
+            if (jj < ii) continue;
+            const int i = o + QB + ii, j = o + QB + jj;
+            double acc = 0.0;
+#pragma unroll 8
+            for (int t = 0; t < QB; ++t) acc += s[(o + t) * DP + i] * s[(o + t) * DP + j];
+            s[i * DP + j] -= acc;
+        }
+        __syncthreads();
+    }
     for (int e = tid; e < nb * nb; e += POTF2_THREADS) {
         const int i = e / nb, j = e % nb;
         if (j >= i) D[(long long)i * lda + j] = s[i * DP + j];
     }
     __syncthreads();
-    // in-place inverse of the upper triangle, column by column (LAPACK dtrti2 order): with
-    // T = inv(U[0:j,0:j]) already in place, column j becomes -T U[0:j,j] / U[j][j].
-    const int ri = tid >> 2, rq = tid & 3;  // row i, quarter q of its dot product
-    for (int j = 0; j < nb; ++j) {
-        const double inv = 1.0 / s[j * DP + j];
-        double part = 0.0;
-        if (ri < j)
-            for (int t = ri + rq; t < j; t += 4) part += s[ri * DP + t] * s[t * DP + j];
-        part += __shfl_xor_sync(0xffffffffu, part, 1);
-        part += __shfl_xor_sync(0xffffffffu, part, 2);
-        __syncthreads();
-        if (rq == 0) {
-            if (ri < j) s[ri * DP + j] = -part * inv;
-            else if (ri == j) s[j * DP + j] = inv;
+
+    // ---- W = U^{-1} in place --------------------------------------------------------------------
+    if (warp < NB / QB) {  // diagonal blocks: lane j solves U w = e_j for column j of the inverse, in registers
+        const int o = warp * QB;
+        double w[QB];
+#pragma unroll
+        for (int i = QB - 1; i >= 0; --i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int t = i + 1; t < QB; ++t) acc += s[(o + i) * DP + o + t] * (t <= lane ? w[t] : 0.0);
+            w[i] = i == lane ? rinv[o + i] : (i < lane ? -acc * rinv[o + i] : 0.0);
         }
-        __syncthreads();
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < QB; ++i)
+            if (lane >= i) s[(o + i) * DP + o + lane] = w[i];
+    }
+    __syncthreads();
+    // off-diagonal blocks: W_ij = -W_ii * sum_{k=i+1..j} U_ik W_kj, block columns right to left (the
+    // U_ik of the columns left of j are still intact), block rows bottom to top
+    for (int bj = NB / QB - 1; bj >= 1; --bj) {
+        for (int bi = bj - 1; bi >= 0; --bi) {
+            double t2[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int e = tid + q * POTF2_THREADS, r = e / QB, c = e % QB;
+                double acc = 0.0;
+                for (int k = (bi + 1) * QB; k < (bj + 1) * QB; ++k) acc += s[(bi * QB + r) * DP + k] * s[k * DP + bj * QB + c];
+                t2[q] = acc;
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int e = tid + q * POTF2_THREADS;
+                tmp[(e / QB) * (QB + 1) + e % QB] = t2[q];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int e = tid + q * POTF2_THREADS, r = e / QB, c = e % QB;
+                double acc = 0.0;
+                for (int t = r; t < QB; ++t) acc += s[(bi * QB + r) * DP + bi * QB + t] * tmp[t * (QB + 1) + c];
+                t2[q] = -acc;
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int e = tid + q * POTF2_THREADS;
+                s[(bi * QB + e / QB) * DP + bj * QB + e % QB] = t2[q];
+            }
+            __syncthreads();
+        }
     }
     for (int e = tid; e < NB * NB; e += POTF2_THREADS) {
         const int i = e / NB, j = e % NB;
@@ -274,7 +355,7 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_inv_kernel(double *A, 
     }
 }
 
-constexpr size_t kPotf2Smem = (size_t)(NB * DP + NB) * sizeof(double);
+constexpr size_t kPotf2Smem = (size_t)(NB * DP + NB + QB * (QB + 1)) * sizeof(double);
 
 // ---- triangular solves with a few right-hand sides ------------------------------------------
 constexpr int NR = 16;  // right-hand sides per pass
@@ -288,6 +369,7 @@ __global__ void __launch_bounds__(512, 1) trsv_block_kernel(const double *U, lon
     double *bs = tr_smem + NB * DP;  // [NB][NR]
     const int tid = threadIdx.x;
     const double *D = U + (long long)kb * lda + kb;
+#pragma unroll 8
     for (int e = tid; e < nb * nb; e += 512) {
         const int i = e / nb, j = e % nb;
         if (j >= i) s[i * DP + j] = D[(long long)i * lda + j];
@@ -343,6 +425,7 @@ __global__ void __launch_bounds__(256) fwd_update_kernel(const double *U, long l
 #pragma unroll
     for (int c = 0; c < NR; ++c) acc[c] = 0.0;
     const double *u = U + (long long)kb * lda + j;
+#pragma unroll 8
     for (int t = 0; t < nb; ++t) {
         const double v = u[(long long)t * lda];
 #pragma unroll
