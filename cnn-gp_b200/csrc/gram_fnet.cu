@@ -170,11 +170,11 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // whole map set (two packed arrays, first S entries each) -> tensor memory.  Array h starts at
 // column h * astride and takes exactly 2 S columns: entries move in groups of 8 (x16), then 4
 // (x8), 2 (x4), 1 (x2).
-template <int S0, int S>
+template <int S0, int S, int NARR>
 __device__ __forceinline__ void stash_store(uint32_t tbase, int astride, const u64 (&M)[2][S0]) {
     constexpr int G8 = S / 8, R8 = S % 8, B4 = G8 * 8, B2 = B4 + (R8 & 4), B1 = B2 + (R8 & 2);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < NARR; ++h) {
         const uint32_t ta = tbase + h * astride;
 #pragma unroll
         for (int c = 0; c < G8; ++c) {
@@ -206,12 +206,12 @@ __device__ __forceinline__ void stash_store(uint32_t tbase, int astride, const u
 
 // M = stash (ADD == false) or M = stash * alpha + M + beta (ADD == true); all loads of one array
 // are in flight together
-template <int S0, int S, bool ADD>
+template <int S0, int S, int NARR, bool ADD>
 __device__ __forceinline__ void stash_load(uint32_t tbase, int astride, u64 (&M)[2][S0], float alpha_f, float beta_f) {
     constexpr int G8 = S / 8, R8 = S % 8, B4 = G8 * 8, B2 = B4 + (R8 & 4), B1 = B2 + (R8 & 2);
     const u64 alpha = pk(alpha_f, alpha_f);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < NARR; ++h) {
         const uint32_t ta = tbase + h * astride;
         uint32_t t[G8 > 0 ? G8 : 1][16];
         uint32_t t8[8], t4[4], t2[2];
@@ -254,7 +254,7 @@ __device__ __forceinline__ void stash_load(uint32_t tbase, int astride, u64 (&M)
     if (ADD && beta_f != 0.f) {  // aliased 1 x 1 convolution with a bias (uniform branch)
         const u64 beta = pk(beta_f, beta_f);
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < NARR; ++h)
 #pragma unroll
             for (int r = 0; r < S; ++r) M[h][r] = add2(M[h][r], beta);
     }
@@ -376,6 +376,80 @@ __device__ __forceinline__ void affine_op(u64 (&M)[2][S0], float scale, float bi
         for (int r = 0; r < S; ++r) M[h][r] = fma2(M[h][r], SC, BI);
 }
 
+// ---- folded mode: maps of edge <= S0 / 2 ------------------------------------------------------
+// After the first stride-2 convolution a map needs at most 16 lanes, so the second packed array is
+// folded into lanes 16..31 of the first (lane = 16 b + l: array b, column l).  Every later op then
+// runs on ONE packed array: half the instructions for the S0/2 and S0/4 stages of a ResNet.
+__device__ __forceinline__ u64 shfl64(u64 v, int src) {
+    uint32_t lo, hi;
+    split64(v, lo, hi);
+    lo = __shfl_sync(0xffffffffu, lo, src);
+    hi = __shfl_sync(0xffffffffu, hi, src);
+    return join64(lo, hi);
+}
+
+template <int S0, int S>
+__device__ __forceinline__ void fold_op(u64 (&M)[2][S0], int lane) {
+#pragma unroll
+    for (int r = 0; r < S; ++r) {
+        const u64 v = shfl64(M[1][r], lane & 15);
+        if (lane >= 16) M[0][r] = v;
+    }
+}
+
+// transposition tile in folded mode: row r holds array 0's columns at [0, L) and array 1's at [L, 2L)
+template <int S0, int R, int L>
+__device__ __forceinline__ void tstore_f(u64 *tile, const u64 (&a)[S0], int lane) {
+    constexpr int PITCH = S0 + 1;
+    const int b = lane >> 4, l = lane & 15;
+    if (l < L) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) tile[r * PITCH + b * L + l] = a[r];
+    }
+}
+template <int S0, int R, int NEWL>
+__device__ __forceinline__ void tload_f(const u64 *tile, u64 (&a)[S0], int lane) {
+    constexpr int PITCH = S0 + 1;
+    const int b = lane >> 4, l = lane & 15;
+    const int lx = l < NEWL ? l : NEWL - 1;
+#pragma unroll
+    for (int r = 0; r < R; ++r) a[r] = tile[lx * PITCH + b * R + r];
+}
+
+template <int S0, int SI, int SO, int LO, int HI, int ST>
+__device__ __forceinline__ void conv_op_f(u64 (&M)[2][S0], u64 *tile, int lane, float scale, float bias) {
+    static_assert(ST == 1 ? SI == SO : SI == 2 * SO, "conv geometry");
+    static_assert(2 * SI <= S0 + 1, "both halves must fit a tile row");
+    auto pass = [](u64 (&v)[S0]) {
+        if (ST == 1) box_s1<S0, SI, LO, HI>(v);
+        else box_s2<S0, SI, SO, LO, HI>(v);
+    };
+    pass(M[0]);
+    tstore_f<S0, SO, SI>(tile, M[0], lane);   // SO rows of SI columns per half
+    __syncwarp();
+    tload_f<S0, SI, SO>(tile, M[0], lane);    // new lane = old row (< SO), registers = old columns (SI)
+    __syncwarp();
+    pass(M[0]);
+    const u64 SC = pk(scale, scale), BI = pk(bias, bias);
+#pragma unroll
+    for (int r = 0; r < SO; ++r) M[0][r] = fma2(M[0][r], SC, BI);
+}
+
+template <int S0, int S>
+__device__ __forceinline__ void transpose_op_f(u64 (&M)[2][S0], u64 *tile, int lane) {
+    tstore_f<S0, S, S>(tile, M[0], lane);
+    __syncwarp();
+    tload_f<S0, S, S>(tile, M[0], lane);
+    __syncwarp();
+}
+
+template <int S0, int S>
+__device__ __forceinline__ void affine_op_f(u64 (&M)[2][S0], float scale, float bias) {
+    const u64 SC = pk(scale, scale), BI = pk(bias, bias);
+#pragma unroll
+    for (int r = 0; r < S; ++r) M[0][r] = fma2(M[0][r], SC, BI);
+}
+
 // 2 * H(e), degree-5 minimax fit on [0,1] (gram_fused.cu)
 #define FNET_C5 1.678542030e-04f
 #define FNET_C4 -1.571319990e-05f
@@ -416,6 +490,35 @@ __device__ __forceinline__ void relu_rows(u64 (&M)[2][S0], const float4 *ai, con
     }
 }
 
+// folded: lanes 16..31 hold (i0 j1, i1 j0), i.e. they need the j-pair's operands swapped
+template <int S0, int S>
+__device__ __forceinline__ void relu_rows_f(u64 (&M)[2][S0], const float4 *ai, const float4 *bj, int lane) {
+    const u64 C5 = pk(FNET_C5, FNET_C5), C4 = pk(FNET_C4, FNET_C4), C3 = pk(FNET_C3, FNET_C3),
+              C2 = pk(FNET_C2, FNET_C2), C1 = pk(FNET_C1, FNET_C1), C0 = pk(FNET_C0, FNET_C0), ONE = pk(1.f, 1.f);
+    const bool sw = lane >= 16;
+#pragma unroll
+    for (int r = 0; r < S; ++r) {
+        const float4 A = ai[r * S], B = bj[r * S];
+        const u64 SA = pk(A.x, A.y), RA = pk(A.z, A.w);
+        const u64 SB = pk(sw ? B.y : B.x, sw ? B.x : B.y);
+        const u64 RB = pk(sw ? B.w : B.z, sw ? B.z : B.w);
+        float c0, c1;
+        upk(M[0][r], c0, c1);
+        const u64 NC = pk(neg_abs(c0), neg_abs(c1));
+        const u64 D = fma2(SA, SB, NC);
+        const u64 E = fma2(NC, mul2(RA, RB), ONE);
+        float e0, e1;
+        upk(E, e0, e1);
+        const u64 W = mul2(D, pk(sqrt_approx(fabsf(e0)), sqrt_approx(fabsf(e1))));
+        u64 H = fma2(C5, E, C4);
+        H = fma2(H, E, C3);
+        H = fma2(H, E, C2);
+        H = fma2(H, E, C1);
+        H = fma2(H, E, C0);
+        M[0][r] = fma2(W, H, pk(fmaxf(c0, 0.f), fmaxf(c1, 0.f)));
+    }
+}
+
 // the same step on one pixel in scalar code (1 x 1 maps after the pooling convolution); returns
 // the doubled value like the packed version
 __device__ __forceinline__ float relu_scalar(float c, float vx, float vy) {
@@ -453,6 +556,26 @@ __device__ __forceinline__ void dense_op(const u64 (&M)[2][S0], int lane, float 
         tot[h == 0 ? 0 : 1] = fmaf(a0, scale, bias);
         tot[h == 0 ? 3 : 2] = fmaf(a1, scale, bias);
     }
+}
+
+template <int S0, int S>
+__device__ __forceinline__ void dense_op_f(const u64 (&M)[2][S0], int lane, float scale, float bias, float (&tot)[4]) {
+    u64 acc = M[0][0];
+#pragma unroll
+    for (int r = 1; r < S; ++r) acc = add2(acc, M[0][r]);
+    float a0, a1;
+    upk(acc, a0, a1);
+    if ((lane & 15) >= S) { a0 = 0.f; a1 = 0.f; }
+#pragma unroll
+    for (int d = 8; d > 0; d >>= 1) {  // within each 16-lane half
+        a0 += __shfl_xor_sync(0xffffffffu, a0, d);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, d);
+    }
+    // half 0 = (i0j0, i1j1), half 1 = (i0j1, i1j0); tot index = 2a + b
+    tot[0] = fmaf(__shfl_sync(0xffffffffu, a0, 0), scale, bias);
+    tot[3] = fmaf(__shfl_sync(0xffffffffu, a1, 0), scale, bias);
+    tot[1] = fmaf(__shfl_sync(0xffffffffu, a0, 16), scale, bias);
+    tot[2] = fmaf(__shfl_sync(0xffffffffu, a1, 16), scale, bias);
 }
 
 template <int S0, int NW, int NST>
@@ -613,27 +736,31 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
         NOp o = p.ops[0];
         for (int k = 0; k < p.n_ops; ++k) {
             const NOp nxt = p.ops[k + 1 < p.n_ops ? k + 1 : k];  // descriptor of the next op: fetched under this op's work
-#define FNET_3(CODE, CALL)                                              \
-    case CODE + 0: { constexpr int S = S0; CALL; break; }               \
-    case CODE + 1: { constexpr int S = S0 / 2; CALL; break; }           \
-    case CODE + 2: { constexpr int S = S0 / 4; CALL; break; }
+#define FNET_3(CODE, FULL, HALF)                                        \
+    case CODE + 0: { constexpr int S = S0; FULL; break; }               \
+    case CODE + 1: { constexpr int S = S0 / 2; HALF; break; }           \
+    case CODE + 2: { constexpr int S = S0 / 4; HALF; break; }
             switch (o.code) {
                 case C_CONV + 0: conv_op<S0, S0, S0, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
                 case C_CONV + 1: conv_op<S0, S0, S0, 1, 2, 1>(M, tile, lane, o.scale, o.bias); break;
                 case C_CONV + 2: conv_op<S0, S0, S0, 2, 2, 1>(M, tile, lane, o.scale, o.bias); break;
                 case C_CONV + 3: conv_op<S0, S0, S0, 3, 3, 1>(M, tile, lane, o.scale, o.bias); break;
-                case C_CONV + 4: conv_op<S0, S0, S0 / 2, 1, 1, 2>(M, tile, lane, o.scale, o.bias); break;
-                case C_CONV + 5: conv_op<S0, S0, S0 / 2, 0, 0, 2>(M, tile, lane, o.scale, o.bias); break;
-                case C_CONV + 6: conv_op<S0, S0 / 2, S0 / 2, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
-                case C_CONV + 7: conv_op<S0, S0 / 2, S0 / 4, 1, 1, 2>(M, tile, lane, o.scale, o.bias); break;
-                case C_CONV + 8: conv_op<S0, S0 / 2, S0 / 4, 0, 0, 2>(M, tile, lane, o.scale, o.bias); break;
-                case C_CONV + 9: conv_op<S0, S0 / 4, S0 / 4, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
-                FNET_3(C_AFFINE, (affine_op<S0, S>(M, o.scale, o.bias)))
-                FNET_3(C_TRANSPOSE, (transpose_op<S0, S>(M, tile, lane)))
-                FNET_3(C_STASH, (stash_store<S0, S>(tm_warp + o.slot * TM_SLOT1, o.slot ? TM_A1 : TM_A0, M)))
-                FNET_3(C_UNSTASH, (stash_load<S0, S, false>(tm_warp + o.slot * TM_SLOT1, o.slot ? TM_A1 : TM_A0, M, 1.f, 0.f)))
-                FNET_3(C_ADD, (stash_load<S0, S, true>(tm_warp + o.slot * TM_SLOT1, o.slot ? TM_A1 : TM_A0, M, o.scale, o.bias)))
-                FNET_3(C_DENSE, (dense_op<S0, S>(M, lane, o.scale, o.bias, tot)))
+                // stride 2 out of the full size: unfolded op, then the result is folded
+                case C_CONV + 4: conv_op<S0, S0, S0 / 2, 1, 1, 2>(M, tile, lane, o.scale, o.bias); fold_op<S0, S0 / 2>(M, lane); break;
+                case C_CONV + 5: conv_op<S0, S0, S0 / 2, 0, 0, 2>(M, tile, lane, o.scale, o.bias); fold_op<S0, S0 / 2>(M, lane); break;
+                case C_CONV + 6: conv_op_f<S0, S0 / 2, S0 / 2, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
+                case C_CONV + 7: conv_op_f<S0, S0 / 2, S0 / 4, 1, 1, 2>(M, tile, lane, o.scale, o.bias); break;
+                case C_CONV + 8: conv_op_f<S0, S0 / 2, S0 / 4, 0, 0, 2>(M, tile, lane, o.scale, o.bias); break;
+                case C_CONV + 9: conv_op_f<S0, S0 / 4, S0 / 4, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
+                FNET_3(C_AFFINE, (affine_op<S0, S>(M, o.scale, o.bias)), (affine_op_f<S0, S>(M, o.scale, o.bias)))
+                FNET_3(C_TRANSPOSE, (transpose_op<S0, S>(M, tile, lane)), (transpose_op_f<S0, S>(M, tile, lane)))
+                FNET_3(C_STASH, (stash_store<S0, S, 2>(tm_warp + o.slot * TM_SLOT1, o.slot ? TM_A1 : TM_A0, M)),
+                       (stash_store<S0, S, 1>(tm_warp + o.slot * TM_SLOT1, 0, M)))
+                FNET_3(C_UNSTASH, (stash_load<S0, S, 2, false>(tm_warp + o.slot * TM_SLOT1, o.slot ? TM_A1 : TM_A0, M, 1.f, 0.f)),
+                       (stash_load<S0, S, 1, false>(tm_warp + o.slot * TM_SLOT1, 0, M, 1.f, 0.f)))
+                FNET_3(C_ADD, (stash_load<S0, S, 2, true>(tm_warp + o.slot * TM_SLOT1, o.slot ? TM_A1 : TM_A0, M, o.scale, o.bias)),
+                       (stash_load<S0, S, 1, true>(tm_warp + o.slot * TM_SLOT1, 0, M, o.scale, o.bias)))
+                FNET_3(C_DENSE, (dense_op<S0, S>(M, lane, o.scale, o.bias, tot)), (dense_op_f<S0, S>(M, lane, o.scale, o.bias, tot)))
                 case C_RELU + 0: {  // two stages: rows [0, S0/2) from the pair's first row, the rest from the second
                     const int lx = lane < S0 ? lane : S0 - 1;
                     {
@@ -657,18 +784,19 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
                     break;
                 }
                 case C_RELU + 1:
-                case C_RELU + 2: {
+                case C_RELU + 2: {  // folded maps: one stage holds the whole layer
                     const unsigned buf = stage_l % NST;
                     mbar_wait(&full[buf], (stage_l / NST) & 1);
                     const float4 *st4 = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE);
+                    const int l = lane & 15;
                     if (o.code == C_RELU + 1) {
                         constexpr int S = S0 / 2;
-                        const float4 *sb = st4 + (lane < S ? lane : S - 1);
-                        relu_rows<S0, S, 0, S>(M, sb + wi * 2 * o.half, sb + (kTileI / 2 + wj) * 2 * o.half);
+                        const float4 *sb = st4 + (l < S ? l : S - 1);
+                        relu_rows_f<S0, S>(M, sb + wi * 2 * o.half, sb + (kTileI / 2 + wj) * 2 * o.half, lane);
                     } else {
                         constexpr int S = S0 / 4;
-                        const float4 *sb = st4 + (lane < S ? lane : S - 1);
-                        relu_rows<S0, S, 0, S>(M, sb + wi * 2 * o.half, sb + (kTileI / 2 + wj) * 2 * o.half);
+                        const float4 *sb = st4 + (l < S ? l : S - 1);
+                        relu_rows_f<S0, S>(M, sb + wi * 2 * o.half, sb + (kTileI / 2 + wj) * 2 * o.half, lane);
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[buf]);
