@@ -213,20 +213,30 @@ __device__ __forceinline__ void stash_load(uint32_t tbase, int astride, u64 (&M)
 #pragma unroll
     for (int h = 0; h < NARR; ++h) {
         const uint32_t ta = tbase + h * astride;
-        uint32_t t[G8 > 0 ? G8 : 1][16];
         uint32_t t8[8], t4[4], t2[2];
-#pragma unroll
-        for (int c = 0; c < G8; ++c) tmem_ld16(ta + c * 16, t[c]);
         if (R8 & 4) tmem_ld8(ta + 2 * B4, t8);
         if (R8 & 2) tmem_ld4(ta + 2 * B2, t4);
         if (R8 & 1) tmem_ld2(ta + 2 * B1, t2);
+        // groups of eight entries, two loads in flight at a time (32 temporaries: the 12-warp
+        // variant runs at 160 registers with 112 of them holding the maps)
 #pragma unroll
-        for (int c = 0; c < G8; ++c) {
-            tmem_landed16(t[c]);
+        for (int c = 0; c < G8; c += 2) {
+            uint32_t ta0[16], ta1[16];
+            tmem_ld16(ta + c * 16, ta0);
+            if (c + 1 < G8) tmem_ld16(ta + (c + 1) * 16, ta1);
+            tmem_landed16(ta0);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const u64 v = join64(t[c][2 * q], t[c][2 * q + 1]);
+                const u64 v = join64(ta0[2 * q], ta0[2 * q + 1]);
                 M[h][c * 8 + q] = ADD ? fma2(v, alpha, M[h][c * 8 + q]) : v;
+            }
+            if (c + 1 < G8) {
+                tmem_landed16(ta1);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const u64 v = join64(ta1[2 * q], ta1[2 * q + 1]);
+                    M[h][(c + 1) * 8 + q] = ADD ? fma2(v, alpha, M[h][(c + 1) * 8 + q]) : v;
+                }
             }
         }
         if (R8 & 4) {
