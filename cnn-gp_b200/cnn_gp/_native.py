@@ -32,6 +32,7 @@ _SIGNATURES = {
     "cnngp_plan_aux_elems": (ctypes.c_int64, [ctypes.c_void_p]),
     "cnngp_plan_flops_per_pair": (ctypes.c_double, [ctypes.c_void_p, ctypes.c_int32]),
     "cnngp_plan_has_fused": (ctypes.c_int, [ctypes.c_void_p]),
+    "cnngp_plan_describe": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
     "cnngp_variances": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                        ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p]),
@@ -100,6 +101,14 @@ class Plan:
         self.has_fused = self.fused_kind != 0
         self.H, self.W, self.dtype_code = H, W, dtype_code
         self.n_ops, self.n_slots = len(ops), n_slots
+
+    def describe(self):
+        """How the plan will run: kernel family and the fused kernels' register-level op list."""
+        L = lib()
+        n = int(L.cnngp_plan_describe(self.handle, None, 0))
+        buf = ctypes.create_string_buffer(n)
+        L.cnngp_plan_describe(self.handle, buf, n)
+        return buf.value.decode()
 
     def flops_per_pair(self, C):
         return float(lib().cnngp_plan_flops_per_pair(self.handle, C))

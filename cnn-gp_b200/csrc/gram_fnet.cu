@@ -1155,6 +1155,20 @@ FNetPlan *fnet_plan_create(const Plan *plan_const) {
 
 void fnet_plan_destroy(FNetPlan *fp) { delete fp; }
 
+std::string fnet_plan_describe(const FNetPlan *fp) {
+    std::string t = "fused_net S0=" + std::to_string(fp->S0) + " warps=" + std::to_string(fp->nw) + " stages=" +
+                    std::to_string(fp->nst) + " :";
+    static const char *names[] = {"CONV", "AFFINE", "RELU", "STASH", "UNSTASH", "ADD", "TRANSPOSE", "DENSE", "T_RELU", "T_AFFINE"};
+    for (int k = 0; k < fp->n_ops; ++k) {
+        const NOp &o = fp->ops[k];
+        t += std::string(" ") + names[o.kind] + "(" + std::to_string(o.si);
+        if (o.kind == N_CONV) t += "," + std::to_string(o.lo) + "," + std::to_string(o.hi) + ",s" + std::to_string(o.st);
+        if (o.kind == N_STASH || o.kind == N_UNSTASH || o.kind == N_ADD) t += ",t" + std::to_string(o.slot);
+        t += ")";
+    }
+    return t;
+}
+
 int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2, int32_t C,
                      const void *d_aux_x, const void *d_aux_z, int32_t symmetric, const void *d_kdiag,
                      void *d_out, int64_t ld_out, void *stream) {

@@ -495,6 +495,17 @@ FusedPlan *fused_plan_create(const Plan *plan_const) {
 
 void fused_plan_destroy(FusedPlan *fp) { delete fp; }
 
+std::string fused_plan_describe(const FusedPlan *fp) {
+    std::string t = "fused S=" + std::to_string(fp->S) + " window=" + std::to_string(fp->lo) + "," + std::to_string(fp->hi) + " :";
+    for (int k = 0; k < fp->n_ops; ++k) {
+        const FOp &o = fp->ops[k];
+        if (o.kind == F_CONV) t += " CONV(" + std::to_string(o.lo) + "," + std::to_string(o.hi) + ")";
+        else if (o.kind == F_RELU) t += " RELU";
+        else t += " DENSE";
+    }
+    return t;
+}
+
 namespace {
 
 struct Variant { int nw, nsplit, nst; };

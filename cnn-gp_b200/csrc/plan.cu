@@ -184,6 +184,21 @@ int cnngp_plan_has_fused(const cnngp_plan *plan) {
     return p->fused ? CNNGP_PATH_FUSED : (p->fnet ? CNNGP_PATH_FUSED_NET : 0);
 }
 
+int64_t cnngp_plan_describe(const cnngp_plan *plan, char *buf, int64_t cap) {
+    const Plan *p = reinterpret_cast<const Plan *>(plan);
+    std::string t;
+    if (!p) t = "null plan";
+    else if (p->fused) t = fused_plan_describe(p->fused);
+    else if (p->fnet) t = fnet_plan_describe(p->fnet);
+    else t = "generic: " + std::to_string(p->ops.size()) + " ops, " + std::to_string(p->n_slots) + " slots";
+    if (buf && cap > 0) {
+        const size_t n = std::min<size_t>((size_t)cap - 1, t.size());
+        memcpy(buf, t.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)t.size() + 1;
+}
+
 int cnngp_variances(const cnngp_plan *plan, const void *d_x, const void *d_z, int64_t N, int32_t C,
                     void *d_aux_x, void *d_aux_z, void *d_kdiag, void *stream) {
     const Plan *p = reinterpret_cast<const Plan *>(plan);

@@ -87,6 +87,12 @@ double cnngp_plan_flops_per_pair(const cnngp_plan *plan, int32_t C);
  * memory), or 0 (generic kernel only). */
 int cnngp_plan_has_fused(const cnngp_plan *plan);
 
+/* Human-readable description of how the plan will be executed (kernel family and, for the fused
+ * kernels, the register-level op list the host translator produced), written NUL-terminated into
+ * buf (at most cap bytes).  Returns the number of bytes the full text needs.  For tests and
+ * debugging of the host-side translation; no GPU is involved. */
+int64_t cnngp_plan_describe(const cnngp_plan *plan, char *buf, int64_t cap);
+
 /* Per-image variance recursion: the xx / yy maps of kernels.py:48-49 pushed through the
  * program (Conv2d acts on them as on xy, kernels.py:98; ReLU halves them, kernels.py:154,164).
  *   d_x        [N, C, H, W] images

@@ -249,3 +249,46 @@ def test_merge_fills_only_nan(tmp_path):
     block_store.merge_into(a, b)
     np.testing.assert_array_equal(a["K"][0], [[1, 2], [3, 4]])
     assert "only_b" not in a
+
+
+def test_fused_translation_of_shipped_programs():
+    """Host-side translation into register-level ops (cnngp_plan_describe; no GPU needed): which
+    kernel family covers which shipped program, and the structure of the fused-net op lists --
+    one ReLU per program ReLU, every Sum an ADD fed by a STASH, strided maps half / quarter size."""
+    import re
+    models = golden_models()
+    expect = {"readme": ("fused_net", 28), "mnist_paper_convnet_gp": ("fused", 28),
+              "mnist_paper_residual_cnn_gp": ("fused_net", 28), "mnist_as_tf": ("fused_net", 28),
+              "mnist": ("fused_net", 28), "cifar10": ("fused_net", 32)}
+    for name, (family, S) in expect.items():
+        ops, ns = program.compile_model(models[name])
+        plan = nat.Plan(ops, ns, S, S, nat.F32)
+        text = plan.describe()
+        assert text.split()[0] == family, (name, text[:80])
+        n_relu = sum(1 for o in ops if o.opcode == nat.OP_RELU)
+        n_add = sum(1 for o in ops if o.opcode == nat.OP_ADD)
+        toks = text.split(":", 1)[1].split()
+        assert sum(t.startswith(("RELU", "T_RELU")) for t in toks) == n_relu, name
+        if family == "fused":
+            assert toks[-1] == "DENSE" and n_add == 0
+            continue
+        assert sum(t.startswith("ADD") for t in toks) == n_add, name
+        assert sum(t.startswith("DENSE") for t in toks) == 1, name
+        # every ADD reads a tensor-memory slot that an earlier STASH filled and nobody re-filled since
+        live = {}
+        for t in toks:
+            m = re.match(r"(STASH|UNSTASH|ADD)\((\d+),t(\d)\)", t)
+            if not m:
+                continue
+            kind, size, slot = m.group(1), int(m.group(2)), int(m.group(3))
+            if kind == "STASH":
+                live[slot] = size
+            else:
+                assert live.get(slot) == size, (name, t)
+        sizes = {int(re.match(r"\w+\((\d+)", t).group(1)) for t in toks}
+        assert sizes <= {S, S // 2, S // 4, 1}, (name, sizes)
+    # float64 and odd input sizes stay on the generic kernel
+    ops, ns = program.compile_model(models["mnist_as_tf"])
+    assert nat.Plan(ops, ns, 28, 28, nat.F64).describe().startswith("generic")
+    ops, ns = program.compile_model(models["edge_linear"])
+    assert nat.Plan(ops, ns, 12, 12, nat.F32).describe().startswith("generic")
