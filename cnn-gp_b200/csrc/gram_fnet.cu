@@ -30,7 +30,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <string>
 #include <vector>
 
@@ -1175,9 +1174,7 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
     const FNetPlan *fp = plan->fnet;
     if (!fp) { set_error("fused-net kernel: unsupported call"); return 4; }
     if (N1 > 2000000000LL || N2 > 2000000000LL) { set_error("fused-net kernel: too many images"); return 8; }
-    static NParams p;  // 6 KB of ops: filled per call under a lock, passed by value at launch
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lk(mu);
+    NParams p;  // ~6 KB, passed by value at launch
     memset(&p, 0, sizeof p);
     memcpy(p.ops, fp->ops, sizeof(NOp) * fp->n_ops);
     p.n_ops = fp->n_ops;
