@@ -1,0 +1,235 @@
+"""Float64 Cholesky solve with the matrix spread over several GPUs (one process per GPU,
+``torch.distributed`` over NCCL / NVLink) -- SURVEY.md 8(f) rank 1: after the Gram kernels the
+single-GPU solve of exp_mnist_resnet/classify_gp.py:17-27 is the longest step of the pipeline.
+
+Layout: block rows of 256 rows, dealt out cyclically (block b lives on rank b % world), each
+stored full width, so a rank holds n / world rows (3.6 GB of the 28.8 GB at n = 60 000, world 8).
+Right-looking factorisation, per block row b:
+
+  owner      cnngp_potrf_panel_f64 on its rows      (the same panel code as the one-GPU potrf)
+  everybody  receives the factored panel X = U[b, b+1:] by NCCL broadcast (<= 123 MB)
+  everybody  cnngp_syrk_upper_f64: rank-256 update of the block rows it owns (DMMA)
+
+with one block row of look-ahead: the owner of block b + 1 updates that block first, factorises
+it and starts its broadcast on a side stream while all ranks are still busy with update b, so the
+NVLink transfer and the latency-bound panel hide under the tensor-pipe work.
+
+The compute calls go through a small backend object; the CUDA backend is the C ABI
+(include/cnngp.h).  Tests drive the same orchestration over gloo with a numpy backend.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+BLK = 256   # rows per block row (= the panel height of cnngp_potrf_panel_f64)
+TILE = 128  # row-tile height of cnngp_syrk_upper_f64
+
+
+def n_blocks(n):
+    return -(-n // BLK)
+
+
+def owned_blocks(rank, world, n):
+    return list(range(rank, n_blocks(n), world))
+
+
+def block_rows(b, n):
+    return min(BLK, n - b * BLK)
+
+
+class CudaBackend:
+    """The sm_100a kernels behind include/cnngp.h."""
+
+    def __init__(self):
+        from . import _native as nat
+        self.nat = nat
+        self._work = {}  # device -> 128 x 128 doubles of panel scratch
+
+    @staticmethod
+    def _stream():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def panel(self, rows, col0, n, info):
+        """Factorise the block row held in ``rows`` [nb, n] whose diagonal starts at column col0."""
+        work = self._work.get(rows.device)
+        if work is None:
+            work = self._work[rows.device] = torch.empty(128 * 128, dtype=torch.float64, device=rows.device)
+        self.nat.check(self.nat.lib().cnngp_potrf_panel_f64(
+            rows.data_ptr() + 8 * col0, rows.stride(0), n - col0, col0, info.data_ptr(), work.data_ptr(),
+            self._stream()), "cnngp_potrf_panel_f64")
+
+    def syrk(self, X, K, m, rows, col0, t_row0):
+        """rows[r, col0 + j] -= sum_k X[k, t_row0 + r] X[k, j] for j >= t_row0 + r: the update of one
+        owned block row that starts at trailing-relative row t_row0 (a multiple of 128)."""
+        nr = rows.shape[0]
+        base = rows.data_ptr() + 8 * col0 - 8 * t_row0 * rows.stride(0)
+        self.nat.check(self.nat.lib().cnngp_syrk_upper_f64(
+            X.data_ptr(), m, K, ctypes.c_void_p(base), rows.stride(0), m, t_row0 // TILE,
+            (t_row0 + nr + TILE - 1) // TILE, self._stream()), "cnngp_syrk_upper_f64")
+
+    def potrs(self, U, B):
+        from . import linalg
+        return linalg.potrs_upper_(U, B)
+
+
+class DistributedCholesky:
+    """Block rows of one symmetric positive definite matrix on this rank + the factorisation."""
+
+    def __init__(self, n, device, group=None, backend=None):
+        self.n, self.device, self.group = n, device, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.backend = backend if backend is not None else CudaBackend()
+        self.blocks = owned_blocks(self.rank, self.world, n)
+        self.offsets, off = {}, 0
+        for b in self.blocks:
+            self.offsets[b] = off
+            off += block_rows(b, n)
+        self.local = torch.empty((max(off, 1), n), dtype=torch.float64, device=device)
+        self.n_local = off
+
+    def rows_of(self, b):
+        o = self.offsets[b]
+        return self.local[o:o + block_rows(b, self.n)]
+
+    # -- data movement ---------------------------------------------------------------------------
+    def scatter_from(self, K, src=0):
+        """Deal the block rows of ``K`` (on rank ``src``; float32 or float64, only j >= i is used)
+        out to their owners, widened to float64 on the way."""
+        n, world = self.n, self.world
+        for r in range(world):
+            blocks = owned_blocks(r, world, n)
+            if not blocks:
+                continue
+            if self.rank == src:
+                idx = torch.cat([torch.arange(b * BLK, b * BLK + block_rows(b, n), device=K.device) for b in blocks])
+                chunk = K.index_select(0, idx).to(torch.float64)
+                if r == src:
+                    self.local[:len(idx)].copy_(chunk)
+                else:
+                    dist.send(chunk, dst=r, group=self.group)
+                del chunk
+            elif self.rank == r:
+                dist.recv(self.local[:self.n_local], src=src, group=self.group)
+
+    def gather_to(self, dst=0):
+        """The factor's block rows back on rank ``dst`` as one [n, n] matrix (None elsewhere)."""
+        n, world = self.n, self.world
+        full = torch.empty((n, n), dtype=torch.float64, device=self.device) if self.rank == dst else None
+        for r in range(world):
+            blocks = owned_blocks(r, world, n)
+            if not blocks:
+                continue
+            rows = sum(block_rows(b, n) for b in blocks)
+            if self.rank == dst:
+                buf = self.local[:rows] if r == dst else torch.empty((rows, n), dtype=torch.float64, device=self.device)
+                if r != dst:
+                    dist.recv(buf, src=r, group=self.group)
+                o = 0
+                for b in blocks:
+                    nb = block_rows(b, n)
+                    full[b * BLK:b * BLK + nb].copy_(buf[o:o + nb])
+                    o += nb
+            elif self.rank == r:
+                dist.send(self.local[:rows], dst=dst, group=self.group)
+        return full
+
+    # -- factorisation ---------------------------------------------------------------------------
+    def factorize(self, lookahead=True):
+        """In place: every block row becomes the matching rows of U (A = U^T U).  Returns LAPACK's
+        info (0 = success) as a Python int, identical on every rank."""
+        n, rank, world, be = self.n, self.rank, self.world, self.backend
+        nblk = n_blocks(n)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        use_cuda = self.device.type == "cuda"
+        side = torch.cuda.Stream(device=self.device, priority=-1) if (use_cuda and lookahead) else None
+        xbufs = [torch.empty(BLK * max(n - BLK, 1), dtype=torch.float64, device=self.device) for _ in range(2)]
+
+        def factor_and_pack(b, xb):
+            """Owner of block b: factorise it and pack U[b, b+1:] contiguously into xb."""
+            kb, nb = b * BLK, block_rows(b, n)
+            rows = self.rows_of(b)
+            be.panel(rows, kb, n, info)
+            m = n - kb - nb
+            if m > 0:
+                xb[:nb * m].view(nb, m).copy_(rows[:, kb + nb:])
+
+        def update(b, xb, blocks):
+            kb, nb = b * BLK, block_rows(b, n)
+            m = n - kb - nb
+            X = xb[:nb * m].view(nb, m)
+            for i in blocks:
+                be.syrk(X, nb, m, self.rows_of(i), kb + nb, (i - b - 1) * BLK)
+
+        # block 0: factor + broadcast up front
+        if rank == 0 % world:
+            factor_and_pack(0, xbufs[0])
+        pending = None
+        for b in range(nblk):
+            kb, nb = b * BLK, block_rows(b, n)
+            m = n - kb - nb
+            if m <= 0:
+                break
+            xb = xbufs[b % 2]
+            if pending is not None:
+                pending()  # the broadcast of panel b started during update b - 1
+                pending = None
+            else:
+                dist.broadcast(xb[:nb * m], src=b % world, group=self.group)
+            mine = [i for i in self.blocks if i > b]
+            nxt = b + 1
+            if side is not None and nxt < nblk:
+                # look-ahead: block b + 1 first; its owner factorises it and everybody starts the
+                # broadcast on the side stream while the remaining updates of step b run
+                if nxt in self.offsets:
+                    update(b, xb, [nxt])
+                    mine = [i for i in mine if i != nxt]
+                ev = torch.cuda.Event()
+                ev.record()
+                nb2 = block_rows(nxt, n)
+                m2 = n - nxt * BLK - nb2
+                xb2 = xbufs[nxt % 2]
+                with torch.cuda.stream(side):
+                    side.wait_event(ev)
+                    if nxt in self.offsets:
+                        factor_and_pack(nxt, xb2)
+                    work = dist.broadcast(xb2[:nb2 * m2], src=nxt % world, group=self.group, async_op=True) if m2 > 0 else None
+
+                def finish(work=work):
+                    if work is not None:
+                        work.wait()  # orders the current stream after the collective
+                    torch.cuda.current_stream().wait_stream(side)
+                pending = finish
+                update(b, xb, mine)
+            else:
+                update(b, xb, mine)
+                if nxt < nblk and nxt in self.offsets:
+                    factor_and_pack(nxt, xbufs[nxt % 2])
+        if pending is not None:
+            pending()
+        code = info.clone()
+        dist.all_reduce(code, op=dist.ReduceOp.MAX, group=self.group)
+        # the first failing pivot is the smallest non-zero info; MAX is enough to know about failure,
+        # the exact index comes from the minimum over the ranks that saw one
+        if int(code) != 0:
+            big = torch.where(info > 0, info, torch.full_like(info, 2 ** 31 - 1))
+            dist.all_reduce(big, op=dist.ReduceOp.MIN, group=self.group)
+            return int(big)
+        return 0
+
+
+@torch.no_grad()
+def solve_pos_upper_distributed(K, Y, n, device, group=None, src=0, backend=None, lookahead=True):
+    """A = K^{-1} Y with K (upper triangle, float32 or float64) and Y on rank ``src``; the
+    factorisation runs on all ranks of ``group``, the two triangular solves on ``src`` after the
+    factor has been gathered there.  Returns A on ``src`` and None elsewhere."""
+    from .linalg import NotPositiveDefiniteError
+    ch = DistributedCholesky(n, device, group=group, backend=backend)
+    ch.scatter_from(K, src=src)
+    info = ch.factorize(lookahead=lookahead)
+    if info != 0:
+        raise NotPositiveDefiniteError(info)
+    U = ch.gather_to(dst=src)
+    if ch.rank != src:
+        return None
+    return ch.backend.potrs(U, Y.to(torch.float64).clone().contiguous())

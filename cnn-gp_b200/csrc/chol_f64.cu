@@ -226,7 +226,7 @@ constexpr int POTF2_THREADS = 512;
 constexpr int QB = 32;
 
 __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_inv_kernel(double *A, long long lda, int kb, int nb,
-                                                                     double *W, int *info) {
+                                                                     double *W, int *info, long long info_base) {
     extern __shared__ __align__(16) double ps_smem[];
     double *s = ps_smem;                 // [NB][DP]
     double *rinv = ps_smem + NB * DP;    // [NB] reciprocals of the diagonal of U
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_inv_kernel(double *A, 
             for (int c = 0; c < QB; ++c) {
                 const double d = __shfl_sync(0xffffffffu, a[c], c);
                 const bool bad = !(d > 0.0);
-                if (bad && lane == 0 && *info == 0) *info = kb + o + c + 1;
+                if (bad && lane == 0 && *info == 0) *info = (int)(info_base + kb + o + c + 1);
                 const double r = bad ? nan("") : sqrt(d), ri = 1.0 / r;
                 const double u = lane == c ? r : a[c] * ri;  // row c of U at this lane's column (valid for lane >= c)
                 a[c] = u;
@@ -545,6 +545,60 @@ bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 // Tj column tiles; row tile ib holds jb in [2 ib, Tj)
 long long tri_prefix(long long ib, long long Tj) { return ib * Tj - ib * (ib - 1); }
 
+bool ensure_attrs() {
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && attr_done[dev]) return true;
+    if (!check(cudaFuncSetAttribute(tn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTnSmem), "attr") ||
+        !check(cudaFuncSetAttribute(tn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTnSmem), "attr") ||
+        !check(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotf2Smem), "attr"))
+        return false;
+    if (dev < 64) attr_done[dev] = true;
+    return true;
+}
+
+// C[i][j] -= sum_k X[k][i] X[k][j] for j >= i, i, j < m, row tiles [ib_lo, ib_hi) of TI rows; C + i*ldc + j
+void launch_syrk(const double *X, int64_t ldx, int K, double *C, int64_t ldc, int64_t m, int ib_lo, int ib_hi,
+                 cudaStream_t st) {
+    if (m <= 0) return;
+    TnParams g{};
+    g.P = X; g.ldp = ldx; g.Q = X; g.ldq = ldx; g.C = C; g.ldc = ldc;
+    g.M = (int)m; g.N = (int)m; g.K = K;
+    g.vec_ok = (ldx % 2 == 0) && (ldc % 2 == 0) && aligned16(X) && aligned16(C);
+    g.Tj = (int)((m + TJ - 1) / TJ);
+    const int Ti = (int)((m + TI - 1) / TI);
+    if (ib_hi > Ti) ib_hi = Ti;
+    if (ib_lo >= ib_hi) return;
+    g.ib_lo = ib_lo; g.t_off = tri_prefix(ib_lo, g.Tj);
+    const long long tiles = tri_prefix(ib_hi, g.Tj) - g.t_off;
+    tn_kernel<0><<<(unsigned)tiles, TN_THREADS, kTnSmem, st>>>(g);
+}
+
+// X = W^T X in place: X [nb, ldx] with m columns
+void launch_trsm(const double *W, double *X, int64_t ldx, int nb, int64_t m, cudaStream_t st) {
+    if (m <= 0) return;
+    TnParams g{};
+    g.P = W; g.ldp = NB; g.Q = X; g.ldq = ldx; g.C = X; g.ldc = ldx;
+    g.M = nb; g.N = (int)m; g.K = nb;
+    g.vec_ok = (ldx % 2 == 0) && aligned16(X) && aligned16(W);
+    g.Tj = (int)((m + TJ - 1) / TJ);
+    tn_kernel<1><<<(unsigned)g.Tj, TN_THREADS, kTnSmem, st>>>(g);
+}
+
+// factorise the block row P[0:rows, 0:width] (rows <= 2 NB; P[0][0] is its diagonal element): two
+// diagonal blocks and their row panels, with the rank-128 update of the second half in between
+void launch_panel(double *P, int64_t ldp, int64_t width, double *W, int *info, int64_t info_base, cudaStream_t st) {
+    const int nb1 = (int)(width < NB ? width : NB);
+    potf2_inv_kernel<<<1, POTF2_THREADS, kPotf2Smem, st>>>(P, ldp, 0, nb1, W, info, info_base);
+    if (width <= NB) return;
+    launch_trsm(W, P + NB, ldp, nb1, width - NB, st);
+    launch_syrk(P + NB, ldp, nb1, P + NB * ldp + NB, ldp, width - NB, 0, 1, st);  // the second half only
+    const int nb2 = (int)(width - NB < NB ? width - NB : NB);
+    potf2_inv_kernel<<<1, POTF2_THREADS, kPotf2Smem, st>>>(P, ldp, NB, nb2, W, info, info_base);
+    launch_trsm(W, P + NB * ldp + 2 * NB, ldp, nb2, width - 2 * NB, st);
+}
+
 }  // namespace
 }  // namespace cnngp
 
@@ -552,22 +606,30 @@ using namespace cnngp;
 
 extern "C" {
 
+// ---- building blocks of a right-looking Cholesky, for drivers that keep block rows on several GPUs
+int cnngp_potrf_panel_f64(double *d_P, int64_t ldp, int64_t width, int64_t info_base, int32_t *d_info,
+                          double *d_work, void *stream_) {
+    if (!d_P || width < 1 || ldp < width || !d_info || !d_work) { set_error("cnngp_potrf_panel_f64: bad arguments"); return 1; }
+    if (!ensure_attrs()) return 7;
+    launch_panel(d_P, ldp, width, d_work, d_info, info_base, (cudaStream_t)stream_);
+    return check(cudaGetLastError(), "cnngp_potrf_panel_f64") ? 0 : 9;
+}
+
+int cnngp_syrk_upper_f64(const double *d_X, int64_t ldx, int32_t K, double *d_C, int64_t ldc, int64_t m, int32_t ib_lo,
+                         int32_t ib_hi, void *stream_) {
+    if (!d_X || !d_C || K < 1 || K > 2 * NB || m < 0 || ldx < m || ib_lo < 0) { set_error("cnngp_syrk_upper_f64: bad arguments"); return 1; }
+    if (!ensure_attrs()) return 7;
+    launch_syrk(d_X, ldx, K, d_C, ldc, m, ib_lo, ib_hi, (cudaStream_t)stream_);
+    return check(cudaGetLastError(), "cnngp_syrk_upper_f64") ? 0 : 9;
+}
+
 int cnngp_potrf_upper_f64(double *d_A, int64_t n, int64_t lda, int32_t *d_info, void *stream_) {
     if (!d_A || n < 0 || lda < n || !d_info) { set_error("cnngp_potrf_upper_f64: bad arguments"); return 1; }
     if (n > 2000000000LL) { set_error("cnngp_potrf_upper_f64: n too large"); return 1; }
     cudaStream_t s = (cudaStream_t)stream_;
     if (!check(cudaMemsetAsync(d_info, 0, sizeof(int32_t), s), "potrf memset")) return 5;
     if (n == 0) return 0;
-    static bool attr_done[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 64 && !attr_done[dev]) {
-        if (!check(cudaFuncSetAttribute(tn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTnSmem), "attr") ||
-            !check(cudaFuncSetAttribute(tn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTnSmem), "attr") ||
-            !check(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotf2Smem), "attr"))
-            return 7;
-        attr_done[dev] = true;
-    }
+    if (!ensure_attrs()) return 7;
     double *W = nullptr;
     if (!check(cudaMallocAsync((void **)&W, sizeof(double) * NB * NB, s), "potrf workspace")) return 6;
     cudaStream_t s2 = nullptr;
@@ -582,56 +644,24 @@ int cnngp_potrf_upper_f64(double *d_A, int64_t n, int64_t lda, int32_t *d_info, 
         cudaFreeAsync(W, s);
         return 6;
     }
-    const int vec_ok = (lda % 2 == 0) && aligned16(d_A);
     constexpr int NBO = 2 * NB;
-
-    // SYRK launch: C = A[r0:, r0:] (size m) -= X^T X with X = A[k0:k0+K, r0:], row tiles [ib_lo, ib_hi)
-    auto syrk = [&](int64_t k0, int K, int64_t r0, int ib_lo, int ib_hi, cudaStream_t st) {
-        const int64_t m = n - r0;
-        if (m <= 0) return;
-        TnParams g{};
-        g.P = d_A + k0 * lda + r0; g.ldp = lda; g.Q = g.P; g.ldq = lda;
-        g.C = d_A + r0 * lda + r0; g.ldc = lda;
-        g.M = (int)m; g.N = (int)m; g.K = K; g.vec_ok = vec_ok;
-        g.Tj = (int)((m + TJ - 1) / TJ);
-        const int Ti = (int)((m + TI - 1) / TI);
-        if (ib_hi > Ti) ib_hi = Ti;
-        if (ib_lo >= ib_hi) return;
-        g.ib_lo = ib_lo; g.t_off = tri_prefix(ib_lo, g.Tj);
-        const long long tiles = tri_prefix(ib_hi, g.Tj) - g.t_off;
-        tn_kernel<0><<<(unsigned)tiles, TN_THREADS, kTnSmem, st>>>(g);
+    // trailing update with the block row at kb: C = A[r0:, r0:], X = A[kb:kb+NBO, r0:]
+    auto update = [&](int64_t kb, int ib_lo, int ib_hi, cudaStream_t st) {
+        const int64_t r0 = kb + NBO;
+        launch_syrk(d_A + kb * lda + r0, lda, NBO, d_A + r0 * lda + r0, lda, n - r0, ib_lo, ib_hi, st);
     };
-    // X = W^T A[k0:k0+nb, c0:n] in place
-    auto trsm = [&](int64_t k0, int nb, int64_t c0, cudaStream_t st) {
-        const int64_t m = n - c0;
-        if (m <= 0) return;
-        TnParams g{};
-        g.P = W; g.ldp = NB; g.Q = d_A + k0 * lda + c0; g.ldq = lda; g.C = d_A + k0 * lda + c0; g.ldc = lda;
-        g.M = nb; g.N = (int)m; g.K = nb; g.vec_ok = vec_ok;
-        g.Tj = (int)((m + TJ - 1) / TJ);
-        tn_kernel<1><<<(unsigned)g.Tj, TN_THREADS, kTnSmem, st>>>(g);
-    };
-    // factorise the block row starting at kb (up to 2 NB rows): diagonal blocks and row panels
     auto panel = [&](int64_t kb, cudaStream_t st) {
-        const int nb1 = (int)(n - kb < NB ? n - kb : NB);
-        potf2_inv_kernel<<<1, POTF2_THREADS, kPotf2Smem, st>>>(d_A, lda, (int)kb, nb1, W, d_info);
-        if (n - kb <= NB) return;
-        trsm(kb, nb1, kb + NB, st);
-        syrk(kb, nb1, kb + NB, 0, 1, st);  // only the panel's second half needs the rank-128 update now
-        const int nb2 = (int)(n - kb - NB < NB ? n - kb - NB : NB);
-        potf2_inv_kernel<<<1, POTF2_THREADS, kPotf2Smem, st>>>(d_A, lda, (int)(kb + NB), nb2, W, d_info);
-        trsm(kb + NB, nb2, kb + NBO, st);
+        launch_panel(d_A + kb * lda + kb, lda, n - kb, W, d_info, kb, st);
     };
 
     panel(0, s);
     for (int64_t kb = 0; kb + NBO < n; kb += NBO) {
-        const int64_t r0 = kb + NBO;  // trailing matrix origin
-        syrk(kb, NBO, r0, 0, NBO / TI, s);  // look-ahead: the next panel's rows first
+        update(kb, 0, NBO / TI, s);  // look-ahead: the next panel's rows first
         cudaEventRecord(ev_head, s);
         cudaStreamWaitEvent(s2, ev_head, 0);
-        panel(r0, s2);
+        panel(kb + NBO, s2);
         cudaEventRecord(ev_panel, s2);
-        syrk(kb, NBO, r0, NBO / TI, 1 << 30, s);
+        update(kb, NBO / TI, 1 << 30, s);
         cudaStreamWaitEvent(s, ev_panel, 0);
     }
     cudaFreeAsync(W, s);

@@ -22,7 +22,7 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [p for p in (os.path.join(_ROOT, "cnn-gp_b200"), _ROOT) if p not in sys.path]
 
 from cnn_gp import DatasetFromConfig  # noqa: E402
-from cnn_gp import linalg  # noqa: E402
+from cnn_gp import linalg, linalg_dist  # noqa: E402
 from cnn_gp.block_store import open_store  # noqa: E402
 from cnn_gp.kernel_save_tools import create_h5py_dataset  # noqa: E402
 from cnn_gp.tiles import GramJob, compute_worker_blocks, gather_blocks  # noqa: E402
@@ -65,17 +65,25 @@ def main(_):
                 for name, K in (("Kxx", Kxx), ("Kxvx", Kxvx), ("Kxtx", Kxtx)):
                     ds = create_h5py_dataset(f, FLAGS.batch_size, name, False, K.shape[0], K.shape[1])
                     ds[0, :, :] = K.cpu().numpy()
-        Y = sets["train"].labels
-        n_classes = int(Y.max()) + 1
-        Y_1hot = torch.ones((len(Y), n_classes), dtype=torch.float64).neg_()
-        Y_1hot[torch.arange(len(Y)), Y] = 1.
-        t1 = time.perf_counter()
+    Y = sets["train"].labels
+    n_classes = int(Y.max()) + 1
+    Y_1hot = torch.ones((len(Y), n_classes), dtype=torch.float64).neg_()
+    Y_1hot[torch.arange(len(Y)), Y] = 1.
+    t1 = time.perf_counter()
+    if world > 1 and FLAGS.dist_solve:
+        # block rows of Kxx dealt out to all GPUs, panel broadcasts over NVLink (cnn_gp.linalg_dist)
+        if rank == 0 and FLAGS.jitter:
+            Kxx.diagonal().add_(FLAGS.jitter)
+        A = linalg_dist.solve_pos_upper_distributed(Kxx, Y_1hot.to(dev) if rank == 0 else None, len(Y), dev)
+    elif rank == 0:
         K64 = Kxx.to(torch.float64)
-        del Kxx
         K64.diagonal().add_(FLAGS.jitter)
         A = linalg.solve_pos_upper(K64, Y_1hot.to(dev), overwrite_a=True)
+        del K64
+    if rank == 0:
         torch.cuda.synchronize()
-        print(f"solve: {time.perf_counter() - t1:.3f} s (n = {len(Y)})")
+        print(f"solve: {time.perf_counter() - t1:.3f} s (n = {len(Y)}, "
+              f"{'distributed over ' + str(world) + ' GPUs' if world > 1 and FLAGS.dist_solve else 'one GPU'})")
         for key, K in (("validation", Kxvx), ("test", Kxtx)):
             pred = linalg.predict_argmax(K, A).cpu()
             acc = float((pred == sets[key].labels).double().mean())
@@ -92,4 +100,5 @@ if __name__ == '__main__':
     f.DEFINE_string("config", "synthetic", "which config to load from `configs`")
     f.DEFINE_string('out_path', None, "optional: store to write the merged kernels to")
     f.DEFINE_float("jitter", 0.0, "add to the diagonal")
+    f.DEFINE_boolean("dist_solve", True, "with several GPUs: factorise Kxx across all of them")
     absl.app.run(main)

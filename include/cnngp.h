@@ -137,6 +137,20 @@ int cnngp_relu_maps(void *d_xy, const void *d_xx, const void *d_yy, int64_t Nx, 
  * the leading minor of order k is not positive definite.  potrs solves U^T U X = B in place,
  * B row-major [n, ldb] with nrhs columns. */
 int cnngp_potrf_upper_f64(double *d_A, int64_t n, int64_t lda, int32_t *d_info, void *stream);
+/* Building blocks of the same factorisation for drivers that keep block rows of A on several GPUs
+ * (cnn-gp_b200/cnn_gp/linalg_dist.py).
+ * panel: factorise one block row of up to 256 rows in place.  d_P points at its diagonal element:
+ *        rows i < min(256, width), columns i <= j < width, row stride ldp; on return they hold
+ *        U[k, k:].  *d_info is NOT cleared; the first non-positive pivot sets it to
+ *        info_base + (row within the panel) + 1 if it is still 0.  d_work: 128 * 128 doubles of
+ *        caller-owned scratch (the inverse of the current diagonal block).
+ * syrk:  C[i][j] -= sum_k X[k][i] X[k][j] for j >= i, i, j < m and i in the 128-row tiles
+ *        [ib_lo, ib_hi); X is the factored panel [K <= 256, ldx] restricted to the trailing columns and
+ *        C is addressed as d_C + i*ldc + j, so a rank that holds only some rows passes a shifted base. */
+int cnngp_potrf_panel_f64(double *d_P, int64_t ldp, int64_t width, int64_t info_base, int32_t *d_info,
+                          double *d_work, void *stream);
+int cnngp_syrk_upper_f64(const double *d_X, int64_t ldx, int32_t K, double *d_C, int64_t ldc, int64_t m,
+                         int32_t ib_lo, int32_t ib_hi, void *stream);
 int cnngp_potrs_upper_f64(const double *d_U, int64_t n, int64_t lda, double *d_B, int32_t nrhs,
                           int64_t ldb, void *stream);
 /* classify_gp.py:39-41: pred[r] = argmax_c (K[r,:] . A[:,c]); K row-major float32 [R, ldk]

@@ -130,3 +130,47 @@ def test_cpu_tensors_are_rejected():
     from cnn_gp import linalg
     with pytest.raises(RuntimeError):
         linalg.potrf_upper_(torch.eye(3, dtype=torch.float64))
+
+
+def test_distributed_driver_on_one_gpu_matches_single_gpu_factor():
+    """cnn_gp.linalg_dist with world size 1 (NCCL): the building-block entry points
+    cnngp_potrf_panel_f64 / cnngp_syrk_upper_f64 must reproduce cnngp_potrf_upper_f64 bit for bit,
+    NaN below the diagonal untouched, LAPACK info on failure."""
+    import socket
+    import torch.distributed as dist
+    from cnn_gp import linalg, linalg_dist
+    created = False
+    if not dist.is_initialized():
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+        created = True
+    try:
+        dev = torch.device("cuda", 0)
+        for n in (100, 257, 1000, 1537):
+            K = _spd(n, 40 + n)
+            K = (K + K.T) / 2
+            Kd = torch.from_numpy(np.triu(K) + np.tril(np.full((n, n), np.nan), -1)).to(dev)
+            Y = torch.from_numpy(np.random.default_rng(n).standard_normal((n, 4))).to(dev)
+            A = linalg_dist.solve_pos_upper_distributed(Kd, Y, n, dev)
+            ch = linalg_dist.DistributedCholesky(n, dev)
+            ch.scatter_from(Kd)
+            assert ch.factorize() == 0
+            U = ch.gather_to(0)
+            U1 = Kd.clone()
+            linalg.potrf_upper_(U1)
+            iu = np.triu_indices(n)
+            np.testing.assert_array_equal(U.cpu().numpy()[iu], U1.cpu().numpy()[iu])
+            want = np.linalg.solve(K, Y.cpu().numpy())
+            np.testing.assert_allclose(A.cpu().numpy(), want, rtol=0, atol=1e-10 * np.abs(want).max())
+        K = _spd(600, 3)
+        K = (K + K.T) / 2
+        K[300, 300] = -2.0
+        with pytest.raises(linalg.NotPositiveDefiniteError) as ei:
+            linalg_dist.solve_pos_upper_distributed(torch.from_numpy(K).to(dev), torch.zeros(600, 1, dtype=torch.float64, device=dev), 600, dev)
+        assert ei.value.info == 301
+    finally:
+        if created:
+            dist.destroy_process_group()

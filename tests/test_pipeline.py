@@ -256,3 +256,76 @@ def test_balanced_split_is_a_contiguous_partition_with_even_pair_counts(N, N2, b
     assert sum(cost) == total
     biggest = max(tile_pairs(s, i, j, N, N if same else N2, bs) for s, i, j in full)
     assert max(cost) - sum(cost) / n <= biggest
+
+
+# ----------------------------------------------------- distributed Cholesky orchestration (gloo, CPU)
+class _NumpyBackend:
+    """The two compute calls of cnn_gp.linalg_dist restated with numpy / scipy (test-only), so that
+    ownership, packing, broadcasts and the shifted-base indexing can be checked without a GPU."""
+
+    def panel(self, rows, col0, n, info):
+        import scipy.linalg
+        a = rows.numpy()
+        nb = a.shape[0]
+        D = np.triu(a[:, col0:col0 + nb])
+        D = D + np.triu(D, 1).T
+        try:
+            U = np.linalg.cholesky(D).T
+        except np.linalg.LinAlgError:
+            info[0] = col0 + 1
+            return
+        a[:, col0:col0 + nb] = np.triu(U) + np.tril(a[:, col0:col0 + nb], -1)
+        if col0 + nb < n:
+            a[:, col0 + nb:] = scipy.linalg.solve_triangular(U, a[:, col0 + nb:], trans="T", lower=False)
+
+    def syrk(self, X, K, m, rows, col0, t_row0):
+        x, a = X.numpy(), rows.numpy()
+        for r in range(a.shape[0]):
+            i = t_row0 + r
+            a[r, col0 + i:col0 + m] -= x[:K, i] @ x[:K, i:m]
+
+    def potrs(self, U, B):
+        import scipy.linalg
+        u = np.triu(U.numpy())
+        y = scipy.linalg.solve_triangular(u, B.numpy(), trans="T", lower=False)
+        return torch.from_numpy(scipy.linalg.solve_triangular(u, y, lower=False))
+
+
+def _dist_solve_worker(rank, world, port, n, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path[:0] = [os.path.join(ROOT, "cnn-gp_b200"), ROOT, os.path.join(ROOT, "tests")]
+    import torch.distributed as dist
+    from cnn_gp import linalg_dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    K = Y = None
+    if rank == 0:
+        rng = np.random.default_rng(n)
+        B = rng.standard_normal((n, n + 20))
+        Kfull = B @ B.T / n + 0.1 * np.eye(n)
+        Y = torch.from_numpy(rng.standard_normal((n, 3)))
+        K = torch.from_numpy(np.triu(Kfull) + np.tril(np.full((n, n), np.nan), -1))  # lower triangle never read
+        ret["K"], ret["Y"] = Kfull, Y.numpy()
+    A = linalg_dist.solve_pos_upper_distributed(K, Y, n, torch.device("cpu"), backend=_NumpyBackend(), lookahead=False)
+    if rank == 0:
+        ret["A"] = A.numpy()
+    else:
+        assert A is None
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,world", [(700, 2), (513, 3), (200, 2)])
+def test_distributed_cholesky_orchestration_over_gloo(n, world):
+    """Block-row-cyclic ownership, panel broadcast and trailing updates of cnn_gp.linalg_dist with
+    a numpy compute backend: the solution must equal scipy's on the same matrix."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_dist_solve_worker, args=(r, world, port, n, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    want = np.linalg.solve(ret["K"], ret["Y"])
+    np.testing.assert_allclose(ret["A"], want, rtol=0, atol=1e-9 * np.abs(want).max())
