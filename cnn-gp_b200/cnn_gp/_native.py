@@ -52,6 +52,9 @@ _SIGNATURES = {
     "cnngp_syrk_upper_f64": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p,
                                             ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                             ctypes.c_void_p]),
+    "cnngp_syrk_upper_strided_f64": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p,
+                                                    ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                                    ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
     "cnngp_potrs_upper_f64": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                              ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p]),
     "cnngp_predict_argmax": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,

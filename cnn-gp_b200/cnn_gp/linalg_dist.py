@@ -68,6 +68,13 @@ class CudaBackend:
             X.data_ptr(), m, K, ctypes.c_void_p(base), rows.stride(0), m, t_row0 // TILE,
             (t_row0 + nr + TILE - 1) // TILE, self._stream()), "cnngp_syrk_upper_f64")
 
+    def syrk_strided(self, X, K, m, local, col0, ti0, stride, q0, n_blocks):
+        """The same update for the owned trailing blocks ti0, ti0 + stride, ... (stacked in ``local``
+        from local block q0) in one launch."""
+        self.nat.check(self.nat.lib().cnngp_syrk_upper_strided_f64(
+            X.data_ptr(), m, K, ctypes.c_void_p(local.data_ptr() + 8 * col0), local.stride(0), m, ti0, stride, q0,
+            n_blocks, self._stream()), "cnngp_syrk_upper_strided_f64")
+
     def potrs(self, U, B):
         from . import linalg
         return linalg.potrs_upper_(U, B)
@@ -158,8 +165,15 @@ class DistributedCholesky:
             kb, nb = b * BLK, block_rows(b, n)
             m = n - kb - nb
             X = xb[:nb * m].view(nb, m)
-            for i in blocks:
-                be.syrk(X, nb, m, self.rows_of(i), kb + nb, (i - b - 1) * BLK)
+            if not blocks:
+                return
+            if hasattr(be, "syrk_strided"):
+                # owned blocks are an arithmetic progression (stride = world) stacked 256 rows apart
+                i0 = blocks[0]
+                be.syrk_strided(X, nb, m, self.local, kb + nb, i0 - b - 1, world, (i0 - rank) // world, len(blocks))
+            else:
+                for i in blocks:
+                    be.syrk(X, nb, m, self.rows_of(i), kb + nb, (i - b - 1) * BLK)
 
         # block 0: factor + broadcast up front
         if rank == 0 % world:

@@ -58,6 +58,8 @@ __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
                  : "d"(a), "d"(b));
 }
 
+constexpr int kMaxRowTiles = 512;
+
 struct TnParams {
     const double *P;  // [K, ldp]: operand giving the rows of C (C row i <- column i of P)
     const double *Q;  // [K, ldq]: operand giving the columns of C
@@ -68,6 +70,12 @@ struct TnParams {
     int ib_lo;         // first row tile of this launch
     long long t_off;   // linear index of tile (ib_lo, first column) in the triangular enumeration
     int vec_ok;        // every row of P, Q, C is 16-byte aligned at even columns
+    // strided row-tile list (a rank that owns every rt_stride-th 256-row block of the trailing matrix,
+    // stored stacked from local block rt_q0): row tile k of the launch is trailing row tile
+    // 2 (rt_ti0 + rt_stride (k / 2)) + k % 2 and lives at local row 256 (rt_q0 + k / 2) + 128 (k % 2)
+    int rt_n;          // 0 = contiguous mode (ib_lo / t_off above)
+    int rt_ti0, rt_stride, rt_q0;
+    int rt_prefix[kMaxRowTiles + 1];  // tiles before row tile k
 };
 
 // C (op)= P^T Q on TI x TJ tiles.  MODE 0: C -= P^T Q restricted to j >= i (SYRK; tiles are
@@ -80,7 +88,18 @@ __global__ void __launch_bounds__(TN_THREADS, 2) tn_kernel(const TnParams g) {
     double *Qs = tn_smem + STAGES * KC * PP;    // [STAGES][KC][PQ]
 
     int ib, jb;
-    if (MODE == 0) {
+    long long crow0 = -1;  // row of C holding the tile's first row (-1: the trailing row index itself)
+    if (MODE == 0 && g.rt_n > 0) {
+        const int t = (int)blockIdx.x;
+        int lo = 0, hi = g.rt_n - 1;  // last k with rt_prefix[k] <= t
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (g.rt_prefix[mid] <= t) lo = mid; else hi = mid - 1;
+        }
+        ib = 2 * (g.rt_ti0 + g.rt_stride * (lo >> 1)) + (lo & 1);
+        jb = 2 * ib + (t - g.rt_prefix[lo]);
+        crow0 = 256LL * (g.rt_q0 + (lo >> 1)) + 128 * (lo & 1);
+    } else if (MODE == 0) {
         // row tile ib holds column tiles jb >= 2 ib: prefix(ib) = ib*Tj - ib*(ib-1)
         const long long t = g.t_off + blockIdx.x;
         const double b = (double)g.Tj + 1.0;
@@ -95,6 +114,7 @@ __global__ void __launch_bounds__(TN_THREADS, 2) tn_kernel(const TnParams g) {
         jb = blockIdx.x;
     }
     const int i0 = ib * TI, j0 = jb * TJ;
+    if (crow0 < 0) crow0 = i0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wi = warp >> 1, wj = warp & 1;  // 4 x 2 warps of 32 x 32
     const int nchunks = (g.K + KC - 1) / KC;
@@ -137,7 +157,7 @@ __global__ void __launch_bounds__(TN_THREADS, 2) tn_kernel(const TnParams g) {
         // now so that those loads do not pay HBM latency with the tensor pipe idle
         const int row = i0 + (tid >> 1);
         if (row < g.M) {
-            const double *c = g.C + (long long)row * g.ldc + j0 + (tid & 1) * 32;
+            const double *c = g.C + (crow0 + (tid >> 1)) * g.ldc + j0 + (tid & 1) * 32;
             if (j0 + (tid & 1) * 32 < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(c));
             if (j0 + (tid & 1) * 32 + 16 < g.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + 16));
         }
@@ -183,7 +203,7 @@ __global__ void __launch_bounds__(TN_THREADS, 2) tn_kernel(const TnParams g) {
     for (int fi = 0; fi < 4; ++fi) {
         const int i = i0 + wi * 32 + fi * 8 + lr;
         if (i >= g.M) continue;
-        double *crow = g.C + (long long)i * g.ldc;
+        double *crow = g.C + (crow0 + (i - i0)) * g.ldc;
 #pragma unroll
         for (int fj = 0; fj < 4; ++fj) {
             const int j = j0 + wj * 32 + fj * 8 + 2 * lk;
@@ -575,6 +595,33 @@ void launch_syrk(const double *X, int64_t ldx, int K, double *C, int64_t ldc, in
     tn_kernel<0><<<(unsigned)tiles, TN_THREADS, kTnSmem, st>>>(g);
 }
 
+// the same update for a rank that owns every `stride`-th 256-row block of the trailing matrix:
+// blocks ti0, ti0 + stride, ... (nblk of them), stored stacked in C_local from local block q0
+void launch_syrk_strided(const double *X, int64_t ldx, int K, double *C_local, int64_t ldc, int64_t m, int ti0,
+                         int stride, int q0, int nblk, cudaStream_t st) {
+    if (m <= 0) return;
+    const int Tj = (int)((m + TJ - 1) / TJ), Ti = (int)((m + TI - 1) / TI);
+    for (int b0 = 0; b0 < nblk; b0 += kMaxRowTiles / 2) {
+        const int nb = nblk - b0 < kMaxRowTiles / 2 ? nblk - b0 : kMaxRowTiles / 2;
+        TnParams g{};
+        g.P = X; g.ldp = ldx; g.Q = X; g.ldq = ldx; g.C = C_local; g.ldc = ldc;
+        g.M = (int)m; g.N = (int)m; g.K = K;
+        g.vec_ok = (ldx % 2 == 0) && (ldc % 2 == 0) && aligned16(X) && aligned16(C_local);
+        g.Tj = Tj;
+        g.rt_n = 2 * nb; g.rt_ti0 = ti0 + stride * b0; g.rt_stride = stride; g.rt_q0 = q0 + b0;
+        int acc = 0;
+        for (int k = 0; k < 2 * nb; ++k) {
+            const int ib = 2 * (g.rt_ti0 + stride * (k >> 1)) + (k & 1);
+            g.rt_prefix[k] = acc;
+            if (ib < Ti && Tj - 2 * ib > 0) acc += Tj - 2 * ib;
+        }
+        g.rt_prefix[2 * nb] = acc;
+        // trailing empty row tiles would break the search for the last k with prefix <= t: drop them
+        while (g.rt_n > 0 && g.rt_prefix[g.rt_n - 1] == acc) --g.rt_n;
+        if (acc > 0) tn_kernel<0><<<(unsigned)acc, TN_THREADS, kTnSmem, st>>>(g);
+    }
+}
+
 // X = W^T X in place: X [nb, ldx] with m columns
 void launch_trsm(const double *W, double *X, int64_t ldx, int nb, int64_t m, cudaStream_t st) {
     if (m <= 0) return;
@@ -621,6 +668,17 @@ int cnngp_syrk_upper_f64(const double *d_X, int64_t ldx, int32_t K, double *d_C,
     if (!ensure_attrs()) return 7;
     launch_syrk(d_X, ldx, K, d_C, ldc, m, ib_lo, ib_hi, (cudaStream_t)stream_);
     return check(cudaGetLastError(), "cnngp_syrk_upper_f64") ? 0 : 9;
+}
+
+int cnngp_syrk_upper_strided_f64(const double *d_X, int64_t ldx, int32_t K, double *d_C_local, int64_t ldc, int64_t m,
+                                 int32_t ti0, int32_t stride, int32_t q0, int32_t n_blocks, void *stream_) {
+    if (!d_X || !d_C_local || K < 1 || K > 2 * NB || m < 0 || ldx < m || ti0 < 0 || stride < 1 || q0 < 0 || n_blocks < 0) {
+        set_error("cnngp_syrk_upper_strided_f64: bad arguments");
+        return 1;
+    }
+    if (!ensure_attrs()) return 7;
+    launch_syrk_strided(d_X, ldx, K, d_C_local, ldc, m, ti0, stride, q0, n_blocks, (cudaStream_t)stream_);
+    return check(cudaGetLastError(), "cnngp_syrk_upper_strided_f64") ? 0 : 9;
 }
 
 int cnngp_potrf_upper_f64(double *d_A, int64_t n, int64_t lda, int32_t *d_info, void *stream_) {

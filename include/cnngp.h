@@ -151,6 +151,13 @@ int cnngp_potrf_panel_f64(double *d_P, int64_t ldp, int64_t width, int64_t info_
                           double *d_work, void *stream);
 int cnngp_syrk_upper_f64(const double *d_X, int64_t ldx, int32_t K, double *d_C, int64_t ldc, int64_t m,
                          int32_t ib_lo, int32_t ib_hi, void *stream);
+/* syrk for a rank that owns every `stride`-th 256-row block of the trailing matrix, in ONE launch:
+ * trailing blocks ti0, ti0 + stride, ... (n_blocks of them; trailing block t = trailing rows
+ * [256 t, 256 t + 256)) are stored stacked, 256 rows apart, from local block q0 of d_C_local, whose
+ * column 0 is the trailing matrix's column 0. */
+int cnngp_syrk_upper_strided_f64(const double *d_X, int64_t ldx, int32_t K, double *d_C_local, int64_t ldc,
+                                 int64_t m, int32_t ti0, int32_t stride, int32_t q0, int32_t n_blocks,
+                                 void *stream);
 int cnngp_potrs_upper_f64(const double *d_U, int64_t n, int64_t lda, double *d_B, int32_t nrhs,
                           int64_t ldb, void *stream);
 /* classify_gp.py:39-41: pred[r] = argmax_c (K[r,:] . A[:,c]); K row-major float32 [R, ldk]

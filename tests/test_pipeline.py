@@ -284,6 +284,12 @@ class _NumpyBackend:
             i = t_row0 + r
             a[r, col0 + i:col0 + m] -= x[:K, i] @ x[:K, i:m]
 
+    def syrk_strided(self, X, K, m, local, col0, ti0, stride, q0, n_blocks):
+        for k in range(n_blocks):
+            rows = local[256 * (q0 + k):256 * (q0 + k + 1)]
+            t_row0 = 256 * (ti0 + stride * k)
+            self.syrk(X, K, m, rows[:max(0, min(256, m - t_row0))], col0, t_row0)
+
     def potrs(self, U, B):
         import scipy.linalg
         u = np.triu(U.numpy())
