@@ -44,17 +44,22 @@ for n in [int(a) for a in sys.argv[1:]] or [8192]:
         del ch
     if rank == 0:
         X = linalg.potrs_upper_(U, Y.clone())
-        Kf = torch.triu(K) + torch.triu(K, 1).T
-        out["residual"] = float((Kf @ X - Y).abs().max() / (Kf.abs().max() * X.abs().max()))
-        U1 = torch.triu(K).clone()
+        if n <= 40000:  # the symmetrised copy costs 3 more n x n buffers
+            Kf = torch.triu(K) + torch.triu(K, 1).T
+            out["residual"] = float((Kf @ X - Y).abs().max() / (Kf.abs().max() * X.abs().max()))
+            del Kf
+        U1 = K  # the single-GPU factorisation may overwrite the input now
+        K = None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         linalg.potrf_upper_(U1)
         e1.record()
         torch.cuda.synchronize()
         out["single_gpu_potrf_ms"] = e0.elapsed_time(e1)
-        out["max_diff_vs_single_gpu_factor"] = float((torch.triu(U) - torch.triu(U1)).abs().max() / U1.abs().max())
+        U.sub_(U1)
+        del U1
+        out["max_diff_vs_single_gpu_factor"] = float(torch.triu(U).abs().max())
         print(json.dumps(out))
-        del U, U1, Kf, X
+        del U, X
     dist.barrier()
 dist.destroy_process_group()
