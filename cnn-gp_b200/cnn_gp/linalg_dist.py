@@ -100,45 +100,58 @@ class DistributedCholesky:
         return self.local[o:o + block_rows(b, self.n)]
 
     # -- data movement ---------------------------------------------------------------------------
-    def scatter_from(self, K, src=0):
+    # Collectives only (broadcast / gather): they run on the communicator's established rings,
+    # whereas first-use point-to-point channels between every pair of GPUs cost seconds to set up.
+    def scatter_from(self, K, src=0, chunk_rows=16 * BLK):
         """Deal the block rows of ``K`` (on rank ``src``; float32 or float64, only j >= i is used)
-        out to their owners, widened to float64 on the way."""
-        n, world = self.n, self.world
-        for r in range(world):
-            blocks = owned_blocks(r, world, n)
-            if not blocks:
-                continue
+        out to their owners, widened to float64 on arrival: ``K`` is broadcast in chunks of
+        ``chunk_rows`` rows and every rank keeps the blocks it owns."""
+        n = self.n
+        meta = torch.zeros(1, dtype=torch.int64, device=self.device)
+        if self.rank == src:
+            meta[0] = 1 if K.dtype == torch.float64 else 0
+        dist.broadcast(meta, src=src, group=self.group)
+        dtype = torch.float64 if int(meta[0]) else torch.float32
+        buf = None
+        for r0 in range(0, n, chunk_rows):
+            r1 = min(n, r0 + chunk_rows)
             if self.rank == src:
-                idx = torch.cat([torch.arange(b * BLK, b * BLK + block_rows(b, n), device=K.device) for b in blocks])
-                chunk = K.index_select(0, idx).to(torch.float64)
-                if r == src:
-                    self.local[:len(idx)].copy_(chunk)
-                else:
-                    dist.send(chunk, dst=r, group=self.group)
-                del chunk
-            elif self.rank == r:
-                dist.recv(self.local[:self.n_local], src=src, group=self.group)
+                chunk = K[r0:r1]
+                if not chunk.is_contiguous():
+                    chunk = chunk.contiguous()
+            else:
+                if buf is None:
+                    buf = torch.empty((chunk_rows, n), dtype=dtype, device=self.device)
+                chunk = buf[:r1 - r0]
+            if self.world > 1:
+                dist.broadcast(chunk, src=src, group=self.group)
+            for b in range(r0 // BLK, -(-r1 // BLK)):
+                if b in self.offsets:
+                    lo = b * BLK - r0
+                    self.rows_of(b).copy_(chunk[lo:lo + block_rows(b, n)])
 
     def gather_to(self, dst=0):
         """The factor's block rows back on rank ``dst`` as one [n, n] matrix (None elsewhere)."""
         n, world = self.n, self.world
-        full = torch.empty((n, n), dtype=torch.float64, device=self.device) if self.rank == dst else None
+        rows_max = max(sum(block_rows(b, n) for b in owned_blocks(r, world, n)) for r in range(world))
+        send = self.local if self.local.shape[0] == rows_max else torch.cat(
+            [self.local[:self.n_local], self.local.new_zeros((rows_max - self.n_local, n))])
+        # all_gather (a ring collective) rather than gather, which NCCL runs as point-to-point
+        # transfers over channels that first have to be set up
+        if world > 1:
+            parts = torch.empty((world, rows_max, n), dtype=torch.float64, device=self.device)
+            dist.all_gather_into_tensor(parts.view(world * rows_max, n), send[:rows_max].contiguous(), group=self.group)
+        else:
+            parts = send[:rows_max].unsqueeze(0)
+        if self.rank != dst:
+            return None
+        full = torch.empty((n, n), dtype=torch.float64, device=self.device)
         for r in range(world):
-            blocks = owned_blocks(r, world, n)
-            if not blocks:
-                continue
-            rows = sum(block_rows(b, n) for b in blocks)
-            if self.rank == dst:
-                buf = self.local[:rows] if r == dst else torch.empty((rows, n), dtype=torch.float64, device=self.device)
-                if r != dst:
-                    dist.recv(buf, src=r, group=self.group)
-                o = 0
-                for b in blocks:
-                    nb = block_rows(b, n)
-                    full[b * BLK:b * BLK + nb].copy_(buf[o:o + nb])
-                    o += nb
-            elif self.rank == r:
-                dist.send(self.local[:rows], dst=dst, group=self.group)
+            o = 0
+            for b in owned_blocks(r, world, n):
+                nb = block_rows(b, n)
+                full[b * BLK:b * BLK + nb].copy_(parts[r][o:o + nb])
+                o += nb
         return full
 
     # -- factorisation ---------------------------------------------------------------------------
@@ -237,13 +250,30 @@ def solve_pos_upper_distributed(K, Y, n, device, group=None, src=0, backend=None
     """A = K^{-1} Y with K (upper triangle, float32 or float64) and Y on rank ``src``; the
     factorisation runs on all ranks of ``group``, the two triangular solves on ``src`` after the
     factor has been gathered there.  Returns A on ``src`` and None elsewhere."""
+    import os
+    import time
     from .linalg import NotPositiveDefiniteError
+    verbose = bool(os.environ.get("CNNGP_DIST_VERBOSE")) and dist.get_rank(group) == src
+
+    def lap(what, t0):
+        if verbose:
+            if device.type == "cuda":
+                torch.cuda.synchronize()
+            print(f"  dist solve: {what} {time.perf_counter() - t0:.3f} s")
+        return time.perf_counter()
+
+    t = time.perf_counter()
     ch = DistributedCholesky(n, device, group=group, backend=backend)
     ch.scatter_from(K, src=src)
+    t = lap("scatter", t)
     info = ch.factorize(lookahead=lookahead)
+    t = lap("potrf", t)
     if info != 0:
         raise NotPositiveDefiniteError(info)
     U = ch.gather_to(dst=src)
+    t = lap("gather", t)
     if ch.rank != src:
         return None
-    return ch.backend.potrs(U, Y.to(torch.float64).clone().contiguous())
+    A = ch.backend.potrs(U, Y.to(torch.float64).clone().contiguous())
+    lap("potrs", t)
+    return A
