@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(512, 1) trsv_block_kernel(const double *U, lon
                                                            double *B, long long ldb, int c0, int nr) {
     extern __shared__ __align__(16) double tr_smem[];
     double *s = tr_smem;             // [NB][DP]
-    double *bs = tr_smem + NB * DP;  // [NB][NR]
+    double *bs = tr_smem + NB * DP;  // [NR][DP]: right-hand side c of row r at bs[c * DP + r] (lanes = rows: conflict-free)
     const int tid = threadIdx.x;
     const double *D = U + (long long)kb * lda + kb;
 #pragma unroll 8
@@ -396,11 +396,11 @@ __global__ void __launch_bounds__(512, 1) trsv_block_kernel(const double *U, lon
     }
     for (int e = tid; e < nb * nr; e += 512) {
         const int r = e / nr, c = e % nr;
-        bs[r * NR + c] = B[(long long)(kb + r) * ldb + c0 + c];
+        bs[c * DP + r] = B[(long long)(kb + r) * ldb + c0 + c];
     }
     // reciprocals of the diagonal once (LAPACK's dtrsm scales by the reciprocal too), so that the
     // 128 dependent steps below carry a multiply instead of a division
-    double *invd = bs + NB * NR;
+    double *invd = bs + NR * DP;
     __syncthreads();
     if (tid < nb) invd[tid] = 1.0 / s[tid * DP + tid];
     const int r = tid & (NB - 1), cg = tid >> 7;  // 4 column groups
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(512, 1) trsv_block_kernel(const double *U, lon
             __syncthreads();
             if (r > t && r < nb) {
                 const double f = s[t * DP + r] * invd[t];
-                for (int c = cg; c < nr; c += 4) bs[r * NR + c] -= f * bs[t * NR + c];
+                for (int c = cg; c < nr; c += 4) bs[c * DP + r] -= f * bs[c * DP + t];
             }
         }
     } else {
@@ -417,18 +417,18 @@ __global__ void __launch_bounds__(512, 1) trsv_block_kernel(const double *U, lon
             __syncthreads();
             if (r < t) {
                 const double f = s[r * DP + t] * invd[t];
-                for (int c = cg; c < nr; c += 4) bs[r * NR + c] -= f * bs[t * NR + c];
+                for (int c = cg; c < nr; c += 4) bs[c * DP + r] -= f * bs[c * DP + t];
             }
         }
     }
     __syncthreads();
     for (int e = tid; e < nb * nr; e += 512) {
         const int rr = e / nr, c = e % nr;
-        B[(long long)(kb + rr) * ldb + c0 + c] = bs[rr * NR + c] * invd[rr];
+        B[(long long)(kb + rr) * ldb + c0 + c] = bs[c * DP + rr] * invd[rr];
     }
 }
 
-constexpr size_t kTrsvSmem = (size_t)(NB * DP + NB * NR + NB) * sizeof(double);
+constexpr size_t kTrsvSmem = (size_t)(NB * DP + NR * DP + NB) * sizeof(double);
 
 // forward update: B[j] -= sum_t U[kb+t][j] * Y[t]  for j >= kb + nb   (thread per row j of B)
 __global__ void __launch_bounds__(256) fwd_update_kernel(const double *U, long long lda, int kb, int nb, int n,
