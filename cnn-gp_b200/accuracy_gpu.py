@@ -8,7 +8,8 @@ sys.path[:0] = [os.path.join(ROOT, "cnn-gp_b200"), ROOT]
 import torch  # noqa: E402
 from cnn_gp import engine  # noqa: E402
 
-for cfg, C, S in (("mnist_paper_convnet_gp", 1, 28), ("mnist_paper_residual_cnn_gp", 1, 28), ("mnist_as_tf", 1, 28)):
+for cfg, C, S in (("mnist_paper_convnet_gp", 1, 28), ("mnist_paper_residual_cnn_gp", 1, 28), ("mnist_as_tf", 1, 28),
+                  ("cifar10", 3, 32)):
     model = importlib.import_module("configs." + cfg).initial_model
     gen = torch.Generator().manual_seed(1)
     for kind in ("rand", "randn", "near-dup"):
