@@ -31,6 +31,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "fused_common.cuh"
@@ -587,17 +588,23 @@ __device__ __forceinline__ void dense_op_f(const u64 (&M)[2][S0], int lane, floa
     tot[2] = fmaf(__shfl_sync(0xffffffffu, a1, 16), scale, bias);
 }
 
-template <int S0, int NW, int NST>
+// NSPLIT: row bands (= stages) a full-size ReLU layer's variance maps arrive in (2 or 4); a channel
+// of the tile's images arrives in NSPLIT / 2 bands.
+template <int S0, int NW, int NST, int NSPLIT>
 __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __grid_constant__ NParams p) {
     using G = NGeo<NW>;
     constexpr int kWarps = G::kWarps, kTileI = G::kTileI, kTileJ = G::kTileJ, kImgs = G::kImgs, kPairs = G::kPairs;
     constexpr int P0 = S0 * S0;
     constexpr int PITCH = S0 + 1;
-    constexpr int STAGE = kImgs * P0 * 4;  // bytes: kImgs images of one channel == kPairs half maps of float4
+    constexpr int IMG_PARTS = NSPLIT / 2, IBAND = P0 / IMG_PARTS;  // pixels of one image band
+    constexpr int BAND = P0 / NSPLIT;                              // pixels of one full-size ReLU band
+    constexpr int STAGE = kImgs * IBAND * 4;  // bytes: one image band of kImgs images == kPairs ReLU bands of float4
+    static_assert(NSPLIT == 2 || NSPLIT == 4, "band split");
+    static_assert(kPairs * BAND * 16 == STAGE && S0 % NSPLIT == 0, "stage geometry");
     // tensor-memory window of a warp: 8 warps: 256 columns, slots at 0 / 128 with 64 columns per
-    // array; 12 warps (three per lane quadrant): 6 S0 columns, slot 0 (full size) at 0 with 2 S0
-    // per array, slot 1 (at most half size) at 4 S0 with S0 per array
-    constexpr int TM_WARP = NW == 8 ? 256 : 6 * S0, TM_SLOT1 = NW == 8 ? 128 : 4 * S0;
+    // array; 12 warps (three per lane quadrant): 5 S0 columns, slot 0 (full size) at 0 with 2 S0
+    // per array, slot 1 (a folded map of at most half the edge: one array of S0 columns) at 4 S0
+    constexpr int TM_WARP = NW == 8 ? 256 : 5 * S0, TM_SLOT1 = NW == 8 ? 128 : 4 * S0;
     constexpr int TM_A0 = NW == 8 ? 64 : 2 * S0, TM_A1 = NW == 8 ? 64 : S0;
     static_assert((NW / 4) * TM_WARP <= kTmemCols, "tensor-memory budget");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -660,23 +667,25 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
                 if (!decode(t, ib, jb)) continue;
                 const int i_base = ib * kTileI, j_base = jb * kTileJ;
                 for (int c = 0; c < p.C; ++c) {
-                    float *dst = reinterpret_cast<float *>(acquire(kImgs * P0 * 4));
-                    uint64_t *bar = &full[l % NST];
-                    for (int s = 0; s < kImgs; ++s) {
-                        const float *src;
-                        if (s < kTileI) src = p.x + ((long long)min(i_base + s, p.N1 - 1) * p.C + c) * P0;
-                        else src = p.z + ((long long)min(j_base + s - kTileI, p.N2 - 1) * p.C + c) * P0;
-                        bulk_g2s(dst + s * P0, src, P0 * 4, bar);
+                    for (int ip = 0; ip < IMG_PARTS; ++ip) {
+                        float *dst = reinterpret_cast<float *>(acquire(kImgs * IBAND * 4));
+                        uint64_t *bar = &full[l % NST];
+                        for (int s = 0; s < kImgs; ++s) {
+                            const float *src;
+                            if (s < kTileI) src = p.x + ((long long)min(i_base + s, p.N1 - 1) * p.C + c) * P0;
+                            else src = p.z + ((long long)min(j_base + s - kTileI, p.N2 - 1) * p.C + c) * P0;
+                            bulk_g2s(dst + s * IBAND, src + ip * IBAND, IBAND * 4, bar);
+                        }
+                        ++l;
                     }
-                    ++l;
                 }
                 for (int k = 0; k < p.n_ops; ++k) {
                     if (p.ops[k].kind != N_RELU) continue;
                     const int half = p.ops[k].half;
                     const long long off = p.aux_f_off + (long long)p.ops[k].aux;
-                    const bool split = p.ops[k].si == S0;  // full-size layers: one stage per row of the pair
-                    for (int part = 0; part < (split ? 2 : 1); ++part) {
-                        const unsigned bytes = (unsigned)(kPairs * half * 16 * (split ? 1 : 2));
+                    const bool split = p.ops[k].si == S0;  // full-size layers: NSPLIT row bands, one stage each
+                    for (int part = 0; part < (split ? NSPLIT : 1); ++part) {
+                        const unsigned bytes = split ? (unsigned)(kPairs * BAND * 16) : (unsigned)(kPairs * half * 32);
                         float4 *dst = reinterpret_cast<float4 *>(acquire(bytes));
                         uint64_t *bar = &full[l % NST];
                         for (int s = 0; s < kPairs; ++s) {
@@ -685,8 +694,9 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
                             if (s < kTileI / 2) { pr = min((i_base >> 1) + s, last_pi); base = p.aux_x; }
                             else { pr = min((j_base >> 1) + s - kTileI / 2, last_pj); base = p.aux_z; }
                             const float *src = base + 2 * pr * p.aux_stride + off;
-                            if (split) {
-                                bulk_g2s(dst + s * half, src + part * p.aux_stride, half * 16, bar);
+                            if (split) {  // band `part`: pixels [part * BAND, +BAND); the first half of the pixels is in row 2k
+                                bulk_g2s(dst + s * BAND, src + (part / (NSPLIT / 2)) * p.aux_stride + (part % (NSPLIT / 2)) * BAND * 4,
+                                         BAND * 16, bar);
                             } else {
                                 bulk_g2s(dst + s * 2 * half, src, half * 16, bar);
                                 bulk_g2s(dst + s * 2 * half + half, src + p.aux_stride, half * 16, bar);
@@ -722,21 +732,26 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
 #pragma unroll
                 for (int r = 0; r < S0; ++r) M[h][r] = 0ull;
             for (int c = 0; c < p.C; ++c) {
-                const unsigned buf = stage_l % NST;
-                mbar_wait(&full[buf], (stage_l / NST) & 1);
-                const float *sb = reinterpret_cast<const float *>(stage + (size_t)buf * STAGE) + lx;
-                const float *x0 = sb + (wi * 2 + 0) * P0, *x1 = sb + (wi * 2 + 1) * P0;
-                const float *z0 = sb + (kTileI + wj * 2 + 0) * P0, *z1 = sb + (kTileI + wj * 2 + 1) * P0;
 #pragma unroll
-                for (int r = 0; r < S0; ++r) {
-                    const float a0 = x0[r * S0], a1 = x1[r * S0], b0 = z0[r * S0], b1 = z1[r * S0];
-                    const u64 A = pk(a0, a1);
-                    M[0][r] = fma2(A, pk(b0, b1), M[0][r]);
-                    M[1][r] = fma2(A, pk(b1, b0), M[1][r]);
+                for (int ip = 0; ip < IMG_PARTS; ++ip) {
+                    const unsigned buf = stage_l % NST;
+                    mbar_wait(&full[buf], (stage_l / NST) & 1);
+                    const float *sb = reinterpret_cast<const float *>(stage + (size_t)buf * STAGE) + lx;
+                    const float *x0 = sb + (wi * 2 + 0) * IBAND, *x1 = sb + (wi * 2 + 1) * IBAND;
+                    const float *z0 = sb + (kTileI + wj * 2 + 0) * IBAND, *z1 = sb + (kTileI + wj * 2 + 1) * IBAND;
+                    constexpr int R = S0 / IMG_PARTS;
+#pragma unroll
+                    for (int rr = 0; rr < R; ++rr) {
+                        const int r = ip * R + rr;
+                        const float a0 = x0[rr * S0], a1 = x1[rr * S0], b0 = z0[rr * S0], b1 = z1[rr * S0];
+                        const u64 A = pk(a0, a1);
+                        M[0][r] = fma2(A, pk(b0, b1), M[0][r]);
+                        M[1][r] = fma2(A, pk(b1, b0), M[1][r]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[buf]);
+                    ++stage_l;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[buf]);
-                ++stage_l;
             }
             if (p.C > 1) affine_op<S0, S0>(M, p.inv_c, 0.f);
         }
@@ -770,25 +785,24 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
                 FNET_3(C_ADD, (stash_load<S0, S, 2, true>(tm_warp + o.slot * TM_SLOT1, o.slot ? TM_A1 : TM_A0, M, o.scale, o.bias)),
                        (stash_load<S0, S, 1, true>(tm_warp + o.slot * TM_SLOT1, 0, M, o.scale, o.bias)))
                 FNET_3(C_DENSE, (dense_op<S0, S>(M, lane, o.scale, o.bias, tot)), (dense_op_f<S0, S>(M, lane, o.scale, o.bias, tot)))
-                case C_RELU + 0: {  // two stages: rows [0, S0/2) from the pair's first row, the rest from the second
+                case C_RELU + 0: {  // NSPLIT stages, one row band each
                     const int lx = lane < S0 ? lane : S0 - 1;
-                    {
+                    auto band = [&](auto Q) {
+                        constexpr int q = decltype(Q)::value;
                         const unsigned buf = stage_l % NST;
                         mbar_wait(&full[buf], (stage_l / NST) & 1);
-                        const float4 *sb = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE) + lx;
-                        relu_rows<S0, S0, 0, S0 / 2>(M, sb + wi * o.half, sb + (kTileI / 2 + wj) * o.half);
+                        // the stage holds pixels [q * BAND, +BAND) of every pair: bias the pointer so that r * S0 + lx indexes it
+                        const float4 *sb = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE) + lx - q * BAND;
+                        relu_rows<S0, S0, q * (S0 / NSPLIT), (q + 1) * (S0 / NSPLIT)>(M, sb + wi * BAND, sb + (kTileI / 2 + wj) * BAND);
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&empty[buf]);
                         ++stage_l;
-                    }
-                    {
-                        const unsigned buf = stage_l % NST;
-                        mbar_wait(&full[buf], (stage_l / NST) & 1);
-                        const float4 *sb = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE) + lx - o.half;
-                        relu_rows<S0, S0, S0 / 2, S0>(M, sb + wi * o.half, sb + (kTileI / 2 + wj) * o.half);
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&empty[buf]);
-                        ++stage_l;
+                    };
+                    band(std::integral_constant<int, 0>{});
+                    band(std::integral_constant<int, 1>{});
+                    if (NSPLIT == 4) {
+                        band(std::integral_constant<int, NSPLIT == 4 ? 2 : 0>{});
+                        band(std::integral_constant<int, NSPLIT == 4 ? 3 : 1>{});
                     }
                     break;
                 }
@@ -1094,9 +1108,9 @@ struct Translator {
     }
 };
 
-template <int S0, int NW, int NST>
+template <int S0, int NW, int NST, int NSPLIT>
 constexpr size_t fnet_smem() {
-    return (size_t)NST * NGeo<NW>::kImgs * S0 * S0 * 4 + (size_t)NW * S0 * (S0 + 1) * 8 + (size_t)2 * NST * 8 + 16;
+    return (size_t)NST * NGeo<NW>::kImgs * S0 * S0 * 4 / (NSPLIT / 2) + (size_t)NW * S0 * (S0 + 1) * 8 + (size_t)2 * NST * 8 + 16;
 }
 
 }  // namespace
@@ -1142,11 +1156,14 @@ FNetPlan *fnet_plan_create(const Plan *plan_const) {
         }
         fp->ops[k] = n;
     }
-    // 28 x 28: twelve consumer warps when the second tensor-memory slot only ever holds maps of at
-    // most half the edge (3 warps share a 512-column lane quadrant: 3 x (112 + 56) columns)
-    if (S0 == 28 && tr.slot1_max <= S0 / 2 && !getenv("CNNGP_FNET_8WARPS")) { fp->nw = 12; fp->nst = 2; fp->smem = fnet_smem<28, 12, 2>(); }
-    else if (S0 == 28) { fp->nw = 8; fp->nst = 4; fp->smem = fnet_smem<28, 8, 4>(); }
-    else { fp->nw = 8; fp->nst = 3; fp->smem = fnet_smem<32, 8, 3>(); }
+    // twelve consumer warps when the second tensor-memory slot only ever holds folded maps of at most
+    // half the edge (3 warps share a 512-column lane quadrant: 3 x 5 S0 columns)
+    const bool twelve = tr.slot1_max <= S0 / 2 && !getenv("CNNGP_FNET_8WARPS");
+    if (S0 == 28 && twelve) { fp->nw = 12; fp->nst = 2; fp->smem = fnet_smem<28, 12, 2, 2>(); }
+    else if (S0 == 28) { fp->nw = 8; fp->nst = 4; fp->smem = fnet_smem<28, 8, 4, 2>(); }
+    // 32 x 32: the maps alone are 128 registers per thread, which leaves a 160-register warp nothing to
+    // work with (measured: 21 M pairs/s with twelve spilling warps against 62 M with eight) -- eight warps
+    else { fp->nw = 8; fp->nst = 3; fp->smem = fnet_smem<32, 8, 3, 2>(); }
     for (const DevOp &o : plan->ops)
         if (o.opcode == CNNGP_OP_RELU) fp->fused_row_floats += 4 * o.aux_half;
     return fp;
@@ -1210,7 +1227,8 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);
-    void (*kern)(const NParams) = fp->S0 == 32 ? fnet_kernel<32, 8, 3> : (fp->nw == 12 ? fnet_kernel<28, 12, 2> : fnet_kernel<28, 8, 4>);
+    void (*kern)(const NParams) = fp->S0 == 32 ? fnet_kernel<32, 8, 3, 2>
+                                               : (fp->nw == 12 ? fnet_kernel<28, 12, 2, 2> : fnet_kernel<28, 8, 4, 2>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem);
     if (e != cudaSuccess) { set_error(std::string("fused-net cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 7; }
     kern<<<grid, (fp->nw + 4) * 32, fp->smem, (cudaStream_t)stream>>>(p);
