@@ -291,7 +291,16 @@ int launch(const Plan *plan, GenericParams<T> &gp, int NP, cudaStream_t st) {
     if (G < NP) { set_error("generic kernel: maps do not fit shared memory"); return 6; }
     if (G > kMaxG) G = kMaxG;
     if ((int64_t)G > gp.Q) G = (int)((gp.Q + NP - 1) / NP * NP);
+    {   // small problems (the variance rows of one 200-image tile): fewer entries per CTA so that at
+        // least two CTAs per SM exist -- with the shared-memory maximum only ~10 SMs would work
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int64_t g_par = (gp.Q + 2 * sms - 1) / (2 * sms);
+        if (g_par < NP) g_par = NP;
+        if ((int64_t)G > g_par) G = (int)g_par;
+    }
     G -= G % NP;
+    if (G < NP) G = NP;
     gp.G = G;
     const size_t smem = per_entry * G;
     auto kern = generic_kernel<T, MODE>;
