@@ -23,3 +23,28 @@ def resnet_gp(final_pool, stage_blocks=5, tail=()):
                        out_channel_multiplier=4))
     mods += list(tail)
     return Sequential(*mods)
+
+
+def tf_mnist_split():
+    """(train, validation, test) index ranges of the paper's TensorFlow-style MNIST split: the
+    middle 50 000 training images, the 10 000 around them for validation, the official test set."""
+    lo, hi, n_train, n_all = 5000, 55000, 60000, 70000
+    return range(lo, hi), [*range(hi, n_train), *range(lo)], range(n_train, n_all)
+
+
+def lazy_dataset(module_globals):
+    """Module-level ``__getattr__`` that resolves ``dataset`` to the torchvision class named by the
+    module's ``dataset_name`` on first use (importing a config must not need torchvision)."""
+    def __getattr__(name):
+        if name == "dataset":
+            return dataset_class(module_globals["dataset_name"])
+        raise AttributeError(name)
+    return __getattr__
+
+
+def stacked(n, make_layer, *tail):
+    """Sequential of ``n`` repetitions of ``make_layer()`` (a list of modules) followed by ``tail``."""
+    mods = []
+    for _ in range(n):
+        mods.extend(make_layer())
+    return Sequential(*mods, *tail)

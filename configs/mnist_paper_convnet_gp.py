@@ -2,35 +2,19 @@
 seven [7x7 "same" conv, ReLU] layers and a 28x28 valid convolution as the dense layer, with the
 randomly-searched variances var_weight = 2.79 (per tap sum, hence the k^2 factor) and
 var_bias = 7.86.  This is the program BASELINE.json's headline metric is quoted on."""
-from cnn_gp import Conv2d, ReLU, Sequential
-from ._common import dataset_class
+from cnn_gp import Conv2d, ReLU
+from ._common import lazy_dataset, stacked, tf_mnist_split
 
-train_range = range(5000, 55000)
-validation_range = list(range(55000, 60000)) + list(range(0, 5000))
-test_range = range(60000, 70000)
+train_range, validation_range, test_range = tf_mnist_split()
+dataset_name, model_name = "MNIST", "ResNet"
+in_channels, out_channels, epochs, transforms = 1, 10, 0, []
 
-dataset_name = "MNIST"
-model_name = "ResNet"
-transforms = []
-epochs = 0
-in_channels = 1
-out_channels = 10
-
-var_bias = 7.86
-var_weight = 2.79
-n_layers = 7
+var_weight, var_bias, n_layers, window = 2.79, 7.86, 7, 7
 
 
-def _hidden_layer():
-    return [Conv2d(kernel_size=7, padding="same", var_weight=var_weight * 7 ** 2, var_bias=var_bias), ReLU()]
+def _hidden():
+    return [Conv2d(window, padding="same", var_weight=var_weight * window ** 2, var_bias=var_bias), ReLU()]
 
 
-initial_model = Sequential(
-    *[m for _ in range(n_layers) for m in _hidden_layer()],
-    Conv2d(kernel_size=28, padding=0, var_weight=var_weight, var_bias=var_bias))
-
-
-def __getattr__(name):
-    if name == "dataset":
-        return dataset_class(dataset_name)
-    raise AttributeError(name)
+initial_model = stacked(n_layers, _hidden, Conv2d(28, padding=0, var_weight=var_weight, var_bias=var_bias))
+__getattr__ = lazy_dataset(globals())

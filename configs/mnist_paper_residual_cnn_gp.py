@@ -4,35 +4,23 @@ the skip connections add *post-ReLU* maps, which does not correspond to a finite
 limit but is kept so that the published numbers stay reproducible: eight blocks
 ``x + relu(conv4(x))``, one more conv4 + ReLU, and a 28x28 valid convolution."""
 from cnn_gp import Conv2d, ReLU, Sequential, Sum
-from ._common import dataset_class
+from ._common import lazy_dataset, stacked, tf_mnist_split
 
-train_range = range(5000, 55000)
-validation_range = list(range(55000, 60000)) + list(range(0, 5000))
-test_range = range(60000, 70000)
+train_range, validation_range, test_range = tf_mnist_split()
+dataset_name, model_name = "MNIST", "ResNet"
+in_channels, out_channels, epochs, transforms = 1, 10, 0, []
 
-dataset_name = "MNIST"
-model_name = "ResNet"
-transforms = []
-epochs = 0
-in_channels = 1
-out_channels = 10
-
-var_bias = 4.69
-var_weight = 7.27
-n_blocks = 8
+var_weight, var_bias, n_blocks, window = 7.27, 4.69, 8, 4
 
 
-def _conv4():
-    return Conv2d(kernel_size=4, padding="same", var_weight=var_weight * 4 ** 2, var_bias=var_bias)
+def _conv():
+    return Conv2d(window, padding="same", var_weight=var_weight * window ** 2, var_bias=var_bias)
 
 
-initial_model = Sequential(
-    *[Sum([Sequential(), Sequential(_conv4(), ReLU())]) for _ in range(n_blocks)],
-    _conv4(), ReLU(),
-    Conv2d(kernel_size=28, padding=0, var_weight=var_weight, var_bias=var_bias))
+def _block():
+    return [Sum([Sequential(), Sequential(_conv(), ReLU())])]
 
 
-def __getattr__(name):
-    if name == "dataset":
-        return dataset_class(dataset_name)
-    raise AttributeError(name)
+initial_model = stacked(n_blocks, _block, _conv(), ReLU(),
+                        Conv2d(28, padding=0, var_weight=var_weight, var_bias=var_bias))
+__getattr__ = lazy_dataset(globals())
