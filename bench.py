@@ -11,8 +11,9 @@ unique pair of the symmetric Gram, result written to HBM.  At N > 1 (torchrun, o
 GPU) the workload grows with N (weak scaling: round(10000*sqrt(N)) images, N x the pairs), the
 reference's tile list (cnn_gp/data.py:11-29, tile `--tile`) is split contiguously over the
 ranks like its `_this_worker_batch` but with the cut points balanced by pair count
-(cnn_gp.data.worker_tiles_balanced), ranks compute with no communication, and the blocks are
-gathered on rank 0 (timed in `e2e`, not in `value`).
+(cnn_gp.data.worker_tiles_balanced), and ranks compute with no communication; in `e2e` every
+worker also uploads the images and copies the block rows it owns to its own host buffer (the
+reference's workers write per-worker files).
 
 JSON keys beyond the base contract:
   roofline      dominant kernel (the Gram kernel) against the FP32 CUDA-core peak measured live
@@ -34,6 +35,19 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [os.path.join(ROOT, "cnn-gp_b200"), ROOT]
+
+
+def _claim_stdout():
+    """stdout must carry exactly one JSON line, but libraries write there too (NCCL prints its
+    version banner through C stdio).  Point file descriptor 1 at stderr for the whole run and
+    return a writer on the original stdout for the result line."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(keep, (line + "\n").encode())
+    return emit
 
 CONFIG = "mnist_paper_convnet_gp"
 N_IMAGES = 10000
@@ -79,6 +93,8 @@ def cpu_rate(model, config, seconds, repeats=1):
     c, s = workload_dims(config)
     gen = torch.Generator().manual_seed(SEED)
     X = torch.rand(512, c, s, s, generator=gen).numpy()
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    oracle.set_num_threads(os.cpu_count() or 1)
     cores = oracle.num_threads()
     t0 = time.perf_counter()
     oracle.gram(model, X[:48], X[48:96])  # calibration
@@ -100,6 +116,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    emit = _claim_stdout()
     model = importlib.import_module("configs." + args.config).initial_model
     rates = []
     cores = sample = None
@@ -110,7 +127,7 @@ def run_reference(args):
             rates.append(r)
     v = statistics.mean(rates)
     edge = int(sample.split("x")[0])
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * edge * edge / v,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -166,10 +183,11 @@ def fp32_peak_tflops():
 
 # ----------------------------------------------------------------------------- GPU arm
 def run_ours(args):
+    emit = _claim_stdout()
     import torch
     import torch.distributed as dist
     from cnn_gp import engine
-    from cnn_gp.tiles import GramJob, compute_worker_blocks, gather_blocks
+    from cnn_gp.tiles import GramJob, compute_worker_blocks
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -246,18 +264,28 @@ def run_ours(args):
     n_launch = launches[0]
 
     # ---- end to end through the public API with host buffers ----------------------------
-    K_host = torch.empty((n, n), dtype=torch.float32).pin_memory() if rank == 0 else None
+    # one GPU: model(x) from pinned host images to a pinned host result.  Several GPUs: every
+    # worker copies the block rows it owns to its own pinned host buffer -- the reference's
+    # workers likewise keep their tiles in per-worker files (exp_mnist_resnet/run.bash:28-36,
+    # merged offline) -- so the device->host traffic runs over all PCIe links at once.
+    from cnn_gp.data import worker_tiles_balanced
+    if world == 1:
+        row_lo, row_hi = 0, n
+    else:
+        mine = worker_tiles_balanced(n, None, args.tile, rank, world)
+        row_lo = min(t[1] for t in mine) * args.tile if mine else 0
+        row_hi = min(n, (max(t[1] for t in mine) + 1) * args.tile) if mine else 0
+    K_host = torch.empty((row_hi - row_lo, n), dtype=torch.float32).pin_memory()
+    K_dev = torch.empty((n, n), dtype=torch.float32, device=dev) if world > 1 else None
 
     def step_e2e():
         x = X_host.to(dev, non_blocking=True)
         if world == 1:
             K = model(x)  # public call: plan lookup, variances, one fused launch
-        else:
-            K = torch.full((n, n), float("nan"), dtype=torch.float32, device=dev)
-            compute_worker_blocks(GramJob(model, x), K, args.tile, rank, world, balanced=True)
-            K = gather_blocks(K, dst=0)
-        if rank == 0:
             K_host.copy_(K, non_blocking=True)
+        else:
+            compute_worker_blocks(GramJob(model, x), K_dev, args.tile, rank, world, balanced=True)
+            K_host.copy_(K_dev[row_lo:row_hi], non_blocking=True)
         torch.cuda.synchronize()
 
     step_e2e()
@@ -268,10 +296,14 @@ def run_ours(args):
         step_e2e()
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    d2h_bytes = K_host.numel() * 4
     if world > 1:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
+        t = torch.tensor([d2h_bytes], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        d2h_bytes = int(t[0])
 
     if rank == 0:
         plan = engine.plan_for(model, s, s, torch.float32)
@@ -311,15 +343,17 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_obj(args, world),
             "roofline": roof,
-            "e2e": {"value": total_pairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": X_host.numel() * 4,
-                    "d2h_bytes_per_step": n * n * 4, "ms_per_step": e2e_s * 1e3},
+            "e2e": {"value": total_pairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": X_host.numel() * 4 * world,
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s * 1e3,
+                    "note": "per-worker host buffers (block rows a worker owns), all workers in parallel"
+                            if world > 1 else "model(x): pinned host images -> pinned host result"},
             "gpu_launches": n_launch,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_rate(model.cpu(), args.config, args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
