@@ -50,6 +50,10 @@ def build(force=False, verbose=False):
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _newer_than(LIB, objs):
         run([NVCC, "-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart"])
+    # the HDF5 block store: host code only, its own library (include/cnngp_h5.h)
+    h5_src, h5_lib = os.path.join(CSRC, "h5store.cpp"), os.path.join(HERE, "libcnngp_h5.so")
+    if force or _newer_than(h5_lib, [h5_src, os.path.join(HERE, "..", "include", "cnngp_h5.h")]):
+        run(["/usr/bin/g++", "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared", "-pthread", h5_src, "-o", h5_lib])
     # measurement-only probes (roofline denominators for bench.py)
     mb_src, mb_lib = os.path.join(CSRC, "microbench.cu"), os.path.join(HERE, "libcnngp_bench.so")
     if force or _newer_than(mb_lib, [mb_src]):

@@ -1,9 +1,12 @@
-"""A directory of ``.npy`` memmaps that answers the subset of the h5py API the cnn-gp scripts
-use (``create_dataset``, ``keys``, item access, slicing, ``read_direct``, context manager).
+"""Where Gram blocks are stored: ``open_store`` and the worker-file merge.
 
-h5py and libhdf5 are absent from this image, so this is the always-available store for the
-``save_K`` block layout (reference cnn_gp/kernel_save_tools.py:7-23).  When h5py is importable
-``open_store`` returns a real ``h5py.File`` for ``*.h5`` paths instead.
+``*.h5`` / ``*.hdf5`` paths are real HDF5 files, the reference's format (``h5py.File`` at
+exp_mnist_resnet/save_kernel.py:26,33; layout cnn_gp/kernel_save_tools.py:7-23): written and read
+by this repository's native implementation of the file format (``cnn_gp.h5store`` ->
+libcnngp_h5.so), because h5py and libhdf5 are absent from the B200 image; set ``CNNGP_USE_H5PY=1``
+to go through an installed h5py instead -- the files are interchangeable.  Any other path is a
+directory of ``.npy`` memmaps (``NpyStore``) that answers the same subset of the h5py API
+(``create_dataset``, ``keys``, item access, slicing, ``read_direct``, context manager).
 """
 import json
 import os
@@ -130,21 +133,28 @@ class NpyStore:
 
 
 def open_store(path, mode="r"):
-    """``h5py.File`` for ``*.h5`` / ``*.hdf5`` paths when h5py is importable, else ``NpyStore``."""
+    """An HDF5 file for ``*.h5`` / ``*.hdf5`` paths (native store; h5py on request), else ``NpyStore``."""
+    path = str(path)
     if path.endswith((".h5", ".hdf5")):
-        try:
+        if os.environ.get("CNNGP_USE_H5PY") == "1":
             import h5py
             return h5py.File(path, mode)
-        except ImportError:
-            pass
+        from . import h5store
+        return h5store.File(path, mode)
     return NpyStore(path, mode)
 
 
 def merge_into(dest, src):
     """exp_mnist_resnet/merge_h5_files.py:15-30: for every dataset present in both stores copy
     ``src`` into ``dest`` wherever ``dest`` is NaN, one leading index at a time."""
+    from . import h5store
     for k in [k for k in dest.keys() if k in src.keys()]:
         d, s = dest[k], src[k]
+        if isinstance(dest, h5store.File) and isinstance(src, h5store.File) and d.chunks is not None \
+                and (d.shape, d.chunks, d.dtype) == (s.shape, s.chunks, s.dtype):
+            # chunk by chunk in native code: cost proportional to what the workers wrote
+            h5store.merge_nan(dest, src, k)
+            continue
         for i in range(len(d)):
             block = d[i, ...]
             other = s[i, ...]

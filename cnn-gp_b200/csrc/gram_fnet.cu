@@ -26,6 +26,8 @@
 //     pixel, 1 x 1 convolutions) runs on the four scalars of the warp.
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
@@ -50,7 +52,7 @@ struct NGeo {
     static constexpr int kImgs = kTileI + kTileJ;
     static constexpr int kPairs = kImgs / 2;
     static constexpr int kThreads = (NW + 4) * 32;
-    static constexpr int kRegsProducer = 24;
+    static constexpr int kRegsProducer = 32;
     static constexpr int kRegsConsumer = NW == 8 ? 240 : 160;
 };
 constexpr int kMaxNOps = 192;
@@ -87,6 +89,7 @@ struct NParams {
     const float *kdiag;
     int nbi, nbj, sti, stj, nst_j, nst;
     long long n_tiles;
+    unsigned long long *tile_ctr;  // zeroed before the launch: the next tile index to hand out
     float inv_c;
 };
 
@@ -612,7 +615,10 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
     u64 *tiles = reinterpret_cast<u64 *>(smem_raw + (size_t)NST * STAGE);
     uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + kWarps * S0 * PITCH);
     uint64_t *full = bars, *empty = bars + NST;
-    uint32_t *tmem_word = reinterpret_cast<uint32_t *>(bars + 2 * NST);
+    // tile index each stage belongs to (-1: no more tiles); tiles are handed out by a global atomic
+    // counter so that all CTAs stay on consecutive tiles of one super-tile (see gram_fused.cu)
+    long long *stage_tile = reinterpret_cast<long long *>(bars + 2 * NST);
+    uint32_t *tmem_word = reinterpret_cast<uint32_t *>(bars + 3 * NST);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -656,15 +662,18 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
         if (lane == 0) {
             unsigned l = 0;
             const int last_pi = (p.N1 - 1) >> 1, last_pj = (p.N2 - 1) >> 1;
+            long long t = 0;
             auto acquire = [&](unsigned bytes) -> unsigned char * {
                 const unsigned buf = l % NST;
                 if (l >= NST) mbar_wait_relaxed(&empty[buf], ((l / NST) - 1) & 1);
+                stage_tile[buf] = t;  // published by the release of the arrive below
                 mbar_arrive_expect_tx(&full[buf], bytes);
                 return stage + (size_t)buf * STAGE;
             };
-            for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+            for (;;) {
                 int ib, jb;
-                if (!decode(t, ib, jb)) continue;
+                do { t = (long long)atomicAdd(p.tile_ctr, 1ull); } while (t < p.n_tiles && !decode(t, ib, jb));
+                if (t >= p.n_tiles) break;
                 const int i_base = ib * kTileI, j_base = jb * kTileJ;
                 for (int c = 0; c < p.C; ++c) {
                     for (int ip = 0; ip < IMG_PARTS; ++ip) {
@@ -706,6 +715,8 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
                     }
                 }
             }
+            t = -1;  // end marker: one empty stage
+            acquire(0);
         }
         return;
     }
@@ -718,9 +729,13 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
     const uint32_t tm_warp = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TM_WARP);
     unsigned stage_l = 0;
 
-    for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+    for (;;) {
+        // the tile this CTA works on next travels with its first stage
+        mbar_wait(&full[stage_l % NST], (stage_l / NST) & 1);
+        const long long t = stage_tile[stage_l % NST];
+        if (t < 0) break;
         int ib, jb;
-        if (!decode(t, ib, jb)) continue;
+        decode(t, ib, jb);
         const int i_base = ib * kTileI, j_base = jb * kTileJ;
 
         u64 M[2][S0];
@@ -1110,7 +1125,7 @@ struct Translator {
 
 template <int S0, int NW, int NST, int NSPLIT>
 constexpr size_t fnet_smem() {
-    return (size_t)NST * NGeo<NW>::kImgs * S0 * S0 * 4 / (NSPLIT / 2) + (size_t)NW * S0 * (S0 + 1) * 8 + (size_t)2 * NST * 8 + 16;
+    return (size_t)NST * NGeo<NW>::kImgs * S0 * S0 * 4 / (NSPLIT / 2) + (size_t)NW * S0 * (S0 + 1) * 8 + (size_t)3 * NST * 8 + 16;
 }
 
 }  // namespace
@@ -1185,6 +1200,11 @@ std::string fnet_plan_describe(const FNetPlan *fp) {
     return t;
 }
 
+// tile counters of the launches in flight (one slot per launch, reused round-robin)
+constexpr int kCtrSlots = 64;
+__device__ unsigned long long g_fnet_tile_ctr[kCtrSlots];
+static std::atomic<unsigned> g_fnet_next_ctr{0};
+
 int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2, int32_t C,
                      const void *d_aux_x, const void *d_aux_z, int32_t symmetric, const void *d_kdiag,
                      void *d_out, int64_t ld_out, void *stream) {
@@ -1229,7 +1249,14 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
     const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);
     void (*kern)(const NParams) = fp->S0 == 32 ? fnet_kernel<32, 8, 3, 2>
                                                : (fp->nw == 12 ? fnet_kernel<28, 12, 2, 2> : fnet_kernel<28, 8, 4, 2>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem);
+    unsigned long long *ctr = nullptr;
+    cudaError_t e = cudaGetSymbolAddress((void **)&ctr, g_fnet_tile_ctr);
+    if (e == cudaSuccess) {
+        p.tile_ctr = ctr + g_fnet_next_ctr.fetch_add(1) % kCtrSlots;
+        e = cudaMemsetAsync(p.tile_ctr, 0, sizeof(unsigned long long), (cudaStream_t)stream);
+    }
+    if (e != cudaSuccess) { set_error(std::string("fused-net tile counter: ") + cudaGetErrorString(e)); return 7; }
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem);
     if (e != cudaSuccess) { set_error(std::string("fused-net cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 7; }
     kern<<<grid, (fp->nw + 4) * 32, fp->smem, (cudaStream_t)stream>>>(p);
     e = cudaGetLastError();

@@ -20,6 +20,7 @@
 //          The factor 1/2 is folded into the next convolution's tap (exact: power of two).
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
@@ -42,8 +43,8 @@ struct Geo {
     static constexpr int kImgs = kTileI + kTileJ;
     static constexpr int kPairs = kImgs / 2;              // image pairs whose interleaved variance maps are staged
     static constexpr int kThreads = (NW + 4) * 32;
-    static constexpr int kRegsProducer = 24;
-    static constexpr int kRegsConsumer = NW == 8 ? 240 : 160;  // 8*32*240 + 4*32*24 = 12*32*160 + 4*32*24 = 64512
+    static constexpr int kRegsProducer = 32;
+    static constexpr int kRegsConsumer = NW == 8 ? 240 : 160;  // 8*32*240 + 4*32*32 = 12*32*160 + 4*32*32 = 65536
 };
 constexpr int kMaxOps = 40;
 constexpr int kSuperEdge = 504;              // super-tile edge in images (L2-resident variance maps); 4 | 504, 8 | 504, 12 | 504
@@ -75,6 +76,7 @@ struct FParams {
     int nst_j;         // super-tiles along j (non-symmetric)
     int nst;           // super-tiles per side (symmetric)
     long long n_tiles; // CTA tiles enumerated (super-tile padded)
+    unsigned long long *tile_ctr;  // zeroed before the launch: the next tile index to hand out
     float inv_c;       // 1 / C
 };
 
@@ -165,6 +167,12 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) fused_kernel(const __gri
     u64 *tiles = reinterpret_cast<u64 *>(stage + NST * STAGE_F4);
     uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + kWarps * S * PITCH);
     uint64_t *full = bars, *empty = bars + NST;
+    // tile index each stage belongs to (-1: no more tiles).  Tiles are handed out by a global
+    // atomic counter, not by a fixed stride: all CTAs then work on consecutive tiles of one
+    // super-tile at any time (static strides let CTAs drift apart over the triangular
+    // enumeration, and the variance rows of several super-tiles competed for L2), and the tail
+    // of the launch is balanced to one tile.
+    long long *stage_tile = reinterpret_cast<long long *>(bars + 2 * NST);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -204,15 +212,18 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) fused_kernel(const __gri
         if (lane == 0) {
             unsigned l = 0;  // running stage counter over all tiles of this CTA
             const int last_pi = (p.N1 - 1) >> 1, last_pj = (p.N2 - 1) >> 1;
+            long long t = 0;
             auto acquire = [&](unsigned bytes) -> float4 * {
                 const unsigned buf = l % NST;
                 if (l >= NST) mbar_wait_relaxed(&empty[buf], ((l / NST) - 1) & 1);
+                stage_tile[buf] = t;  // published by the release of the arrive below
                 mbar_arrive_expect_tx(&full[buf], bytes);
                 return stage + buf * STAGE_F4;
             };
-            for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+            for (;;) {
                 int ib, jb;
-                if (!decode(t, ib, jb)) continue;
+                do { t = (long long)atomicAdd(p.tile_ctr, 1ull); } while (t < p.n_tiles && !decode(t, ib, jb));
+                if (t >= p.n_tiles) break;
                 const int i_base = ib * kTileI, j_base = jb * kTileJ;
                 for (int c = 0; c < p.C; ++c) {
                     for (int ip = 0; ip < IMG_PARTS; ++ip) {
@@ -253,6 +264,8 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) fused_kernel(const __gri
                     }
                 }
             }
+            t = -1;  // end marker: one empty stage
+            acquire(0);
         }
         return;
     }
@@ -269,9 +282,13 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) fused_kernel(const __gri
               C1 = pk(1.500756294e-02f, 1.500756294e-02f), C0 = pk(3.001053929e-01f, 3.001053929e-01f),
               ONE = pk(1.f, 1.f);
 
-    for (long long t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+    for (;;) {
+        // the tile this CTA works on next travels with its first stage
+        mbar_wait(&full[stage_l % NST], (stage_l / NST) & 1);
+        const long long t = stage_tile[stage_l % NST];
+        if (t < 0) break;
         int ib, jb;
-        if (!decode(t, ib, jb)) continue;
+        decode(t, ib, jb);
         const int i_base = ib * kTileI, j_base = jb * kTileJ;
 
         u64 M[2][S];  // lane = column, register = row after init
@@ -415,7 +432,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) fused_kernel(const __gri
 
 template <int NW, int NSPLIT, int NST>
 constexpr size_t fused_smem(int S) {
-    return (size_t)NST * (Geo<NW>::kPairs * S * S / NSPLIT) * 16 + (size_t)NW * S * (S + 1) * 8 + 2 * NST * 8;
+    return (size_t)NST * (Geo<NW>::kPairs * S * S / NSPLIT) * 16 + (size_t)NW * S * (S + 1) * 8 + 3 * NST * 8;
 }
 
 }  // namespace
@@ -508,6 +525,11 @@ std::string fused_plan_describe(const FusedPlan *fp) {
 
 namespace {
 
+// tile counters of the launches in flight (one slot per launch, reused round-robin)
+constexpr int kCtrSlots = 64;
+__device__ unsigned long long g_tile_ctr[kCtrSlots];
+std::atomic<unsigned> g_next_ctr{0};
+
 struct Variant { int nw, nsplit, nst; };
 
 template <int NW, int NSPLIT, int NST>
@@ -543,7 +565,14 @@ int launch_variant(const FusedPlan *fp, FParams &p, int64_t N1, int64_t N2, cuda
     else if (kDefault) kern = fused_kernel<28, -1, -1, 12, 2, 2>;
     else return -1;  // experimental variants exist for the 7x7 window only: caller falls back to the default
     const size_t smem = fused_smem<NW, NSPLIT, NST>(28);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    unsigned long long *ctr = nullptr;
+    cudaError_t e = cudaGetSymbolAddress((void **)&ctr, g_tile_ctr);
+    if (e == cudaSuccess) {
+        p.tile_ctr = ctr + g_next_ctr.fetch_add(1) % kCtrSlots;
+        e = cudaMemsetAsync(p.tile_ctr, 0, sizeof(unsigned long long), stream);
+    }
+    if (e != cudaSuccess) { set_error(std::string("fused tile counter: ") + cudaGetErrorString(e)); return 7; }
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error(std::string("fused cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 7; }
     kern<<<grid, G::kThreads, smem, stream>>>(p);
     e = cudaGetLastError();
