@@ -52,7 +52,7 @@ struct NGeo {
     static constexpr int kImgs = kTileI + kTileJ;
     static constexpr int kPairs = kImgs / 2;
     static constexpr int kThreads = (NW + 4) * 32;
-    static constexpr int kRegsProducer = 32;
+    static constexpr int kRegsProducer = NW == 8 ? 24 : 32;  // what the pool holds: launch registers x threads
     static constexpr int kRegsConsumer = NW == 8 ? 240 : 160;
 };
 constexpr int kMaxNOps = 192;
@@ -670,10 +670,16 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
                 mbar_arrive_expect_tx(&full[buf], bytes);
                 return stage + (size_t)buf * STAGE;
             };
+            // tile_ctr == NULL: fixed stride (tile = blockIdx.x + k * gridDim.x), kept for comparison
+            const bool dyn = p.tile_ctr != nullptr;
+            long long t_raw = dyn ? (long long)atomicAdd(p.tile_ctr, 1ull) : (long long)blockIdx.x;
             for (;;) {
                 int ib, jb;
-                do { t = (long long)atomicAdd(p.tile_ctr, 1ull); } while (t < p.n_tiles && !decode(t, ib, jb));
+                t = t_raw;
+                while (t < p.n_tiles && !decode(t, ib, jb)) t = dyn ? (long long)atomicAdd(p.tile_ctr, 1ull) : t + gridDim.x;
                 if (t >= p.n_tiles) break;
+                // the next index is requested now and first looked at when this tile's stages are out
+                t_raw = dyn ? (long long)atomicAdd(p.tile_ctr, 1ull) : t + gridDim.x;
                 const int i_base = ib * kTileI, j_base = jb * kTileJ;
                 for (int c = 0; c < p.C; ++c) {
                     for (int ip = 0; ip < IMG_PARTS; ++ip) {
@@ -1251,7 +1257,10 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
                                                : (fp->nw == 12 ? fnet_kernel<28, 12, 2, 2> : fnet_kernel<28, 8, 4, 2>);
     unsigned long long *ctr = nullptr;
     cudaError_t e = cudaGetSymbolAddress((void **)&ctr, g_fnet_tile_ctr);
-    if (e == cudaSuccess) {
+    const char *order = getenv("CNNGP_TILE_ORDER");  // "static": fixed stride instead of the counter
+    if (order && !strcmp(order, "static")) {
+        p.tile_ctr = nullptr;
+    } else if (e == cudaSuccess) {
         p.tile_ctr = ctr + g_fnet_next_ctr.fetch_add(1) % kCtrSlots;
         e = cudaMemsetAsync(p.tile_ctr, 0, sizeof(unsigned long long), (cudaStream_t)stream);
     }

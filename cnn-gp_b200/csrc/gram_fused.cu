@@ -43,7 +43,7 @@ struct Geo {
     static constexpr int kImgs = kTileI + kTileJ;
     static constexpr int kPairs = kImgs / 2;              // image pairs whose interleaved variance maps are staged
     static constexpr int kThreads = (NW + 4) * 32;
-    static constexpr int kRegsProducer = 32;
+    static constexpr int kRegsProducer = NW == 8 ? 24 : 32;  // what the pool holds: launch registers x threads
     static constexpr int kRegsConsumer = NW == 8 ? 240 : 160;  // 8*32*240 + 4*32*32 = 12*32*160 + 4*32*32 = 65536
 };
 constexpr int kMaxOps = 40;
@@ -220,10 +220,16 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) fused_kernel(const __gri
                 mbar_arrive_expect_tx(&full[buf], bytes);
                 return stage + buf * STAGE_F4;
             };
+            // tile_ctr == NULL: fixed stride (tile = blockIdx.x + k * gridDim.x), kept for comparison
+            const bool dyn = p.tile_ctr != nullptr;
+            long long t_raw = dyn ? (long long)atomicAdd(p.tile_ctr, 1ull) : (long long)blockIdx.x;
             for (;;) {
                 int ib, jb;
-                do { t = (long long)atomicAdd(p.tile_ctr, 1ull); } while (t < p.n_tiles && !decode(t, ib, jb));
+                t = t_raw;
+                while (t < p.n_tiles && !decode(t, ib, jb)) t = dyn ? (long long)atomicAdd(p.tile_ctr, 1ull) : t + gridDim.x;
                 if (t >= p.n_tiles) break;
+                // the next index is requested now and first looked at when this tile's stages are out
+                t_raw = dyn ? (long long)atomicAdd(p.tile_ctr, 1ull) : t + gridDim.x;
                 const int i_base = ib * kTileI, j_base = jb * kTileJ;
                 for (int c = 0; c < p.C; ++c) {
                     for (int ip = 0; ip < IMG_PARTS; ++ip) {
@@ -567,7 +573,10 @@ int launch_variant(const FusedPlan *fp, FParams &p, int64_t N1, int64_t N2, cuda
     const size_t smem = fused_smem<NW, NSPLIT, NST>(28);
     unsigned long long *ctr = nullptr;
     cudaError_t e = cudaGetSymbolAddress((void **)&ctr, g_tile_ctr);
-    if (e == cudaSuccess) {
+    const char *order = getenv("CNNGP_TILE_ORDER");  // "static": fixed stride instead of the counter
+    if (order && !strcmp(order, "static")) {
+        p.tile_ctr = nullptr;
+    } else if (e == cudaSuccess) {
         p.tile_ctr = ctr + g_next_ctr.fetch_add(1) % kCtrSlots;
         e = cudaMemsetAsync(p.tile_ctr, 0, sizeof(unsigned long long), stream);
     }

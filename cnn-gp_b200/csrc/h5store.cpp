@@ -15,6 +15,7 @@
 
 #include <fcntl.h>
 #include <sys/stat.h>
+#include <sys/uio.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -623,6 +624,49 @@ void copy_box(int rank, const int64_t *lo, const int64_t *hi, const int64_t *cor
     }
 }
 
+// A chunk that lies wholly inside the selection is one contiguous file range and a set of equally
+// long rows in the user's buffer: move it with preadv / pwritev, no staging copy.
+bool whole_chunk_io(const File *f, int rank, const int64_t *corg, const int64_t *cdim, const int64_t *sorg,
+                    const int64_t *sdim, uint8_t *ubuf, int esize, uint64_t addr, bool write) {
+    int64_t sstr[kMaxRank], idx[kMaxRank];
+    sstr[rank - 1] = esize;
+    for (int i = rank - 2; i >= 0; --i) sstr[i] = sstr[i + 1] * sdim[i + 1];
+    for (int i = 0; i < rank; ++i) idx[i] = corg[i];
+    const size_t row = (size_t)cdim[rank - 1] * (size_t)esize;
+    std::vector<iovec> iov;
+    iov.reserve(1024);
+    uint64_t off = f->base + addr;
+    auto flush = [&]() -> bool {
+        size_t done = 0, want = iov.size() * row;
+        size_t first = 0;
+        while (done < want) {
+            const ssize_t r = write ? pwritev(f->fd, iov.data() + first, (int)(iov.size() - first), (off_t)(off + done))
+                                    : preadv(f->fd, iov.data() + first, (int)(iov.size() - first), (off_t)(off + done));
+            if (r < 0 && errno == EINTR) continue;
+            if (r <= 0) return false;
+            done += (size_t)r;
+            size_t rem = (size_t)r;  // advance past what was transferred (short transfers are rare)
+            while (rem && first < iov.size()) {
+                if (rem >= iov[first].iov_len) { rem -= iov[first].iov_len; ++first; }
+                else { iov[first].iov_base = (uint8_t *)iov[first].iov_base + rem; iov[first].iov_len -= rem; rem = 0; }
+            }
+        }
+        off += want;
+        iov.clear();
+        return true;
+    };
+    for (;;) {
+        int64_t so = 0;
+        for (int i = 0; i < rank; ++i) so += (idx[i] - sorg[i]) * sstr[i];
+        iov.push_back(iovec{ubuf + so, row});
+        if (iov.size() == 1024 && !flush()) return false;
+        int k = rank - 2;
+        for (; k >= 0; --k) { if (++idx[k] < corg[k] + cdim[k]) break; idx[k] = corg[k]; }
+        if (k < 0) break;
+    }
+    return iov.empty() || flush();
+}
+
 void fill_pattern(const Dataset *d, uint8_t *buf, size_t bytes) {
     bool zero = true;
     for (int i = 0; i < d->esize; ++i) zero = zero && d->fill[i] == 0;
@@ -745,6 +789,7 @@ int transfer(File *f, Dataset *d, const int64_t *start, const int64_t *count, ui
             }
             return true;
         }
+        if (covers && !edge) return whole_chunk_io(f, r, corg, d->chunk, start, count, user, d->esize, j.addr, write);
         std::vector<uint8_t> buf(d->chunk_bytes);
         if (!write) {
             if (!pread_all(f, buf.data(), buf.size(), j.addr)) return false;

@@ -153,10 +153,11 @@ def test_two_workers_cover_the_matrix_and_gather_like_merge(N, N2, bs, same):
     assert np.isnan(merged[~owned]).all()
 
 
-def test_merge_script_fills_only_nan(tmp_path):
+@pytest.mark.parametrize("suffix", ["", ".h5"])  # .npy directory store / native HDF5 file
+def test_merge_script_fills_only_nan(tmp_path, suffix):
     from cnn_gp.block_store import open_store
     from exp_mnist_resnet.merge_h5_files import merge
-    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    a, b = str(tmp_path / ("a" + suffix)), str(tmp_path / ("b" + suffix))
     with open_store(a, "w") as f:
         d = f.create_dataset("Kxx", shape=(1, 4, 4), dtype=np.float32, fillvalue=np.nan)
         d[0, :2, :] = 1.0
@@ -186,7 +187,7 @@ def test_save_kernel_resident_equals_reference_loop_and_classify_matches_scipy(t
     paths = {}
     for resident in (True, False):
         for rank in range(2):
-            p = str(tmp_path / f"{'res' if resident else 'ref'}_{rank}")
+            p = str(tmp_path / f"{'res' if resident else 'ref'}_{rank}.h5")  # real HDF5 files (native store)
             save_kernel.compute_all(cfg, ds, p, batch_size=64, n_workers=2, worker_rank=rank, resident=resident)
             paths[resident, rank] = p
     for rank in range(2):
