@@ -69,12 +69,30 @@ def print_accuracy(A, Kxvx, Y, key):
     return acc
 
 
-def load_kern(dset, i, dtype=torch.float64, device=DEVICE):
+def load_kern(dset, i, dtype=torch.float64, device=DEVICE, block_bytes=256 << 20):
     """Slab ``i`` of a stored kernel as a ``dtype`` tensor on ``device`` (reference: float64 on the
-    CPU, classify_gp.py:45-48; here the widening happens in HBM)."""
-    A = np.empty(dset.shape[1:], dtype=np.float32)
-    dset.read_direct(A, source_sel=np.s_[i, :, :])
-    return torch.from_numpy(A).to(device).to(dtype)
+    CPU, classify_gp.py:45-48).  Row blocks go file -> pinned buffer -> HBM through two buffers, so
+    reading the next block overlaps the upload of the previous one, and the widening happens in
+    HBM; the host never holds more than two blocks."""
+    n, m = dset.shape[1:]
+    out = torch.empty((n, m), dtype=dtype, device=device)
+    rows = max(1, min(n, block_bytes // max(1, 4 * m)))
+    bufs = [torch.empty((rows, m), dtype=torch.float32).pin_memory() for _ in range(min(2, -(-n // rows)))]
+    done = [None] * len(bufs)
+    side = torch.cuda.Stream(device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    for k, r0 in enumerate(range(0, n, rows)):
+        r1 = min(n, r0 + rows)
+        b = bufs[k % len(bufs)]
+        if done[k % len(bufs)] is not None:
+            done[k % len(bufs)].synchronize()  # the upload that last used this buffer
+        dset.read_direct(b.numpy()[:r1 - r0], source_sel=np.s_[i, r0:r1, :])
+        with torch.cuda.stream(side):
+            out[r0:r1].copy_(b[:r1 - r0].to(device, non_blocking=True))
+            done[k % len(bufs)] = torch.cuda.Event()
+            done[k % len(bufs)].record(side)
+    torch.cuda.current_stream(device).wait_stream(side)
+    return out
 
 
 def classify(config, dataset, in_path, jitter=0.0):
