@@ -104,12 +104,15 @@ def save_K_resident(f, model, name, X, X2, diag, batch_size, worker_rank=0, n_wo
         width = N2
         dev_bufs = [torch.empty((batch_size, width), dtype=torch.float32, device=device) for _ in range(2)]
         host_bufs = [torch.empty((batch_size, width), dtype=torch.float32).pin_memory() for _ in range(2)]
-        pending = []  # (event, host view, i0, i1, j0, j1)
+        flags = torch.ones(2, dtype=torch.bool).pin_memory()  # per buffer: "every entry of the row is finite"
+        pending = []  # (event, buffer index, host view, i0, i1, j0, j1)
 
         def drain(keep):
             while len(pending) > keep:
-                ev, host, i0, i1, j0, j1 = pending.pop(0)
+                ev, b, host, i0, i1, j0, j1 = pending.pop(0)
                 ev.synchronize()
+                if not bool(flags[b]):
+                    raise FloatingPointError(f"nan or inf in kernel block row {name}[{i0}:{i1}]")
                 out[0, i0:i1, j0:j1] = host.numpy()
 
         segs = print_timings(segs, desc=f"{name} rows (worker {worker_rank}/{n_workers})",
@@ -118,21 +121,22 @@ def save_K_resident(f, model, name, X, X2, diag, batch_size, worker_rank=0, n_wo
             i0, i1 = r * batch_size, min(N, (r + 1) * batch_size)
             j0 = i0 if has_diag else c0 * batch_size
             j1 = min(N2, c1 * batch_size) if c0 is not None else i1
-            drain(keep=1)  # buffer k % 2 was last used by row k - 2
+            # buffer k % 2 was last used by row k - 2, which the drain of the previous iteration wrote
             buf = dev_bufs[k % 2][:i1 - i0, :j1 - j0]
             if has_diag:
                 job.block_into(buf[:, :i1 - i0], i0, i1, i0, i1, symmetric=True)
             if c0 is not None:
                 js = c0 * batch_size
                 job.block_into(buf[:, js - j0:], i0, i1, js, j1, symmetric=False)
-            if not bool(torch.isfinite(buf).all()):
-                raise FloatingPointError(f"nan or inf in kernel block row {name}[{i0}:{i1}]")
+            finite = torch.isfinite(buf).all()  # stays on the device: no host sync in this loop
             host = host_bufs[k % 2][:i1 - i0, :j1 - j0]
             copy_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(copy_stream):
                 host.copy_(buf, non_blocking=True)
+                flags[k % 2:k % 2 + 1].copy_(finite.reshape(1), non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
-            # (drain(keep=1) above waits for this event before the device buffer is reused)
-            pending.append((ev, host, i0, i1, j0, j1))
+            pending.append((ev, k % 2, host, i0, i1, j0, j1))
+            # row k is queued on the GPU: write row k - 1 to the store underneath it
+            drain(keep=1)
         drain(keep=0)

@@ -22,6 +22,7 @@
 
 #include <atomic>
 #include <cfloat>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -54,7 +55,8 @@ enum { F_CONV = 0, F_RELU = 1, F_DENSE = 2 };
 struct FOp {
     int kind;
     int lo, hi;     // F_CONV: window offsets [-lo, +hi] along each axis
-    float scale, bias;
+    float pre_bias; // F_CONV with a window: added inside the second sliding sum (two adds per map, see below)
+    float scale, bias;  // F_CONV: applied as one FMA pass only when scale != 1 or the conv is pointwise; F_DENSE
     int aux_off;    // F_RELU: offset (floats) of this layer inside the fused section of a row
 };
 
@@ -86,12 +88,14 @@ using namespace fusedk;
 // maps at once (packed lanes), as two sliding windows that start at the two ends and meet in
 // the middle: independent dependency chains (ILP) and half the rounding-error accumulation of
 // one long slide.
-template <int S, int LO, int HI>
-__device__ __forceinline__ void box_pass(u64 (&v)[S]) {
+// BIAS: both windows start from v + B, so every output carries the constant B (the folded conv bias).
+template <int S, int LO, int HI, bool BIAS>
+__device__ __forceinline__ void box_pass(u64 (&v)[S], u64 B) {
     if (LO == 0 && HI == 0) return;
     constexpr int MID = S / 2;
     u64 o[S];
     u64 top = v[0], bot = v[S - 1];
+    if (BIAS) { top = add2(top, B); bot = add2(bot, B); }
 #pragma unroll
     for (int t = 1; t <= HI && t < S; ++t) top = add2(top, v[t]);
 #pragma unroll
@@ -115,15 +119,15 @@ __device__ __forceinline__ void box_pass(u64 (&v)[S]) {
 }
 
 // LO < 0 selects the window at run time (programs that mix window shapes).
-template <int S, int LO, int HI>
-__device__ __forceinline__ void box_any(u64 (&v)[S], int lo, int hi) {
+template <int S, int LO, int HI, bool BIAS>
+__device__ __forceinline__ void box_any(u64 (&v)[S], int lo, int hi, u64 B) {
     if (LO >= 0) {
-        box_pass<S, (LO >= 0 ? LO : 0), HI>(v);
+        box_pass<S, (LO >= 0 ? LO : 0), HI, BIAS>(v, B);
     } else {
-        if (lo == 3 && hi == 3) box_pass<S, 3, 3>(v);
-        else if (lo == 1 && hi == 1) box_pass<S, 1, 1>(v);
-        else if (lo == 1 && hi == 2) box_pass<S, 1, 2>(v);
-        else if (lo == 2 && hi == 2) box_pass<S, 2, 2>(v);
+        if (lo == 3 && hi == 3) box_pass<S, 3, 3, BIAS>(v, B);
+        else if (lo == 1 && hi == 1) box_pass<S, 1, 1, BIAS>(v, B);
+        else if (lo == 1 && hi == 2) box_pass<S, 1, 2, BIAS>(v, B);
+        else if (lo == 2 && hi == 2) box_pass<S, 2, 2, BIAS>(v, B);
     }
 }
 
@@ -338,27 +342,36 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) fused_kernel(const __gri
         for (int k = 0; k < p.n_ops; ++k) {
             const FOp o = p.ops[k];
             if (o.kind == F_CONV) {
-                if (o.lo != 0 || o.hi != 0) {
+                const bool window = o.lo != 0 || o.hi != 0;
+                if (window) {
                     // pass 1, transposition, pass 2 -- software-pipelined over the two packed
-                    // arrays so that the smem traffic of one overlaps the adds of the other
-                    box_any<S, LO, HI>(M[0], o.lo, o.hi);
+                    // arrays so that the smem traffic of one overlaps the adds of the other.
+                    // The maps are kept divided by the product of the conv taps so far (the host
+                    // scales each ReLU's variance maps to match: the arccos kernel is homogeneous),
+                    // so "* tap + bias" is only "+ bias / taps", and a constant added to the two
+                    // starting windows of the second sliding sum is in every output: two adds per
+                    // map instead of one FMA per pixel.
+                    const u64 PB = pk(o.pre_bias, o.pre_bias);
+                    box_any<S, LO, HI, false>(M[0], o.lo, o.hi, 0ull);
                     tile_store<S>(tile, M[0], lane);
                     __syncwarp();
                     tile_load_t<S>(tile, M[0], lx);
-                    box_any<S, LO, HI>(M[1], o.lo, o.hi);
+                    box_any<S, LO, HI, false>(M[1], o.lo, o.hi, 0ull);
                     __syncwarp();
                     tile_store<S>(tile, M[1], lane);
-                    box_any<S, LO, HI>(M[0], o.lo, o.hi);
+                    box_any<S, LO, HI, true>(M[0], o.lo, o.hi, PB);
                     __syncwarp();
                     tile_load_t<S>(tile, M[1], lx);
                     __syncwarp();
-                    box_any<S, LO, HI>(M[1], o.lo, o.hi);
+                    box_any<S, LO, HI, true>(M[1], o.lo, o.hi, PB);
                 }
-                const u64 SC = pk(o.scale, o.scale), BI = pk(o.bias, o.bias);
+                if (!window || o.scale != 1.f) {  // pointwise convs, and the host's rare explicit rescale
+                    const u64 SC = pk(o.scale, o.scale), BI = pk(o.bias, o.bias);
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
+                    for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int r = 0; r < S; ++r) M[h][r] = fma2(M[h][r], SC, BI);
+                        for (int r = 0; r < S; ++r) M[h][r] = fma2(M[h][r], SC, BI);
+                }
             } else if (o.kind == F_RELU) {
 #pragma unroll
                 for (int q = 0; q < NSPLIT; ++q) {
@@ -462,7 +475,10 @@ FusedPlan *fused_plan_create(const Plan *plan_const) {
     fp.S = S;
     int cur = 0;             // the slot the straight-line program lives in
     bool transposed = false;  // current register layout: lane = row?
-    float pending = 1.f;     // power-of-two factor owed by the ReLU's doubled output
+    double rho = 1.0;        // true map = rho * the kernel's registers: conv taps and the 1/2 of the ReLU's
+                             // doubled output are never applied to the maps, only carried here
+    bool after_relu = false;
+    const bool fold = getenv("CNNGP_NO_FOLD") == nullptr;  // measurement aid: one explicit FMA pass per conv
     bool done = false;
     int n_windows = 0;
     for (size_t k = 0; k < plan->ops.size(); ++k) {
@@ -492,16 +508,29 @@ FusedPlan *fused_plan_create(const Plan *plan_const) {
             } else {
                 return nullptr;
             }
-            f.scale = o.scale_f * pending;
-            f.bias = o.bias_f;
-            pending = 1.f;
+            const double alpha = o.scale_d * rho;  // true output = alpha * (box(registers) + bias / alpha)
+            if (f.kind == F_DENSE) {
+                f.scale = (float)alpha; f.bias = (float)o.bias_d;
+            } else if (fold && alpha > 1e-30 && alpha < 1e30 && alpha == alpha) {
+                const float b = (float)(o.bias_d / alpha);
+                if (f.lo || f.hi) { f.pre_bias = b; f.scale = 1.f; f.bias = 0.f; }
+                else { f.pre_bias = 0.f; f.scale = 1.f; f.bias = b; }
+                rho = alpha;
+            } else {  // the carried factor would leave float range: apply it once, explicitly
+                f.pre_bias = 0.f; f.scale = (float)alpha; f.bias = (float)o.bias_d;
+                rho = 1.0;
+            }
+            after_relu = false;
         } else if (o.opcode == CNNGP_OP_RELU) {
-            if (pending != 1.f) return nullptr;  // ReLU directly after ReLU: not in the set
+            if (after_relu) return nullptr;  // ReLU directly after ReLU: not in the set
             if (o.Hi != S || o.Wi != S) return nullptr;
             f.kind = F_RELU;
             f.aux_off = o.aux_foff;
             o.aux_t = transposed ? 1 : 0;
-            pending = 0.5f;
+            // relu_k(rho * m; s) = rho * relu_k(m; s / rho): each image's s map carries 1 / sqrt(rho)
+            o.aux_scale = (float)(1.0 / std::sqrt(rho));
+            rho *= 0.5;  // the kernel's ReLU output is doubled
+            after_relu = true;
             ++fp.n_relu;
         } else {
             return nullptr;
@@ -510,7 +539,7 @@ FusedPlan *fused_plan_create(const Plan *plan_const) {
         fp.ops[fp.n_ops++] = f;
     }
     if (!done) {
-        for (DevOp &o : plan->ops) o.aux_t = 0;
+        for (DevOp &o : plan->ops) { o.aux_t = 0; o.aux_scale = 1.f; }
         return nullptr;
     }
     return new FusedPlan(fp);

@@ -210,8 +210,9 @@ __global__ void __launch_bounds__(kThreads) generic_kernel(GenericParams<T> p) {
                             const T sd = add_rn(sqrt_rn(v0), (T)1.0842021724855044e-19);
                             T *f = p.aux_x_out + (size_t)((n & ~(int64_t)1) + hi) * p.aux_elems + p.aux_f_off +
                                    (size_t)o.aux_foff + 4 * (size_t)(tp - hi * half) + (n & 1);
-                            f[0] = sd;
-                            f[2] = div_rn((T)1, sd);
+                            const T ss = mul_rn(sd, (T)o.aux_scale);  // 1 unless the fused kernel folds conv taps
+                            f[0] = ss;
+                            f[2] = div_rn((T)1, ss);
                         }
                         const T h0 = div_rn(v0, (T)2);  // kernels.py:154
                         if (p.NP == 2) {

@@ -49,7 +49,7 @@ int build_plan(const cnngp_op *ops, int32_t n_ops, int32_t n_slots, int32_t H, i
         DevOp d{};
         d.opcode = o.opcode; d.src = o.src; d.dst = o.dst;
         d.Hi = slot[o.src].h; d.Wi = slot[o.src].w; d.Ho = d.Hi; d.Wo = d.Wi;
-        d.aux_off = 0; d.relu_index = -1; d.aux_t = 0; d.aux_foff = 0; d.aux_half = 0;
+        d.aux_off = 0; d.relu_index = -1; d.aux_t = 0; d.aux_foff = 0; d.aux_half = 0; d.aux_scale = 1.f;
         d.scale_d = o.scale; d.bias_d = o.bias; d.scale_f = (float)o.scale; d.bias_f = (float)o.bias;
         switch (o.opcode) {
             case CNNGP_OP_CONV: {
@@ -99,7 +99,10 @@ int build_plan(const cnngp_op *ops, int32_t n_ops, int32_t n_slots, int32_t H, i
             foff += 4 * d.aux_half;
         }
         p->fused = fused_plan_create(p);
-        if (!p->fused) p->fnet = fnet_plan_create(p);
+        if (!p->fused) {
+            for (DevOp &d : p->ops) { d.aux_t = 0; d.aux_scale = 1.f; }  // whatever a partial translation left
+            p->fnet = fnet_plan_create(p);
+        }
         if (p->fused || p->fnet) {  // rows grow by the pair-interleaved maps, 16-byte aligned
             p->aux_f_off = (p->relu_elems + 3) / 4 * 4;
             p->aux_elems = (int64_t)p->aux_f_off + foff;

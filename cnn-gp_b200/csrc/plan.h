@@ -22,6 +22,8 @@ struct DevOp {
     int32_t aux_foff;                  // RELU: offset (floats) of its pair-interleaved (s, 1/s) maps inside the
                                        // fused section of a row; the section of this layer is 4*aux_half floats
     int32_t aux_half;                  // RELU: ceil(pixels / 2): pixels [0, half) live in row 2k, the rest in 2k+1
+    float aux_scale;                   // RELU: factor on the fused s map (1/s gets its inverse): the straight-line
+                                       // fused kernel keeps its maps divided by the product of the conv taps so far
     float scale_f, bias_f;
     double scale_d, bias_d;
 };
