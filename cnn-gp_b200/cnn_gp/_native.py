@@ -4,7 +4,8 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_PKG), "libcnngp.so")
+# CNNGP_LIB: another build of the same library (A/B measurements of kernel changes)
+LIB_PATH = os.environ.get("CNNGP_LIB") or os.path.join(os.path.dirname(_PKG), "libcnngp.so")
 
 F32, F64 = 0, 1
 OP_CONV, OP_RELU, OP_COPY, OP_ADD, OP_SCALE = 1, 2, 3, 4, 5

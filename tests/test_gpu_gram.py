@@ -243,6 +243,47 @@ def test_fused_headline_program_large():
     assert rel_err(Kr[off], Kq[off]) < 5e-6
 
 
+@pytest.mark.parametrize("name,C,S,n", [("mnist_paper_convnet_gp", 1, 28, 1100), ("mnist_as_tf", 1, 28, 300),
+                                        ("cifar10", 3, 32, 200)])
+def test_tile_order_is_invisible(name, C, S, n, monkeypatch):
+    """Tiles are handed to the CTAs by an atomic counter; which CTA computes a tile must not
+    matter: bit-identical to the fixed-stride order (CNNGP_TILE_ORDER=static), symmetric and
+    rectangular calls, several super-tiles and ragged edges."""
+    model = MODELS[name].float().cuda()
+    gen = torch.Generator().manual_seed(11)
+    X = torch.rand(n, C, S, S, generator=gen).cuda()
+    Z = torch.rand(n // 2 + 3, C, S, S, generator=gen).cuda()
+    got = (model(X), model(X, Z))
+    assert engine.last_path() in ("fused", "fused_net")
+    monkeypatch.setenv("CNNGP_TILE_ORDER", "static")
+    want = (model(X), model(X, Z))
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
+
+
+def test_carried_conv_factor_matches_explicit_scaling(monkeypatch):
+    """The straight-line fused kernel never multiplies a map by a conv tap (the factor is
+    carried and the variance maps are scaled to match); CNNGP_NO_FOLD=1 builds the plan with one
+    explicit scale-and-bias pass per conv instead.  Same values up to float32 rounding."""
+    from cnn_gp import Conv2d, ReLU, Sequential
+
+    def build():
+        return Sequential(Conv2d(7, var_weight=2.79, var_bias=7.86), ReLU(), Conv2d(1, var_weight=0.3, var_bias=0.1),
+                          Conv2d(4, var_weight=1e-3, var_bias=0.0), ReLU(), Conv2d(3, var_weight=40.0, var_bias=2.0),
+                          ReLU(), Conv2d(28, padding=0, var_weight=1.1, var_bias=0.05)).cuda()
+    gen = torch.Generator().manual_seed(12)
+    X = torch.rand(50, 1, 28, 28, generator=gen).cuda()
+    Z = torch.rand(31, 1, 28, 28, generator=gen).cuda()
+    K = build()(X, Z)
+    assert engine.last_path() == "fused"
+    monkeypatch.setenv("CNNGP_NO_FOLD", "1")
+    Ke = build()(X, Z)  # a new module: plans are cached per module
+    assert engine.last_path() == "fused"
+    assert rel_err(K.cpu().numpy(), Ke.cpu().numpy()) < 2e-6
+    want = oracle.gram(build().cpu(), X.cpu().numpy(), Z.cpu().numpy())
+    assert rel_err(K.cpu().numpy(), want) < 1e-5
+
+
 # ---- fused-net kernel: Sum / stride / several map sizes, skip maps in tensor memory ------------
 def _net_models():
     from cnn_gp import Conv2d, ReLU, Sequential, Sum, Mixture, resnet_block
