@@ -42,6 +42,8 @@ _SIGNATURES = {
     "cnngp_h5_dataset_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(Info)]),
     "cnngp_h5_write": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _I64P, _I64P, ctypes.c_void_p]),
     "cnngp_h5_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _I64P, _I64P, ctypes.c_void_p]),
+    "cnngp_h5_write_strided": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _I64P, _I64P, ctypes.c_void_p, _I64P]),
+    "cnngp_h5_read_strided": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _I64P, _I64P, ctypes.c_void_p, _I64P]),
     "cnngp_h5_resize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, _I64P]),
     "cnngp_h5_merge_nan": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]),
 }
@@ -121,7 +123,7 @@ class Dataset:
         return self.shape[0]
 
     def _select(self, key):
-        """key -> (start, count, result shape)."""
+        """key -> (start, count, result shape, which dimensions the result keeps)."""
         shape = self.shape
         if not isinstance(key, tuple):
             key = (key,)
@@ -134,6 +136,7 @@ class Dataset:
             raise IndexError("too many indices")
         key = key + (slice(None),) * (len(shape) - len(key))
         start, count, out = [], [], []
+        kept = []  # which dataset dimensions survive in the result (slices do, integers do not)
         for k, n in zip(key, shape):
             if isinstance(k, (int, np.integer)):
                 k = int(k)
@@ -143,6 +146,7 @@ class Dataset:
                     raise IndexError(f"index {k} out of range for extent {n}")
                 start.append(k)
                 count.append(1)
+                kept.append(False)
             elif isinstance(k, slice):
                 a, b, s = k.indices(n)
                 if s != 1:
@@ -150,12 +154,23 @@ class Dataset:
                 start.append(a)
                 count.append(max(0, b - a))
                 out.append(max(0, b - a))
+                kept.append(True)
             else:
                 raise IndexError(f"unsupported index {k!r}")
-        return start, count, tuple(out)
+        return start, count, tuple(out), kept
+
+    def _strides_of(self, arr, kept, out_shape):
+        """Byte strides per dataset dimension if ``arr`` (shape ``out_shape``) can be handed to the
+        library as it is -- right dtype, last dimension contiguous, no negative strides -- else None."""
+        if not isinstance(arr, np.ndarray) or arr.dtype != self.dtype or arr.shape != out_shape or arr.ndim == 0:
+            return None
+        if arr.strides[-1] != arr.itemsize or any(st < 0 for st in arr.strides) or not kept[-1]:
+            return None
+        it = iter(arr.strides)  # dimensions indexed by an integer have no axis in arr: stride 0
+        return [next(it) if k else 0 for k in kept]
 
     def __getitem__(self, key):
-        start, count, out_shape = self._select(key)
+        start, count, out_shape, _ = self._select(key)
         arr = np.empty(count, dtype=self.dtype)
         if arr.size:
             _check(lib().cnngp_h5_read(self._f._handle(), self._id, _i64(start), _i64(count),
@@ -164,7 +179,12 @@ class Dataset:
         return arr[()] if arr.ndim == 0 else arr
 
     def __setitem__(self, key, value):
-        start, count, out_shape = self._select(key)
+        start, count, out_shape, kept = self._select(key)
+        strides = self._strides_of(value, kept, out_shape)
+        if strides is not None and value.size:  # a strided view (e.g. columns of a row buffer): no packing copy
+            _check(lib().cnngp_h5_write_strided(self._f._handle(), self._id, _i64(start), _i64(count),
+                                                value.ctypes.data_as(ctypes.c_void_p), _i64(strides)), f"write {self.name}")
+            return
         arr = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=self.dtype), out_shape)).reshape(count)
         if arr.size:
             _check(lib().cnngp_h5_write(self._f._handle(), self._id, _i64(start), _i64(count),
@@ -172,14 +192,16 @@ class Dataset:
 
     def read_direct(self, dest, source_sel=None, dest_sel=None):
         """Read straight into ``dest`` (C-contiguous destination selections avoid the copy)."""
-        start, count, out_shape = self._select(source_sel if source_sel is not None else Ellipsis)
+        start, count, out_shape, kept = self._select(source_sel if source_sel is not None else Ellipsis)
         target = dest if dest_sel is None else dest[dest_sel]
         if target.shape != out_shape:
             raise TypeError(f"cannot read {out_shape} into {target.shape}")
-        if target.dtype == self.dtype and target.flags.c_contiguous and target.flags.writeable:
+        strides = self._strides_of(target, kept, out_shape) if target.flags.writeable else None
+        if strides is not None:
             if target.size:
-                _check(lib().cnngp_h5_read(self._f._handle(), self._id, _i64(start), _i64(count),
-                                           target.ctypes.data_as(ctypes.c_void_p)), f"read {self.name}")
+                _check(lib().cnngp_h5_read_strided(self._f._handle(), self._id, _i64(start), _i64(count),
+                                                   target.ctypes.data_as(ctypes.c_void_p), _i64(strides)),
+                       f"read {self.name}")
         else:
             target[...] = self[source_sel if source_sel is not None else Ellipsis]
 

@@ -107,13 +107,21 @@ def save_K_resident(f, model, name, X, X2, diag, batch_size, worker_rank=0, n_wo
         flags = torch.ones(2, dtype=torch.bool).pin_memory()  # per buffer: "every entry of the row is finite"
         pending = []  # (event, buffer index, host view, i0, i1, j0, j1)
 
+        import os
+        import time
+        spent = {"wait_gpu": 0.0, "write": 0.0, "t0": time.perf_counter()}
+
         def drain(keep):
             while len(pending) > keep:
                 ev, b, host, i0, i1, j0, j1 = pending.pop(0)
+                t = time.perf_counter()
                 ev.synchronize()
+                spent["wait_gpu"] += time.perf_counter() - t
                 if not bool(flags[b]):
                     raise FloatingPointError(f"nan or inf in kernel block row {name}[{i0}:{i1}]")
+                t = time.perf_counter()
                 out[0, i0:i1, j0:j1] = host.numpy()
+                spent["write"] += time.perf_counter() - t
 
         segs = print_timings(segs, desc=f"{name} rows (worker {worker_rank}/{n_workers})",
                              print_interval=print_interval)
@@ -140,3 +148,6 @@ def save_K_resident(f, model, name, X, X2, diag, batch_size, worker_rank=0, n_wo
             # row k is queued on the GPU: write row k - 1 to the store underneath it
             drain(keep=1)
         drain(keep=0)
+        if os.environ.get("CNNGP_SAVE_TIMING"):
+            print(f"{name}: {time.perf_counter() - spent['t0']:.2f} s in the row loop, of which "
+                  f"{spent['wait_gpu']:.2f} s waiting for the GPU and {spent['write']:.2f} s writing to the store")

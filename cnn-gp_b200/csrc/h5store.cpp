@@ -608,10 +608,10 @@ int flush_locked(File *f) {
 // Copy the box [lo, hi) (dataset coordinates) between a chunk-shaped buffer whose origin is `corg`
 // and a selection-shaped buffer whose origin is `sorg`.  to_user: chunk -> user, else user -> chunk.
 void copy_box(int rank, const int64_t *lo, const int64_t *hi, const int64_t *corg, const int64_t *cdim,
-              uint8_t *cbuf, const int64_t *sorg, const int64_t *sdim, uint8_t *ubuf, int esize, bool to_user) {
-    int64_t cstr[kMaxRank], sstr[kMaxRank], idx[kMaxRank];
-    cstr[rank - 1] = sstr[rank - 1] = esize;
-    for (int i = rank - 2; i >= 0; --i) { cstr[i] = cstr[i + 1] * cdim[i + 1]; sstr[i] = sstr[i + 1] * sdim[i + 1]; }
+              uint8_t *cbuf, const int64_t *sorg, const int64_t *sstr, uint8_t *ubuf, int esize, bool to_user) {
+    int64_t cstr[kMaxRank], idx[kMaxRank];
+    cstr[rank - 1] = esize;
+    for (int i = rank - 2; i >= 0; --i) cstr[i] = cstr[i + 1] * cdim[i + 1];
     for (int i = 0; i < rank; ++i) { if (hi[i] <= lo[i]) return; idx[i] = lo[i]; }
     const size_t row = (size_t)(hi[rank - 1] - lo[rank - 1]) * (size_t)esize;
     for (;;) {
@@ -627,10 +627,8 @@ void copy_box(int rank, const int64_t *lo, const int64_t *hi, const int64_t *cor
 // A chunk that lies wholly inside the selection is one contiguous file range and a set of equally
 // long rows in the user's buffer: move it with preadv / pwritev, no staging copy.
 bool whole_chunk_io(const File *f, int rank, const int64_t *corg, const int64_t *cdim, const int64_t *sorg,
-                    const int64_t *sdim, uint8_t *ubuf, int esize, uint64_t addr, bool write) {
-    int64_t sstr[kMaxRank], idx[kMaxRank];
-    sstr[rank - 1] = esize;
-    for (int i = rank - 2; i >= 0; --i) sstr[i] = sstr[i + 1] * sdim[i + 1];
+                    const int64_t *sstr, uint8_t *ubuf, int esize, uint64_t addr, bool write) {
+    int64_t idx[kMaxRank];
     for (int i = 0; i < rank; ++i) idx[i] = corg[i];
     const size_t row = (size_t)cdim[rank - 1] * (size_t)esize;
     std::vector<iovec> iov;
@@ -697,10 +695,22 @@ int check_sel(const Dataset *d, const int64_t *start, const int64_t *count) {
     return 0;
 }
 
-int transfer(File *f, Dataset *d, const int64_t *start, const int64_t *count, uint8_t *user, bool write) {
+// ustride: byte strides of the caller's array per dimension (the last one must be the element size),
+// or NULL for a C-contiguous array of shape count[]
+int transfer(File *f, Dataset *d, const int64_t *start, const int64_t *count, uint8_t *user, bool write,
+             const int64_t *ustride = nullptr) {
     if (!d->unsupported.empty()) return fail("dataset '" + d->name + "': " + d->unsupported);
     if (check_sel(d, start, count)) return 1;
     const int r = d->rank;
+    int64_t sstr[kMaxRank] = {0};
+    if (r > 0) {
+        sstr[r - 1] = d->esize;
+        for (int i = r - 2; i >= 0; --i) sstr[i] = sstr[i + 1] * count[i + 1];
+        if (ustride) {
+            if (ustride[r - 1] != d->esize) return fail("strided transfer: the last dimension must be contiguous");
+            for (int i = 0; i < r; ++i) sstr[i] = ustride[i];
+        }
+    }
     int64_t total = 1;
     for (int i = 0; i < r; ++i) total *= count[i];
     if (total == 0) return 0;
@@ -710,25 +720,23 @@ int transfer(File *f, Dataset *d, const int64_t *start, const int64_t *count, ui
         for (int i = 0; i < r; ++i) { lo[i] = start[i]; hi[i] = start[i] + count[i]; }
         if (d->compact) {
             if (write) return fail("compact datasets are read-only here");
-            copy_box(r, lo, hi, zero, d->shape, d->compact_data.data(), start, count, user, d->esize, true);
+            copy_box(r, lo, hi, zero, d->shape, d->compact_data.data(), start, sstr, user, d->esize, true);
             return 0;
         }
-        if (d->data_addr == UNDEF) {
-            if (write) return fail("contiguous dataset without allocated storage");
-            fill_pattern(d, user, (size_t)total * (size_t)d->esize);
-            return 0;
-        }
-        // row by row straight to / from the file
-        int64_t str[kMaxRank], idx[kMaxRank], sstr[kMaxRank];
-        str[r - 1] = sstr[r - 1] = d->esize;
-        for (int i = r - 2; i >= 0; --i) { str[i] = str[i + 1] * d->shape[i + 1]; sstr[i] = sstr[i + 1] * count[i + 1]; }
+        // row by row straight to / from the file (storage never allocated: rows of the fill value)
+        int64_t str[kMaxRank], idx[kMaxRank];
+        str[r - 1] = d->esize;
+        for (int i = r - 2; i >= 0; --i) str[i] = str[i + 1] * d->shape[i + 1];
         for (int i = 0; i < r; ++i) idx[i] = lo[i];
         const size_t row = (size_t)count[r - 1] * (size_t)d->esize;
+        if (d->data_addr == UNDEF && write) return fail("contiguous dataset without allocated storage");
         for (;;) {
             int64_t fo = 0, so = 0;
             for (int i = 0; i < r; ++i) { fo += idx[i] * str[i]; so += (idx[i] - start[i]) * sstr[i]; }
-            const bool ok = write ? pwrite_all(f, user + so, row, d->data_addr + (uint64_t)fo)
-                                  : pread_all(f, user + so, row, d->data_addr + (uint64_t)fo);
+            bool ok = true;
+            if (d->data_addr == UNDEF) fill_pattern(d, user + so, row);
+            else ok = write ? pwrite_all(f, user + so, row, d->data_addr + (uint64_t)fo)
+                            : pread_all(f, user + so, row, d->data_addr + (uint64_t)fo);
             if (!ok) return fail("I/O error on '" + d->name + "'");
             int k = r - 2;
             for (; k >= 0; --k) { if (++idx[k] < hi[k]) break; idx[k] = lo[k]; }
@@ -776,9 +784,6 @@ int transfer(File *f, Dataset *d, const int64_t *start, const int64_t *count, ui
             // one row of fill values, reused for every row of the box
             int64_t idx[kMaxRank];
             for (int i = 0; i < r; ++i) idx[i] = lo[i];
-            int64_t sstr[kMaxRank];
-            sstr[r - 1] = d->esize;
-            for (int i = r - 2; i >= 0; --i) sstr[i] = sstr[i + 1] * count[i + 1];
             for (;;) {
                 int64_t so = 0;
                 for (int i = 0; i < r; ++i) so += (idx[i] - start[i]) * sstr[i];
@@ -789,16 +794,16 @@ int transfer(File *f, Dataset *d, const int64_t *start, const int64_t *count, ui
             }
             return true;
         }
-        if (covers && !edge) return whole_chunk_io(f, r, corg, d->chunk, start, count, user, d->esize, j.addr, write);
+        if (covers && !edge) return whole_chunk_io(f, r, corg, d->chunk, start, sstr, user, d->esize, j.addr, write);
         std::vector<uint8_t> buf(d->chunk_bytes);
         if (!write) {
             if (!pread_all(f, buf.data(), buf.size(), j.addr)) return false;
-            copy_box(r, lo, hi, corg, d->chunk, buf.data(), start, count, user, d->esize, true);
+            copy_box(r, lo, hi, corg, d->chunk, buf.data(), start, sstr, user, d->esize, true);
             return true;
         }
         if (!covers && j.existed) { if (!pread_all(f, buf.data(), buf.size(), j.addr)) return false; }
         else if (!covers || edge) fill_pattern(d, buf.data(), buf.size());
-        copy_box(r, lo, hi, corg, d->chunk, buf.data(), start, count, user, d->esize, false);
+        copy_box(r, lo, hi, corg, d->chunk, buf.data(), start, sstr, user, d->esize, false);
         return pwrite_all(f, buf.data(), buf.size(), j.addr);
     });
     if (!ok) return fail("I/O error on '" + d->name + "' (" + f->path + ")");
@@ -1018,6 +1023,25 @@ int cnngp_h5_read(cnngp_h5 *f, int id, const int64_t *start, const int64_t *coun
     Dataset *d = get(f, id);
     if (!d) return 1;
     return transfer(f, d, start, count, (uint8_t *)data, false);
+}
+
+int cnngp_h5_write_strided(cnngp_h5 *f, int id, const int64_t *start, const int64_t *count, const void *data,
+                           const int64_t *stride_bytes) {
+    if (!f || !start || !count || !data || !stride_bytes) return fail("NULL argument");
+    std::lock_guard<std::mutex> g(f->mu);
+    Dataset *d = get(f, id);
+    if (!d) return 1;
+    if (!f->writable) return fail("file is open read-only: " + f->path);
+    return transfer(f, d, start, count, (uint8_t *)const_cast<void *>(data), true, stride_bytes);
+}
+
+int cnngp_h5_read_strided(cnngp_h5 *f, int id, const int64_t *start, const int64_t *count, void *data,
+                          const int64_t *stride_bytes) {
+    if (!f || !start || !count || !data || !stride_bytes) return fail("NULL argument");
+    std::lock_guard<std::mutex> g(f->mu);
+    Dataset *d = get(f, id);
+    if (!d) return 1;
+    return transfer(f, d, start, count, (uint8_t *)data, false, stride_bytes);
 }
 
 int cnngp_h5_resize(cnngp_h5 *f, int id, const int64_t *new_shape) {

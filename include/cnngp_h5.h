@@ -74,6 +74,14 @@ int cnngp_h5_dataset_info(cnngp_h5 *f, int id, cnngp_h5_info *info);
  * Elements never written read as the fill value. */
 int cnngp_h5_write(cnngp_h5 *f, int id, const int64_t *start, const int64_t *count, const void *data);
 int cnngp_h5_read(cnngp_h5 *f, int id, const int64_t *start, const int64_t *count, void *data);
+/* The same for a caller's array that is a strided view (a column range of a wider row buffer,
+ * as save_K_resident hands over): stride_bytes[i] = distance between consecutive indices of
+ * dimension i; the last dimension must be contiguous (stride = element size).  Saves the packing
+ * copy h5py makes for such selections. */
+int cnngp_h5_write_strided(cnngp_h5 *f, int id, const int64_t *start, const int64_t *count, const void *data,
+                           const int64_t *stride_bytes);
+int cnngp_h5_read_strided(cnngp_h5 *f, int id, const int64_t *start, const int64_t *count, void *data,
+                          const int64_t *stride_bytes);
 /* dset.resize(new_shape): every extent within maxshape; stored chunks outside the new extent
  * stay in the file but are no longer reachable */
 int cnngp_h5_resize(cnngp_h5 *f, int id, const int64_t *new_shape);

@@ -181,6 +181,28 @@ def test_random_hyperslabs_against_numpy(tmp_path):
     np.testing.assert_array_equal(OracleFile(p).datasets["a"].read(), ref32)
 
 
+def test_strided_views_are_transferred_in_place(tmp_path):
+    """save_K_resident hands over column ranges of a wider pinned row buffer; read_direct may
+    target a window of a larger array: no packing copy, same bytes."""
+    rng = np.random.default_rng(3)
+    p = str(tmp_path / "s.h5")
+    wide = rng.standard_normal((9, 40)).astype(np.float32)
+    ref = np.full((1, 9, 23), np.nan, np.float32)
+    with h5store.File(p, "w") as f:
+        d = f.create_dataset("K", shape=(1, 9, 23), dtype=np.float32, fillvalue=np.nan, chunks=(1, 4, 4), maxshape=(None, 9, 23))
+        view = wide[:, 7:30]
+        assert d._strides_of(view, [False, True, True], (9, 23)) == [0, 160, 4]
+        _model_write(d, ref, (0, slice(0, 9), slice(0, 23)), view)
+        _model_write(d, ref, (0, slice(2, 9, None), slice(5, 17)), wide[1:8, 20:32])
+        assert d._strides_of(wide[:, ::2], [False, True, True], (9, 20)) is None  # falls back to the packing copy
+        _model_write(d, ref, (0, slice(0, 9), slice(0, 20)), wide[:, ::2])
+        big = np.zeros((3, 12, 30), np.float32)
+        d.read_direct(big, source_sel=np.s_[0, 1:8, 3:20], dest_sel=np.s_[1, 2:9, 5:22])
+        np.testing.assert_array_equal(big[1, 2:9, 5:22], ref[0, 1:8, 3:20])
+        assert np.count_nonzero(big) == np.count_nonzero(big[1, 2:9, 5:22]) == 7 * 17  # nothing outside the window
+    np.testing.assert_array_equal(OracleFile(p).datasets["K"].read(), ref)
+
+
 def test_deep_chunk_index(tmp_path):
     """More than 64 x 64 chunks: a three-level version-1 B-tree, bulk-written, in key order."""
     p = str(tmp_path / "deep.h5")
