@@ -101,9 +101,11 @@ def save_K_resident(f, model, name, X, X2, diag, batch_size, worker_rank=0, n_wo
         copy_stream = torch.cuda.Stream()
         # two device row buffers and two pinned host buffers, allocated once and used alternately:
         # row k is copied out and written to the store while row k + 1 is being computed
-        width = N2
-        dev_bufs = [torch.empty((batch_size, width), dtype=torch.float32, device=device) for _ in range(2)]
-        host_bufs = [torch.empty((batch_size, width), dtype=torch.float32).pin_memory() for _ in range(2)]
+        # (flat: every row segment is viewed as a CONTIGUOUS [rows, cols] matrix, so the device-to-host
+        # copy is one plain async memcpy -- torch stages non-contiguous cross-device copies through
+        # pageable memory and blocks)
+        dev_bufs = [torch.empty(batch_size * N2, dtype=torch.float32, device=device) for _ in range(2)]
+        host_bufs = [torch.empty(batch_size * N2, dtype=torch.float32).pin_memory() for _ in range(2)]
         flags = torch.ones(2, dtype=torch.bool).pin_memory()  # per buffer: "every entry of the row is finite"
         pending = []  # (event, buffer index, host view, i0, i1, j0, j1)
 
@@ -130,14 +132,15 @@ def save_K_resident(f, model, name, X, X2, diag, batch_size, worker_rank=0, n_wo
             j0 = i0 if has_diag else c0 * batch_size
             j1 = min(N2, c1 * batch_size) if c0 is not None else i1
             # buffer k % 2 was last used by row k - 2, which the drain of the previous iteration wrote
-            buf = dev_bufs[k % 2][:i1 - i0, :j1 - j0]
+            rows, cols = i1 - i0, j1 - j0
+            buf = dev_bufs[k % 2][:rows * cols].view(rows, cols)
             if has_diag:
                 job.block_into(buf[:, :i1 - i0], i0, i1, i0, i1, symmetric=True)
             if c0 is not None:
                 js = c0 * batch_size
                 job.block_into(buf[:, js - j0:], i0, i1, js, j1, symmetric=False)
             finite = torch.isfinite(buf).all()  # stays on the device: no host sync in this loop
-            host = host_bufs[k % 2][:i1 - i0, :j1 - j0]
+            host = host_bufs[k % 2][:rows * cols].view(rows, cols)
             copy_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(copy_stream):
                 host.copy_(buf, non_blocking=True)
