@@ -134,10 +134,11 @@ __device__ __forceinline__ void box_any(u64 (&v)[S], int lo, int hi, u64 B) {
 template <int S>
 __device__ __forceinline__ void tile_store(u64 *tile, const u64 (&a)[S], int lane) {
     constexpr int PITCH = S + 1;  // odd: row-wise writes and column-wise reads are both conflict-free
-    if (lane < S) {
+    // lanes >= S hold nothing: they all write the pad column (no branch around the stores, so the
+    // compiler can sink them into the sliding sums that produce the values)
+    const int col = lane < S ? lane : S;
 #pragma unroll
-        for (int r = 0; r < S; ++r) tile[r * PITCH + lane] = a[r];
-    }
+    for (int r = 0; r < S; ++r) tile[r * PITCH + col] = a[r];
 }
 template <int S>
 __device__ __forceinline__ void tile_load_t(const u64 *tile, u64 (&a)[S], int lx) {
