@@ -327,10 +327,11 @@ __device__ __forceinline__ void box_s2(u64 (&v)[S0]) {
 template <int S0, int R, int L>
 __device__ __forceinline__ void tstore(u64 *tile, const u64 (&a)[S0], int lane) {
     constexpr int PITCH = S0 + 1;  // odd: row-wise writes and column-wise reads are both conflict-free
-    if (lane < L) {
+    // lanes >= L hold nothing: they all write the pad column S0, which is never read (no branch
+    // around the stores, so the compiler can sink them into the sums that produce the values)
+    const int col = lane < L ? lane : S0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) tile[r * PITCH + lane] = a[r];
-    }
+    for (int r = 0; r < R; ++r) tile[r * PITCH + col] = a[r];
 }
 template <int S0, int R>
 __device__ __forceinline__ void tload(const u64 *tile, u64 (&a)[S0], int lx) {
