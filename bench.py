@@ -275,20 +275,24 @@ def run_ours(args):
         mine = worker_tiles_balanced(n, None, args.tile, rank, world)
         row_lo = min(t[1] for t in mine) * args.tile if mine else 0
         row_hi = min(n, (max(t[1] for t in mine) + 1) * args.tile) if mine else 0
-    K_host = torch.empty((row_hi - row_lo, n), dtype=torch.float32).pin_memory()
+    K_host = torch.empty((row_hi - row_lo, n), dtype=torch.float32).pin_memory() if world > 1 else None
     K_dev = torch.empty((n, n), dtype=torch.float32, device=dev) if world > 1 else None
 
+    e2e_out = {}
+
     def step_e2e():
-        x = X_host.to(dev, non_blocking=True)
         if world == 1:
-            K = model(x)  # public call: plan lookup, variances, one fused launch
-            K_host.copy_(K, non_blocking=True)
-        else:
-            compute_worker_blocks(GramJob(model, x), K_dev, args.tile, rank, world, balanced=True)
-            K_host.copy_(K_dev[row_lo:row_hi], non_blocking=True)
+            # public call with host tensors: upload, variances, one fused launch whose finished
+            # row bands are copied to the pinned result while it is still running
+            e2e_out["K"] = model(X_host)
+            return
+        x = X_host.to(dev, non_blocking=True)
+        compute_worker_blocks(GramJob(model, x), K_dev, args.tile, rank, world, balanced=True)
+        K_host.copy_(K_dev[row_lo:row_hi], non_blocking=True)
         torch.cuda.synchronize()
 
     step_e2e()
+    step_e2e()  # the pinned result buffers of the host call come from torch's caching host allocator
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
@@ -296,7 +300,7 @@ def run_ours(args):
         step_e2e()
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    d2h_bytes = K_host.numel() * 4
+    d2h_bytes = (K_host.numel() if world > 1 else n * n) * 4
     if world > 1:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -346,7 +350,7 @@ def run_ours(args):
             "e2e": {"value": total_pairs / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": X_host.numel() * 4 * world,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s * 1e3,
                     "note": "per-worker host buffers (block rows a worker owns), all workers in parallel"
-                            if world > 1 else "model(x): pinned host images -> pinned host result"},
+                            if world > 1 else "model(x_host): pinned host images -> pinned host result, row bands copied out while the launch runs"},
             "gpu_launches": n_launch,
             "clocks": clocks,
         }

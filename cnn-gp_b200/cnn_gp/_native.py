@@ -41,6 +41,10 @@ _SIGNATURES = {
                                   ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                   ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                                   ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p]),
+    "cnngp_gram_symmetric_to_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
+                                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                                    ctypes.c_void_p, ctypes.c_void_p]),
     "cnngp_conv_maps": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                        ctypes.POINTER(Op), ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     "cnngp_relu_maps": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,

@@ -93,6 +93,9 @@ def gram_with_aux(plan, x, z, aux_x, aux_z, same, diag, symmetric, out=None, kdi
 @torch.no_grad()
 def gram(model, x, y, same, diag):
     """model(x, y, same, diag) -- reference kernels.py:18-57."""
+    if not x.is_cuda and not y.is_cuda and _model_device(model) is not None:
+        # host tensors, model on a GPU: host in, host out (the reference returns on the input device)
+        return gram_host(model, x, None if y is x else y, same, diag)
     _require_cuda(x, "x")
     _require_cuda(y, "y")
     if x.dtype != y.dtype or x.device != y.device:
@@ -121,6 +124,60 @@ def gram(model, x, y, same, diag):
             aux_z = aux_x if identical else variances(plan, y)[0]
         return gram_with_aux(plan, x, y, aux_x, aux_z, same, diag, symmetric,
                              kdiag=kdiag if symmetric else None)
+
+
+def _model_device(model):
+    for t in list(model.buffers()) + list(model.parameters()):
+        if t.is_cuda:
+            return t.device
+    return None
+
+
+@torch.no_grad()
+def gram_host(model, x, y=None, same=None, diag=False, out=None):
+    """``model(x, y, same, diag)`` for HOST tensors and a model that lives on a GPU: host in, host out.
+
+    This is the round trip the reference's tile driver makes per tile (``model(x.cuda(), ...)
+    .cpu()``, exp_mnist_resnet/save_kernel.py:21-24), as one call.  For ``model(X)`` on a program
+    the straight-line fused kernel covers, bands of finished rows are copied to the (pinned) result
+    while the kernel is still running (cnngp_gram_symmetric_to_host); anything else is upload,
+    compute, copy.  ``out``: optional pinned float32 ``[N1, N2]`` result buffer to reuse."""
+    dev = _model_device(model)
+    if dev is None:
+        raise RuntimeError("cnn_gp (B200): neither the inputs nor the model are on a CUDA device; "
+                           "this implementation has no CPU path")
+    if y is None:
+        y, same = x, True if same is None else same
+    identical = y is x
+    with torch.cuda.device(dev):
+        xd = x.to(dev, non_blocking=True)
+        yd = xd if identical else y.to(dev, non_blocking=True)
+        N = xd.shape[0]
+        streamed = (identical and same and not diag and xd.dtype == torch.float32 and N > 0
+                    and _force_path != "generic")
+        if streamed:
+            xd = xd.contiguous()
+            plan = plan_for(model, xd.shape[2], xd.shape[3], xd.dtype)
+            streamed = plan.fused_kind == 2
+        if not streamed:
+            res = gram(model, xd, yd, bool(same), bool(diag))
+            if out is None:
+                return res.cpu()
+            out.copy_(res)
+            return out
+        aux, _, kdiag = variances(plan, xd)
+        K = torch.empty((N, N), dtype=torch.float32, device=dev)
+        if out is None:
+            out = torch.empty((N, N), dtype=torch.float32, pin_memory=True)
+        assert out.shape == (N, N) and out.dtype == torch.float32 and out.stride(1) == 1 and not out.is_cuda
+        scratch = torch.empty(max(64, N // 256 + 8), dtype=torch.int32, device=dev)
+        side = torch.cuda.Stream(dev)
+        nat.check(nat.lib().cnngp_gram_symmetric_to_host(
+            plan.handle, xd.data_ptr(), N, xd.shape[1], aux.data_ptr(), kdiag.data_ptr(), K.data_ptr(), K.stride(0),
+            out.data_ptr(), out.stride(0), scratch.data_ptr(), scratch.numel() * 4, _stream(),
+            ctypes.c_void_p(side.cuda_stream)), "cnngp_gram_symmetric_to_host")
+        side.synchronize()
+        return out
 
 
 def _conv_op(mod):

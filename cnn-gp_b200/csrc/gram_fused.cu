@@ -79,6 +79,7 @@ struct FParams {
     int nst;           // super-tiles per side (symmetric)
     long long n_tiles; // CTA tiles enumerated (super-tile padded)
     unsigned long long *tile_ctr;  // zeroed before the launch: the next tile index to hand out
+    unsigned *row_done;            // optional: finished (tile, warp) units per super-row (RowProgress)
     float inv_c;       // 1 / C
 };
 
@@ -445,6 +446,11 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) fused_kernel(const __gri
                         }
                     }
                 }
+                if (p.row_done) {  // the entries above are visible device-wide before the count moves
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(&p.row_done[ib / p.sti], 1u);
+                }
             }
         }
     }
@@ -569,7 +575,7 @@ std::atomic<unsigned> g_next_ctr{0};
 struct Variant { int nw, nsplit, nst; };
 
 template <int NW, int NSPLIT, int NST>
-int launch_variant(const FusedPlan *fp, FParams &p, int64_t N1, int64_t N2, cudaStream_t stream) {
+int launch_variant(const FusedPlan *fp, FParams &p, int64_t N1, int64_t N2, cudaStream_t stream, RowProgress *prog) {
     using G = Geo<NW>;
     p.nbi = (int)((N1 + G::kTileI - 1) / G::kTileI);
     p.nbj = (int)((N2 + G::kTileJ - 1) / G::kTileJ);
@@ -588,6 +594,21 @@ int launch_variant(const FusedPlan *fp, FParams &p, int64_t N1, int64_t N2, cuda
         n_super = p.symmetric ? (long long)p.nst * (p.nst + 1) / 2 : (long long)nsi * nsj;
     }
     p.n_tiles = n_super * p.sti * p.stj;
+    if (prog) {  // what the kernel will count per super-row: valid tiles x consumer warps (decode() below)
+        prog->n_super_rows = (p.nbi + p.sti - 1) / p.sti;
+        prog->rows_per_super = (int64_t)p.sti * G::kTileI;
+        if (!p.symmetric || prog->n_super_rows > prog->capacity) { set_error("fused kernel: progress counters too few"); return 8; }
+        prog->expected.assign(prog->n_super_rows, 0u);
+        for (int ib = 0; ib < p.nbi; ++ib) {
+            const int si = ib / p.sti;
+            // jb >= si * stj (upper-triangular super-tiles) and the tile reaches the diagonal or beyond
+            long long jb_lo = (long long)si * p.stj;
+            const long long need = ((long long)ib * G::kTileI - (G::kTileJ - 1) + G::kTileJ - 1) / G::kTileJ;
+            if (need > jb_lo) jb_lo = need;
+            if (jb_lo < p.nbj) prog->expected[si] += (unsigned)((p.nbj - jb_lo) * NW);
+        }
+        p.row_done = prog->d_done;
+    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -623,7 +644,8 @@ int launch_variant(const FusedPlan *fp, FParams &p, int64_t N1, int64_t N2, cuda
 
 int launch_fused_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2,
                       int32_t C, const void *d_aux_x, const void *d_aux_z, int32_t same, int32_t diag,
-                      int32_t symmetric, const void *d_kdiag, void *d_out, int64_t ld_out, void *stream) {
+                      int32_t symmetric, const void *d_kdiag, void *d_out, int64_t ld_out, void *stream,
+                      RowProgress *progress) {
     (void)same;
     const FusedPlan *fp = plan->fused;
     if (!fp || diag) { set_error("fused kernel: unsupported call"); return 4; }
@@ -647,10 +669,10 @@ int launch_fused_gram(const Plan *plan, const void *d_x, int64_t N1, const void 
     if (const char *e = getenv("CNNGP_FUSED_VARIANT")) sscanf(e, "%d,%d,%d", &v.nw, &v.nsplit, &v.nst);
     int rc = -1;
     cudaStream_t st = (cudaStream_t)stream;
-    if (v.nw == 12 && v.nsplit == 4 && v.nst == 4) rc = launch_variant<12, 4, 4>(fp, p, N1, N2, st);
-    else if (v.nw == 8 && v.nsplit == 1 && v.nst == 2) rc = launch_variant<8, 1, 2>(fp, p, N1, N2, st);
-    else if (v.nw == 8 && v.nsplit == 2 && v.nst == 4) rc = launch_variant<8, 2, 4>(fp, p, N1, N2, st);
-    if (rc < 0) rc = launch_variant<12, 2, 2>(fp, p, N1, N2, st);
+    if (v.nw == 12 && v.nsplit == 4 && v.nst == 4) rc = launch_variant<12, 4, 4>(fp, p, N1, N2, st, progress);
+    else if (v.nw == 8 && v.nsplit == 1 && v.nst == 2) rc = launch_variant<8, 1, 2>(fp, p, N1, N2, st, progress);
+    else if (v.nw == 8 && v.nsplit == 2 && v.nst == 4) rc = launch_variant<8, 2, 4>(fp, p, N1, N2, st, progress);
+    if (rc < 0) rc = launch_variant<12, 2, 2>(fp, p, N1, N2, st, progress);
     return rc;
 }
 

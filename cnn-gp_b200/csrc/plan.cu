@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 
@@ -243,6 +244,59 @@ int cnngp_gram(const cnngp_plan *plan, const void *d_x, int64_t N1, const void *
     if (use_fused)
         return launch_fnet_gram(p, d_x, N1, d_z, N2, C, d_aux_x, d_aux_z, symmetric, d_kdiag, d_out, ld_out, stream);
     return launch_generic_gram(p, d_x, N1, d_z, N2, C, d_aux_x, d_aux_z, same, diag, symmetric, d_out, ld_out, stream);
+}
+
+// model(X) with the result streamed to host memory while the launch is still running: the kernel
+// counts finished tiles per band of rows (RowProgress), the copy stream waits on each band's counter
+// with a stream memory operation (cuStreamWaitValue32) and copies the band out -- mirrored entries
+// of a band are written by the bands before it, which the in-order waits cover.
+int cnngp_gram_symmetric_to_host(const cnngp_plan *plan, const void *d_x, int64_t N, int32_t C, const void *d_aux,
+                                 const void *d_kdiag, void *d_out, int64_t ld_out, void *h_out, int64_t ld_host,
+                                 void *d_scratch, int64_t scratch_bytes, void *stream, void *copy_stream) {
+    const Plan *p = reinterpret_cast<const Plan *>(plan);
+    if (!p || !d_x || !d_aux || !d_out || !h_out || !d_scratch || N < 1 || C < 1 || ld_out < N || ld_host < N) {
+        set_error("cnngp_gram_symmetric_to_host: bad arguments");
+        return 1;
+    }
+    if (!p->fused) { set_error("cnngp_gram_symmetric_to_host: only the straight-line fused kernel reports progress"); return 4; }
+    typedef int (*WaitValue32)(void *, unsigned long long, unsigned int, unsigned int);
+    static WaitValue32 wait_value = nullptr;
+    if (!wait_value) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+            set_error("cnngp_gram_symmetric_to_host: cuStreamWaitValue32 unavailable");
+            return 7;
+        }
+        wait_value = reinterpret_cast<WaitValue32>(fn);
+    }
+    cudaStream_t st = (cudaStream_t)stream, cs = (cudaStream_t)copy_stream;
+    RowProgress prog;
+    prog.d_done = (unsigned *)d_scratch;
+    prog.capacity = scratch_bytes / (int64_t)sizeof(unsigned);
+    cudaError_t e = cudaMemsetAsync(d_scratch, 0, (size_t)scratch_bytes, st);
+    cudaEvent_t ev = nullptr;
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ev, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ev, 0);  // no band is waited for before the counters are zero
+    if (ev) cudaEventDestroy(ev);
+    if (e != cudaSuccess) { set_error(std::string("cnngp_gram_symmetric_to_host: ") + cudaGetErrorString(e)); return 7; }
+    g_last_path = CNNGP_PATH_FUSED;
+    int rc = launch_fused_gram(p, d_x, N, d_x, N, C, d_aux, d_aux, 1, 0, 1, d_kdiag, d_out, ld_out, stream, &prog);
+    if (rc) return rc;  // nothing was queued on the copy stream yet: it cannot wait for a launch that never ran
+    const size_t esz = sizeof(float);
+    for (int b = 0; b < prog.n_super_rows; ++b) {
+        const int64_t r0 = (int64_t)b * prog.rows_per_super;
+        const int64_t rows = std::min<int64_t>(prog.rows_per_super, N - r0);
+        if (rows <= 0) break;
+        const int wr = wait_value(cs, (unsigned long long)(uintptr_t)(prog.d_done + b), prog.expected[b], 1u /* GEQ */);
+        if (wr != 0) { set_error("cnngp_gram_symmetric_to_host: cuStreamWaitValue32 failed (" + std::to_string(wr) + ")"); return 7; }
+        e = cudaMemcpy2DAsync((char *)h_out + (size_t)r0 * ld_host * esz, (size_t)ld_host * esz,
+                              (const char *)d_out + (size_t)r0 * ld_out * esz, (size_t)ld_out * esz, (size_t)N * esz,
+                              (size_t)rows, cudaMemcpyDeviceToHost, cs);
+        if (e != cudaSuccess) { set_error(std::string("cnngp_gram_symmetric_to_host: ") + cudaGetErrorString(e)); return 7; }
+    }
+    return 0;
 }
 
 int cnngp_conv_maps(const void *d_in, int64_t M, int32_t Hi, int32_t Wi, const cnngp_op *conv,

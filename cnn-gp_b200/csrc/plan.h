@@ -67,13 +67,26 @@ int launch_conv_maps(const void *d_in, int64_t M, int32_t Hi, int32_t Wi, const 
 int launch_relu_maps(void *d_xy, const void *d_xx, const void *d_yy, int64_t Nx, int64_t Ny, int64_t P,
                      int32_t same, int32_t diag, int32_t dtype, void *stream);
 
+// Optional progress reporting of a symmetric fused launch, for streaming the result out while the
+// launch is still running: the kernel counts finished (tile, warp) units per SUPER-ROW (a band of
+// `rows_per_super` image rows, enumerated first to last); band b of the output is final -- mirrored
+// entries included -- once bands 0..b have reached their expected counts.
+struct RowProgress {
+    unsigned *d_done = nullptr;       // in: device counters, zeroed on the launch stream before the launch
+    int64_t capacity = 0;             // in: number of counters available
+    int n_super_rows = 0;             // out
+    int64_t rows_per_super = 0;       // out
+    std::vector<unsigned> expected;   // out: count at which super-row b is complete
+};
+
 // gram_fused.cu
 FusedPlan *fused_plan_create(const Plan *plan);  // nullptr if not covered
 void fused_plan_destroy(FusedPlan *fp);
 std::string fused_plan_describe(const FusedPlan *fp);
 int launch_fused_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2,
                       int32_t C, const void *d_aux_x, const void *d_aux_z, int32_t same, int32_t diag,
-                      int32_t symmetric, const void *d_kdiag, void *d_out, int64_t ld_out, void *stream);
+                      int32_t symmetric, const void *d_kdiag, void *d_out, int64_t ld_out, void *stream,
+                      RowProgress *progress = nullptr);
 
 // gram_fnet.cu
 FNetPlan *fnet_plan_create(const Plan *plan);  // nullptr if not covered

@@ -124,6 +124,19 @@ int cnngp_gram(const cnngp_plan *plan, const void *d_x, int64_t N1, const void *
                int32_t diag, int32_t symmetric, void *d_out, int64_t ld_out, int32_t path, void *stream);
 int cnngp_last_path(void);
 
+/* model(X) for a caller that wants the result in HOST memory (what save_kernel's `kern` does with
+ * .cpu(), exp_mnist_resnet/save_kernel.py:21-24): the symmetric Gram of d_x is computed into
+ * d_out [N, ld_out] as by cnngp_gram(symmetric = 1), and bands of finished rows are copied to the
+ * pinned host array h_out [N, ld_host] on `copy_stream` WHILE the launch is still running -- the
+ * kernel counts finished tiles per band in d_scratch (device memory, scratch_bytes >= 4 bytes per
+ * 504 rows; zeroed here), and the copy stream waits on those counters with stream memory
+ * operations.  Both streams must differ; the caller synchronises `copy_stream` before reading
+ * h_out.  Returns 4 if the plan's kernel family does not report progress (use cnngp_gram + a
+ * copy then). */
+int cnngp_gram_symmetric_to_host(const cnngp_plan *plan, const void *d_x, int64_t N, int32_t C, const void *d_aux,
+                                 const void *d_kdiag, void *d_out, int64_t ld_out, void *h_out, int64_t ld_host,
+                                 void *d_scratch, int64_t scratch_bytes, void *stream, void *copy_stream);
+
 /* Map-level steps behind module.propagate(kp): a stack of M maps [M, Hi, Wi]. */
 int cnngp_conv_maps(const void *d_in, int64_t M, int32_t Hi, int32_t Wi, const cnngp_op *conv,
                     int32_t dtype, void *d_out, void *stream);                 /* kernels.py:94-97 */

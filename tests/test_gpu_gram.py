@@ -261,6 +261,32 @@ def test_tile_order_is_invisible(name, C, S, n, monkeypatch):
         assert torch.equal(g, w)
 
 
+@pytest.mark.parametrize("n", [2, 505, 1100])
+def test_host_call_streams_the_same_bytes(n):
+    """model(x_host) on a GPU-resident model: host in, host out (the per-tile round trip of
+    save_kernel.py:21-24 as one call).  For model(X) on the headline program bands of finished rows
+    leave the GPU while the kernel is still running; the bytes must be those of model(x.cuda())."""
+    model = MODELS["mnist_paper_convnet_gp"].float().cuda()
+    gen = torch.Generator().manual_seed(13)
+    X = torch.rand(n, 1, 28, 28, generator=gen)
+    want = model(X.cuda())
+    got = model(X.pin_memory())
+    assert not got.is_cuda and got.dtype == torch.float32 and engine.last_path() == "fused"
+    assert torch.equal(got, want.cpu())
+    out = torch.empty((n, n), dtype=torch.float32).pin_memory()
+    assert engine.gram_host(model, X, out=out) is out and torch.equal(out, want.cpu())
+    # anything else is upload, compute, copy: rectangular, diag, float64, a fused-net program
+    Z = torch.rand(7, 1, 28, 28, generator=gen)
+    assert torch.equal(model(X, Z), model(X.cuda(), Z.cuda()).cpu())
+    assert torch.equal(model(X, diag=True), model(X.cuda(), diag=True).cpu())
+    if n == 2:
+        m64 = MODELS["mnist_paper_convnet_gp"].double().cuda()
+        assert torch.equal(m64(X.double()), m64(X.double().cuda()).cpu())
+        MODELS["mnist_paper_convnet_gp"].float()
+        net = MODELS["mnist_as_tf"].float().cuda()
+        assert torch.equal(net(X), net(X.cuda()).cpu())
+
+
 def test_carried_conv_factor_matches_explicit_scaling(monkeypatch):
     """The straight-line fused kernel never multiplies a map by a conv tap (the factor is
     carried and the variance maps are scaled to match); CNNGP_NO_FOLD=1 builds the plan with one
