@@ -67,10 +67,12 @@ def row_segments(tiles):
     return [(i, rows[i][0], rows[i][1], rows[i][2]) for i in order]
 
 
-def compute_worker_blocks(job, out, batch_size, worker_rank=0, n_workers=1, balanced=False):
+def compute_worker_blocks(job, out, batch_size, worker_rank=0, n_workers=1, balanced=False, on_row=None):
     """Fill ``out`` ([N, N2], any float dtype matching the job) with this worker's tiles; entries
     owned by other workers are left untouched.  Returns the number of unique pairs computed.
-    ``balanced`` cuts the reference's tile list by pair count instead of tile count."""
+    ``balanced`` cuts the reference's tile list by pair count instead of tile count.
+    ``on_row(i0, i1)`` is called after the launches of each block row have been queued (e.g. to
+    record an event and start copying the row out on another stream)."""
     N, N2 = job.X.shape[0], job.X2.shape[0]
     split = worker_tiles_balanced if balanced else worker_tiles
     tiles = split(N, None if job.same else N2, batch_size, worker_rank, n_workers)
@@ -84,6 +86,8 @@ def compute_worker_blocks(job, out, batch_size, worker_rank=0, n_workers=1, bala
             j0, j1 = c0 * batch_size, min(N2, c1 * batch_size)
             job.block(out, i0, i1, j0, j1, symmetric=False)
             pairs += (i1 - i0) * (j1 - j0)
+        if on_row is not None:
+            on_row(i0, i1)
     return pairs
 
 
