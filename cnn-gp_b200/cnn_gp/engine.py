@@ -139,7 +139,7 @@ def gram_host(model, x, y=None, same=None, diag=False, out=None):
 
     This is the round trip the reference's tile driver makes per tile (``model(x.cuda(), ...)
     .cpu()``, exp_mnist_resnet/save_kernel.py:21-24), as one call.  For ``model(X)`` on a program
-    the straight-line fused kernel covers, bands of finished rows are copied to the (pinned) result
+    a fused kernel covers, bands of finished rows are copied to the (pinned) result
     while the kernel is still running (cnngp_gram_symmetric_to_host); anything else is upload,
     compute, copy.  ``out``: optional pinned float32 ``[N1, N2]`` result buffer to reuse."""
     dev = _model_device(model)
@@ -158,7 +158,7 @@ def gram_host(model, x, y=None, same=None, diag=False, out=None):
         if streamed:
             xd = xd.contiguous()
             plan = plan_for(model, xd.shape[2], xd.shape[3], xd.dtype)
-            streamed = plan.fused_kind == 2
+            streamed = plan.fused_kind in (2, 3)
         if not streamed:
             res = gram(model, xd, yd, bool(same), bool(diag))
             if out is None:
@@ -170,12 +170,17 @@ def gram_host(model, x, y=None, same=None, diag=False, out=None):
         if out is None:
             out = torch.empty((N, N), dtype=torch.float32, pin_memory=True)
         assert out.shape == (N, N) and out.dtype == torch.float32 and out.stride(1) == 1 and not out.is_cuda
-        scratch = torch.empty(max(64, N // 256 + 8), dtype=torch.int32, device=dev)
+        scratch = torch.empty(max(64, N // 32 + 8), dtype=torch.int32, device=dev)  # one counter per band of >= 48 rows
         side = torch.cuda.Stream(dev)
-        nat.check(nat.lib().cnngp_gram_symmetric_to_host(
+        rc = nat.lib().cnngp_gram_symmetric_to_host(
             plan.handle, xd.data_ptr(), N, xd.shape[1], aux.data_ptr(), kdiag.data_ptr(), K.data_ptr(), K.stride(0),
             out.data_ptr(), out.stride(0), scratch.data_ptr(), scratch.numel() * 4, _stream(),
-            ctypes.c_void_p(side.cuda_stream)), "cnngp_gram_symmetric_to_host")
+            ctypes.c_void_p(side.cuda_stream))
+        if rc == 7:  # no stream memory operations on this driver / setup: plain launch + copy
+            gram_with_aux(plan, xd, xd, aux, aux, True, False, True, out=K, kdiag=kdiag)
+            out.copy_(K)
+            return out
+        nat.check(rc, "cnngp_gram_symmetric_to_host")
         side.synchronize()
         return out
 

@@ -90,6 +90,7 @@ struct NParams {
     int nbi, nbj, sti, stj, nst_j, nst;
     long long n_tiles;
     unsigned long long *tile_ctr;  // zeroed before the launch: the next tile index to hand out
+    unsigned *row_done;            // optional: finished (tile, warp) units per super-row (RowProgress, plan.h)
     float inv_c;
 };
 
@@ -884,6 +885,11 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
                 }
             }
         }
+        if (p.row_done) {  // the entries above are visible device-wide before the count moves
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(&p.row_done[ib / p.sti], 1u);
+        }
     }
 
     // all consumers are done with tensor memory before the allocating warp frees it
@@ -1214,7 +1220,7 @@ static std::atomic<unsigned> g_fnet_next_ctr{0};
 
 int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2, int32_t C,
                      const void *d_aux_x, const void *d_aux_z, int32_t symmetric, const void *d_kdiag,
-                     void *d_out, int64_t ld_out, void *stream) {
+                     void *d_out, int64_t ld_out, void *stream, RowProgress *prog) {
     const FNetPlan *fp = plan->fnet;
     if (!fp) { set_error("fused-net kernel: unsupported call"); return 4; }
     if (N1 > 2000000000LL || N2 > 2000000000LL) { set_error("fused-net kernel: too many images"); return 8; }
@@ -1249,6 +1255,20 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
         n_super = p.symmetric ? (long long)p.nst * (p.nst + 1) / 2 : (long long)nsi * nsj;
     }
     p.n_tiles = n_super * p.sti * p.stj;
+    if (prog) {  // what the kernel will count per super-row: valid tiles x consumer warps (see gram_fused.cu)
+        prog->n_super_rows = (p.nbi + p.sti - 1) / p.sti;
+        prog->rows_per_super = (int64_t)p.sti * kTileI;
+        if (!p.symmetric || prog->n_super_rows > prog->capacity) { set_error("fused-net kernel: progress counters too few"); return 8; }
+        prog->expected.assign(prog->n_super_rows, 0u);
+        for (int ib = 0; ib < p.nbi; ++ib) {
+            const int si = ib / p.sti;
+            long long jb_lo = (long long)si * p.stj;
+            const long long need = ((long long)ib * kTileI) / kTileJ;  // first tile that reaches the diagonal
+            if (need > jb_lo) jb_lo = need;
+            if (jb_lo < p.nbj) prog->expected[si] += (unsigned)((p.nbj - jb_lo) * fp->nw);
+        }
+        p.row_done = prog->d_done;
+    }
     p.inv_c = 1.0f / (float)C;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

@@ -258,7 +258,7 @@ int cnngp_gram_symmetric_to_host(const cnngp_plan *plan, const void *d_x, int64_
         set_error("cnngp_gram_symmetric_to_host: bad arguments");
         return 1;
     }
-    if (!p->fused) { set_error("cnngp_gram_symmetric_to_host: only the straight-line fused kernel reports progress"); return 4; }
+    if (!p->fused && !p->fnet) { set_error("cnngp_gram_symmetric_to_host: only the fused kernels report progress"); return 4; }
     typedef int (*WaitValue32)(void *, unsigned long long, unsigned int, unsigned int);
     static WaitValue32 wait_value = nullptr;
     if (!wait_value) {
@@ -281,15 +281,22 @@ int cnngp_gram_symmetric_to_host(const cnngp_plan *plan, const void *d_x, int64_
     if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ev, 0);  // no band is waited for before the counters are zero
     if (ev) cudaEventDestroy(ev);
     if (e != cudaSuccess) { set_error(std::string("cnngp_gram_symmetric_to_host: ") + cudaGetErrorString(e)); return 7; }
-    g_last_path = CNNGP_PATH_FUSED;
-    int rc = launch_fused_gram(p, d_x, N, d_x, N, C, d_aux, d_aux, 1, 0, 1, d_kdiag, d_out, ld_out, stream, &prog);
+    g_last_path = p->fused ? CNNGP_PATH_FUSED : CNNGP_PATH_FUSED_NET;
+    int rc = p->fused ? launch_fused_gram(p, d_x, N, d_x, N, C, d_aux, d_aux, 1, 0, 1, d_kdiag, d_out, ld_out, stream, &prog)
+                      : launch_fnet_gram(p, d_x, N, d_x, N, C, d_aux, d_aux, 1, d_kdiag, d_out, ld_out, stream, &prog);
     if (rc) return rc;  // nothing was queued on the copy stream yet: it cannot wait for a launch that never ran
+    // behind the launch every counter is raised to 0x7f7f7f7f (>= any expected count in the signed
+    // comparison the wait uses): whatever happens, the copy stream's waits end when the kernel has
+    // (a band can then only leave late, never hang the stream)
+    e = cudaMemsetAsync(d_scratch, 0x7F, (size_t)scratch_bytes, st);
+    if (e != cudaSuccess) { set_error(std::string("cnngp_gram_symmetric_to_host: ") + cudaGetErrorString(e)); return 7; }
     const size_t esz = sizeof(float);
     for (int b = 0; b < prog.n_super_rows; ++b) {
         const int64_t r0 = (int64_t)b * prog.rows_per_super;
         const int64_t rows = std::min<int64_t>(prog.rows_per_super, N - r0);
         if (rows <= 0) break;
-        const int wr = wait_value(cs, (unsigned long long)(uintptr_t)(prog.d_done + b), prog.expected[b], 1u /* GEQ */);
+        // CU_STREAM_WAIT_VALUE_GEQ = 0: waits until (int32_t)(*addr - value) >= 0
+        const int wr = wait_value(cs, (unsigned long long)(uintptr_t)(prog.d_done + b), prog.expected[b], 0u);
         if (wr != 0) { set_error("cnngp_gram_symmetric_to_host: cuStreamWaitValue32 failed (" + std::to_string(wr) + ")"); return 7; }
         e = cudaMemcpy2DAsync((char *)h_out + (size_t)r0 * ld_host * esz, (size_t)ld_host * esz,
                               (const char *)d_out + (size_t)r0 * ld_out * esz, (size_t)ld_out * esz, (size_t)N * esz,

@@ -94,6 +94,6 @@ void fnet_plan_destroy(FNetPlan *fp);
 std::string fnet_plan_describe(const FNetPlan *fp);
 int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2, int32_t C,
                      const void *d_aux_x, const void *d_aux_z, int32_t symmetric, const void *d_kdiag,
-                     void *d_out, int64_t ld_out, void *stream);
+                     void *d_out, int64_t ld_out, void *stream, RowProgress *progress = nullptr);
 
 }  // namespace cnngp

@@ -129,7 +129,7 @@ int cnngp_last_path(void);
  * d_out [N, ld_out] as by cnngp_gram(symmetric = 1), and bands of finished rows are copied to the
  * pinned host array h_out [N, ld_host] on `copy_stream` WHILE the launch is still running -- the
  * kernel counts finished tiles per band in d_scratch (device memory, scratch_bytes >= 4 bytes per
- * 504 rows; zeroed here), and the copy stream waits on those counters with stream memory
+ * 48 rows -- bands are 504 rows unless the program's variance maps are large; zeroed here), and the copy stream waits on those counters with stream memory
  * operations.  Both streams must differ; the caller synchronises `copy_stream` before reading
  * h_out.  Returns 4 if the plan's kernel family does not report progress (use cnngp_gram + a
  * copy then). */

@@ -275,7 +275,7 @@ def test_host_call_streams_the_same_bytes(n):
     assert torch.equal(got, want.cpu())
     out = torch.empty((n, n), dtype=torch.float32).pin_memory()
     assert engine.gram_host(model, X, out=out) is out and torch.equal(out, want.cpu())
-    # anything else is upload, compute, copy: rectangular, diag, float64, a fused-net program
+    # anything else is upload, compute, copy: rectangular, diag, float64
     Z = torch.rand(7, 1, 28, 28, generator=gen)
     assert torch.equal(model(X, Z), model(X.cuda(), Z.cuda()).cpu())
     assert torch.equal(model(X, diag=True), model(X.cuda(), diag=True).cpu())
@@ -283,8 +283,10 @@ def test_host_call_streams_the_same_bytes(n):
         m64 = MODELS["mnist_paper_convnet_gp"].double().cuda()
         assert torch.equal(m64(X.double()), m64(X.double().cuda()).cpu())
         MODELS["mnist_paper_convnet_gp"].float()
-        net = MODELS["mnist_as_tf"].float().cuda()
-        assert torch.equal(net(X), net(X.cuda()).cpu())
+    for name, C, S in (("mnist_as_tf", 1, 28), ("cifar10", 3, 32)):  # fused-net programs stream too
+        net = MODELS[name].float().cuda()
+        Xn = torch.rand(min(n, 505), C, S, S, generator=gen)
+        assert torch.equal(net(Xn), net(Xn.cuda()).cpu()) and engine.last_path() == "fused_net"
 
 
 def test_carried_conv_factor_matches_explicit_scaling(monkeypatch):
