@@ -24,6 +24,8 @@ dataset_name = "SYNTHETIC"
 model_name = "ConvNet"
 transforms = []
 epochs = 0
-in_channels = 1
+# CNNGP_SYNTH_SHAPE = "C,H,W" of the images (default 1,28,28; "3,32,32" for the CIFAR-10 architecture)
+_shape = tuple(int(v) for v in os.environ.get("CNNGP_SYNTH_SHAPE", "1,28,28").split(","))
+in_channels = _shape[0]
 out_channels = 10
-dataset = synthetic_dataset(_n_train + _n_val, _n_test)
+dataset = synthetic_dataset(_n_train + _n_val, _n_test, shape=_shape)

@@ -15,6 +15,8 @@ n = int(sys.argv[1])
 os.environ.update(CNNGP_SYNTH_TRAIN=str(n), CNNGP_SYNTH_VAL=str(n // 10), CNNGP_SYNTH_TEST=str(n // 5))
 if len(sys.argv) > 2 and sys.argv[2] not in ("h5", "npy"):
     os.environ["CNNGP_SYNTH_MODEL"] = sys.argv[2]
+    if sys.argv[2] == "cifar10":
+        os.environ["CNNGP_SYNTH_SHAPE"] = "3,32,32"
 store = "npy" if sys.argv[-1] == "npy" else "h5"
 import torch  # noqa: E402
 from cnn_gp import DatasetFromConfig  # noqa: E402
