@@ -660,65 +660,77 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
     if (warp >= kWarps) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::kRegsProducer));
         if (warp != kWarps) return;
-        // ---- producer --------------------------------------------------------------------
-        if (lane == 0) {
+        // ---- producer warp ----------------------------------------------------------------
+        // Lane 0 owns the ring protocol (waits for a free stage, publishes the tile index, posts the
+        // expected byte count); the copies of a stage are issued by the lanes in parallel, each
+        // from a base pointer it worked out ONCE per tile: lane u < 2 kPairs serves image row
+        // 2 pr + (u & 1) of tile pair u >> 1 (variance maps), lane s < kImgs serves tile image s.
+        // A single lane doing all of it was the bottleneck of the small (folded) layers, whose
+        // sixteen copies cost more to set up than the layer costs to compute.
+        {
             unsigned l = 0;
             const int last_pi = (p.N1 - 1) >> 1, last_pj = (p.N2 - 1) >> 1;
             long long t = 0;
             auto acquire = [&](unsigned bytes) -> unsigned char * {
                 const unsigned buf = l % NST;
-                if (l >= NST) mbar_wait_relaxed(&empty[buf], ((l / NST) - 1) & 1);
-                stage_tile[buf] = t;  // published by the release of the arrive below
-                mbar_arrive_expect_tx(&full[buf], bytes);
+                if (lane == 0) {
+                    if (l >= NST) mbar_wait_relaxed(&empty[buf], ((l / NST) - 1) & 1);
+                    stage_tile[buf] = t;  // published by the release of the arrive below
+                    mbar_arrive_expect_tx(&full[buf], bytes);
+                }
+                __syncwarp();
                 return stage + (size_t)buf * STAGE;
             };
             // tile_ctr == NULL: fixed stride (tile = blockIdx.x + k * gridDim.x), kept for comparison
             const bool dyn = p.tile_ctr != nullptr;
-            long long t_raw = dyn ? (long long)atomicAdd(p.tile_ctr, 1ull) : (long long)blockIdx.x;
+            auto next_index = [&](long long stat) -> long long {
+                if (!dyn) return stat;
+                long long v = 0;
+                if (lane == 0) v = (long long)atomicAdd(p.tile_ctr, 1ull);
+                return __shfl_sync(0xffffffffu, v, 0);
+            };
+            long long t_raw = next_index((long long)blockIdx.x);
             for (;;) {
                 int ib, jb;
                 t = t_raw;
-                while (t < p.n_tiles && !decode(t, ib, jb)) t = dyn ? (long long)atomicAdd(p.tile_ctr, 1ull) : t + gridDim.x;
+                while (t < p.n_tiles && !decode(t, ib, jb)) t = next_index(t + gridDim.x);
                 if (t >= p.n_tiles) break;
                 // the next index is requested now and first looked at when this tile's stages are out
-                t_raw = dyn ? (long long)atomicAdd(p.tile_ctr, 1ull) : t + gridDim.x;
+                t_raw = next_index(t + gridDim.x);
                 const int i_base = ib * kTileI, j_base = jb * kTileJ;
+                // this lane's sources for the whole tile
+                const float *img = nullptr, *var = nullptr;
+                if (lane < kImgs)
+                    img = lane < kTileI ? p.x + (long long)min(i_base + lane, p.N1 - 1) * p.C * P0
+                                        : p.z + (long long)min(j_base + lane - kTileI, p.N2 - 1) * p.C * P0;
+                const int vs = lane >> 1, vh = lane & 1;  // pair of the tile, image row of the pair
+                if (lane < 2 * kPairs) {
+                    const long long pr = vs < kTileI / 2 ? min((i_base >> 1) + vs, last_pi)
+                                                         : min((j_base >> 1) + vs - kTileI / 2, last_pj);
+                    var = (vs < kTileI / 2 ? p.aux_x : p.aux_z) + (2 * pr + vh) * p.aux_stride + p.aux_f_off;
+                }
                 for (int c = 0; c < p.C; ++c) {
                     for (int ip = 0; ip < IMG_PARTS; ++ip) {
                         float *dst = reinterpret_cast<float *>(acquire(kImgs * IBAND * 4));
-                        uint64_t *bar = &full[l % NST];
-                        for (int s = 0; s < kImgs; ++s) {
-                            const float *src;
-                            if (s < kTileI) src = p.x + ((long long)min(i_base + s, p.N1 - 1) * p.C + c) * P0;
-                            else src = p.z + ((long long)min(j_base + s - kTileI, p.N2 - 1) * p.C + c) * P0;
-                            bulk_g2s(dst + s * IBAND, src + ip * IBAND, IBAND * 4, bar);
-                        }
+                        if (lane < kImgs) bulk_g2s(dst + lane * IBAND, img + (long long)c * P0 + ip * IBAND, IBAND * 4, &full[l % NST]);
                         ++l;
                     }
                 }
                 for (int k = 0; k < p.n_ops; ++k) {
                     if (p.ops[k].kind != N_RELU) continue;
                     const int half = p.ops[k].half;
-                    const long long off = p.aux_f_off + (long long)p.ops[k].aux;
-                    const bool split = p.ops[k].si == S0;  // full-size layers: NSPLIT row bands, one stage each
-                    for (int part = 0; part < (split ? NSPLIT : 1); ++part) {
-                        const unsigned bytes = split ? (unsigned)(kPairs * BAND * 16) : (unsigned)(kPairs * half * 32);
-                        float4 *dst = reinterpret_cast<float4 *>(acquire(bytes));
-                        uint64_t *bar = &full[l % NST];
-                        for (int s = 0; s < kPairs; ++s) {
-                            const float *base;
-                            long long pr;
-                            if (s < kTileI / 2) { pr = min((i_base >> 1) + s, last_pi); base = p.aux_x; }
-                            else { pr = min((j_base >> 1) + s - kTileI / 2, last_pj); base = p.aux_z; }
-                            const float *src = base + 2 * pr * p.aux_stride + off;
-                            if (split) {  // band `part`: pixels [part * BAND, +BAND); the first half of the pixels is in row 2k
-                                bulk_g2s(dst + s * BAND, src + (part / (NSPLIT / 2)) * p.aux_stride + (part % (NSPLIT / 2)) * BAND * 4,
-                                         BAND * 16, bar);
-                            } else {
-                                bulk_g2s(dst + s * 2 * half, src, half * 16, bar);
-                                bulk_g2s(dst + s * 2 * half + half, src + p.aux_stride, half * 16, bar);
-                            }
+                    const int off = p.ops[k].aux;
+                    if (p.ops[k].si == S0) {  // full-size layers: NSPLIT row bands, one stage each
+                        for (int part = 0; part < NSPLIT; ++part) {
+                            float4 *dst = reinterpret_cast<float4 *>(acquire((unsigned)(kPairs * BAND * 16)));
+                            // band `part`: pixels [part * BAND, +BAND); the first half of the pixels is in row 2k
+                            if (lane < 2 * kPairs && vh == part / (NSPLIT / 2))
+                                bulk_g2s(dst + vs * BAND, var + off + (part % (NSPLIT / 2)) * BAND * 4, BAND * 16, &full[l % NST]);
+                            ++l;
                         }
+                    } else {  // folded maps: both halves of the layer in one stage
+                        float4 *dst = reinterpret_cast<float4 *>(acquire((unsigned)(kPairs * half * 32)));
+                        if (lane < 2 * kPairs) bulk_g2s(dst + vs * 2 * half + vh * half, var + off, half * 16, &full[l % NST]);
                         ++l;
                     }
                 }
