@@ -211,66 +211,72 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) fused_kernel(const __gri
         // last warpgroup: hand its registers to the consumers; only its first warp works
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::kRegsProducer));
         if (warp != kWarps) return;
-        // ---- producer: one elected thread stages, up to NST - 1 stages ahead, first the tile's
-        // images (per channel) and then each ReLU layer's pair-interleaved
-        // (s_a, s_b, 1/s_a, 1/s_b) maps of the tile's image pairs.  It runs on across tile
-        // boundaries, so the next tile's first stages are in flight while the consumers finish.
-        if (lane == 0) {
+        // ---- producer warp: stages, up to NST - 1 stages ahead, first the tile's images (per
+        // channel) and then each ReLU layer's pair-interleaved (s_a, s_b, 1/s_a, 1/s_b) maps of the
+        // tile's image pairs.  It runs on across tile boundaries, so the next tile's first stages
+        // are in flight while the consumers finish.  Lane 0 owns the ring protocol; the copies of a
+        // stage are issued by the lanes in parallel, each from a base pointer worked out once per
+        // tile (lane u < 2 kPairs: image row 2 pr + (u & 1) of tile pair u >> 1; lane s < kImgs:
+        // tile image s).
+        {
             unsigned l = 0;  // running stage counter over all tiles of this CTA
             const int last_pi = (p.N1 - 1) >> 1, last_pj = (p.N2 - 1) >> 1;
             long long t = 0;
             auto acquire = [&](unsigned bytes) -> float4 * {
                 const unsigned buf = l % NST;
-                if (l >= NST) mbar_wait_relaxed(&empty[buf], ((l / NST) - 1) & 1);
-                stage_tile[buf] = t;  // published by the release of the arrive below
-                mbar_arrive_expect_tx(&full[buf], bytes);
+                if (lane == 0) {
+                    if (l >= NST) mbar_wait_relaxed(&empty[buf], ((l / NST) - 1) & 1);
+                    stage_tile[buf] = t;  // published by the release of the arrive below
+                    mbar_arrive_expect_tx(&full[buf], bytes);
+                }
+                __syncwarp();
                 return stage + buf * STAGE_F4;
             };
             // tile_ctr == NULL: fixed stride (tile = blockIdx.x + k * gridDim.x), kept for comparison
             const bool dyn = p.tile_ctr != nullptr;
-            long long t_raw = dyn ? (long long)atomicAdd(p.tile_ctr, 1ull) : (long long)blockIdx.x;
+            auto next_index = [&](long long stat) -> long long {
+                if (!dyn) return stat;
+                long long v = 0;
+                if (lane == 0) v = (long long)atomicAdd(p.tile_ctr, 1ull);
+                return __shfl_sync(0xffffffffu, v, 0);
+            };
+            long long t_raw = next_index((long long)blockIdx.x);
             for (;;) {
                 int ib, jb;
                 t = t_raw;
-                while (t < p.n_tiles && !decode(t, ib, jb)) t = dyn ? (long long)atomicAdd(p.tile_ctr, 1ull) : t + gridDim.x;
+                while (t < p.n_tiles && !decode(t, ib, jb)) t = next_index(t + gridDim.x);
                 if (t >= p.n_tiles) break;
                 // the next index is requested now and first looked at when this tile's stages are out
-                t_raw = dyn ? (long long)atomicAdd(p.tile_ctr, 1ull) : t + gridDim.x;
+                t_raw = next_index(t + gridDim.x);
                 const int i_base = ib * kTileI, j_base = jb * kTileJ;
+                const float *img = nullptr, *var = nullptr;  // this lane's sources for the whole tile
+                if (lane < kImgs)
+                    img = lane < kTileI ? p.x + (long long)min(i_base + lane, p.N1 - 1) * p.C * P
+                                        : p.z + (long long)min(j_base + lane - kTileI, p.N2 - 1) * p.C * P;
+                const int vs = lane >> 1, vh = lane & 1;  // pair of the tile, image row of the pair
+                if (lane < 2 * kPairs) {
+                    const long long pr = vs < kTileI / 2 ? min((i_base >> 1) + vs, last_pi)
+                                                         : min((j_base >> 1) + vs - kTileI / 2, last_pj);
+                    var = (vs < kTileI / 2 ? p.aux_x : p.aux_z) + (2 * pr + vh) * p.aux_stride + p.aux_f_off;
+                }
                 for (int c = 0; c < p.C; ++c) {
                     for (int ip = 0; ip < IMG_PARTS; ++ip) {
                         float *dst = reinterpret_cast<float *>(acquire(kImgs * IBAND * 4));
-                        uint64_t *bar = &full[l % NST];
-                        for (int s = 0; s < kImgs; ++s) {
-                            const float *src;
-                            if (s < kTileI) src = p.x + ((long long)min(i_base + s, p.N1 - 1) * p.C + c) * P;
-                            else src = p.z + ((long long)min(j_base + s - kTileI, p.N2 - 1) * p.C + c) * P;
-                            bulk_g2s(dst + s * IBAND, src + ip * IBAND, IBAND * 4, bar);
-                        }
+                        if (lane < kImgs) bulk_g2s(dst + lane * IBAND, img + (long long)c * P + ip * IBAND, IBAND * 4, &full[l % NST]);
                         ++l;
                     }
                 }
                 for (int k = 0; k < p.n_ops; ++k) {
                     if (p.ops[k].kind != F_RELU) continue;
-                    const long long off = p.aux_f_off + (long long)p.ops[k].aux_off;
+                    const int off = p.ops[k].aux_off;
                     for (int q = 0; q < NSPLIT; ++q) {
                         float4 *dst = acquire(STAGE_F4 * 16);
                         uint64_t *bar = &full[l % NST];
-                        for (int s = 0; s < kPairs; ++s) {
-                            // pair s of the tile; its float4 map is split over the two images' rows
-                            const float *base;
-                            long long pr;
-                            if (s < kTileI / 2) { pr = min((i_base >> 1) + s, last_pi); base = p.aux_x; }
-                            else { pr = min((j_base >> 1) + s - kTileI / 2, last_pj); base = p.aux_z; }
-                            const float *src = base + 2 * pr * p.aux_stride + off;
-                            if (NSPLIT == 1) {
-                                bulk_g2s(dst + s * P, src, P * 8, bar);
-                                bulk_g2s(dst + s * P + P / 2, src + p.aux_stride, P * 8, bar);
-                            } else if (NSPLIT == 2) {
-                                bulk_g2s(dst + s * BAND, src + q * p.aux_stride, BAND * 16, bar);
-                            } else {
-                                bulk_g2s(dst + s * BAND, src + (q >> 1) * p.aux_stride + (q & 1) * BAND * 4, BAND * 16, bar);
-                            }
+                        // the float4 map of a pair is split over the two images' rows (first half of the pixels in row 2k)
+                        if (lane < 2 * kPairs) {
+                            if (NSPLIT == 1) bulk_g2s(dst + vs * P + vh * (P / 2), var + off, P * 8, bar);
+                            else if (NSPLIT == 2) { if (vh == q) bulk_g2s(dst + vs * BAND, var + off, BAND * 16, bar); }
+                            else if (vh == (q >> 1)) bulk_g2s(dst + vs * BAND, var + off + (q & 1) * BAND * 4, BAND * 16, bar);
                         }
                         ++l;
                     }
