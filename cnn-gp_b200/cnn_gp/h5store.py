@@ -337,3 +337,28 @@ class File:
 def merge_nan(dest, src, name):
     """exp_mnist_resnet/merge_h5_files.py:24-30 for one dataset, natively and chunk by chunk."""
     _check(lib().cnngp_h5_merge_nan(dest._handle(), dest[name]._id, src._handle(), src[name]._id), f"merge {name}")
+
+
+def _main(argv):
+    """``python -m cnn_gp.h5store FILE...``: list the datasets of HDF5 files (an ``h5ls`` for this store)."""
+    if not argv:
+        print("usage: python -m cnn_gp.h5store FILE...")
+        return 1
+    for path in argv:
+        with File(path, "r") as f:
+            print(f"{path}: {len(f)} dataset(s)")
+            for name in f.keys():
+                d = f[name]
+                info = d._info()
+                if info.dtype not in _DTYPES:
+                    print(f"  {name:12s} shape {d.shape}  (element type not read by this store)")
+                    continue
+                layout = f"chunks {d.chunks}, {d.n_chunks_stored} stored" if d.chunks else "contiguous"
+                fill = f", fill {d.fillvalue}" if info.has_fill else ""
+                print(f"  {name:12s} shape {d.shape}  maxshape {d.maxshape}  {d.dtype}  {layout}{fill}")
+    return 0
+
+
+if __name__ == "__main__":
+    import sys
+    sys.exit(_main(sys.argv[1:]))
