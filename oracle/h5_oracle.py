@@ -236,8 +236,9 @@ class OracleFile:
         self.base, self.freespace, self.eof, self.driver = struct.unpack_from("<QQQQ", d, p)
         p += 32
         self.root_entry = self._entry(d[p:p + 40])
-        if self.eof + 0 > len(self.data) - 0 and self.base + self.eof > len(self.data):
+        if self.eof > len(self.data):
             raise H5FormatError("end-of-file address beyond the file (truncated)")
+        self.eof_matches_size = self.eof == len(self.data)  # true for every file libhdf5 closed cleanly
         self.datasets = {}
         self.groups = []
         self._group(self.root_entry, "")
@@ -259,6 +260,11 @@ class OracleFile:
         if ver != 1:
             raise H5FormatError(f"object header version {ver} at {addr}")
         refcount, hsize = struct.unpack_from("<II", hdr, 4)
+        # what libhdf5 insists on when it loads a version-1 header (H5Ocache.c): chunk and message
+        # sizes are multiples of 8, messages start 8-byte aligned, and the message count in the
+        # prefix is exactly the number of messages found (NIL and continuation messages included)
+        if hsize % 8 or addr % 8:
+            raise H5FormatError(f"object header at {addr}: size {hsize} / address not 8-byte aligned")
         blocks = [(addr + 16, hsize)]
         msgs = []
         while blocks:
@@ -267,12 +273,21 @@ class OracleFile:
             p = 0
             while p + 8 <= n and len(msgs) < nmsg:
                 mtype, msize, mflags = struct.unpack_from("<HHB", blk, p)
+                if msize % 8 or p + 8 + msize > n:
+                    raise H5FormatError(f"object header at {addr}: message 0x{mtype:04x} of {msize} bytes is "
+                                        "misaligned or overruns its block")
                 body = blk[p + 8:p + 8 + msize]
                 p += 8 + msize
                 msgs.append((mtype, body))
                 if mtype == 0x0010:
                     ca, cn = struct.unpack_from("<QQ", body, 0)
                     blocks.append((ca, cn))
+            if len(msgs) < nmsg and not blocks and p + 8 <= n:
+                raise H5FormatError(f"object header at {addr}: trailing bytes without a message header")
+        if len(msgs) != nmsg:
+            raise H5FormatError(f"object header at {addr}: prefix says {nmsg} messages, found {len(msgs)}")
+        if refcount < 1:
+            raise H5FormatError(f"object header at {addr}: reference count {refcount}")
         return [(t, b) for t, b in msgs if t not in (0x0000, 0x0010)]
 
     def _group(self, entry, prefix):

@@ -172,6 +172,7 @@ def test_random_hyperslabs_against_numpy(tmp_path):
             np.testing.assert_array_equal(OracleFile(p).datasets[name].read(), ref)
         _model_write(a, ref32, (0, slice(0, 37), slice(0, 53)), 7.0)
     o = OracleFile(p)
+    assert o.eof_matches_size and OracleFile(REAL).eof_matches_size
     for name, ref in (("a", ref32), ("b", ref64), ("c", refc)):
         np.testing.assert_array_equal(o.datasets[name].read(), ref)
     assert o.datasets["c"].layout[0] == "contiguous" and not o.datasets["c"].fill_defined
