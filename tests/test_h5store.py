@@ -328,3 +328,21 @@ def test_merge_semantics_on_nan_only(tmp_path):
     a.close()
     b.close()
     np.testing.assert_array_equal(OracleFile(str(tmp_path / "a.h5")).datasets["K"].read(), want)
+
+
+def test_plain_c_client(tmp_path):
+    """include/cnngp_h5.h is a C ABI: a C99 program (tests/c_abi/h5_roundtrip.c) writes worker
+    files block by block, merges and reads them; the oracle reader then decodes the result."""
+    import subprocess
+    exe = str(tmp_path / "h5_roundtrip")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-O1", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_abi", "h5_roundtrip.c"), "-o", exe,
+                    h5store.LIB_PATH, "-lm", "-Wl,-rpath," + os.path.dirname(h5store.LIB_PATH)], check=True)
+    r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", (r.returncode, r.stdout, r.stderr)
+    K = OracleFile(str(tmp_path / "w0.h5")).datasets["Kxx"].read()[0]
+    i, j = np.indices((23, 23))
+    upper = j // 5 >= i // 5
+    np.testing.assert_array_equal(K[upper], (1000 * i + j)[upper].astype(np.float32))
+    assert np.isnan(K[~upper]).all()
+
