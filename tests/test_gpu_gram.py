@@ -395,3 +395,35 @@ def test_fused_net_large(name, n):
     assert rel_err(a, b) < 2e-6
     ev = torch.linalg.eigvalsh(K.double())
     assert ev.min() > -1e-6 * ev.max()
+
+
+def test_plain_c_client(tmp_path):
+    """include/cnngp.h is a C ABI with plain pointers: a C99 program (tests/c_abi/gram_client.c, CUDA
+    runtime allocations, no Python, no torch) evaluates the README model; the Python front end must
+    return the very same numbers for the same images, and both must match the oracle."""
+    import subprocess
+    from cnn_gp import _native as nat
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe, out = str(tmp_path / "gram_client"), str(tmp_path / "k.bin")
+    libdir = os.path.dirname(nat.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-O1", "-I", os.path.join(root, "include"),
+                    "-I", os.path.join(cuda, "include"), os.path.join(root, "tests", "c_abi", "gram_client.c"),
+                    "-o", exe, nat.LIB_PATH, "-L" + os.path.join(cuda, "lib64"), "-lcudart",
+                    "-Wl,-rpath," + libdir, "-Wl,-rpath," + os.path.join(cuda, "lib64")], check=True)
+    r = subprocess.run([exe, out], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok path=3 kernel_family=3"), (r.returncode, r.stdout, r.stderr)
+    n1, n2, c, s = 10, 7, 3, 28
+    state, vals = 12345, np.empty((n1 + n2) * c * s * s, np.float32)
+    for k in range(vals.size):  # the client's generator
+        state = (state * 1664525 + 1013904223) & 0xFFFFFFFF
+        vals[k] = np.float32(state >> 8) / np.float32(16777216.0)
+    X = torch.from_numpy(vals[:n1 * c * s * s].reshape(n1, c, s, s))
+    Z = torch.from_numpy(vals[n1 * c * s * s:].reshape(n2, c, s, s))
+    got = np.fromfile(out, np.float32)
+    kxz, kxx = got[:n1 * n2].reshape(n1, n2), got[n1 * n2:].reshape(n1, n1)
+    model = readme_model().cuda()
+    np.testing.assert_array_equal(kxz, model(X.cuda(), Z.cuda()).cpu().numpy())
+    np.testing.assert_array_equal(kxx, model(X.cuda()).cpu().numpy())
+    assert rel_err(kxz, oracle.gram(readme_model(), X.numpy(), Z.numpy())) < 1e-5
+
