@@ -1,5 +1,8 @@
 """Throughput of the blocked fp64 Cholesky / solve / prediction on the GPU box.
-usage: python scripts/bench_solve.py [n ...]   -> one JSON line per n"""
+usage: python scripts/bench_solve.py [--cpu] [n ...]   -> one JSON line per n
+--cpu also times the reference's solve, scipy.linalg.solve(assume_a='pos', lower=False)
+(exp_mnist_resnet/classify_gp.py:24-26) through the oracle on the box's host cores, for n <= 8192
+(larger sizes are extrapolated with n^3 from the largest one timed, and say so)."""
 import ctypes
 import json
 import os
@@ -18,9 +21,23 @@ def dmma_peak_tflops():
     return 2.0 * max(L.mb_probe(20, 4, 2000), L.mb_probe(20, 8, 2000)) / 1e12, 2.0 * L.mb_probe(21, 8, 2000) / 1e12
 
 
+def cpu_solve_seconds(K, Y):
+    """The reference's CPU solve on the same matrix (oracle.solve_system = scipy posv, upper)."""
+    import time
+    import numpy as np
+    from oracle import oracle
+    Kh, Yh = np.triu(K.cpu().numpy()), Y.cpu().numpy()
+    t0 = time.perf_counter()
+    oracle.solve_system(Kh, Yh)
+    return time.perf_counter() - t0
+
+
 def main():
-    ns = [int(a) for a in sys.argv[1:]] or [8192, 16384, 32768]
+    args = [a for a in sys.argv[1:] if a != "--cpu"]
+    with_cpu = "--cpu" in sys.argv[1:]
+    ns = [int(a) for a in args] or [8192, 16384, 32768]
     peak, dfma = dmma_peak_tflops()
+    cpu_ref = None  # (n, seconds) of the largest CPU solve timed
     for n in ns:
         g = torch.Generator(device="cuda").manual_seed(n)
         K = torch.empty((n, n), dtype=torch.float64, device="cuda")
@@ -50,6 +67,15 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         tf = n ** 3 / 3 / (times["potrf_ms"] * 1e-3) / 1e12
+        if with_cpu:
+            if n <= 8192:
+                cpu_ref = (n, cpu_solve_seconds(K, Y))
+                times["cpu_scipy_solve_s"] = cpu_ref[1]
+                times["cpu_cores"] = os.cpu_count()
+            elif cpu_ref:
+                times["cpu_scipy_solve_s_extrapolated"] = cpu_ref[1] * (n / cpu_ref[0]) ** 3
+                times["cpu_extrapolated_from_n"] = cpu_ref[0]
+                times["cpu_cores"] = os.cpu_count()
         print(json.dumps({"n": n, **times, "potrf_tflops": tf, "dmma_peak_tflops": peak, "dfma_peak_tflops": dfma,
                           "frac_of_dmma_peak": tf / peak, "residual": float(r.abs().max() / (X.abs().max() * K.abs().max())),
                           "predict_ms_4096rows": e0.elapsed_time(e1),
