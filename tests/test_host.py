@@ -292,3 +292,107 @@ def test_fused_translation_of_shipped_programs():
     assert nat.Plan(ops, ns, 28, 28, nat.F64).describe().startswith("generic")
     ops, ns = program.compile_model(models["edge_linear"])
     assert nat.Plan(ops, ns, 12, 12, nat.F32).describe().startswith("generic")
+
+
+# ---- the program compiler against the recursive tree walk, on random module trees ----------------
+class _ReLUTag:
+    pass
+
+
+_ReLUTag.__name__ = "ReLU"  # the oracle recognises modules by class name
+
+
+def _run_program(ops, n_slots, X, Z):
+    """Interpret the three-address program (include/cnngp.h) with the oracle's C primitives."""
+    import ctypes
+    from oracle import oracle
+    L = oracle.lib()
+    N1, N2, (C, H, W) = X.shape[0], Z.shape[0], X.shape[1:]
+    xy, xx, yy = np.empty((N1 * N2, H, W)), np.empty((N1, H, W)), np.empty((N2, H, W))
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    L.oracle_init_f64(vp(X), vp(Z), N1, N2, C, H * W, 0, vp(xy), vp(xx), vp(yy))
+    slots = [None] * n_slots
+    slots[0] = oracle.Patch(False, False, xy, xx, yy, N1, N2)
+
+    def conv(a, o):
+        M, Hi, Wi = a.shape
+        Ho = oracle.conv_out_size(Hi, o.ke, o.stride, o.pad, o.dil)
+        Wo = oracle.conv_out_size(Wi, o.ke, o.stride, o.pad, o.dil)
+        out = np.empty((M, Ho, Wo))
+        L.oracle_conv_f64(vp(np.ascontiguousarray(a)), M, Hi, Wi, o.ke, o.zero_first, o.stride, o.pad, o.dil,
+                          o.scale, o.bias, vp(out), Ho, Wo)
+        return out
+    for o in ops:
+        s = slots[o.src]
+        assert s is not None, "slot read before it is written"
+        if o.opcode == nat.OP_CONV:
+            slots[o.dst] = oracle.Patch(False, False, conv(s.xy, o), conv(s.xx, o), conv(s.yy, o), N1, N2)
+        elif o.opcode == nat.OP_RELU:
+            slots[o.dst] = oracle._propagate(_ReLUTag(), s)
+        elif o.opcode == nat.OP_COPY:
+            slots[o.dst] = oracle.Patch(False, False, s.xy.copy(), s.xx.copy(), s.yy.copy(), N1, N2)
+        elif o.opcode == nat.OP_ADD:
+            slots[o.dst] = slots[o.dst] + s
+        elif o.opcode == nat.OP_SCALE:
+            slots[o.dst] = s * o.scale
+        else:
+            raise AssertionError(o.opcode)
+    return slots[ops[-1].dst].xy.reshape(N1, N2)
+
+
+def _random_tree(rng, size):
+    """A random Sequential over `size` x `size` maps that ends in a 1 x 1 map."""
+    def same_conv():
+        k = rng.choice([1, 2, 3, 4, 5])
+        dil = rng.choice([1, 1, 2]) if size >= 2 * k else 1
+        return Conv2d(k, dilation=dil, var_weight=rng.uniform(0.5, 3.0), var_bias=rng.choice([0.0, rng.uniform(0, 1)]))
+
+    def preserving(depth):  # shape-preserving modules only: usable inside Sum / Mixture branches
+        kind = rng.choice(["conv", "relu", "seq", "sum", "mix"] if depth < 3 else ["conv", "relu"])
+        if kind == "conv":
+            return same_conv()
+        if kind == "relu":
+            return ReLU()
+        if kind == "seq":
+            return Sequential(*[preserving(depth + 1) for _ in range(rng.randint(0, 3))])
+        branches = [preserving(depth + 1) for _ in range(rng.randint(1, 3))]
+        if kind == "sum":
+            return Sum(branches)
+        return Mixture(branches, logit_proportions=torch.tensor([rng.uniform(-1, 1) for _ in branches]))
+    mods, cur = [], size
+    for _ in range(rng.randint(1, 5)):
+        if cur > 3 and rng.random() < 0.3:  # a size-changing conv at the top level
+            k, st = rng.choice([2, 3]), rng.choice([1, 2])
+            pad = rng.choice([0, 1])
+            out = (cur + 2 * pad - (k - 1) - 1) // st + 1
+            if out >= 1:
+                mods.append(Conv2d(k, stride=st, padding=pad, var_weight=rng.uniform(0.5, 2.0)))
+                cur = out
+                continue
+        mods.append(preserving(0))
+    if cur > 1:
+        mods.append(Conv2d(cur, padding=0, var_bias=rng.choice([0.0, 0.1])))
+    return Sequential(*mods)
+
+
+def test_compiled_program_equals_tree_walk_on_random_trees():
+    """program.compile_model flattens Sequential / Sum / Mixture trees into ops over reusable slots;
+    the reference evaluates the tree recursively (kernels.py:184-187, 221-225, 252-254).  Both must
+    give the same numbers for arbitrary trees: same C primitives on both sides, float64."""
+    import random
+    from oracle import oracle
+    rng = random.Random(2024)
+    g = np.random.default_rng(7)
+    worst_slots = 0
+    for case in range(60):
+        size = rng.choice([6, 9, 10])
+        model = _random_tree(rng, size).double()  # Mixture takes its softmax in the parameter dtype (kernels.py:222)
+        X, Z = g.random((3, 2, size, size)), g.standard_normal((2, 2, size, size))
+        ops, ns = program.compile_model(model)
+        worst_slots = max(worst_slots, ns)
+        nat.Plan(ops, ns, size, size, nat.F64)  # shape inference and validation agree with the tree
+        want = oracle.gram(model, X, Z)
+        got = _run_program(ops, ns, X, Z)
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=0, err_msg=f"case {case}: {model}")
+    assert worst_slots <= 6
+
