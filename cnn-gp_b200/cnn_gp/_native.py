@@ -34,6 +34,7 @@ _SIGNATURES = {
     "cnngp_plan_flops_per_pair": (ctypes.c_double, [ctypes.c_void_p, ctypes.c_int32]),
     "cnngp_plan_has_fused": (ctypes.c_int, [ctypes.c_void_p]),
     "cnngp_plan_describe": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
+    "cnngp_plan_dump": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
     "cnngp_variances": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                        ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p]),
@@ -121,6 +122,14 @@ class Plan:
         n = int(L.cnngp_plan_describe(self.handle, None, 0))
         buf = ctypes.create_string_buffer(n)
         L.cnngp_plan_describe(self.handle, buf, n)
+        return buf.value.decode()
+
+    def dump(self):
+        """The fused kernels' op lists with every numeric field, one op per line."""
+        L = lib()
+        n = int(L.cnngp_plan_dump(self.handle, None, 0))
+        buf = ctypes.create_string_buffer(n)
+        L.cnngp_plan_dump(self.handle, buf, n)
         return buf.value.decode()
 
     def flops_per_pair(self, C):

@@ -1230,6 +1230,21 @@ constexpr int kCtrSlots = 64;
 __device__ unsigned long long g_fnet_tile_ctr[kCtrSlots];
 static std::atomic<unsigned> g_fnet_next_ctr{0};
 
+// one line per register-level op, every field, floats with nine significant digits (exact for float32)
+std::string fnet_plan_dump(const FNetPlan *fp) {
+    static const char *names[] = {"CONV", "AFFINE", "RELU", "STASH", "UNSTASH", "ADD", "TRANSPOSE", "DENSE", "T_RELU", "T_AFFINE"};
+    std::string t = "fused_net S0=" + std::to_string(fp->S0) + "\n";
+    char line[256];
+    for (int k = 0; k < fp->n_ops; ++k) {
+        const NOp &o = fp->ops[k];
+        snprintf(line, sizeof line, "%s si=%d so=%d lo=%d hi=%d st=%d slot=%d scale=%.9g bias=%.9g aux=%d half=%d\n",
+                 names[o.kind], (int)o.si, (int)o.so, (int)o.lo, (int)o.hi, (int)o.st, (int)o.slot, (double)o.scale,
+                 (double)o.bias, o.aux, o.half);
+        t += line;
+    }
+    return t;
+}
+
 int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2, int32_t C,
                      const void *d_aux_x, const void *d_aux_z, int32_t symmetric, const void *d_kdiag,
                      void *d_out, int64_t ld_out, void *stream, RowProgress *prog) {

@@ -27,6 +27,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "fused_common.cuh"
 #include "plan.h"
@@ -567,6 +568,29 @@ std::string fused_plan_describe(const FusedPlan *fp) {
         if (o.kind == F_CONV) t += " CONV(" + std::to_string(o.lo) + "," + std::to_string(o.hi) + ")";
         else if (o.kind == F_RELU) t += " RELU";
         else t += " DENSE";
+    }
+    return t;
+}
+
+// one line per op, every field; RELU lines carry the factor the host put on that layer's s maps
+std::string fused_plan_dump(const FusedPlan *fp, const Plan *plan) {
+    std::string t = "fused S=" + std::to_string(fp->S) + "\n";
+    char line[256];
+    std::vector<const DevOp *> relus;
+    for (const DevOp &o : plan->ops)
+        if (o.opcode == CNNGP_OP_RELU) relus.push_back(&o);
+    size_t r = 0;
+    for (int k = 0; k < fp->n_ops; ++k) {
+        const FOp &o = fp->ops[k];
+        if (o.kind == F_RELU) {
+            snprintf(line, sizeof line, "RELU aux=%d aux_scale=%.9g transposed=%d\n", o.aux_off,
+                     (double)relus[r]->aux_scale, relus[r]->aux_t);
+            ++r;
+        } else {
+            snprintf(line, sizeof line, "%s lo=%d hi=%d pre_bias=%.9g scale=%.9g bias=%.9g\n", o.kind == F_CONV ? "CONV" : "DENSE",
+                     o.lo, o.hi, (double)o.pre_bias, (double)o.scale, (double)o.bias);
+        }
+        t += line;
     }
     return t;
 }

@@ -203,6 +203,21 @@ int64_t cnngp_plan_describe(const cnngp_plan *plan, char *buf, int64_t cap) {
     return (int64_t)t.size() + 1;
 }
 
+int64_t cnngp_plan_dump(const cnngp_plan *plan, char *buf, int64_t cap) {
+    const Plan *p = reinterpret_cast<const Plan *>(plan);
+    std::string t;
+    if (!p) t = "null plan\n";
+    else if (p->fused) t = fused_plan_dump(p->fused, p);
+    else if (p->fnet) t = fnet_plan_dump(p->fnet);
+    else t = "generic\n";
+    if (buf && cap > 0) {
+        const size_t n = std::min<size_t>((size_t)cap - 1, t.size());
+        memcpy(buf, t.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)t.size() + 1;
+}
+
 int cnngp_variances(const cnngp_plan *plan, const void *d_x, const void *d_z, int64_t N, int32_t C,
                     void *d_aux_x, void *d_aux_z, void *d_kdiag, void *stream) {
     const Plan *p = reinterpret_cast<const Plan *>(plan);

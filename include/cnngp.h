@@ -92,6 +92,10 @@ int cnngp_plan_has_fused(const cnngp_plan *plan);
  * buf (at most cap bytes).  Returns the number of bytes the full text needs.  For tests and
  * debugging of the host-side translation; no GPU is involved. */
 int64_t cnngp_plan_describe(const cnngp_plan *plan, char *buf, int64_t cap);
+/* The same translation with every numeric field, one op per line ("KIND key=value ..."), so that a
+ * CPU interpreter can re-evaluate what the fused kernels will compute (tests/test_host.py checks the
+ * translators that way against the recursive tree walk on random programs).  Same calling convention. */
+int64_t cnngp_plan_dump(const cnngp_plan *plan, char *buf, int64_t cap);
 
 /* Per-image variance recursion: the xx / yy maps of kernels.py:48-49 pushed through the
  * program (Conv2d acts on them as on xy, kernels.py:98; ReLU halves them, kernels.py:154,164).

@@ -302,8 +302,10 @@ class _ReLUTag:
 _ReLUTag.__name__ = "ReLU"  # the oracle recognises modules by class name
 
 
-def _run_program(ops, n_slots, X, Z):
-    """Interpret the three-address program (include/cnngp.h) with the oracle's C primitives."""
+def _run_program(ops, n_slots, X, Z, relu_inputs=None, first=None):
+    """Interpret the three-address program (include/cnngp.h) with the oracle's C primitives.
+    ``relu_inputs``: list that receives (xx, yy) at every RELU op, in program order; ``first``: list
+    that receives the initial xy maps."""
     import ctypes
     from oracle import oracle
     L = oracle.lib()
@@ -313,6 +315,8 @@ def _run_program(ops, n_slots, X, Z):
     L.oracle_init_f64(vp(X), vp(Z), N1, N2, C, H * W, 0, vp(xy), vp(xx), vp(yy))
     slots = [None] * n_slots
     slots[0] = oracle.Patch(False, False, xy, xx, yy, N1, N2)
+    if first is not None:
+        first.append(xy.copy())
 
     def conv(a, o):
         M, Hi, Wi = a.shape
@@ -328,6 +332,8 @@ def _run_program(ops, n_slots, X, Z):
         if o.opcode == nat.OP_CONV:
             slots[o.dst] = oracle.Patch(False, False, conv(s.xy, o), conv(s.xx, o), conv(s.yy, o), N1, N2)
         elif o.opcode == nat.OP_RELU:
+            if relu_inputs is not None:
+                relu_inputs.append((s.xx.copy(), s.yy.copy()))
             slots[o.dst] = oracle._propagate(_ReLUTag(), s)
         elif o.opcode == nat.OP_COPY:
             slots[o.dst] = oracle.Patch(False, False, s.xy.copy(), s.xx.copy(), s.yy.copy(), N1, N2)
@@ -395,4 +401,161 @@ def test_compiled_program_equals_tree_walk_on_random_trees():
         got = _run_program(ops, ns, X, Z)
         np.testing.assert_allclose(got, want, rtol=1e-12, atol=0, err_msg=f"case {case}: {model}")
     assert worst_slots <= 6
+
+
+# ---- the fused kernels' host translators, re-evaluated on the CPU --------------------------------
+def _box(R, lo, hi, st):
+    """out[y, x] = sum of in[st*y + dy, st*x + dx], dy, dx in [-lo, hi], zero padding (both fused kernels)."""
+    M, H, W = R.shape
+    P = np.zeros((M, H + lo + hi, W + lo + hi))
+    P[:, lo:lo + H, lo:lo + W] = R
+    k = lo + hi + 1
+    full = sum(P[:, dy:dy + H, dx:dx + W] for dy in range(k) for dx in range(k))
+    return full[:, ::st, ::st]
+
+
+def _relu2(R, xx, yy, N1, N2):
+    """The kernels keep the ReLU output doubled: 2 * arccos kernel of kernels.py:146-152."""
+    from oracle import oracle
+    kp = oracle.Patch(False, False, np.ascontiguousarray(R), np.ascontiguousarray(xx), np.ascontiguousarray(yy), N1, N2)
+    return 2.0 * oracle._propagate(_ReLUTag(), kp).xy
+
+
+def _parse(dump):
+    lines = dump.strip().splitlines()
+    out = []
+    for ln in lines[1:]:
+        kind, *kv = ln.split()
+        out.append((kind, {k: float(v) if ("." in v or "e" in v or "inf" in v or "nan" in v) else int(v)
+                           for k, v in (f.split("=") for f in kv)}))
+    return lines[0], out
+
+
+def _simulate_translation(plan, xy0, relu_vars, N1, N2):
+    """What the fused / fused-net kernel will compute, from cnngp_plan_dump's register-level op list."""
+    head, prog = _parse(plan.dump())
+    px = [v[0].shape[1] * v[0].shape[2] for v in relu_vars]
+    off = np.concatenate([[0], np.cumsum(px)])[:-1].tolist()                        # plain xx offsets (T_RELU)
+    foff = np.concatenate([[0], np.cumsum([4 * ((q + 1) // 2) for q in px])])[:-1].tolist()  # fused section (RELU)
+    R, T, tot, nth = xy0.copy(), {}, None, 0
+    for kind, f in prog:
+        if head.startswith("fused S="):
+            if kind == "CONV":
+                window = f["lo"] or f["hi"]
+                if window:
+                    R = _box(R, f["lo"], f["hi"], 1) + f["pre_bias"]
+                if not window or f["scale"] != 1:
+                    R = R * f["scale"] + f["bias"]
+            elif kind == "RELU":
+                xx, yy = relu_vars[nth]
+                nth += 1
+                a2 = float(f["aux_scale"]) ** 2
+                R = _relu2(R, xx * a2, yy * a2, N1, N2)
+            else:
+                tot = R.sum(axis=(1, 2)) * f["scale"] + f["bias"]
+            continue
+        if kind == "CONV":
+            R = _box(R, f["lo"], f["hi"], f["st"]) * f["scale"] + f["bias"]
+            assert R.shape[1] == f["so"]
+        elif kind == "AFFINE":
+            R = R * f["scale"] + f["bias"]
+        elif kind == "RELU":
+            xx, yy = relu_vars[foff.index(f["aux"])]
+            assert xx.shape[1] == f["si"] and f["half"] == (f["si"] ** 2 + 1) // 2
+            R = _relu2(R, xx, yy, N1, N2)
+        elif kind == "STASH":
+            T[f["slot"]] = R.copy()
+        elif kind == "UNSTASH":
+            R = T[f["slot"]].copy()
+        elif kind == "ADD":
+            R = R + f["scale"] * T[f["slot"]] + f["bias"]
+        elif kind == "TRANSPOSE":
+            pass
+        elif kind == "DENSE":
+            tot = R.sum(axis=(1, 2)) * f["scale"] + f["bias"]
+        elif kind == "T_AFFINE":
+            tot = tot * f["scale"] + f["bias"]
+        elif kind == "T_RELU":
+            xx, yy = relu_vars[off.index(f["aux"])]
+            tot = _relu2(tot.reshape(-1, 1, 1), xx, yy, N1, N2).reshape(-1)
+        else:
+            raise AssertionError(kind)
+    return tot.reshape(N1, N2)
+
+
+def _random_straight_line(rng):
+    mods, last_relu = [], True
+    for _ in range(rng.randint(2, 7)):
+        if not last_relu and rng.random() < 0.5:
+            mods.append(ReLU())
+            last_relu = True
+        else:
+            mods.append(Conv2d(rng.choice([1, 3, 4, 5, 7]), var_weight=rng.choice([0.01, 0.7, 2.79, 40.0]),
+                               var_bias=rng.choice([0.0, 1e-3, 0.5, 7.86])))
+            last_relu = False
+    if rng.random() < 0.7 and not last_relu:
+        mods.append(ReLU())
+    mods.append(Conv2d(28, padding=0, var_weight=rng.uniform(0.5, 2), var_bias=rng.choice([0.0, 0.05])))
+    return Sequential(*mods)
+
+
+def _random_resnet(rng, S0):
+    def conv(k=None, **kw):
+        return Conv2d(k or rng.choice([3, 3, 3, 4, 5, 7]), var_weight=rng.uniform(0.5, 3.0),
+                      var_bias=rng.choice([0.0, 0.1, 1.0]), **kw)
+    mods, size = [conv()], S0
+    for _ in range(rng.randint(1, 5)):
+        kind = rng.choice(["identity", "projection", "strided", "sum", "mixture", "relu_conv"])
+        if kind == "identity":
+            mods.append(resnet_block(stride=1))
+        elif kind == "projection":
+            mods.append(resnet_block(stride=1, projection_shortcut=True))
+        elif kind == "strided" and size > S0 // 4:
+            mods.append(resnet_block(stride=2, projection_shortcut=True))
+            size //= 2
+        elif kind == "sum":
+            k = 3 if size < S0 else None
+            mods.append(Sum([Sequential(), Sequential(ReLU(), conv(k), ReLU(), conv(k))]))
+        elif kind == "mixture":
+            k = 3 if size < S0 else None
+            mods.append(Mixture([Sequential(), Sequential(ReLU(), conv(k))],
+                                logit_proportions=torch.tensor([rng.uniform(-1, 1), rng.uniform(-1, 1)])))
+        else:
+            mods += [ReLU(), conv(3 if size < S0 else None)]
+    if rng.random() < 0.8:
+        mods.append(ReLU())
+    mods.append(Conv2d(size, padding=0, var_bias=rng.choice([0.0, 0.2])))
+    if rng.random() < 0.3:  # a tail on the 1 x 1 map
+        mods += [ReLU(), Conv2d(1, var_weight=1.3, var_bias=0.1)]
+    return Sequential(*mods)
+
+
+@pytest.mark.parametrize("family", ["fused", "fused_net_28", "fused_net_32"])
+def test_fused_translations_reevaluated_on_cpu(family):
+    """The host translators turn a layer program into the register-level op lists the fused kernels
+    run (carried conv factors and scaled variance maps in gram_fused.cu; stash / alias / doubled-ReLU
+    bookkeeping in gram_fnet.cu).  cnngp_plan_dump exposes those lists; evaluated on the CPU in
+    float64 they must reproduce the recursive tree walk of the reference (kernels.py:184-254) on
+    random programs -- the only differences are the float32 roundings of the folded constants."""
+    import random
+    from oracle import oracle
+    rng = random.Random({"fused": 1, "fused_net_28": 2, "fused_net_32": 3}[family])
+    g = np.random.default_rng(11)
+    S0 = 32 if family.endswith("32") else 28
+    hits = 0
+    for case in range(30 if family == "fused" else 40):
+        model = (_random_straight_line(rng) if family == "fused" else _random_resnet(rng, S0)).double()
+        ops, ns = program.compile_model(model)
+        plan = nat.Plan(ops, ns, S0, S0, nat.F32)
+        if plan.fused_kind != (2 if family == "fused" else 3):
+            continue  # outside the kernel's set: the generic kernel runs it
+        hits += 1
+        N1, N2 = 2, 2
+        X, Z = g.random((N1, 1, S0, S0)), g.random((N2, 1, S0, S0))
+        relu_vars, first = [], []
+        want = _run_program(ops, ns, X, Z, relu_vars, first)
+        np.testing.assert_allclose(want, oracle.gram(model, X, Z), rtol=1e-12)
+        got = _simulate_translation(plan, first[0], relu_vars, N1, N2)
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=0, err_msg=f"{family} case {case}:\n{plan.describe()}")
+    assert hits >= 25, hits
 
