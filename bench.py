@@ -4,7 +4,9 @@ Gram recursion (BASELINE.json `metric`, quoted on configs[1]: mnist_paper_convne
 symmetric Gram of 10k synthetic 28x28x1 images).
 
     python bench.py --gpus N --steps K --warmup W            our CUDA path
-    python bench.py --impl reference --steps K --warmup W    the CPU arm (oracle port, all threads)
+    python bench.py --impl reference --steps K --warmup W    the CPU arm: the UNMODIFIED reference
+                                                             (oracle/_ref, see oracle/make_ref.sh) on all
+                                                             host cores; the C port only if _ref is absent
 
 One "step" = one full pass of the hot path over the workload: per-image variance maps + every
 unique pair of the symmetric Gram, result written to HBM.  At N > 1 (torchrun, one rank per
@@ -19,8 +21,14 @@ JSON keys beyond the base contract:
   roofline      dominant kernel (the Gram kernel) against the FP32 CUDA-core peak measured live
                 with an FFMA probe (MEASURED_PEAKS.json carries no FP32 figure); algorithmic
                 flop per pair from SURVEY.md 8(d) via cnngp_plan_flops_per_pair
-  cpu_baseline  the oracle port on the host cores, bounded sample (rank 0, N=1 only)
+  cpu_baseline  the reference's own PyTorch CPU path (kind "reference") on the host cores, bounded
+                sample (rank 0, N=1 only); the C/OpenMP port's rate rides along as `port`
   e2e           same metric through model(x) with HOST (pinned) inputs and outputs
+  extra         the other north_star measurements on the same box, a few steps each: pairs/s and
+                roofline fraction of mnist_paper_residual_cnn_gp, mnist_as_tf and cifar10 (3x32x32),
+                and the float64 solve (potrf TFLOP/s against the DMMA probe, potrs / predict ms);
+                at N > 1 the cifar10 rate over all ranks and the distributed Cholesky with a
+                bit-identity check against the one-GPU factor
 """
 import argparse
 import ctypes
@@ -67,6 +75,9 @@ def parse():
     ap.add_argument("--tile", type=int, default=500, help="tile edge for the multi-GPU tile list")
     ap.add_argument("--path", default="auto", choices=["auto", "generic", "fused"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the `extra` measurements (other configs, solve)")
+    ap.add_argument("--extra-images", type=int, default=6000, help="images of the extra Gram configs (x sqrt(N))")
+    ap.add_argument("--solve-n", type=int, default=32768, help="matrix size of the float64 solve in `extra`")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the baseline sample")
     return ap.parse_args()
 
@@ -85,8 +96,8 @@ def config_obj(args, world):
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_rate(model, config, seconds, repeats=1):
-    """pairs/s of the oracle port (all host threads) on a bounded tile of the same workload."""
+def port_rate(model, config, seconds, repeats=1):
+    """pairs/s of the oracle port (C/OpenMP restatement, all host threads) on a bounded tile."""
     import numpy as np
     import torch
     from oracle import oracle
@@ -111,28 +122,61 @@ def cpu_rate(model, config, seconds, repeats=1):
     return edge * edge / best, cores, f"{edge}x{edge} tile of {config}, same=False, float32, best of {repeats}"
 
 
+def reference_rate(config, steps, warmup, seconds_per_step):
+    """pairs/s of the UNMODIFIED reference (oracle/_ref, its own process: it is also called cnn_gp)
+    -> dict from oracle/ref_cpu.py, or None when oracle/_ref is not there."""
+    script = os.path.join(ROOT, "oracle", "ref_cpu.py")
+    if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "cnn_gp")):
+        return None
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):  # torchrun pins these to 1
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, script, config, "--steps", str(steps), "--warmup", str(warmup),
+                        "--seconds", str(seconds_per_step)], capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        sys.stderr.write(r.stderr[-2000:])
+        return None
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    return None if "unavailable" in d else d
+
+
+def cpu_baseline(model_cpu, config, seconds):
+    """The reported CPU baseline of one config: the reference's own code when oracle/_ref travelled
+    with the snapshot (kind "reference"), with the C port's rate next to it; the port alone otherwise."""
+    ref = reference_rate(config, steps=2, warmup=1, seconds_per_step=max(1.0, seconds / 3.0))
+    pv, pcores, psample = port_rate(model_cpu, config, seconds / 2.0 if ref else seconds)
+    port = {"value": pv, "unit": "pairs/s", "cores": pcores, "kind": "port", "sample": psample}
+    if ref is None:
+        return dict(port, note="oracle/_ref absent: C port of the reference (oracle/), not the reference's code")
+    return {"value": ref["value"], "unit": "pairs/s", "cores": ref["cores"], "kind": "reference",
+            "sample": ref["sample"], "port": port}
+
+
 def run_reference(args):
-    """CPU arm: each step is one bounded tile of the workload through the oracle port."""
+    """CPU arm: each step is one bounded tile (at most the reference's default 200 x 200) of the
+    workload through the reference's own forward on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     emit = _claim_stdout()
-    model = importlib.import_module("configs." + args.config).initial_model
-    rates = []
-    cores = sample = None
-    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
-    for k in range(args.warmup + args.steps):
-        r, cores, sample = cpu_rate(model, args.config, per_step)
-        if k >= args.warmup:
-            rates.append(r)
-    v = statistics.mean(rates)
-    edge = int(sample.split("x")[0])
+    per_step = max(1.5, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    ref = reference_rate(args.config, args.steps, args.warmup, per_step)
+    if ref is not None:
+        v, cores, sample, kind, edge = ref["value"], ref["cores"], ref["sample"], "reference", ref["edge"]
+    else:  # no oracle/_ref on this box: the pinned C restatement stands in, and says so
+        model = importlib.import_module("configs." + args.config).initial_model
+        rates = []
+        for k in range(args.warmup + args.steps):
+            r, cores, sample = port_rate(model, args.config, per_step)
+            if k >= args.warmup:
+                rates.append(r)
+        v, kind, edge = statistics.mean(rates), "port", int(sample.split("x")[0])
     emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * edge * edge / v,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(config_obj(args, args.gpus), sample=sample),
-        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": config_obj(args, args.gpus),
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -179,6 +223,164 @@ def fp32_peak_tflops():
     L.mb_probe.restype = ctypes.c_double
     L.mb_probe.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
     return 2.0 * max(L.mb_probe(0, 8, 4000), L.mb_probe(0, 4, 4000)) / 1e12  # FMA = 2 flop
+
+
+# ----------------------------------------------------------------------------- the other north_star measurements
+EXTRA_CONFIGS = ("mnist_paper_residual_cnn_gp", "mnist_as_tf", "cifar10")
+
+
+def dmma_peak_tflops():
+    L = ctypes.CDLL(os.path.join(ROOT, "cnn-gp_b200", "libcnngp_bench.so"))
+    L.mb_probe.restype = ctypes.c_double
+    L.mb_probe.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    return 2.0 * max(L.mb_probe(20, 4, 2000), L.mb_probe(20, 8, 2000)) / 1e12
+
+
+def _spd(n, dev, seed):
+    """Synthetic SPD matrix (float64, low rank + ridge: no n^3 product to build it) and +-1 labels."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(seed)
+    B = torch.randn(n, 64, generator=g, device=dev, dtype=torch.float64)
+    K = torch.mm(B, B.T)
+    K.diagonal().add_(1.0)
+    Y = torch.randn(n, 10, generator=g, device=dev, dtype=torch.float64).sign()
+    return K, Y
+
+
+def extra_gram(config, n0, steps, warmup, dev, rank, world, tile, fp32_peak):
+    """pairs/s of one more BASELINE config: same step as the headline (variance rows + every unique
+    pair of the symmetric Gram from images in HBM), CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from cnn_gp import engine
+    from cnn_gp.tiles import GramJob, compute_worker_blocks
+    c, s = workload_dims(config)
+    n = int(round(n0 * world ** 0.5))
+    model = importlib.import_module("configs." + config).initial_model.to(dev)
+    X = torch.rand(n, c, s, s, generator=torch.Generator().manual_seed(SEED)).to(dev)
+    out = torch.empty((n, n), dtype=torch.float32, device=dev)
+    total = n * (n + 1) // 2
+
+    def step():
+        job = GramJob(model, X)
+        if world == 1:
+            job.block(out, 0, n, 0, n, symmetric=True)
+        else:
+            compute_worker_blocks(job, out, tile, rank, world, balanced=True)
+        return job.launches
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launches = sum(step() for _ in range(steps))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    f_alg = engine.plan_for(model, s, s, torch.float32).flops_per_pair(c)
+    rate = total * steps / (ms * 1e-3)
+    res = {"value": rate, "unit": "pairs/s", "n_images": n, "pairs_per_step": total, "steps": steps, "warmup": warmup,
+           "ms_per_step": ms / steps, "flops_per_pair": f_alg, "kernel": engine.last_path(),
+           "roofline_frac": rate * f_alg / 1e12 / (fp32_peak * world), "gpu_launches": launches,
+           "workload": f"{config} full symmetric Gram, {n} synthetic {s}x{s}x{c} images"}
+    del out, X
+    model.cpu()
+    return res
+
+
+def extra_solve(n, dev):
+    """The float64 stage (classify_gp.py:17-27,39-42) on one GPU: potrf against the DMMA probe, potrs, predict."""
+    import torch
+    from cnn_gp import linalg
+    peak = dmma_peak_tflops()
+    Kw, Yw = _spd(2048, dev, 1)  # first-call set-up (function attributes, side streams) outside the timing
+    linalg.potrf_upper_(Kw, check=False)
+    linalg.potrs_upper_(Kw, Yw)
+    del Kw, Yw
+    K, Y = _spd(n, dev, n)
+    best = None
+    for _ in range(2):
+        U = K.clone()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        info = linalg.potrf_upper_(U, check=False)
+        e[1].record()
+        A = linalg.potrs_upper_(U, Y.clone())
+        e[2].record()
+        torch.cuda.synchronize()
+        t = (e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]))
+        best = t if best is None or t[0] < best[0] else best
+        del U
+    assert int(info.item()) == 0
+    resid = float((K @ A - Y).abs().max() / (A.abs().max() * K.abs().max()))
+    rows = 4096
+    Kp = torch.randn(rows, n, generator=torch.Generator(device=dev).manual_seed(7), device=dev, dtype=torch.float32)
+    linalg.predict_argmax(Kp, A)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    linalg.predict_argmax(Kp, A)
+    p1.record()
+    torch.cuda.synchronize()
+    tf = n ** 3 / 3 / (best[0] * 1e-3) / 1e12
+    pm = p0.elapsed_time(p1)
+    return {"n": n, "nrhs": 10, "potrf_ms": best[0], "potrf_tflops": tf, "dmma_peak_tflops": peak, "frac_of_dmma_peak": tf / peak,
+            "potrs_ms": best[1], "potrs_gbs": 2 * (n * n / 2 * 8) / (best[1] * 1e-3) / 1e9,
+            "predict_ms": pm, "predict_rows": rows, "predict_gbs": rows * n * 4 / (pm * 1e-3) / 1e9,
+            "residual": resid, "bound": "fp64 tensor pipe (DMMA.8x8x4; tcgen05 has no f64 kind), work n^3/3"}
+
+
+def extra_solve_dist(n, n_check, dev, rank, world):
+    """N > 1: the Cholesky with block rows dealt over the ranks, timed (max over ranks), plus a
+    bit-identity check of the distributed factor and solve against the one-GPU path at n_check."""
+    import torch
+    import torch.distributed as dist
+    from cnn_gp import linalg, linalg_dist
+    res = {"n": n, "world": world}
+    # bit identity at a size one GPU factorises in milliseconds
+    K, Y = _spd(n_check, dev, 11) if rank == 0 else (None, None)
+    A_dist = linalg_dist.solve_pos_upper_distributed(K.to(torch.float32) if rank == 0 else None, Y, n_check, dev)
+    if rank == 0:
+        K1 = K.to(torch.float32).to(torch.float64)
+        A_one = linalg.solve_pos_upper(K1, Y)
+        res["check_n"] = n_check
+        res["solve_bit_identical_to_one_gpu"] = bool(torch.equal(A_dist, A_one))
+        res["solve_max_abs_diff"] = float((A_dist - A_one).abs().max())
+    ch = linalg_dist.DistributedCholesky(n_check, dev)
+    ch.scatter_from(K.to(torch.float32) if rank == 0 else None)
+    ch.factorize()
+    U = ch.gather_to(0)
+    if rank == 0:
+        U1 = K1.clone()
+        linalg.potrf_upper_(U1)
+        iu = torch.triu_indices(n_check, n_check, device=dev)
+        res["factor_bit_identical_to_one_gpu"] = bool(torch.equal(U[iu[0], iu[1]], U1[iu[0], iu[1]]))
+    del ch, U
+    # timing at n
+    K, Y = _spd(n, dev, n) if rank == 0 else (None, None)
+    best = None
+    for _ in range(2):
+        ch = linalg_dist.DistributedCholesky(n, dev)
+        ch.scatter_from(K if rank == 0 else None)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        info = ch.factorize()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best = float(t[0]) if best is None else min(best, float(t[0]))
+        del ch
+    assert info == 0
+    res.update({"potrf_ms": best, "potrf_tflops": n ** 3 / 3 / (best * 1e-3) / 1e12})
+    return res
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -316,10 +518,24 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         d2h_bytes = int(t[0])
 
+    peak = fp32_peak_tflops()
+    extra = None
+    if not args.no_extra:
+        out = K_dev = K_host = None  # noqa: F841 -- release the headline buffers
+        e2e_out.clear()
+        torch.cuda.empty_cache()
+        extra = {"configs": {}}
+        for cfg in EXTRA_CONFIGS:
+            if world == 1 or cfg == "cifar10":
+                extra["configs"][cfg] = extra_gram(cfg, args.extra_images, 3, 3, dev, rank, world, args.tile, peak)
+        torch.cuda.empty_cache()
+        if world == 1:
+            extra["solve"] = extra_solve(args.solve_n, dev)
+        else:
+            extra["solve_distributed"] = extra_solve_dist(args.solve_n, 4096, dev, rank, world)
     if rank == 0:
         plan = engine.plan_for(model, s, s, torch.float32)
         f_alg = plan.flops_per_pair(c)
-        peak = fp32_peak_tflops()
         # dominant kernel = the Gram kernel; achieved = algorithmic flop of this rank's launches / their time
         achieved = f_alg * my_pairs * args.steps / (gram_ms * 1e-3) / 1e12
         traffic = None
@@ -361,9 +577,10 @@ def run_ours(args):
             "gpu_launches": n_launch,
             "clocks": clocks,
         }
+        if extra is not None:
+            line["extra"] = extra
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, sample = cpu_rate(model.cpu(), args.config, args.cpu_seconds)
-            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
+            line["cpu_baseline"] = cpu_baseline(model.cpu(), args.config, args.cpu_seconds)
         emit(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -43,6 +43,16 @@ def build(force=False):
     return _LIB_PATH
 
 
+def build_ref(src="/root/reference"):
+    """oracle/_ref/: the unmodified reference, copied by oracle/make_ref.sh when `src` exists (the
+    authoring container); on the GPU box the copy that travelled with the snapshot is used as is.
+    Only bench.py's CPU legs (through oracle/ref_cpu.py) execute it.  -> path or None"""
+    ref = os.path.join(_HERE, "_ref")
+    if os.path.isdir(os.path.join(src, "cnn_gp")):
+        subprocess.run(["bash", os.path.join(_HERE, "make_ref.sh"), src], check=True, stdout=subprocess.DEVNULL)
+    return ref if os.path.isdir(os.path.join(ref, "cnn_gp")) else None
+
+
 def lib():
     global _lib
     if _lib is None:
