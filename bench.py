@@ -463,6 +463,7 @@ def run_ours(args):
         gram_ms_max = gram_ms
     ms_per_step = ms / args.steps
     value = total_pairs / (ms_per_step * 1e-3)
+    headline_kernel = engine.last_path()
     n_launch = launches[0]
 
     # ---- end to end through the public API with host buffers ----------------------------
@@ -562,7 +563,7 @@ def run_ours(args):
                 "note": "FP32 CUDA-core bound (SURVEY 8d); peak = FFMA probe measured in this run "
                         "(MEASURED_PEAKS.json has no FP32 figure); achieved = F_alg x pairs / CUDA-event time of "
                         "the Gram launches on torch's current stream",
-                "flops_per_pair": f_alg, "kernel": engine.last_path(),
+                "flops_per_pair": f_alg, "kernel": headline_kernel,
                 "avg_launch_ms": gram_ms / max(1, gram_launches)}
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,

@@ -2,26 +2,40 @@
 // branches, strided convolutions and several map sizes: the ResNet GPs of configs/mnist.py,
 // mnist_as_tf.py, cifar10.py, the residual CNN GP and the README model.
 //
-// Same execution model as gram_fused.cu: a persistent CTA per SM, eight consumer warps that each
-// keep the four covariance maps of a 2 x 2 block of image pairs in registers (lane = one map
-// coordinate, register index = the other, two maps per packed f32x2 register), a producer warp
-// that stages images and per-layer (s, 1/s) variance maps with bulk async copies, box
-// convolutions as sliding sums along the register axis + a shared-memory transposition.
+// Same execution model as gram_fused.cu: a persistent CTA per SM, consumer warps that each keep the
+// four covariance maps of a 2 x 2 block of image pairs in registers (lane = one map coordinate,
+// register index = the other, two maps per packed f32x2 register), a producer warp that stages
+// images and per-layer (s, 1/s) variance maps with bulk async copies, box convolutions as sliding
+// sums along the register axis + a shared-memory transposition.
 //
-// What is new here:
+// What is specific to this kernel:
 //   * a two-slot program needs a second live map per pair (the skip connection of a Sum,
 //     reference cnn_gp/kernels.py:246-254).  It does not fit the register file next to the
 //     working map, and shared memory is taken by the staging ring -- so it is stashed in TENSOR
-//     MEMORY: each warp owns 2 x 128 columns of its 32-lane TMEM quadrant and moves a whole map
-//     set with tcgen05.st / tcgen05.ld (SASS STTM / LDTM), off the shared-memory port.
+//     MEMORY: each warp owns a window of its 32-lane TMEM quadrant and moves a whole map set with
+//     tcgen05.st / tcgen05.ld (SASS STTM / LDTM), off the shared-memory port.
 //   * stride-2 convolutions (kernels.py:92-98 with stride 2) subsample along the register axis
-//     in both passes; maps shrink to S/2 and S/4 with lane = column < S'.
+//     in both passes; maps shrink to S/2 and S/4.  Maps of edge <= S/2 are FOLDED: the second
+//     packed array moves into lanes 16..31 of the first, so every later op runs on one array.
+//   * the op loop has three phases with their own register budget: phase A (full-size maps, the
+//     whole M[2][S0] set is live), phase B (folded maps: S0/2 registers are live, the rest of the
+//     register file is free for instruction-level parallelism), and the scalar tail after the
+//     global pooling convolution (1 x 1 maps).
+//   * ops are 16-byte descriptors in shared memory (one LDS.128 per op, fetched one op ahead) and
+//     whole residual blocks are single dispatch cases (`IDBLOCK`: STASH RELU CONV RELU CONV ADD,
+//     `RESBLOCK`: STASH CONV RELU TRANSPOSE ADD): the per-op dispatch of the first version of this
+//     kernel (a 36-byte descriptor in the constant bank, ~40 instructions and two spilled
+//     descriptors per op) was 27 % of the stall samples of an mnist_as_tf launch.
+//   * conv taps and the doubled ReLU outputs are never applied to the maps: every slot carries the
+//     factor it owes (`pend`), the host scales each ReLU layer's per-image (s, 1/s) maps to match
+//     (the arccos kernel is positively homogeneous), a Sum folds the ratio of its operands'
+//     factors into its FMA, and a conv bias rides on the two starting windows of the second
+//     sliding sum (see gram_fused.cu).  An explicit scale pass is emitted only when the carried
+//     factor would leave a safe range.
 //   * every windowed convolution flips the register layout (lane = column <-> lane = row); the
 //     translator tracks the layout of every slot and inserts a transposition where a Sum would
 //     add maps of different layouts, and records for every ReLU the layout its variance maps
 //     must be stored in.
-//   * ReLU outputs are kept doubled (see gram_fused.cu); the power-of-two factor owed by each
-//     slot is tracked and folded into the next convolution tap or into the Sum (exact).
 //   * the tail after the global pooling convolution (1 x 1 maps: kernels.py:134-165 on one
 //     pixel, 1 x 1 convolutions) runs on the four scalars of the warp.
 #include <cuda_runtime.h>
@@ -29,6 +43,7 @@
 #include <atomic>
 
 #include <cfloat>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -55,29 +70,45 @@ struct NGeo {
     static constexpr int kRegsProducer = NW == 8 ? 24 : 32;  // what the pool holds: launch registers x threads
     static constexpr int kRegsConsumer = NW == 8 ? 240 : 160;
 };
-constexpr int kMaxNOps = 192;
+constexpr int kMaxNOps = 192;   // register-level ops of a translated program
+constexpr int kMaxKOps = 224;   // descriptors the kernel sees (ops + phase sentinels)
+constexpr int kMaxRelu = 96;
 constexpr int kTmemCols = 512;
 
+// register-level op kinds of the translator
 enum { N_CONV = 0, N_AFFINE, N_RELU, N_STASH, N_UNSTASH, N_ADD, N_TRANSPOSE, N_DENSE, T_RELU, T_AFFINE };
 
-// dense dispatch codes: kind x size class (0: S0, 1: S0/2, 2: S0/4), convolutions by variant
-enum { C_CONV = 0, C_AFFINE = 10, C_TRANSPOSE = 13, C_STASH = 16, C_UNSTASH = 19, C_ADD = 22, C_DENSE = 25,
-       C_RELU = 28, C_TAFFINE = 31, C_TRELU = 32 };
+// dispatch cases.  Phase A works on the full register set M[2][S0]: kind x size class (0: S0,
+// 1: S0/2, 2: S0/4; folded maps live in M[0]), convolutions by variant.  Phase B works on the
+// folded array F[S0/2] (size classes 1 and 2 only).  The tail works on the four scalars.
+enum { A_CONV = 0, A_AFFINE = 10, A_TRANSPOSE = 13, A_STASH = 16, A_UNSTASH = 19, A_ADD = 22, A_DENSE = 25, A_RELU = 28,
+       A_IDBLOCK = 31, A_RESBLOCK = 32, A_END = 33, A_CASES = 34 };
+enum { B_CONV = 0 /* +0: S/2 s1, +1: S/2 -> S/4 k3 s2, +2: S/2 -> S/4 k1 s2, +3: S/4 s1 */, B_AFFINE = 4, B_TRANSPOSE = 6,
+       B_STASH = 8, B_UNSTASH = 10, B_ADD = 12, B_DENSE = 14, B_RELU = 16, B_IDBLOCK = 18, B_END = 20, B_CASES = 21 };
+enum { T_CASE_AFFINE = 0, T_CASE_RELU = 1, T_END = 2 };
 
 struct NOp {
     int kind;
-    int code;           // filled by assign_codes()
     short si, so;       // map edge before / after the op
     short lo, hi, st;   // N_CONV: window offsets [-lo, +hi] and stride
     short slot;         // N_STASH / N_UNSTASH / N_ADD: tensor-memory slot (0 or 1)
-    float scale, bias;  // N_CONV / N_AFFINE / N_DENSE / T_AFFINE; N_ADD: factor applied to the stashed map
+    float scale, bias;  // N_CONV / N_AFFINE / N_DENSE / T_AFFINE: explicit scale-and-bias pass (1, 0: none);
+                        // N_ADD: factor applied to the stashed map, constant added
+    float pre_bias;     // N_CONV (stride 1, windowed): constant carried by the second sliding sum
+    float aux_scale;    // N_RELU: factor the host puts on this layer's per-image s maps (dump only)
     int aux;            // N_RELU: float offset inside the fused section; T_RELU: float offset of xx in the row
     int half;           // N_RELU: pixels held by the first row of the pair
 };
 
+// what the kernel reads: 16 bytes per op in shared memory.  code: bits 0..7 dispatch case, 8..9
+// tensor-memory slot, 16..31 `half`.  aux: N_RELU / T_RELU offset; N_CONV: pre_bias (float bits).
+struct __align__(16) KOp { int code; float scale; float bias; int aux; };
+
 struct NParams {
-    NOp ops[kMaxNOps];
-    int n_ops;
+    KOp ops[kMaxKOps];
+    int relu_aux[kMaxRelu];   // producer's list of staged ReLU layers, program order: offset in the fused section
+    int relu_half[kMaxRelu];  //   pixels in the first row of the pair; bit 30: full-size layer (NSPLIT bands)
+    int n_ops, n_relu;
     const float *x, *z;
     const float *aux_x, *aux_z;
     long long aux_stride;
@@ -171,118 +202,110 @@ __device__ __forceinline__ void tmem_landed8(uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// whole map set (two packed arrays, first S entries each) -> tensor memory.  Array h starts at
-// column h * astride and takes exactly 2 S columns: entries move in groups of 8 (x16), then 4
-// (x8), 2 (x4), 1 (x2).
-template <int S0, int S, int NARR>
-__device__ __forceinline__ void stash_store(uint32_t tbase, int astride, const u64 (&M)[2][S0]) {
+// one packed array (first S entries of a[NA]) -> S * 2 consecutive tensor-memory columns at `ta`:
+// entries move in groups of 8 (x16), then 4 (x8), 2 (x4), 1 (x2).  The caller waits (tmem_wait_st).
+template <int NA, int S>
+__device__ __forceinline__ void stash_store_arr(uint32_t ta, const u64 (&a)[NA]) {
     constexpr int G8 = S / 8, R8 = S % 8, B4 = G8 * 8, B2 = B4 + (R8 & 4), B1 = B2 + (R8 & 2);
 #pragma unroll
-    for (int h = 0; h < NARR; ++h) {
-        const uint32_t ta = tbase + h * astride;
+    for (int c = 0; c < G8; ++c) {
+        uint32_t r[16];
 #pragma unroll
-        for (int c = 0; c < G8; ++c) {
-            uint32_t r[16];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) split64(M[h][c * 8 + q], r[2 * q], r[2 * q + 1]);
-            tmem_st16(ta + c * 16, r);
-        }
-        if (R8 & 4) {
-            uint32_t r[8];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) split64(M[h][(B4 + q) % S0], r[2 * q], r[2 * q + 1]);
-            tmem_st8(ta + 2 * B4, r);
-        }
-        if (R8 & 2) {
-            uint32_t r[4];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) split64(M[h][(B2 + q) % S0], r[2 * q], r[2 * q + 1]);
-            tmem_st4(ta + 2 * B2, r);
-        }
-        if (R8 & 1) {
-            uint32_t r[2];
-            split64(M[h][B1 % S0], r[0], r[1]);
-            tmem_st2(ta + 2 * B1, r);
-        }
+        for (int q = 0; q < 8; ++q) split64(a[c * 8 + q], r[2 * q], r[2 * q + 1]);
+        tmem_st16(ta + c * 16, r);
     }
-    tmem_wait_st();
+    if (R8 & 4) {
+        uint32_t r[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) split64(a[(B4 + q) % NA], r[2 * q], r[2 * q + 1]);
+        tmem_st8(ta + 2 * B4, r);
+    }
+    if (R8 & 2) {
+        uint32_t r[4];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) split64(a[(B2 + q) % NA], r[2 * q], r[2 * q + 1]);
+        tmem_st4(ta + 2 * B2, r);
+    }
+    if (R8 & 1) {
+        uint32_t r[2];
+        split64(a[B1 % NA], r[0], r[1]);
+        tmem_st2(ta + 2 * B1, r);
+    }
 }
 
-// M = stash (ADD == false) or M = stash * alpha + M + beta (ADD == true); all loads of one array
-// are in flight together
-template <int S0, int S, int NARR, bool ADD>
-__device__ __forceinline__ void stash_load(uint32_t tbase, int astride, u64 (&M)[2][S0], float alpha_f, float beta_f) {
+// a = stash (ADD == false) or a = stash * alpha + a (ADD == true); the loads of the array are in
+// flight together, two 16-register groups at a time (LIGHT: the 12-warp variant runs phase A at 160
+// registers with 112 of them holding the maps) or all of them (phase B: registers are plentiful)
+template <int NA, int S, bool ADD>
+__device__ __forceinline__ void stash_load_arr(uint32_t ta, u64 (&a)[NA], u64 alpha) {
     constexpr int G8 = S / 8, R8 = S % 8, B4 = G8 * 8, B2 = B4 + (R8 & 4), B1 = B2 + (R8 & 2);
-    const u64 alpha = pk(alpha_f, alpha_f);
+    uint32_t t8[8], t4[4], t2[2];
+    if (R8 & 4) tmem_ld8(ta + 2 * B4, t8);
+    if (R8 & 2) tmem_ld4(ta + 2 * B2, t4);
+    if (R8 & 1) tmem_ld2(ta + 2 * B1, t2);
 #pragma unroll
-    for (int h = 0; h < NARR; ++h) {
-        const uint32_t ta = tbase + h * astride;
-        uint32_t t8[8], t4[4], t2[2];
-        if (R8 & 4) tmem_ld8(ta + 2 * B4, t8);
-        if (R8 & 2) tmem_ld4(ta + 2 * B2, t4);
-        if (R8 & 1) tmem_ld2(ta + 2 * B1, t2);
-        // groups of eight entries, two loads in flight at a time (32 temporaries: the 12-warp
-        // variant runs at 160 registers with 112 of them holding the maps)
+    for (int c = 0; c < G8; c += 2) {
+        uint32_t ta0[16], ta1[16];
+        tmem_ld16(ta + c * 16, ta0);
+        if (c + 1 < G8) tmem_ld16(ta + (c + 1) * 16, ta1);
+        tmem_landed16(ta0);
 #pragma unroll
-        for (int c = 0; c < G8; c += 2) {
-            uint32_t ta0[16], ta1[16];
-            tmem_ld16(ta + c * 16, ta0);
-            if (c + 1 < G8) tmem_ld16(ta + (c + 1) * 16, ta1);
-            tmem_landed16(ta0);
+        for (int q = 0; q < 8; ++q) {
+            const u64 v = join64(ta0[2 * q], ta0[2 * q + 1]);
+            a[c * 8 + q] = ADD ? fma2(v, alpha, a[c * 8 + q]) : v;
+        }
+        if (c + 1 < G8) {
+            tmem_landed16(ta1);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const u64 v = join64(ta0[2 * q], ta0[2 * q + 1]);
-                M[h][c * 8 + q] = ADD ? fma2(v, alpha, M[h][c * 8 + q]) : v;
+                const u64 v = join64(ta1[2 * q], ta1[2 * q + 1]);
+                a[(c + 1) * 8 + q] = ADD ? fma2(v, alpha, a[(c + 1) * 8 + q]) : v;
             }
-            if (c + 1 < G8) {
-                tmem_landed16(ta1);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const u64 v = join64(ta1[2 * q], ta1[2 * q + 1]);
-                    M[h][(c + 1) * 8 + q] = ADD ? fma2(v, alpha, M[h][(c + 1) * 8 + q]) : v;
-                }
-            }
-        }
-        if (R8 & 4) {
-            tmem_landed8(t8);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const u64 v = join64(t8[2 * q], t8[2 * q + 1]);
-                M[h][(B4 + q) % S0] = ADD ? fma2(v, alpha, M[h][(B4 + q) % S0]) : v;
-            }
-        }
-        if (R8 & 2) {
-            tmem_landed4(t4);
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const u64 v = join64(t4[2 * q], t4[2 * q + 1]);
-                M[h][(B2 + q) % S0] = ADD ? fma2(v, alpha, M[h][(B2 + q) % S0]) : v;
-            }
-        }
-        if (R8 & 1) {
-            tmem_landed2(t2);
-            const u64 v = join64(t2[0], t2[1]);
-            M[h][B1 % S0] = ADD ? fma2(v, alpha, M[h][B1 % S0]) : v;
         }
     }
-    if (ADD && beta_f != 0.f) {  // aliased 1 x 1 convolution with a bias (uniform branch)
+    if (R8 & 4) {
+        tmem_landed8(t8);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const u64 v = join64(t8[2 * q], t8[2 * q + 1]);
+            a[(B4 + q) % NA] = ADD ? fma2(v, alpha, a[(B4 + q) % NA]) : v;
+        }
+    }
+    if (R8 & 2) {
+        tmem_landed4(t4);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const u64 v = join64(t4[2 * q], t4[2 * q + 1]);
+            a[(B2 + q) % NA] = ADD ? fma2(v, alpha, a[(B2 + q) % NA]) : v;
+        }
+    }
+    if (R8 & 1) {
+        tmem_landed2(t2);
+        const u64 v = join64(t2[0], t2[1]);
+        a[B1 % NA] = ADD ? fma2(v, alpha, a[B1 % NA]) : v;
+    }
+}
+
+template <int NA, int S>
+__device__ __forceinline__ void add_const(u64 (&a)[NA], float beta_f) {
+    if (beta_f != 0.f) {  // aliased 1 x 1 convolution with a bias (uniform branch)
         const u64 beta = pk(beta_f, beta_f);
 #pragma unroll
-        for (int h = 0; h < NARR; ++h)
-#pragma unroll
-            for (int r = 0; r < S; ++r) M[h][r] = add2(M[h][r], beta);
+        for (int r = 0; r < S; ++r) a[r] = add2(a[r], beta);
     }
 }
 
 // ---- box sums along the register axis --------------------------------------------------------
-// stride 1, zero padding: out[y] = sum_{t=-LO..HI} v[y+t] on the first S entries, two sliding
-// windows from both ends (as gram_fused.cu)
-template <int S0, int S, int LO, int HI>
-__device__ __forceinline__ void box_s1(u64 (&v)[S0]) {
+// stride 1, zero padding: out[y] = B + sum_{t=-LO..HI} v[y+t] on the first S entries, two sliding
+// windows from both ends (as gram_fused.cu); BIAS: both windows start from v + B, so every output
+// carries the constant B (the folded conv bias)
+template <int NA, int S, int LO, int HI, bool BIAS>
+__device__ __forceinline__ void box_s1(u64 (&v)[NA], u64 B) {
     if (LO == 0 && HI == 0) return;
     constexpr int MID = S / 2;
     u64 o[S];
     u64 top = v[0], bot = v[S - 1];
+    if (BIAS) { top = add2(top, B); bot = add2(bot, B); }
 #pragma unroll
     for (int t = 1; t <= HI && t < S; ++t) top = add2(top, v[t]);
 #pragma unroll
@@ -306,8 +329,8 @@ __device__ __forceinline__ void box_s1(u64 (&v)[S0]) {
 }
 
 // stride 2: out[y] = sum_{t=-LO..HI} v[2y+t], SI entries -> SO entries
-template <int S0, int SI, int SO, int LO, int HI>
-__device__ __forceinline__ void box_s2(u64 (&v)[S0]) {
+template <int NA, int SI, int SO, int LO, int HI>
+__device__ __forceinline__ void box_s2(u64 (&v)[NA]) {
     u64 o[SO];
 #pragma unroll
     for (int y = 0; y < SO; ++y) {
@@ -341,33 +364,46 @@ __device__ __forceinline__ void tload(const u64 *tile, u64 (&a)[S0], int lx) {
     for (int r = 0; r < R; ++r) a[r] = tile[lx * PITCH + r];
 }
 
-// box convolution SI x SI -> SO x SO: pass, transposition, pass (flips the register layout),
-// software-pipelined over the two packed arrays, then tap * sum + bias
+template <int NA, int S>
+__device__ __forceinline__ void affine_arr(u64 (&a)[NA], float scale, float bias) {
+    const u64 SC = pk(scale, scale), BI = pk(bias, bias);
+#pragma unroll
+    for (int r = 0; r < S; ++r) a[r] = fma2(a[r], SC, BI);
+}
+
+// box convolution SI x SI -> SO x SO on the full register set: pass, transposition, pass (flips the
+// register layout), software-pipelined over the two packed arrays.  Stride 1: the second pass
+// carries `pre_bias`.  The explicit tap * sum + bias pass runs only when the translator asks for it
+// (scale != 1 or bias != 0: strided convolutions with a bias, and the rare reset of the carried factor).
 template <int S0, int SI, int SO, int LO, int HI, int ST>
-__device__ __forceinline__ void conv_op(u64 (&M)[2][S0], u64 *tile, int lane, float scale, float bias) {
+__device__ __forceinline__ void conv_op(u64 (&M)[2][S0], u64 *tile, int lane, float pre_bias, float scale, float bias) {
     static_assert(ST == 1 ? SI == SO : SI == 2 * SO, "conv geometry");
-    auto pass = [](u64 (&v)[S0]) {
-        if (ST == 1) box_s1<S0, SI, LO, HI>(v);
+    const u64 PB = pk(pre_bias, pre_bias);
+    auto pass1 = [](u64 (&v)[S0]) {
+        if (ST == 1) box_s1<S0, SI, LO, HI, false>(v, 0ull);
+        else box_s2<S0, SI, SO, LO, HI>(v);
+    };
+    auto pass2 = [&](u64 (&v)[S0]) {
+        if (ST == 1) box_s1<S0, SI, LO, HI, true>(v, PB);
         else box_s2<S0, SI, SO, LO, HI>(v);
     };
     const int lx = lane < SO ? lane : SO - 1;
-    pass(M[0]);
+    pass1(M[0]);
     tstore<S0, SO, SI>(tile, M[0], lane);
     __syncwarp();
     tload<S0, SI>(tile, M[0], lx);
-    pass(M[1]);
+    pass1(M[1]);
     __syncwarp();
     tstore<S0, SO, SI>(tile, M[1], lane);
-    pass(M[0]);
+    pass2(M[0]);
     __syncwarp();
     tload<S0, SI>(tile, M[1], lx);
     __syncwarp();
-    pass(M[1]);
-    const u64 SC = pk(scale, scale), BI = pk(bias, bias);
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int r = 0; r < SO; ++r) M[h][r] = fma2(M[h][r], SC, BI);
+    pass2(M[1]);
+    if (scale != 1.f || bias != 0.f) {
+        affine_arr<S0, SO>(M[0], scale, bias);
+        affine_arr<S0, SO>(M[1], scale, bias);
+    }
 }
 
 template <int S0, int S>
@@ -382,19 +418,11 @@ __device__ __forceinline__ void transpose_op(u64 (&M)[2][S0], u64 *tile, int lan
     }
 }
 
-template <int S0, int S>
-__device__ __forceinline__ void affine_op(u64 (&M)[2][S0], float scale, float bias) {
-    const u64 SC = pk(scale, scale), BI = pk(bias, bias);
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int r = 0; r < S; ++r) M[h][r] = fma2(M[h][r], SC, BI);
-}
-
 // ---- folded mode: maps of edge <= S0 / 2 ------------------------------------------------------
 // After the first stride-2 convolution a map needs at most 16 lanes, so the second packed array is
 // folded into lanes 16..31 of the first (lane = 16 b + l: array b, column l).  Every later op then
-// runs on ONE packed array: half the instructions for the S0/2 and S0/4 stages of a ResNet.
+// runs on ONE packed array a[NA] (M[0] while full-size ops are still to come, the small array F of
+// phase B afterwards): half the instructions for the S0/2 and S0/4 stages of a ResNet.
 __device__ __forceinline__ u64 shfl64(u64 v, int src) {
     uint32_t lo, hi;
     split64(v, lo, hi);
@@ -413,8 +441,8 @@ __device__ __forceinline__ void fold_op(u64 (&M)[2][S0], int lane) {
 }
 
 // transposition tile in folded mode: row r holds array 0's columns at [0, L) and array 1's at [L, 2L)
-template <int S0, int R, int L>
-__device__ __forceinline__ void tstore_f(u64 *tile, const u64 (&a)[S0], int lane) {
+template <int NA, int S0, int R, int L>
+__device__ __forceinline__ void tstore_f(u64 *tile, const u64 (&a)[NA], int lane) {
     constexpr int PITCH = S0 + 1;
     const int b = lane >> 4, l = lane & 15;
     if (l < L) {
@@ -422,8 +450,8 @@ __device__ __forceinline__ void tstore_f(u64 *tile, const u64 (&a)[S0], int lane
         for (int r = 0; r < R; ++r) tile[r * PITCH + b * L + l] = a[r];
     }
 }
-template <int S0, int R, int NEWL>
-__device__ __forceinline__ void tload_f(const u64 *tile, u64 (&a)[S0], int lane) {
+template <int NA, int S0, int R, int NEWL>
+__device__ __forceinline__ void tload_f(const u64 *tile, u64 (&a)[NA], int lane) {
     constexpr int PITCH = S0 + 1;
     const int b = lane >> 4, l = lane & 15;
     const int lx = l < NEWL ? l : NEWL - 1;
@@ -431,38 +459,27 @@ __device__ __forceinline__ void tload_f(const u64 *tile, u64 (&a)[S0], int lane)
     for (int r = 0; r < R; ++r) a[r] = tile[lx * PITCH + b * R + r];
 }
 
-template <int S0, int SI, int SO, int LO, int HI, int ST>
-__device__ __forceinline__ void conv_op_f(u64 (&M)[2][S0], u64 *tile, int lane, float scale, float bias) {
+template <int NA, int S0, int SI, int SO, int LO, int HI, int ST>
+__device__ __forceinline__ void conv_op_f(u64 (&a)[NA], u64 *tile, int lane, float pre_bias, float scale, float bias) {
     static_assert(ST == 1 ? SI == SO : SI == 2 * SO, "conv geometry");
     static_assert(2 * SI <= S0 + 1, "both halves must fit a tile row");
-    auto pass = [](u64 (&v)[S0]) {
-        if (ST == 1) box_s1<S0, SI, LO, HI>(v);
-        else box_s2<S0, SI, SO, LO, HI>(v);
-    };
-    pass(M[0]);
-    tstore_f<S0, SO, SI>(tile, M[0], lane);   // SO rows of SI columns per half
+    if (ST == 1) box_s1<NA, SI, LO, HI, false>(a, 0ull);
+    else box_s2<NA, SI, SO, LO, HI>(a);
+    tstore_f<NA, S0, SO, SI>(tile, a, lane);   // SO rows of SI columns per half
     __syncwarp();
-    tload_f<S0, SI, SO>(tile, M[0], lane);    // new lane = old row (< SO), registers = old columns (SI)
+    tload_f<NA, S0, SI, SO>(tile, a, lane);    // new lane = old row (< SO), registers = old columns (SI)
     __syncwarp();
-    pass(M[0]);
-    const u64 SC = pk(scale, scale), BI = pk(bias, bias);
-#pragma unroll
-    for (int r = 0; r < SO; ++r) M[0][r] = fma2(M[0][r], SC, BI);
+    if (ST == 1) box_s1<NA, SI, LO, HI, true>(a, pk(pre_bias, pre_bias));
+    else box_s2<NA, SI, SO, LO, HI>(a);
+    if (scale != 1.f || bias != 0.f) affine_arr<NA, SO>(a, scale, bias);
 }
 
-template <int S0, int S>
-__device__ __forceinline__ void transpose_op_f(u64 (&M)[2][S0], u64 *tile, int lane) {
-    tstore_f<S0, S, S>(tile, M[0], lane);
+template <int NA, int S0, int S>
+__device__ __forceinline__ void transpose_op_f(u64 (&a)[NA], u64 *tile, int lane) {
+    tstore_f<NA, S0, S, S>(tile, a, lane);
     __syncwarp();
-    tload_f<S0, S, S>(tile, M[0], lane);
+    tload_f<NA, S0, S, S>(tile, a, lane);
     __syncwarp();
-}
-
-template <int S0, int S>
-__device__ __forceinline__ void affine_op_f(u64 (&M)[2][S0], float scale, float bias) {
-    const u64 SC = pk(scale, scale), BI = pk(bias, bias);
-#pragma unroll
-    for (int r = 0; r < S; ++r) M[0][r] = fma2(M[0][r], SC, BI);
 }
 
 // 2 * H(e), degree-5 minimax fit on [0,1] (gram_fused.cu)
@@ -506,8 +523,8 @@ __device__ __forceinline__ void relu_rows(u64 (&M)[2][S0], const float4 *ai, con
 }
 
 // folded: lanes 16..31 hold (i0 j1, i1 j0), i.e. they need the j-pair's operands swapped
-template <int S0, int S>
-__device__ __forceinline__ void relu_rows_f(u64 (&M)[2][S0], const float4 *ai, const float4 *bj, int lane) {
+template <int NA, int S>
+__device__ __forceinline__ void relu_rows_f(u64 (&a)[NA], const float4 *ai, const float4 *bj, int lane) {
     const u64 C5 = pk(FNET_C5, FNET_C5), C4 = pk(FNET_C4, FNET_C4), C3 = pk(FNET_C3, FNET_C3),
               C2 = pk(FNET_C2, FNET_C2), C1 = pk(FNET_C1, FNET_C1), C0 = pk(FNET_C0, FNET_C0), ONE = pk(1.f, 1.f);
     const bool sw = lane >= 16;
@@ -518,7 +535,7 @@ __device__ __forceinline__ void relu_rows_f(u64 (&M)[2][S0], const float4 *ai, c
         const u64 SB = pk(sw ? B.y : B.x, sw ? B.x : B.y);
         const u64 RB = pk(sw ? B.w : B.z, sw ? B.z : B.w);
         float c0, c1;
-        upk(M[0][r], c0, c1);
+        upk(a[r], c0, c1);
         const u64 NC = pk(neg_abs(c0), neg_abs(c1));
         const u64 D = fma2(SA, SB, NC);
         const u64 E = fma2(NC, mul2(RA, RB), ONE);
@@ -530,7 +547,7 @@ __device__ __forceinline__ void relu_rows_f(u64 (&M)[2][S0], const float4 *ai, c
         H = fma2(H, E, C2);
         H = fma2(H, E, C1);
         H = fma2(H, E, C0);
-        M[0][r] = fma2(W, H, pk(fmaxf(c0, 0.f), fmaxf(c1, 0.f)));
+        a[r] = fma2(W, H, pk(fmaxf(c0, 0.f), fmaxf(c1, 0.f)));
     }
 }
 
@@ -573,11 +590,11 @@ __device__ __forceinline__ void dense_op(const u64 (&M)[2][S0], int lane, float 
     }
 }
 
-template <int S0, int S>
-__device__ __forceinline__ void dense_op_f(const u64 (&M)[2][S0], int lane, float scale, float bias, float (&tot)[4]) {
-    u64 acc = M[0][0];
+template <int NA, int S>
+__device__ __forceinline__ void dense_op_f(const u64 (&a)[NA], int lane, float scale, float bias, float (&tot)[4]) {
+    u64 acc = a[0];
 #pragma unroll
-    for (int r = 1; r < S; ++r) acc = add2(acc, M[0][r]);
+    for (int r = 1; r < S; ++r) acc = add2(acc, a[r]);
     float a0, a1;
     upk(acc, a0, a1);
     if ((lane & 15) >= S) { a0 = 0.f; a1 = 0.f; }
@@ -601,6 +618,7 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
     constexpr int kWarps = G::kWarps, kTileI = G::kTileI, kTileJ = G::kTileJ, kImgs = G::kImgs, kPairs = G::kPairs;
     constexpr int P0 = S0 * S0;
     constexpr int PITCH = S0 + 1;
+    constexpr int SF = S0 / 2;                                     // registers of a folded map
     constexpr int IMG_PARTS = NSPLIT / 2, IBAND = P0 / IMG_PARTS;  // pixels of one image band
     constexpr int BAND = P0 / NSPLIT;                              // pixels of one full-size ReLU band
     constexpr int STAGE = kImgs * IBAND * 4;  // bytes: one image band of kImgs images == kPairs ReLU bands of float4
@@ -615,7 +633,8 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *stage = smem_raw;
     u64 *tiles = reinterpret_cast<u64 *>(smem_raw + (size_t)NST * STAGE);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + kWarps * S0 * PITCH);
+    int4 *ops_s = reinterpret_cast<int4 *>(tiles + kWarps * S0 * PITCH);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ops_s + kMaxKOps);
     uint64_t *full = bars, *empty = bars + NST;
     // tile index each stage belongs to (-1: no more tiles); tiles are handed out by a global atomic
     // counter so that all CTAs stay on consecutive tiles of one super-tile (see gram_fused.cu)
@@ -627,6 +646,11 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
 #pragma unroll
         for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // the op descriptors move from the parameter bank to shared memory: one LDS.128 per op
+    for (int q = threadIdx.x; q < p.n_ops; q += blockDim.x) {
+        const KOp o = p.ops[q];
+        ops_s[q] = make_int4(o.code, __float_as_int(o.scale), __float_as_int(o.bias), o.aux);
     }
     if (warp == 0) {  // one warp allocates all of this SM's tensor memory (one CTA per SM)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_word)),
@@ -716,11 +740,10 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
                         ++l;
                     }
                 }
-                for (int k = 0; k < p.n_ops; ++k) {
-                    if (p.ops[k].kind != N_RELU) continue;
-                    const int half = p.ops[k].half;
-                    const int off = p.ops[k].aux;
-                    if (p.ops[k].si == S0) {  // full-size layers: NSPLIT row bands, one stage each
+                for (int k = 0; k < p.n_relu; ++k) {
+                    const int off = p.relu_aux[k];
+                    const int half = p.relu_half[k] & 0xffff;
+                    if (p.relu_half[k] >> 30) {  // full-size layers: NSPLIT row bands, one stage each
                         for (int part = 0; part < NSPLIT; ++part) {
                             float4 *dst = reinterpret_cast<float4 *>(acquire((unsigned)(kPairs * BAND * 16)));
                             // band `part`: pixels [part * BAND, +BAND); the first half of the pixels is in row 2k
@@ -749,6 +772,13 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
     const uint32_t tm_warp = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TM_WARP);
     unsigned stage_l = 0;
 
+    // descriptor fields
+    auto f_scale = [](const int4 &o) { return __int_as_float(o.y); };
+    auto f_bias = [](const int4 &o) { return __int_as_float(o.z); };
+    auto f_pre = [](const int4 &o) { return __int_as_float(o.w); };
+    auto f_slot = [](const int4 &o) { return (o.x >> 8) & 3; };
+    auto f_half = [](const int4 &o) { return (int)((unsigned)o.x >> 16); };
+
     for (;;) {
         // the tile this CTA works on next travels with its first stage
         mbar_wait(&full[stage_l % NST], (stage_l / NST) & 1);
@@ -758,128 +788,251 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
         decode(t, ib, jb);
         const int i_base = ib * kTileI, j_base = jb * kTileJ;
 
-        u64 M[2][S0];
         float tot[4] = {0.f, 0.f, 0.f, 0.f};
-        {   // init, kernels.py:43-49
-            const int lx = lane < S0 ? lane : S0 - 1;
+        u64 F[SF];
+        int k = 0;
+        int4 o = ops_s[0];
+        {   // ================= phase A: the full register set =================================
+            u64 M[2][S0];
+            {   // init, kernels.py:43-49
+                const int lx = lane < S0 ? lane : S0 - 1;
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int r = 0; r < S0; ++r) M[h][r] = 0ull;
-            for (int c = 0; c < p.C; ++c) {
+                    for (int r = 0; r < S0; ++r) M[h][r] = 0ull;
+                for (int c = 0; c < p.C; ++c) {
 #pragma unroll
-                for (int ip = 0; ip < IMG_PARTS; ++ip) {
-                    const unsigned buf = stage_l % NST;
-                    mbar_wait(&full[buf], (stage_l / NST) & 1);
-                    const float *sb = reinterpret_cast<const float *>(stage + (size_t)buf * STAGE) + lx;
-                    const float *x0 = sb + (wi * 2 + 0) * IBAND, *x1 = sb + (wi * 2 + 1) * IBAND;
-                    const float *z0 = sb + (kTileI + wj * 2 + 0) * IBAND, *z1 = sb + (kTileI + wj * 2 + 1) * IBAND;
-                    constexpr int R = S0 / IMG_PARTS;
-#pragma unroll
-                    for (int rr = 0; rr < R; ++rr) {
-                        const int r = ip * R + rr;
-                        const float a0 = x0[rr * S0], a1 = x1[rr * S0], b0 = z0[rr * S0], b1 = z1[rr * S0];
-                        const u64 A = pk(a0, a1);
-                        M[0][r] = fma2(A, pk(b0, b1), M[0][r]);
-                        M[1][r] = fma2(A, pk(b1, b0), M[1][r]);
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[buf]);
-                    ++stage_l;
-                }
-            }
-            if (p.C > 1) affine_op<S0, S0>(M, p.inv_c, 0.f);
-        }
-
-        // one jump per op: the translator precomputes a dense code = kind x size class (x window)
-        NOp o = p.ops[0];
-        for (int k = 0; k < p.n_ops; ++k) {
-            const NOp nxt = p.ops[k + 1 < p.n_ops ? k + 1 : k];  // descriptor of the next op: fetched under this op's work
-#define FNET_3(CODE, FULL, HALF)                                        \
-    case CODE + 0: { constexpr int S = S0; FULL; break; }               \
-    case CODE + 1: { constexpr int S = S0 / 2; HALF; break; }           \
-    case CODE + 2: { constexpr int S = S0 / 4; HALF; break; }
-            switch (o.code) {
-                case C_CONV + 0: conv_op<S0, S0, S0, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
-                case C_CONV + 1: conv_op<S0, S0, S0, 1, 2, 1>(M, tile, lane, o.scale, o.bias); break;
-                case C_CONV + 2: conv_op<S0, S0, S0, 2, 2, 1>(M, tile, lane, o.scale, o.bias); break;
-                case C_CONV + 3: conv_op<S0, S0, S0, 3, 3, 1>(M, tile, lane, o.scale, o.bias); break;
-                // stride 2 out of the full size: unfolded op, then the result is folded
-                case C_CONV + 4: conv_op<S0, S0, S0 / 2, 1, 1, 2>(M, tile, lane, o.scale, o.bias); fold_op<S0, S0 / 2>(M, lane); break;
-                case C_CONV + 5: conv_op<S0, S0, S0 / 2, 0, 0, 2>(M, tile, lane, o.scale, o.bias); fold_op<S0, S0 / 2>(M, lane); break;
-                case C_CONV + 6: conv_op_f<S0, S0 / 2, S0 / 2, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
-                case C_CONV + 7: conv_op_f<S0, S0 / 2, S0 / 4, 1, 1, 2>(M, tile, lane, o.scale, o.bias); break;
-                case C_CONV + 8: conv_op_f<S0, S0 / 2, S0 / 4, 0, 0, 2>(M, tile, lane, o.scale, o.bias); break;
-                case C_CONV + 9: conv_op_f<S0, S0 / 4, S0 / 4, 1, 1, 1>(M, tile, lane, o.scale, o.bias); break;
-                FNET_3(C_AFFINE, (affine_op<S0, S>(M, o.scale, o.bias)), (affine_op_f<S0, S>(M, o.scale, o.bias)))
-                FNET_3(C_TRANSPOSE, (transpose_op<S0, S>(M, tile, lane)), (transpose_op_f<S0, S>(M, tile, lane)))
-                FNET_3(C_STASH, (stash_store<S0, S, 2>(tm_warp + o.slot * TM_SLOT1, o.slot ? TM_A1 : TM_A0, M)),
-                       (stash_store<S0, S, 1>(tm_warp + o.slot * TM_SLOT1, 0, M)))
-                FNET_3(C_UNSTASH, (stash_load<S0, S, 2, false>(tm_warp + o.slot * TM_SLOT1, o.slot ? TM_A1 : TM_A0, M, 1.f, 0.f)),
-                       (stash_load<S0, S, 1, false>(tm_warp + o.slot * TM_SLOT1, 0, M, 1.f, 0.f)))
-                FNET_3(C_ADD, (stash_load<S0, S, 2, true>(tm_warp + o.slot * TM_SLOT1, o.slot ? TM_A1 : TM_A0, M, o.scale, o.bias)),
-                       (stash_load<S0, S, 1, true>(tm_warp + o.slot * TM_SLOT1, 0, M, o.scale, o.bias)))
-                FNET_3(C_DENSE, (dense_op<S0, S>(M, lane, o.scale, o.bias, tot)), (dense_op_f<S0, S>(M, lane, o.scale, o.bias, tot)))
-                case C_RELU + 0: {  // NSPLIT stages, one row band each
-                    const int lx = lane < S0 ? lane : S0 - 1;
-                    auto band = [&](auto Q) {
-                        constexpr int q = decltype(Q)::value;
+                    for (int ip = 0; ip < IMG_PARTS; ++ip) {
                         const unsigned buf = stage_l % NST;
                         mbar_wait(&full[buf], (stage_l / NST) & 1);
-                        // the stage holds pixels [q * BAND, +BAND) of every pair: bias the pointer so that r * S0 + lx indexes it
-                        const float4 *sb = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE) + lx - q * BAND;
-                        relu_rows<S0, S0, q * (S0 / NSPLIT), (q + 1) * (S0 / NSPLIT)>(M, sb + wi * BAND, sb + (kTileI / 2 + wj) * BAND);
+                        const float *sb = reinterpret_cast<const float *>(stage + (size_t)buf * STAGE) + lx;
+                        const float *x0 = sb + (wi * 2 + 0) * IBAND, *x1 = sb + (wi * 2 + 1) * IBAND;
+                        const float *z0 = sb + (kTileI + wj * 2 + 0) * IBAND, *z1 = sb + (kTileI + wj * 2 + 1) * IBAND;
+                        constexpr int R = S0 / IMG_PARTS;
+#pragma unroll
+                        for (int rr = 0; rr < R; ++rr) {
+                            const int r = ip * R + rr;
+                            const float a0 = x0[rr * S0], a1 = x1[rr * S0], b0 = z0[rr * S0], b1 = z1[rr * S0];
+                            const u64 A = pk(a0, a1);
+                            M[0][r] = fma2(A, pk(b0, b1), M[0][r]);
+                            M[1][r] = fma2(A, pk(b1, b0), M[1][r]);
+                        }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&empty[buf]);
                         ++stage_l;
-                    };
-                    band(std::integral_constant<int, 0>{});
-                    band(std::integral_constant<int, 1>{});
-                    if (NSPLIT == 4) {
-                        band(std::integral_constant<int, NSPLIT == 4 ? 2 : 0>{});
-                        band(std::integral_constant<int, NSPLIT == 4 ? 3 : 1>{});
                     }
-                    break;
                 }
-                case C_RELU + 1:
-                case C_RELU + 2: {  // folded maps: one stage holds the whole layer
+                if (p.C > 1) { affine_arr<S0, S0>(M[0], p.inv_c, 0.f); affine_arr<S0, S0>(M[1], p.inv_c, 0.f); }
+            }
+
+            // ---- the ops of phase A as callable pieces (single cases and block cases share them)
+            auto relu_full = [&]() {  // NSPLIT stages, one row band each
+                const int lx = lane < S0 ? lane : S0 - 1;
+                auto band = [&](auto Q) {
+                    constexpr int q = decltype(Q)::value;
                     const unsigned buf = stage_l % NST;
                     mbar_wait(&full[buf], (stage_l / NST) & 1);
-                    const float4 *st4 = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE);
-                    const int l = lane & 15;
-                    if (o.code == C_RELU + 1) {
-                        constexpr int S = S0 / 2;
-                        const float4 *sb = st4 + (l < S ? l : S - 1);
-                        relu_rows_f<S0, S>(M, sb + wi * 2 * o.half, sb + (kTileI / 2 + wj) * 2 * o.half, lane);
-                    } else {
-                        constexpr int S = S0 / 4;
-                        const float4 *sb = st4 + (l < S ? l : S - 1);
-                        relu_rows_f<S0, S>(M, sb + wi * 2 * o.half, sb + (kTileI / 2 + wj) * 2 * o.half, lane);
-                    }
+                    // the stage holds pixels [q * BAND, +BAND) of every pair: bias the pointer so that r * S0 + lx indexes it
+                    const float4 *sb = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE) + lx - q * BAND;
+                    relu_rows<S0, S0, q * (S0 / NSPLIT), (q + 1) * (S0 / NSPLIT)>(M, sb + wi * BAND, sb + (kTileI / 2 + wj) * BAND);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[buf]);
                     ++stage_l;
-                    break;
+                };
+                band(std::integral_constant<int, 0>{});
+                band(std::integral_constant<int, 1>{});
+                if (NSPLIT == 4) {
+                    band(std::integral_constant<int, NSPLIT == 4 ? 2 : 0>{});
+                    band(std::integral_constant<int, NSPLIT == 4 ? 3 : 1>{});
                 }
-                case C_TAFFINE:
+            };
+            auto relu_fold = [&](auto SZ, const int4 &d) {  // folded map in M[0]: one stage holds the whole layer
+                constexpr int S = decltype(SZ)::value;
+                const unsigned buf = stage_l % NST;
+                mbar_wait(&full[buf], (stage_l / NST) & 1);
+                const float4 *st4 = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE);
+                const int l = lane & 15, half = f_half(d);
+                const float4 *sb = st4 + (l < S ? l : S - 1);
+                relu_rows_f<S0, S>(M[0], sb + wi * 2 * half, sb + (kTileI / 2 + wj) * 2 * half, lane);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[buf]);
+                ++stage_l;
+            };
+            auto stash_full = [&](const int4 &d) {
+                const int s = f_slot(d);
+                const uint32_t ta = tm_warp + s * TM_SLOT1;
+                stash_store_arr<S0, S0>(ta, M[0]);
+                stash_store_arr<S0, S0>(ta + (s ? TM_A1 : TM_A0), M[1]);
+                tmem_wait_st();
+            };
+            auto unstash_full = [&](const int4 &d) {
+                const int s = f_slot(d);
+                const uint32_t ta = tm_warp + s * TM_SLOT1;
+                stash_load_arr<S0, S0, false>(ta, M[0], 0ull);
+                stash_load_arr<S0, S0, false>(ta + (s ? TM_A1 : TM_A0), M[1], 0ull);
+            };
+            auto add_full = [&](const int4 &d) {
+                const int s = f_slot(d);
+                const uint32_t ta = tm_warp + s * TM_SLOT1;
+                const float al = f_scale(d);
+                const u64 alpha = pk(al, al);
+                stash_load_arr<S0, S0, true>(ta, M[0], alpha);
+                stash_load_arr<S0, S0, true>(ta + (s ? TM_A1 : TM_A0), M[1], alpha);
+                add_const<S0, S0>(M[0], f_bias(d));
+                add_const<S0, S0>(M[1], f_bias(d));
+            };
+
+            for (bool more = true; more;) {
+                int4 nxt;
+#define FETCH(LEN) nxt = ops_s[k + (LEN)]; k += (LEN)
+#define FOLDED_A(CODE, BODY)                                                               \
+    case CODE + 1: { constexpr int S = S0 / 2; FETCH(1); BODY; break; }                    \
+    case CODE + 2: { constexpr int S = S0 / 4; FETCH(1); BODY; break; }
+                switch (o.x & 0xff) {
+                    case A_CONV + 0: FETCH(1); conv_op<S0, S0, S0, 1, 1, 1>(M, tile, lane, f_pre(o), f_scale(o), f_bias(o)); break;
+                    case A_CONV + 1: FETCH(1); conv_op<S0, S0, S0, 1, 2, 1>(M, tile, lane, f_pre(o), f_scale(o), f_bias(o)); break;
+                    case A_CONV + 2: FETCH(1); conv_op<S0, S0, S0, 2, 2, 1>(M, tile, lane, f_pre(o), f_scale(o), f_bias(o)); break;
+                    case A_CONV + 3: FETCH(1); conv_op<S0, S0, S0, 3, 3, 1>(M, tile, lane, f_pre(o), f_scale(o), f_bias(o)); break;
+                    // stride 2 out of the full size: unfolded op, then the result is folded
+                    case A_CONV + 4: FETCH(1); conv_op<S0, S0, S0 / 2, 1, 1, 2>(M, tile, lane, 0.f, f_scale(o), f_bias(o)); fold_op<S0, S0 / 2>(M, lane); break;
+                    case A_CONV + 5: FETCH(1); conv_op<S0, S0, S0 / 2, 0, 0, 2>(M, tile, lane, 0.f, f_scale(o), f_bias(o)); fold_op<S0, S0 / 2>(M, lane); break;
+                    case A_CONV + 6: FETCH(1); conv_op_f<S0, S0, S0 / 2, S0 / 2, 1, 1, 1>(M[0], tile, lane, f_pre(o), f_scale(o), f_bias(o)); break;
+                    case A_CONV + 7: FETCH(1); conv_op_f<S0, S0, S0 / 2, S0 / 4, 1, 1, 2>(M[0], tile, lane, 0.f, f_scale(o), f_bias(o)); break;
+                    case A_CONV + 8: FETCH(1); conv_op_f<S0, S0, S0 / 2, S0 / 4, 0, 0, 2>(M[0], tile, lane, 0.f, f_scale(o), f_bias(o)); break;
+                    case A_CONV + 9: FETCH(1); conv_op_f<S0, S0, S0 / 4, S0 / 4, 1, 1, 1>(M[0], tile, lane, f_pre(o), f_scale(o), f_bias(o)); break;
+                    case A_AFFINE + 0: FETCH(1); affine_arr<S0, S0>(M[0], f_scale(o), f_bias(o)); affine_arr<S0, S0>(M[1], f_scale(o), f_bias(o)); break;
+                    FOLDED_A(A_AFFINE, (affine_arr<S0, S>(M[0], f_scale(o), f_bias(o))))
+                    case A_TRANSPOSE + 0: FETCH(1); transpose_op<S0, S0>(M, tile, lane); break;
+                    FOLDED_A(A_TRANSPOSE, (transpose_op_f<S0, S0, S>(M[0], tile, lane)))
+                    case A_STASH + 0: FETCH(1); stash_full(o); break;
+                    FOLDED_A(A_STASH, (stash_store_arr<S0, S>(tm_warp + f_slot(o) * TM_SLOT1, M[0]), tmem_wait_st()))
+                    case A_UNSTASH + 0: FETCH(1); unstash_full(o); break;
+                    FOLDED_A(A_UNSTASH, (stash_load_arr<S0, S, false>(tm_warp + f_slot(o) * TM_SLOT1, M[0], 0ull)))
+                    case A_ADD + 0: FETCH(1); add_full(o); break;
+                    FOLDED_A(A_ADD, (stash_load_arr<S0, S, true>(tm_warp + f_slot(o) * TM_SLOT1, M[0], pk(f_scale(o), f_scale(o))),
+                                     add_const<S0, S>(M[0], f_bias(o))))
+                    case A_DENSE + 0: FETCH(1); dense_op<S0, S0>(M, lane, f_scale(o), f_bias(o), tot); break;
+                    FOLDED_A(A_DENSE, (dense_op_f<S0, S>(M[0], lane, f_scale(o), f_bias(o), tot)))
+                    case A_RELU + 0: FETCH(1); relu_full(); break;
+                    case A_RELU + 1: FETCH(1); relu_fold(std::integral_constant<int, S0 / 2>{}, o); break;
+                    case A_RELU + 2: FETCH(1); relu_fold(std::integral_constant<int, S0 / 4>{}, o); break;
+                    case A_IDBLOCK: {  // STASH RELU CONV(3x3) RELU CONV(3x3) ADD: an identity residual block
+                        const int4 c1 = ops_s[k + 2], c2 = ops_s[k + 4], ad = ops_s[k + 5];
+                        FETCH(6);
+                        stash_full(o);
+                        relu_full();
+                        conv_op<S0, S0, S0, 1, 1, 1>(M, tile, lane, f_pre(c1), f_scale(c1), f_bias(c1));
+                        relu_full();
+                        conv_op<S0, S0, S0, 1, 1, 1>(M, tile, lane, f_pre(c2), f_scale(c2), f_bias(c2));
+                        add_full(ad);
+                        break;
+                    }
+                    case A_RESBLOCK: {  // STASH CONV(4x4 "same") RELU TRANSPOSE ADD: mnist_paper_residual_cnn_gp
+                        const int4 c1 = ops_s[k + 1], ad = ops_s[k + 4];
+                        FETCH(5);
+                        stash_full(o);
+                        conv_op<S0, S0, S0, 1, 2, 1>(M, tile, lane, f_pre(c1), f_scale(c1), f_bias(c1));
+                        relu_full();
+                        transpose_op<S0, S0>(M, tile, lane);
+                        add_full(ad);
+                        break;
+                    }
+                    default: FETCH(1); more = false; break;  // A_END
+                }
+#undef FOLDED_A
+                o = nxt;
+            }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) tot[q] = fmaf(tot[q], o.scale, o.bias);
+            for (int r = 0; r < SF; ++r) F[r] = M[0][r];
+        }
+
+        {   // ================= phase B: folded maps, S0 / 2 live registers ====================
+            auto relu_fold = [&](auto SZ, const int4 &d) {
+                constexpr int S = decltype(SZ)::value;
+                const unsigned buf = stage_l % NST;
+                mbar_wait(&full[buf], (stage_l / NST) & 1);
+                const float4 *st4 = reinterpret_cast<const float4 *>(stage + (size_t)buf * STAGE);
+                const int l = lane & 15, half = f_half(d);
+                const float4 *sb = st4 + (l < S ? l : S - 1);
+                relu_rows_f<SF, S>(F, sb + wi * 2 * half, sb + (kTileI / 2 + wj) * 2 * half, lane);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[buf]);
+                ++stage_l;
+            };
+            auto idblock = [&](auto SZ, const int4 &st, const int4 &r1, const int4 &c1, const int4 &r2, const int4 &c2, const int4 &ad) {
+                constexpr int S = decltype(SZ)::value;
+                stash_store_arr<SF, S>(tm_warp + f_slot(st) * TM_SLOT1, F);
+                tmem_wait_st();
+                relu_fold(SZ, r1);
+                conv_op_f<SF, S0, S, S, 1, 1, 1>(F, tile, lane, f_pre(c1), f_scale(c1), f_bias(c1));
+                relu_fold(SZ, r2);
+                conv_op_f<SF, S0, S, S, 1, 1, 1>(F, tile, lane, f_pre(c2), f_scale(c2), f_bias(c2));
+                stash_load_arr<SF, S, true>(tm_warp + f_slot(ad) * TM_SLOT1, F, pk(f_scale(ad), f_scale(ad)));
+                add_const<SF, S>(F, f_bias(ad));
+            };
+            for (bool more = true; more;) {
+                int4 nxt;
+#define FOLDED_B(CODE, BODY)                                                               \
+    case CODE + 0: { constexpr int S = S0 / 2; FETCH(1); BODY; break; }                    \
+    case CODE + 1: { constexpr int S = S0 / 4; FETCH(1); BODY; break; }
+                switch (o.x & 0xff) {
+                    case B_CONV + 0: FETCH(1); conv_op_f<SF, S0, S0 / 2, S0 / 2, 1, 1, 1>(F, tile, lane, f_pre(o), f_scale(o), f_bias(o)); break;
+                    case B_CONV + 1: FETCH(1); conv_op_f<SF, S0, S0 / 2, S0 / 4, 1, 1, 2>(F, tile, lane, 0.f, f_scale(o), f_bias(o)); break;
+                    case B_CONV + 2: FETCH(1); conv_op_f<SF, S0, S0 / 2, S0 / 4, 0, 0, 2>(F, tile, lane, 0.f, f_scale(o), f_bias(o)); break;
+                    case B_CONV + 3: FETCH(1); conv_op_f<SF, S0, S0 / 4, S0 / 4, 1, 1, 1>(F, tile, lane, f_pre(o), f_scale(o), f_bias(o)); break;
+                    FOLDED_B(B_AFFINE, (affine_arr<SF, S>(F, f_scale(o), f_bias(o))))
+                    FOLDED_B(B_TRANSPOSE, (transpose_op_f<SF, S0, S>(F, tile, lane)))
+                    FOLDED_B(B_STASH, (stash_store_arr<SF, S>(tm_warp + f_slot(o) * TM_SLOT1, F), tmem_wait_st()))
+                    FOLDED_B(B_UNSTASH, (stash_load_arr<SF, S, false>(tm_warp + f_slot(o) * TM_SLOT1, F, 0ull)))
+                    FOLDED_B(B_ADD, (stash_load_arr<SF, S, true>(tm_warp + f_slot(o) * TM_SLOT1, F, pk(f_scale(o), f_scale(o))),
+                                     add_const<SF, S>(F, f_bias(o))))
+                    FOLDED_B(B_DENSE, (dense_op_f<SF, S>(F, lane, f_scale(o), f_bias(o), tot)))
+                    case B_RELU + 0: FETCH(1); relu_fold(std::integral_constant<int, S0 / 2>{}, o); break;
+                    case B_RELU + 1: FETCH(1); relu_fold(std::integral_constant<int, S0 / 4>{}, o); break;
+                    case B_IDBLOCK + 0: {
+                        const int4 r1 = ops_s[k + 1], c1 = ops_s[k + 2], r2 = ops_s[k + 3], c2 = ops_s[k + 4], ad = ops_s[k + 5];
+                        FETCH(6);
+                        idblock(std::integral_constant<int, S0 / 2>{}, o, r1, c1, r2, c2, ad);
+                        break;
+                    }
+                    case B_IDBLOCK + 1: {
+                        const int4 r1 = ops_s[k + 1], c1 = ops_s[k + 2], r2 = ops_s[k + 3], c2 = ops_s[k + 4], ad = ops_s[k + 5];
+                        FETCH(6);
+                        idblock(std::integral_constant<int, S0 / 4>{}, o, r1, c1, r2, c2, ad);
+                        break;
+                    }
+                    default: FETCH(1); more = false; break;  // B_END
+                }
+#undef FOLDED_B
+                o = nxt;
+            }
+        }
+
+        // ================= tail: the four scalars of the warp ==================================
+        for (bool more = true; more;) {
+            int4 nxt;
+            switch (o.x & 0xff) {
+                case T_CASE_AFFINE:
+                    FETCH(1);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) tot[q] = fmaf(tot[q], f_scale(o), f_bias(o));
                     break;
-                case C_TRELU: {
+                case T_CASE_RELU: {
+                    FETCH(1);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int i = min(i_base + wi * 2 + (q >> 1), p.N1 - 1), j = min(j_base + wj * 2 + (q & 1), p.N2 - 1);
-                        const float vx = __ldg(p.aux_x + (long long)i * p.aux_stride + o.aux);
-                        const float vy = __ldg(p.aux_z + (long long)j * p.aux_stride + o.aux);
+                        const float vx = __ldg(p.aux_x + (long long)i * p.aux_stride + o.w);
+                        const float vy = __ldg(p.aux_z + (long long)j * p.aux_stride + o.w);
                         tot[q] = relu_scalar(tot[q], vx, vy);
                     }
                     break;
                 }
-                default: break;
+                default: more = false; break;  // T_END
             }
-#undef FNET_3
-            o = nxt;
+            if (more) o = nxt;
         }
+#undef FETCH
 
         if (lane < 4) {
             const int a = lane >> 1, b = lane & 1;
@@ -918,8 +1071,13 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
 // ---- host: translate the two-slot plan into the kernel's op list --------------------------------
 struct FNetPlan {
     int S0 = 0;
-    int n_ops = 0;
+    int n_ops = 0;            // register-level ops (what dump() lists)
     NOp ops[kMaxNOps];
+    int n_kops = 0;           // kernel descriptors: ops with dispatch cases (blocks grouped) + phase sentinels
+    KOp kops[kMaxKOps];
+    int n_relu = 0;           // staged ReLU layers in program order (the producer's list)
+    int relu_aux[kMaxRelu], relu_half[kMaxRelu];
+    int n_blocks = 0;         // residual blocks dispatched as one case
     size_t smem = 0;
     int nst = 0;
     int fused_row_floats = 0;  // floats per image the Gram kernel reads (super-tile sizing)
@@ -944,6 +1102,7 @@ bool conv_supported(int S0, int si, int lo, int hi, int st) {
 struct Translator {
     const std::vector<DevOp> &ops;
     int S0;
+    bool carry;  // carry conv taps / ReLU doublings as per-slot factors instead of applying them
     std::vector<NOp> out;
     bool ok = true;
     // per program slot
@@ -958,7 +1117,8 @@ struct Translator {
     int tm_owner[2] = {-1, -1};
     int slot1_max = 0;  // largest map edge ever stashed in tensor-memory slot 1
 
-    Translator(const std::vector<DevOp> &o, int n_slots, int s0) : ops(o), S0(s0), slot(n_slots) {}
+    Translator(const std::vector<DevOp> &o, int n_slots, int s0, bool carry_)
+        : ops(o), S0(s0), carry(carry_), slot(n_slots) {}
 
     bool reads(const DevOp &o, int s) const { return o.src == s || (o.opcode == CNNGP_OP_ADD && o.dst == s); }
     // is the value now in slot s needed by an op after index k?
@@ -975,10 +1135,19 @@ struct Translator {
         return -1;
     }
     void emit(NOp n) { out.push_back(n); }
+    static NOp blank(int kind, int si, int so) {
+        NOp n{};
+        n.kind = kind; n.si = (short)si; n.so = (short)so; n.scale = 1.f; n.bias = 0.f; n.pre_bias = 0.f; n.aux_scale = 1.f;
+        return n;
+    }
     void affine(int size, float scale, float bias) {
-        NOp n{}; n.kind = size == 1 ? T_AFFINE : N_AFFINE; n.si = n.so = (short)size; n.scale = scale; n.bias = bias;
+        NOp n = blank(size == 1 ? T_AFFINE : N_AFFINE, size, size);
+        n.scale = scale; n.bias = bias;
         emit(n);
     }
+    // the factor a slot may carry: a power-of-two-ish safe range around 1, so that stored values
+    // (pend x true) and the scaled variance maps stay far from the ends of the float32 range
+    static bool pend_ok(double pend) { return pend == pend && pend > 9.5e-7 && pend < 1.05e6; }
 
     void free_tm(int s) {
         if (slot[s].tm >= 0) { tm_owner[slot[s].tm] = -1; slot[s].tm = -1; }
@@ -991,7 +1160,8 @@ struct Translator {
         for (int q = 0; q < 2; ++q) {
             const int t = first ^ q;
             if (tm_owner[t] < 0) {
-                NOp n{}; n.kind = N_STASH; n.si = n.so = (short)slot[s].size; n.slot = (short)t;
+                NOp n = blank(N_STASH, slot[s].size, slot[s].size);
+                n.slot = (short)t;
                 emit(n);
                 tm_owner[t] = s; slot[s].tm = t;
                 if (t == 1 && slot[s].size > slot1_max) slot1_max = slot[s].size;
@@ -1012,7 +1182,8 @@ struct Translator {
             slot[r].in_regs = false;
             if (!needed) { slot[r].valid = false; free_tm(r); }
         }
-        NOp n{}; n.kind = N_UNSTASH; n.si = n.so = (short)slot[s].size; n.slot = (short)slot[s].tm;
+        NOp n = blank(N_UNSTASH, slot[s].size, slot[s].size);
+        n.slot = (short)slot[s].tm;
         emit(n);
         slot[s].in_regs = true;
         if (slot[s].alias) {  // materialise: registers hold pend x true(stash); keep that factor
@@ -1037,14 +1208,13 @@ struct Translator {
                 if (slot[r].alias) return false;  // cannot happen: aliases are never register-resident
                 if (r == o.src && src_live && !stash(o.src)) return false;
                 if (slot[other].tm < 0) return false;
-                if (slot[r].orient != slot[other].orient) {
-                    NOp n{}; n.kind = N_TRANSPOSE; n.si = n.so = (short)slot[r].size;
-                    emit(n);
-                }
-                NOp n{}; n.kind = N_ADD; n.si = n.so = (short)slot[r].size; n.slot = (short)slot[other].tm;
+                if (slot[r].orient != slot[other].orient) emit(blank(N_TRANSPOSE, slot[r].size, slot[r].size));
+                NOp n = blank(N_ADD, slot[r].size, slot[r].size);
+                n.slot = (short)slot[other].tm;
                 // registers (pend_r x true) += pend_r x true(other); the stash holds pend_o x true(stash)
                 n.scale = slot[r].pend / slot[other].pend * (slot[other].alias ? slot[other].a_scale : 1.f);
                 n.bias = slot[other].alias ? slot[r].pend * slot[other].a_bias : 0.f;
+                if (!(n.scale == n.scale) || std::fabs(n.scale) > 1e30f || std::fabs(n.bias) > 1e30f) return false;
                 emit(n);
                 Slot d = slot[r];
                 d.orient = slot[other].orient; d.in_regs = true; d.tm = -1; d.valid = true; d.alias = false;
@@ -1095,28 +1265,44 @@ struct Translator {
             dst.in_regs = true; dst.tm = -1; dst.valid = true;
             switch (o.opcode) {
                 case CNNGP_OP_COPY: break;
-                case CNNGP_OP_SCALE: affine(src.size, o.scale_f, 0.f); break;
+                case CNNGP_OP_SCALE: {
+                    const double np = (double)src.pend / (double)o.scale_f;  // carried: stored stays, the factor moves
+                    if (carry && src.size > 1 && o.scale_f > 0.f && pend_ok(np)) dst.pend = (float)np;
+                    else affine(src.size, o.scale_f, 0.f);
+                    break;
+                }
                 case CNNGP_OP_RELU: {
-                    if (src.pend != 1.f) { affine(src.size, 1.f / src.pend, 0.f); }
                     if (o.Hi != o.Wi || o.Hi != src.size) return false;
-                    NOp n{};
-                    n.si = n.so = (short)src.size;
-                    if (src.size == 1) { n.kind = T_RELU; n.aux = o.aux_off; }
-                    else {
-                        n.kind = N_RELU; n.aux = o.aux_foff; n.half = o.aux_half;
+                    NOp n = blank(src.size == 1 ? T_RELU : N_RELU, src.size, src.size);
+                    if (src.size == 1) {
+                        if (src.pend != 1.f) affine(1, 1.f / src.pend, 0.f);
+                        n.aux = o.aux_off;
+                        dst.pend = 2.f;
+                    } else {
+                        // relu_k(pend * m; sqrt(pend) s) = pend * relu_k(m; s): the layer's per-image s maps
+                        // carry sqrt(pend) (applied once per image by cnngp_variances)
+                        float pend = src.pend;
+                        if (!carry || !pend_ok(pend)) {
+                            if (pend != 1.f) affine(src.size, 1.f / pend, 0.f);
+                            pend = 1.f;
+                        }
+                        n.aux = o.aux_foff; n.half = o.aux_half;
+                        n.aux_scale = (float)std::sqrt((double)pend);
                         mutable_ops[k].aux_t = src.orient;
+                        mutable_ops[k].aux_scale = n.aux_scale;
+                        dst.pend = 2.f * pend;  // the kernel's ReLU output is doubled
                     }
                     emit(n);
-                    dst.pend = 2.f;
                     break;
                 }
                 case CNNGP_OP_CONV: {
                     if (o.dil != 1 || o.Hi != o.Wi || o.Ho != o.Wo || o.Hi != src.size) return false;
                     const int lo = o.pad - o.t0, hi = o.ke - 1 - o.pad;
                     if (lo < 0 || hi < 0) return false;
-                    const float scale = o.scale_f / src.pend;
-                    NOp n{};
-                    n.si = (short)src.size; n.so = (short)o.Ho; n.scale = scale; n.bias = o.bias_f;
+                    NOp n = blank(N_CONV, src.size, o.Ho);
+                    // true_out = scale_f * box(true_in) + bias_f; stored_in = pend * true_in
+                    const double np = (double)src.pend / (double)o.scale_f;  // carried: stored_out = box(stored_in) + bias_f * np
+                    bool carried = false;
                     if (src.size == 1) {
                         if (lo != 0 || hi != 0 || o.Ho != 1) return false;
                         n.kind = T_AFFINE;
@@ -1124,16 +1310,29 @@ struct Translator {
                         n.kind = N_DENSE;
                     } else if (lo == 0 && hi == 0 && o.stride == 1) {
                         n.kind = N_AFFINE;
+                        if (carry && o.scale_f > 0.f && pend_ok(np)) {
+                            carried = true;
+                            n.scale = 1.f; n.bias = (float)(o.bias_d * np);
+                        }
                     } else {
                         if (o.stride != 1 && o.stride != 2) return false;
                         if (!conv_supported(S0, src.size, lo, hi, o.stride)) return false;
                         if (o.Ho != (o.stride == 1 ? src.size : src.size / 2)) return false;
-                        n.kind = N_CONV; n.lo = (short)lo; n.hi = (short)hi; n.st = (short)o.stride;
+                        n.lo = (short)lo; n.hi = (short)hi; n.st = (short)o.stride;
                         dst.orient = src.orient ^ 1;
+                        if (carry && o.scale_f > 0.f && pend_ok(np)) {
+                            carried = true;
+                            n.scale = 1.f;
+                            const float b = (float)(o.bias_d * np);
+                            if (o.stride == 1) { n.pre_bias = b; n.bias = 0.f; }  // rides on the second sliding sum
+                            else { n.pre_bias = 0.f; n.bias = b; }                // strided: explicit pass when non-zero
+                        }
                     }
-                    emit(n);
+                    if (!carried) { n.scale = o.scale_f / src.pend; n.bias = o.bias_f; n.pre_bias = 0.f; }
+                    if (n.kind == N_AFFINE && n.scale == 1.f && n.bias == 0.f) { /* nothing to do */ }
+                    else emit(n);
                     dst.size = o.Ho;
-                    dst.pend = 1.f;
+                    dst.pend = carried ? (float)np : 1.f;
                     break;
                 }
                 default: return false;
@@ -1150,7 +1349,120 @@ struct Translator {
 
 template <int S0, int NW, int NST, int NSPLIT>
 constexpr size_t fnet_smem() {
-    return (size_t)NST * NGeo<NW>::kImgs * S0 * S0 * 4 / (NSPLIT / 2) + (size_t)NW * S0 * (S0 + 1) * 8 + (size_t)3 * NST * 8 + 16;
+    return (size_t)NST * NGeo<NW>::kImgs * S0 * S0 * 4 / (NSPLIT / 2) + (size_t)NW * S0 * (S0 + 1) * 8 + (size_t)kMaxKOps * 16 +
+           (size_t)3 * NST * 8 + 16;
+}
+
+const char *kNames[] = {"CONV", "AFFINE", "RELU", "STASH", "UNSTASH", "ADD", "TRANSPOSE", "DENSE", "T_RELU", "T_AFFINE"};
+
+// dispatch case of one register-level op in phase A (full = false: folded map held in M[0]) or B
+int case_of(const NOp &n, int S0, bool phase_b) {
+    const int sc = n.si == S0 ? 0 : (n.si == S0 / 2 ? 1 : 2);  // size class of the op's input
+    if (!phase_b) {
+        switch (n.kind) {
+            case N_CONV: {
+                const int v = n.st == 1 ? (n.lo == 1 && n.hi == 1 ? 0 : n.lo == 1 && n.hi == 2 ? 1 : n.lo == 2 ? 2 : 3)
+                                        : (n.lo == 1 ? 4 : 5);
+                return A_CONV + (sc == 0 ? v : sc == 1 ? (n.st == 1 ? 6 : (n.lo == 1 ? 7 : 8)) : 9);
+            }
+            case N_AFFINE: return A_AFFINE + sc;
+            case N_TRANSPOSE: return A_TRANSPOSE + sc;
+            case N_STASH: return A_STASH + sc;
+            case N_UNSTASH: return A_UNSTASH + sc;
+            case N_ADD: return A_ADD + sc;
+            case N_DENSE: return A_DENSE + sc;
+            default: return A_RELU + sc;
+        }
+    }
+    const int q = sc - 1;  // 0: S0/2, 1: S0/4
+    switch (n.kind) {
+        case N_CONV: return B_CONV + (sc == 1 ? (n.st == 1 ? 0 : (n.lo == 1 ? 1 : 2)) : 3);
+        case N_AFFINE: return B_AFFINE + q;
+        case N_TRANSPOSE: return B_TRANSPOSE + q;
+        case N_STASH: return B_STASH + q;
+        case N_UNSTASH: return B_UNSTASH + q;
+        case N_ADD: return B_ADD + q;
+        case N_DENSE: return B_DENSE + q;
+        default: return B_RELU + q;
+    }
+}
+
+KOp make_kop(const NOp &n, int code) {
+    KOp k;
+    k.code = code | ((n.slot & 3) << 8) | ((n.half & 0xffff) << 16);
+    k.scale = n.scale; k.bias = n.bias;
+    k.aux = n.aux;
+    if (n.kind == N_CONV) memcpy(&k.aux, &n.pre_bias, 4);
+    return k;
+}
+
+// ops[i..] starts an identity residual block  STASH RELU CONV(3x3, s1) RELU CONV(3x3, s1) ADD  on one map size
+bool is_idblock(const NOp *o, int n_left) {
+    if (n_left < 6) return false;
+    const int s = o[0].si;
+    auto conv33 = [&](const NOp &c) { return c.kind == N_CONV && c.si == s && c.so == s && c.st == 1 && c.lo == 1 && c.hi == 1; };
+    return o[0].kind == N_STASH && o[1].kind == N_RELU && o[1].si == s && conv33(o[2]) && o[3].kind == N_RELU && o[3].si == s &&
+           conv33(o[4]) && o[5].kind == N_ADD && o[5].si == s && o[5].slot == o[0].slot;
+}
+// STASH CONV(4x4 "same") RELU TRANSPOSE ADD at full size (mnist_paper_residual_cnn_gp)
+bool is_resblock(const NOp *o, int n_left, int S0) {
+    if (n_left < 5) return false;
+    return o[0].kind == N_STASH && o[0].si == S0 && o[1].kind == N_CONV && o[1].si == S0 && o[1].so == S0 && o[1].st == 1 &&
+           o[1].lo == 1 && o[1].hi == 2 && o[2].kind == N_RELU && o[2].si == S0 && o[3].kind == N_TRANSPOSE && o[3].si == S0 &&
+           o[4].kind == N_ADD && o[4].si == S0 && o[4].slot == o[0].slot;
+}
+
+// register-level ops -> kernel descriptors: phase split, block grouping, sentinels, producer list
+bool build_kops(FNetPlan *fp, bool blocks) {
+    const int S0 = fp->S0, n = fp->n_ops;
+    int first_tail = n;
+    for (int k = 0; k < n; ++k)
+        if (fp->ops[k].kind == T_RELU || fp->ops[k].kind == T_AFFINE) { first_tail = k; break; }
+    for (int k = first_tail; k < n; ++k)
+        if (fp->ops[k].kind != T_RELU && fp->ops[k].kind != T_AFFINE) return false;  // map ops after the pooling: not in the set
+    int end_a = 0;  // one past the last op that works on a full-size map
+    for (int k = 0; k < first_tail; ++k)
+        if (fp->ops[k].si == S0) end_a = k + 1;
+    int nk = 0;
+    auto push = [&](KOp k) { if (nk < kMaxKOps) fp->kops[nk] = k; ++nk; };
+    KOp sentinel{};
+    sentinel.scale = 1.f;
+    for (int k = 0; k < end_a;) {
+        const NOp *o = fp->ops + k;
+        int len = 1, code = case_of(*o, S0, false);
+        if (blocks && o->si == S0 && is_idblock(o, end_a - k)) { len = 6; code = A_IDBLOCK; }
+        else if (blocks && is_resblock(o, end_a - k, S0)) { len = 5; code = A_RESBLOCK; }
+        if (len > 1) ++fp->n_blocks;
+        push(make_kop(o[0], code));
+        for (int q = 1; q < len; ++q) push(make_kop(o[q], case_of(o[q], S0, false)));
+        k += len;
+    }
+    sentinel.code = A_END; push(sentinel);
+    for (int k = end_a; k < first_tail;) {
+        const NOp *o = fp->ops + k;
+        if (o->si == S0 || o->si == 1) return false;
+        int len = 1, code = case_of(*o, S0, true);
+        if (blocks && is_idblock(o, first_tail - k)) { len = 6; code = B_IDBLOCK + (o->si == S0 / 2 ? 0 : 1); }
+        if (len > 1) ++fp->n_blocks;
+        push(make_kop(o[0], code));
+        for (int q = 1; q < len; ++q) push(make_kop(o[q], case_of(o[q], S0, true)));
+        k += len;
+    }
+    sentinel.code = B_END; push(sentinel);
+    for (int k = first_tail; k < n; ++k) push(make_kop(fp->ops[k], fp->ops[k].kind == T_RELU ? T_CASE_RELU : T_CASE_AFFINE));
+    sentinel.code = T_END; push(sentinel);
+    push(sentinel);  // the one-ahead fetch of the last op reads one descriptor further
+    if (nk > kMaxKOps) return false;
+    fp->n_kops = nk;
+    fp->n_relu = 0;
+    for (int k = 0; k < n; ++k) {
+        if (fp->ops[k].kind != N_RELU) continue;
+        if (fp->n_relu >= kMaxRelu) return false;
+        fp->relu_aux[fp->n_relu] = fp->ops[k].aux;
+        fp->relu_half[fp->n_relu] = fp->ops[k].half | (fp->ops[k].si == S0 ? (1 << 30) : 0);
+        ++fp->n_relu;
+    }
+    return true;
 }
 
 }  // namespace
@@ -1162,7 +1474,9 @@ FNetPlan *fnet_plan_create(const Plan *plan_const) {
     if (plan->n_slots > 2) return nullptr;
     const int S0 = plan->H;
     std::vector<DevOp> saved = plan->ops;
-    Translator tr(saved, plan->n_slots, S0);
+    // measurement aids: CNNGP_FNET_NOCARRY=1 applies every tap explicitly (one FMA pass per conv),
+    // CNNGP_FNET_NOBLOCKS=1 dispatches every op on its own
+    Translator tr(saved, plan->n_slots, S0, getenv("CNNGP_FNET_NOCARRY") == nullptr);
     if (!tr.run(plan->ops, plan->final_slot)) {
         plan->ops = saved;
         return nullptr;
@@ -1170,31 +1484,14 @@ FNetPlan *fnet_plan_create(const Plan *plan_const) {
     // the scalar tail needs the pooled value: exactly one N_DENSE, and nothing map-shaped after it
     int n_dense = 0;
     for (const NOp &n : tr.out) n_dense += n.kind == N_DENSE;
-    if (n_dense != 1) { plan->ops = saved; return nullptr; }
     FNetPlan *fp = new FNetPlan();
     fp->S0 = S0;
     fp->n_ops = (int)tr.out.size();
-    for (int k = 0; k < fp->n_ops; ++k) {
-        NOp n = tr.out[k];
-        const int sc = n.si == S0 ? 0 : (n.si == S0 / 2 ? 1 : 2);  // size class of the op's input
-        switch (n.kind) {
-            case N_CONV: {
-                const int v = n.st == 1 ? (n.lo == 1 && n.hi == 1 ? 0 : n.lo == 1 && n.hi == 2 ? 1 : n.lo == 2 ? 2 : 3)
-                                        : (n.lo == 1 ? 4 : 5);
-                n.code = C_CONV + (sc == 0 ? v : sc == 1 ? (n.st == 1 ? 6 : (n.lo == 1 ? 7 : 8)) : 9);
-                break;
-            }
-            case N_AFFINE: n.code = C_AFFINE + sc; break;
-            case N_TRANSPOSE: n.code = C_TRANSPOSE + sc; break;
-            case N_STASH: n.code = C_STASH + sc; break;
-            case N_UNSTASH: n.code = C_UNSTASH + sc; break;
-            case N_ADD: n.code = C_ADD + sc; break;
-            case N_DENSE: n.code = C_DENSE + sc; break;
-            case N_RELU: n.code = C_RELU + sc; break;
-            case T_AFFINE: n.code = C_TAFFINE; break;
-            default: n.code = C_TRELU; break;
-        }
-        fp->ops[k] = n;
+    for (int k = 0; k < fp->n_ops; ++k) fp->ops[k] = tr.out[k];
+    if (n_dense != 1 || !build_kops(fp, getenv("CNNGP_FNET_NOBLOCKS") == nullptr)) {
+        delete fp;
+        plan->ops = saved;
+        return nullptr;
     }
     // twelve consumer warps when the second tensor-memory slot only ever holds folded maps of at most
     // half the edge (3 warps share a 512-column lane quadrant: 3 x 5 S0 columns)
@@ -1213,11 +1510,10 @@ void fnet_plan_destroy(FNetPlan *fp) { delete fp; }
 
 std::string fnet_plan_describe(const FNetPlan *fp) {
     std::string t = "fused_net S0=" + std::to_string(fp->S0) + " warps=" + std::to_string(fp->nw) + " stages=" +
-                    std::to_string(fp->nst) + " :";
-    static const char *names[] = {"CONV", "AFFINE", "RELU", "STASH", "UNSTASH", "ADD", "TRANSPOSE", "DENSE", "T_RELU", "T_AFFINE"};
+                    std::to_string(fp->nst) + " blocks=" + std::to_string(fp->n_blocks) + " :";
     for (int k = 0; k < fp->n_ops; ++k) {
         const NOp &o = fp->ops[k];
-        t += std::string(" ") + names[o.kind] + "(" + std::to_string(o.si);
+        t += std::string(" ") + kNames[o.kind] + "(" + std::to_string(o.si);
         if (o.kind == N_CONV) t += "," + std::to_string(o.lo) + "," + std::to_string(o.hi) + ",s" + std::to_string(o.st);
         if (o.kind == N_STASH || o.kind == N_UNSTASH || o.kind == N_ADD) t += ",t" + std::to_string(o.slot);
         t += ")";
@@ -1232,14 +1528,14 @@ static std::atomic<unsigned> g_fnet_next_ctr{0};
 
 // one line per register-level op, every field, floats with nine significant digits (exact for float32)
 std::string fnet_plan_dump(const FNetPlan *fp) {
-    static const char *names[] = {"CONV", "AFFINE", "RELU", "STASH", "UNSTASH", "ADD", "TRANSPOSE", "DENSE", "T_RELU", "T_AFFINE"};
     std::string t = "fused_net S0=" + std::to_string(fp->S0) + "\n";
-    char line[256];
+    char line[320];
     for (int k = 0; k < fp->n_ops; ++k) {
         const NOp &o = fp->ops[k];
-        snprintf(line, sizeof line, "%s si=%d so=%d lo=%d hi=%d st=%d slot=%d scale=%.9g bias=%.9g aux=%d half=%d\n",
-                 names[o.kind], (int)o.si, (int)o.so, (int)o.lo, (int)o.hi, (int)o.st, (int)o.slot, (double)o.scale,
-                 (double)o.bias, o.aux, o.half);
+        snprintf(line, sizeof line,
+                 "%s si=%d so=%d lo=%d hi=%d st=%d slot=%d scale=%.9g bias=%.9g pre_bias=%.9g aux_scale=%.9g aux=%d half=%d\n",
+                 kNames[o.kind], (int)o.si, (int)o.so, (int)o.lo, (int)o.hi, (int)o.st, (int)o.slot, (double)o.scale,
+                 (double)o.bias, (double)o.pre_bias, (double)o.aux_scale, o.aux, o.half);
         t += line;
     }
     return t;
@@ -1251,10 +1547,13 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
     const FNetPlan *fp = plan->fnet;
     if (!fp) { set_error("fused-net kernel: unsupported call"); return 4; }
     if (N1 > 2000000000LL || N2 > 2000000000LL) { set_error("fused-net kernel: too many images"); return 8; }
-    NParams p;  // ~6 KB, passed by value at launch
+    NParams p;  // ~4.5 KB, passed by value at launch
     memset(&p, 0, sizeof p);
-    memcpy(p.ops, fp->ops, sizeof(NOp) * fp->n_ops);
-    p.n_ops = fp->n_ops;
+    memcpy(p.ops, fp->kops, sizeof(KOp) * fp->n_kops);
+    p.n_ops = fp->n_kops;
+    memcpy(p.relu_aux, fp->relu_aux, sizeof(int) * fp->n_relu);
+    memcpy(p.relu_half, fp->relu_half, sizeof(int) * fp->n_relu);
+    p.n_relu = fp->n_relu;
     p.x = (const float *)d_x; p.z = (const float *)d_z;
     p.aux_x = (const float *)d_aux_x; p.aux_z = (const float *)d_aux_z;
     p.aux_stride = plan->aux_elems; p.aux_f_off = plan->aux_f_off;

@@ -455,14 +455,16 @@ def _simulate_translation(plan, xy0, relu_vars, N1, N2):
                 tot = R.sum(axis=(1, 2)) * f["scale"] + f["bias"]
             continue
         if kind == "CONV":
-            R = _box(R, f["lo"], f["hi"], f["st"]) * f["scale"] + f["bias"]
+            # the second sliding sum carries pre_bias (the folded conv bias); scale / bias are the explicit pass
+            R = (_box(R, f["lo"], f["hi"], f["st"]) + f["pre_bias"]) * f["scale"] + f["bias"]
             assert R.shape[1] == f["so"]
         elif kind == "AFFINE":
             R = R * f["scale"] + f["bias"]
         elif kind == "RELU":
             xx, yy = relu_vars[foff.index(f["aux"])]
             assert xx.shape[1] == f["si"] and f["half"] == (f["si"] ** 2 + 1) // 2
-            R = _relu2(R, xx, yy, N1, N2)
+            a2 = float(f["aux_scale"]) ** 2  # the factor the host puts on this layer's s maps (carried conv taps)
+            R = _relu2(R, xx * a2, yy * a2, N1, N2)
         elif kind == "STASH":
             T[f["slot"]] = R.copy()
         elif kind == "UNSTASH":
