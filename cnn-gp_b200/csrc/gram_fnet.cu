@@ -109,7 +109,6 @@ struct NParams {
     int relu_aux[kMaxRelu];   // producer's list of staged ReLU layers, program order: offset in the fused section
     int relu_half[kMaxRelu];  //   pixels in the first row of the pair; bit 30: full-size layer (NSPLIT bands)
     int n_ops, n_relu;
-    int k_phase_b;            // index of the first phase-B descriptor (the warp-specialised kernel's light warps start there)
     const float *x, *z;
     const float *aux_x, *aux_z;
     long long aux_stride;
@@ -1067,610 +1066,6 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
     }
 }
 
-// ---- two folded arrays at once (the light warps of the warp-specialised kernel) -----------------
-template <int NA, int S0, int SI, int SO, int LO, int HI, int ST>
-__device__ __forceinline__ void conv_op_f2(u64 (&a)[NA], u64 (&b)[NA], u64 *tile_a, u64 *tile_b, int lane, float pre_bias,
-                                           float scale, float bias) {
-    static_assert(ST == 1 ? SI == SO : SI == 2 * SO, "conv geometry");
-    static_assert(2 * SI <= S0 + 1, "both halves must fit a tile row");
-    if (ST == 1) { box_s1<NA, SI, LO, HI, false>(a, 0ull); box_s1<NA, SI, LO, HI, false>(b, 0ull); }
-    else { box_s2<NA, SI, SO, LO, HI>(a); box_s2<NA, SI, SO, LO, HI>(b); }
-    tstore_f<NA, S0, SO, SI>(tile_a, a, lane);
-    tstore_f<NA, S0, SO, SI>(tile_b, b, lane);
-    __syncwarp();
-    tload_f<NA, S0, SI, SO>(tile_a, a, lane);
-    tload_f<NA, S0, SI, SO>(tile_b, b, lane);
-    __syncwarp();
-    const u64 PB = pk(pre_bias, pre_bias);
-    if (ST == 1) { box_s1<NA, SI, LO, HI, true>(a, PB); box_s1<NA, SI, LO, HI, true>(b, PB); }
-    else { box_s2<NA, SI, SO, LO, HI>(a); box_s2<NA, SI, SO, LO, HI>(b); }
-    if (scale != 1.f || bias != 0.f) { affine_arr<NA, SO>(a, scale, bias); affine_arr<NA, SO>(b, scale, bias); }
-}
-
-// ReLU on the folded maps of two 2 x 2 blocks that share the j-pair: a0 / a1 are the i-pairs' staged maps
-template <int NA, int S>
-__device__ __forceinline__ void relu_rows_f2(u64 (&f0)[NA], u64 (&f1)[NA], const float4 *a0, const float4 *a1, const float4 *bj, int lane) {
-    const u64 C5 = pk(FNET_C5, FNET_C5), C4 = pk(FNET_C4, FNET_C4), C3 = pk(FNET_C3, FNET_C3),
-              C2 = pk(FNET_C2, FNET_C2), C1 = pk(FNET_C1, FNET_C1), C0 = pk(FNET_C0, FNET_C0), ONE = pk(1.f, 1.f);
-    const bool sw = lane >= 16;
-#pragma unroll
-    for (int r = 0; r < S; ++r) {
-        const float4 B = bj[r * S];
-        const u64 SB = pk(sw ? B.y : B.x, sw ? B.x : B.y);
-        const u64 RB = pk(sw ? B.w : B.z, sw ? B.z : B.w);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const float4 A = h ? a1[r * S] : a0[r * S];
-            const u64 SA = pk(A.x, A.y), RA = pk(A.z, A.w);
-            float c0, c1;
-            upk(h ? f1[r] : f0[r], c0, c1);
-            const u64 NC = pk(neg_abs(c0), neg_abs(c1));
-            const u64 D = fma2(SA, SB, NC);
-            const u64 E = fma2(NC, mul2(RA, RB), ONE);
-            float e0, e1;
-            upk(E, e0, e1);
-            const u64 W = mul2(D, pk(sqrt_approx(fabsf(e0)), sqrt_approx(fabsf(e1))));
-            u64 H = fma2(C5, E, C4);
-            H = fma2(H, E, C3);
-            H = fma2(H, E, C2);
-            H = fma2(H, E, C1);
-            H = fma2(H, E, C0);
-            const u64 res = fma2(W, H, pk(fmaxf(c0, 0.f), fmaxf(c1, 0.f)));
-            if (h) f1[r] = res; else f0[r] = res;
-        }
-    }
-}
-
-// ================================================================================================
-// Warp-specialised variant for programs with a folded phase (the ResNet GPs): eight HEAVY warps
-// (two per SM sub-partition, 192 registers) run phase A -- the full-size layers -- of tile n + 1
-// while four LIGHT warps (one per sub-partition, 104 registers) run phase B and the scalar tail of
-// tile n.  Phase B is a chain of short, latency-bound ops (14 or 7 register rows per op); run by the
-// warp that also owns the full-size maps it left the FP32 pipe idle for a third of every tile
-// (measured on mnist_as_tf: 9.3 ns per pair in stage 1, 3.9 ns in the 14 x 14 and 7 x 7 stages).  Here
-// it fills the issue slots the heavy warps leave free, and each light warp works on the folded maps
-// of TWO heavy warps at once (the two 2 x 2 blocks of a tile that share a j-pair): twice the
-// independent work per op.
-//
-// Hand-off: a heavy warp ends phase A by storing its folded map into tensor memory (region H[b],
-// b = tile parity) and arriving on an mbarrier; the light warp of the same lane quadrant loads it.
-// Tensor-memory window of heavy warp w (quadrant w & 3, columns (w >> 2) * 8 S0):
-//   [0, 4 S0)              slot 0: the full-size skip map of phase A (two arrays of 2 S0 columns)
-//   [4 S0 + 2 S0 b, + S0)  H[b]:  hand-off, then phase-B slot 0 of tile parity b
-//   [.. + S0, + S0)        B1[b]: slot 1 of tile parity b: the folded skip map a strided projection
-//                                 block stashes in phase A and adds in phase B
-// Staging: ring A (images, full-size ReLU bands) feeds the heavy warps, ring B (folded ReLU layers)
-// the light warps; one producer warp each.  Producer A draws the tile indices and passes them to
-// producer B through a small FIFO in shared memory.
-template <int S0, int NSPLIT, int NSTA, int NSTB>
-struct WsGeo {
-    static constexpr int kHeavy = 8, kLight = 4;
-    static constexpr int kTileI = 4, kTileJ = 8, kImgs = 12, kPairs = 6;
-    static constexpr int kThreads = 512;
-    static constexpr int P0 = S0 * S0, SF = S0 / 2, PITCH = S0 + 1;
-    static constexpr int IMG_PARTS = NSPLIT / 2, IBAND = P0 / IMG_PARTS, BAND = P0 / NSPLIT;
-    static constexpr int STAGE_A = kImgs * IBAND * 4;           // == kPairs * BAND * 16
-    static constexpr int STAGE_B = kPairs * (SF * SF) * 16;     // a folded layer: SF^2 float4 per pair (both halves)
-    static constexpr int TILE_H = S0 * PITCH * 8, TILE_L = SF * PITCH * 8;
-    static constexpr int kFifo = 16;
-    static constexpr size_t smem = (size_t)NSTA * STAGE_A + (size_t)NSTB * STAGE_B + (size_t)kHeavy * TILE_H +
-                                   (size_t)kLight * 2 * TILE_L + (size_t)kMaxKOps * 16 +
-                                   (size_t)(2 * NSTA + 2 * NSTB + 4 * kHeavy) * 8 + (size_t)(NSTA + NSTB + kFifo) * 8 + 32;
-};
-
-// bounded wait: a protocol error must end in a trap, not in a hung GPU
-__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
-    uint32_t ok = 0;
-    const uint32_t addr = smem_u32(bar);
-    for (int spin = 0; spin < 4000; ++spin) {  // each try suspends up to 10 ms
-        asm volatile(
-            "{\n .reg .pred p;\n"
-            " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-            " selp.u32 %0, 1, 0, p;\n}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity), "r"(0x989680u)
-            : "memory");
-        if (ok) return;
-    }
-    __trap();
-}
-
-template <int S0, int NSPLIT, int NSTA, int NSTB>
-__global__ void __launch_bounds__(512, 1) fnet_ws_kernel(const __grid_constant__ NParams p) {
-    using G = WsGeo<S0, NSPLIT, NSTA, NSTB>;
-    constexpr int kHeavy = G::kHeavy, kLight = G::kLight, kTileI = G::kTileI, kTileJ = G::kTileJ, kImgs = G::kImgs, kPairs = G::kPairs;
-    constexpr int P0 = G::P0, SF = G::SF, PITCH = G::PITCH, IMG_PARTS = G::IMG_PARTS, IBAND = G::IBAND, BAND = G::BAND;
-    constexpr int STAGE_A = G::STAGE_A, STAGE_B = G::STAGE_B;
-    static_assert(kPairs * BAND * 16 == STAGE_A, "stage geometry");
-    static_assert(2 * 8 * S0 <= kTmemCols, "tensor-memory budget");
-    constexpr int TM_HEAVY = 8 * S0, TM_A0 = 2 * S0, TM_PAR = 4 * S0;  // window, array stride of slot 0, first parity region
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *stageA = smem_raw;
-    unsigned char *stageB = stageA + (size_t)NSTA * STAGE_A;
-    u64 *tilesH = reinterpret_cast<u64 *>(stageB + (size_t)NSTB * STAGE_B);
-    u64 *tilesL = tilesH + kHeavy * S0 * PITCH;
-    int4 *ops_s = reinterpret_cast<int4 *>(tilesL + kLight * 2 * SF * PITCH);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(ops_s + kMaxKOps);
-    uint64_t *fullA = bars, *emptyA = fullA + NSTA, *fullB = emptyA + NSTA, *emptyB = fullB + NSTB;
-    uint64_t *hand = emptyB + NSTB;          // [2][kHeavy]: the folded map of heavy warp w, tile parity b, is in tensor memory
-    uint64_t *handE = hand + 2 * kHeavy;     // [2][kHeavy]: the light warp is done with parity b's regions of heavy warp w
-    long long *stage_tileA = reinterpret_cast<long long *>(handE + 2 * kHeavy);
-    long long *stage_tileB = stage_tileA + NSTA;
-    long long *fifo = stage_tileB + NSTB;    // tile indices, producer A -> producer B
-    volatile int *fifo_n = reinterpret_cast<volatile int *>(fifo + G::kFifo);
-    uint32_t *tmem_word = reinterpret_cast<uint32_t *>(const_cast<int *>(fifo_n) + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], kHeavy); }
-        for (int s = 0; s < NSTB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], kLight); }
-        for (int s = 0; s < 2 * kHeavy; ++s) { mbar_init(&hand[s], 1); mbar_init(&handE[s], 1); }
-        *fifo_n = 0;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int q = threadIdx.x; q < p.n_ops; q += blockDim.x) {
-        const KOp o = p.ops[q];
-        ops_s[q] = make_int4(o.code, __float_as_int(o.scale), __float_as_int(o.bias), o.aux);
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_word)),
-                     "r"(kTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_word;
-
-    const int per_st = p.sti * p.stj;
-    auto decode = [&](long long t, int &ib, int &jb) -> bool {
-        const int st = (int)(t / per_st), w_in = (int)(t - (long long)st * per_st);
-        int si, sj;
-        if (p.symmetric) {
-            int r = 0, rem = st;
-            while (rem >= p.nst - r) { rem -= p.nst - r; ++r; }
-            si = r; sj = r + rem;
-        } else {
-            si = st / p.nst_j; sj = st - si * p.nst_j;
-        }
-        ib = si * p.sti + w_in / p.stj;
-        jb = sj * p.stj + w_in % p.stj;
-        if (ib >= p.nbi || jb >= p.nbj) return false;
-        if (p.symmetric && jb * kTileJ + (kTileJ - 1) < ib * kTileI) return false;
-        return true;
-    };
-    auto f_scale = [](const int4 &o) { return __int_as_float(o.y); };
-    auto f_bias = [](const int4 &o) { return __int_as_float(o.z); };
-    auto f_pre = [](const int4 &o) { return __int_as_float(o.w); };
-    auto f_slot = [](const int4 &o) { return (o.x >> 8) & 3; };
-    auto f_half = [](const int4 &o) { return (int)((unsigned)o.x >> 16); };
-
-    if (warp >= kHeavy + kLight) {
-        // =========================== producers ==================================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        const int role = warp - (kHeavy + kLight);
-        if (role > 1) return;
-        const int last_pi = (p.N1 - 1) >> 1, last_pj = (p.N2 - 1) >> 1;
-        unsigned l = 0;
-        long long t = 0;
-        const int vs = lane >> 1, vh = lane & 1;  // pair of the tile, image row of the pair
-        auto var_base = [&](int i_base, int j_base) -> const float * {
-            if (lane >= 2 * kPairs) return nullptr;
-            const long long pr = vs < kTileI / 2 ? min((i_base >> 1) + vs, last_pi) : min((j_base >> 1) + vs - kTileI / 2, last_pj);
-            return (vs < kTileI / 2 ? p.aux_x : p.aux_z) + (2 * pr + vh) * p.aux_stride + p.aux_f_off;
-        };
-        if (role == 0) {
-            // ---- producer A: tile hand-out, images, full-size ReLU bands -> heavy warps
-            auto acquire = [&](unsigned bytes) -> unsigned char * {
-                const unsigned buf = l % NSTA;
-                if (lane == 0) {
-                    if (l >= NSTA) mbar_wait_relaxed(&emptyA[buf], ((l / NSTA) - 1) & 1);
-                    stage_tileA[buf] = t;
-                    mbar_arrive_expect_tx(&fullA[buf], bytes);
-                }
-                __syncwarp();
-                return stageA + (size_t)buf * STAGE_A;
-            };
-            const bool dyn = p.tile_ctr != nullptr;
-            auto next_index = [&](long long stat) -> long long {
-                if (!dyn) return stat;
-                long long v = 0;
-                if (lane == 0) v = (long long)atomicAdd(p.tile_ctr, 1ull);
-                return __shfl_sync(0xffffffffu, v, 0);
-            };
-            int n_pub = 0;
-            auto publish = [&](long long tt) {  // to producer B (it lags by at most a few tiles: see the hand-off depth)
-                if (lane == 0) {
-                    fifo[n_pub % G::kFifo] = tt;
-                    __threadfence_block();
-                    *fifo_n = n_pub + 1;
-                }
-                ++n_pub;
-            };
-            long long t_raw = next_index((long long)blockIdx.x);
-            for (;;) {
-                int ib, jb;
-                t = t_raw;
-                while (t < p.n_tiles && !decode(t, ib, jb)) t = next_index(t + gridDim.x);
-                if (t >= p.n_tiles) break;
-                t_raw = next_index(t + gridDim.x);
-                publish(t);
-                const int i_base = ib * kTileI, j_base = jb * kTileJ;
-                const float *img = nullptr;
-                if (lane < kImgs)
-                    img = lane < kTileI ? p.x + (long long)min(i_base + lane, p.N1 - 1) * p.C * P0
-                                        : p.z + (long long)min(j_base + lane - kTileI, p.N2 - 1) * p.C * P0;
-                const float *var = var_base(i_base, j_base);
-                for (int c = 0; c < p.C; ++c) {
-                    for (int ip = 0; ip < IMG_PARTS; ++ip) {
-                        float *dst = reinterpret_cast<float *>(acquire(kImgs * IBAND * 4));
-                        if (lane < kImgs) bulk_g2s(dst + lane * IBAND, img + (long long)c * P0 + ip * IBAND, IBAND * 4, &fullA[l % NSTA]);
-                        ++l;
-                    }
-                }
-                for (int k = 0; k < p.n_relu; ++k) {
-                    if (!(p.relu_half[k] >> 30)) continue;  // folded layers belong to ring B
-                    const int off = p.relu_aux[k];
-                    for (int part = 0; part < NSPLIT; ++part) {
-                        float4 *dst = reinterpret_cast<float4 *>(acquire((unsigned)(kPairs * BAND * 16)));
-                        if (lane < 2 * kPairs && vh == part / (NSPLIT / 2))
-                            bulk_g2s(dst + vs * BAND, var + off + (part % (NSPLIT / 2)) * BAND * 4, BAND * 16, &fullA[l % NSTA]);
-                        ++l;
-                    }
-                }
-            }
-            t = -1;
-            publish(-1);
-            acquire(0);
-        } else {
-            // ---- producer B: folded ReLU layers -> light warps, tile order from the FIFO
-            auto acquire = [&](unsigned bytes) -> unsigned char * {
-                const unsigned buf = l % NSTB;
-                if (lane == 0) {
-                    if (l >= NSTB) mbar_wait_relaxed(&emptyB[buf], ((l / NSTB) - 1) & 1);
-                    stage_tileB[buf] = t;
-                    mbar_arrive_expect_tx(&fullB[buf], bytes);
-                }
-                __syncwarp();
-                return stageB + (size_t)buf * STAGE_B;
-            };
-            for (int n_got = 0;; ++n_got) {
-                long long tt = 0;
-                if (lane == 0) {
-                    while (*fifo_n <= n_got) __nanosleep(100);
-                    __threadfence_block();
-                    tt = fifo[n_got % G::kFifo];
-                }
-                t = __shfl_sync(0xffffffffu, tt, 0);
-                if (t < 0) break;
-                int ib, jb;
-                decode(t, ib, jb);
-                const float *var = var_base(ib * kTileI, jb * kTileJ);
-                for (int k = 0; k < p.n_relu; ++k) {
-                    if (p.relu_half[k] >> 30) continue;
-                    const int off = p.relu_aux[k], half = p.relu_half[k] & 0xffff;
-                    float4 *dst = reinterpret_cast<float4 *>(acquire((unsigned)(kPairs * half * 32)));
-                    if (lane < 2 * kPairs) bulk_g2s(dst + vs * 2 * half + vh * half, var + off, half * 16, &fullB[l % NSTB]);
-                    ++l;
-                }
-            }
-            t = -1;
-            acquire(0);
-        }
-        return;
-    }
-
-    if (warp < kHeavy) {
-        // =========================== heavy warps: phase A =======================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
-        const int wi = warp / (kHeavy / 2), wj = warp % (kHeavy / 2);
-        u64 *tile = tilesH + warp * S0 * PITCH;
-        const uint32_t tm_warp = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TM_HEAVY);
-        unsigned stage_l = 0;
-        for (unsigned n_tile = 0;; ++n_tile) {
-            mbar_wait_wd(&fullA[stage_l % NSTA], (stage_l / NSTA) & 1);
-            const long long t = stage_tileA[stage_l % NSTA];
-            if (t < 0) break;
-            const unsigned b = n_tile & 1;
-            // parity b's regions of this warp's window are free again once the light warp has finished tile n - 2
-            if (n_tile >= 2) mbar_wait_wd(&handE[b * kHeavy + warp], ((n_tile >> 1) - 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tm_par = tm_warp + TM_PAR + b * 2 * S0;  // H[b]; B1[b] follows at + S0
-
-            u64 M[2][S0];
-            {   // init, kernels.py:43-49
-                const int lx = lane < S0 ? lane : S0 - 1;
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int r = 0; r < S0; ++r) M[h][r] = 0ull;
-                for (int c = 0; c < p.C; ++c) {
-#pragma unroll
-                    for (int ip = 0; ip < IMG_PARTS; ++ip) {
-                        const unsigned buf = stage_l % NSTA;
-                        mbar_wait_wd(&fullA[buf], (stage_l / NSTA) & 1);
-                        const float *sb = reinterpret_cast<const float *>(stageA + (size_t)buf * STAGE_A) + lx;
-                        const float *x0 = sb + (wi * 2 + 0) * IBAND, *x1 = sb + (wi * 2 + 1) * IBAND;
-                        const float *z0 = sb + (kTileI + wj * 2 + 0) * IBAND, *z1 = sb + (kTileI + wj * 2 + 1) * IBAND;
-                        constexpr int R = S0 / IMG_PARTS;
-#pragma unroll
-                        for (int rr = 0; rr < R; ++rr) {
-                            const int r = ip * R + rr;
-                            const float a0 = x0[rr * S0], a1 = x1[rr * S0], b0 = z0[rr * S0], b1 = z1[rr * S0];
-                            const u64 A = pk(a0, a1);
-                            M[0][r] = fma2(A, pk(b0, b1), M[0][r]);
-                            M[1][r] = fma2(A, pk(b1, b0), M[1][r]);
-                        }
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&emptyA[buf]);
-                        ++stage_l;
-                    }
-                }
-                if (p.C > 1) { affine_arr<S0, S0>(M[0], p.inv_c, 0.f); affine_arr<S0, S0>(M[1], p.inv_c, 0.f); }
-            }
-            auto relu_full = [&]() {
-                const int lx = lane < S0 ? lane : S0 - 1;
-                auto band = [&](auto Q) {
-                    constexpr int q = decltype(Q)::value;
-                    const unsigned buf = stage_l % NSTA;
-                    mbar_wait_wd(&fullA[buf], (stage_l / NSTA) & 1);
-                    const float4 *sb = reinterpret_cast<const float4 *>(stageA + (size_t)buf * STAGE_A) + lx - q * BAND;
-                    relu_rows<S0, S0, q * (S0 / NSPLIT), (q + 1) * (S0 / NSPLIT)>(M, sb + wi * BAND, sb + (kTileI / 2 + wj) * BAND);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&emptyA[buf]);
-                    ++stage_l;
-                };
-                band(std::integral_constant<int, 0>{});
-                band(std::integral_constant<int, 1>{});
-                if (NSPLIT == 4) {
-                    band(std::integral_constant<int, NSPLIT == 4 ? 2 : 0>{});
-                    band(std::integral_constant<int, NSPLIT == 4 ? 3 : 1>{});
-                }
-            };
-            auto stash_full = [&]() {  // full-size maps only ever use slot 0 here (the plan is checked for it)
-                stash_store_arr<S0, S0>(tm_warp, M[0]);
-                stash_store_arr<S0, S0>(tm_warp + TM_A0, M[1]);
-                tmem_wait_st();
-            };
-            auto unstash_full = [&]() {
-                stash_load_arr<S0, S0, false>(tm_warp, M[0], 0ull);
-                stash_load_arr<S0, S0, false>(tm_warp + TM_A0, M[1], 0ull);
-            };
-            auto add_full = [&](const int4 &d) {
-                const float al = f_scale(d);
-                const u64 alpha = pk(al, al);
-                stash_load_arr<S0, S0, true>(tm_warp, M[0], alpha);
-                stash_load_arr<S0, S0, true>(tm_warp + TM_A0, M[1], alpha);
-                add_const<S0, S0>(M[0], f_bias(d));
-                add_const<S0, S0>(M[1], f_bias(d));
-            };
-            int k = 0;
-            int4 o = ops_s[0];
-            for (bool more = true; more;) {
-                int4 nxt;
-#define FETCH(LEN) nxt = ops_s[k + (LEN)]; k += (LEN)
-                switch (o.x & 0xff) {
-                    case A_CONV + 0: FETCH(1); conv_op<S0, S0, S0, 1, 1, 1>(M, tile, lane, f_pre(o), f_scale(o), f_bias(o)); break;
-                    case A_CONV + 1: FETCH(1); conv_op<S0, S0, S0, 1, 2, 1>(M, tile, lane, f_pre(o), f_scale(o), f_bias(o)); break;
-                    case A_CONV + 2: FETCH(1); conv_op<S0, S0, S0, 2, 2, 1>(M, tile, lane, f_pre(o), f_scale(o), f_bias(o)); break;
-                    case A_CONV + 3: FETCH(1); conv_op<S0, S0, S0, 3, 3, 1>(M, tile, lane, f_pre(o), f_scale(o), f_bias(o)); break;
-                    case A_CONV + 4: FETCH(1); conv_op<S0, S0, S0 / 2, 1, 1, 2>(M, tile, lane, 0.f, f_scale(o), f_bias(o)); fold_op<S0, S0 / 2>(M, lane); break;
-                    case A_CONV + 5: FETCH(1); conv_op<S0, S0, S0 / 2, 0, 0, 2>(M, tile, lane, 0.f, f_scale(o), f_bias(o)); fold_op<S0, S0 / 2>(M, lane); break;
-                    case A_AFFINE + 0: FETCH(1); affine_arr<S0, S0>(M[0], f_scale(o), f_bias(o)); affine_arr<S0, S0>(M[1], f_scale(o), f_bias(o)); break;
-                    case A_TRANSPOSE + 0: FETCH(1); transpose_op<S0, S0>(M, tile, lane); break;
-                    case A_STASH + 0: FETCH(1); stash_full(); break;
-                    // the folded skip map of a strided projection block: slot 1 of this tile's parity
-                    case A_STASH + 1: FETCH(1); stash_store_arr<S0, S0 / 2>(tm_par + S0, M[0]); tmem_wait_st(); break;
-                    case A_UNSTASH + 0: FETCH(1); unstash_full(); break;
-                    case A_ADD + 0: FETCH(1); add_full(o); break;
-                    case A_RELU + 0: FETCH(1); relu_full(); break;
-                    case A_IDBLOCK: {
-                        const int4 c1 = ops_s[k + 2], c2 = ops_s[k + 4], ad = ops_s[k + 5];
-                        FETCH(6);
-                        stash_full();
-                        relu_full();
-                        conv_op<S0, S0, S0, 1, 1, 1>(M, tile, lane, f_pre(c1), f_scale(c1), f_bias(c1));
-                        relu_full();
-                        conv_op<S0, S0, S0, 1, 1, 1>(M, tile, lane, f_pre(c2), f_scale(c2), f_bias(c2));
-                        add_full(ad);
-                        break;
-                    }
-                    default: more = false; break;  // A_END
-                }
-                if (more) o = nxt;
-            }
-            // hand the folded map over: H[b], then the barrier
-            stash_store_arr<S0, SF>(tm_par, M[0]);
-            tmem_wait_st();
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&hand[b * kHeavy + warp]);
-        }
-    } else {
-        // =========================== light warps: phase B + tail =================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-        const int q = warp - kHeavy;  // serves heavy warps q (wi = 0) and q + 4 (wi = 1): the same j-pair
-        u64 *tile0 = tilesL + (q * 2 + 0) * SF * PITCH, *tile1 = tilesL + (q * 2 + 1) * SF * PITCH;
-        const uint32_t tm_q = tmem_base + ((uint32_t)(q * 32) << 16);
-        unsigned stage_l = 0;
-        for (unsigned n_tile = 0;; ++n_tile) {
-            mbar_wait_wd(&fullB[stage_l % NSTB], (stage_l / NSTB) & 1);
-            const long long t = stage_tileB[stage_l % NSTB];
-            if (t < 0) break;
-            int ib, jb;
-            decode(t, ib, jb);
-            const int i_base = ib * kTileI, j_base = jb * kTileJ;
-            const unsigned b = n_tile & 1;
-            const uint32_t tm0 = tm_q + TM_PAR + b * 2 * S0, tm1 = tm0 + TM_HEAVY;  // H[b] of heavy q / q + 4; B1[b] at + S0
-            u64 F0[SF], F1[SF];
-            mbar_wait_wd(&hand[b * kHeavy + q], (n_tile >> 1) & 1);
-            mbar_wait_wd(&hand[b * kHeavy + q + 4], (n_tile >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            stash_load_arr<SF, SF, false>(tm0, F0, 0ull);
-            stash_load_arr<SF, SF, false>(tm1, F1, 0ull);
-            float tot[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-
-            auto relu_fold = [&](auto SZ, const int4 &d) {
-                constexpr int S = decltype(SZ)::value;
-                const unsigned buf = stage_l % NSTB;
-                mbar_wait_wd(&fullB[buf], (stage_l / NSTB) & 1);
-                const float4 *st4 = reinterpret_cast<const float4 *>(stageB + (size_t)buf * STAGE_B);
-                const int l = lane & 15, half = f_half(d);
-                const float4 *sb = st4 + (l < S ? l : S - 1);
-                relu_rows_f2<SF, S>(F0, F1, sb, sb + 2 * half, sb + (kTileI / 2 + q) * 2 * half, lane);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&emptyB[buf]);
-                ++stage_l;
-            };
-            auto conv2 = [&](auto SI_, auto SO_, auto LO_, auto ST_, const int4 &d) {
-                constexpr int SI = decltype(SI_)::value, SO = decltype(SO_)::value, LO = decltype(LO_)::value, ST = decltype(ST_)::value;
-                conv_op_f2<SF, S0, SI, SO, LO, LO, ST>(F0, F1, tile0, tile1, lane, ST == 1 ? f_pre(d) : 0.f, f_scale(d), f_bias(d));
-            };
-            auto slot_off = [&](const int4 &d) { return f_slot(d) ? (uint32_t)S0 : 0u; };
-            auto stash2 = [&](auto SZ, const int4 &d) {
-                constexpr int S = decltype(SZ)::value;
-                stash_store_arr<SF, S>(tm0 + slot_off(d), F0);
-                stash_store_arr<SF, S>(tm1 + slot_off(d), F1);
-                tmem_wait_st();
-            };
-            auto unstash2 = [&](auto SZ, const int4 &d) {
-                constexpr int S = decltype(SZ)::value;
-                stash_load_arr<SF, S, false>(tm0 + slot_off(d), F0, 0ull);
-                stash_load_arr<SF, S, false>(tm1 + slot_off(d), F1, 0ull);
-            };
-            auto add2s = [&](auto SZ, const int4 &d) {
-                constexpr int S = decltype(SZ)::value;
-                const u64 alpha = pk(f_scale(d), f_scale(d));
-                stash_load_arr<SF, S, true>(tm0 + slot_off(d), F0, alpha);
-                stash_load_arr<SF, S, true>(tm1 + slot_off(d), F1, alpha);
-                add_const<SF, S>(F0, f_bias(d));
-                add_const<SF, S>(F1, f_bias(d));
-            };
-            using I0 = std::integral_constant<int, 0>;
-            using I1 = std::integral_constant<int, 1>;
-            using I2 = std::integral_constant<int, 2>;
-            using IS2 = std::integral_constant<int, S0 / 2>;
-            using IS4 = std::integral_constant<int, S0 / 4>;
-            int k = p.k_phase_b;
-            int4 o = ops_s[k];
-            for (bool more = true; more;) {
-                int4 nxt;
-#define FOLDED_B(CODE, BODY)                                                               \
-    case CODE + 0: { using SZ = IS2; FETCH(1); BODY; break; }                              \
-    case CODE + 1: { using SZ = IS4; FETCH(1); BODY; break; }
-                switch (o.x & 0xff) {
-                    case B_CONV + 0: FETCH(1); conv2(IS2{}, IS2{}, I1{}, I1{}, o); break;
-                    case B_CONV + 1: FETCH(1); conv2(IS2{}, IS4{}, I1{}, I2{}, o); break;
-                    case B_CONV + 2: FETCH(1); conv2(IS2{}, IS4{}, I0{}, I2{}, o); break;
-                    case B_CONV + 3: FETCH(1); conv2(IS4{}, IS4{}, I1{}, I1{}, o); break;
-                    FOLDED_B(B_AFFINE, (affine_arr<SF, SZ::value>(F0, f_scale(o), f_bias(o)), affine_arr<SF, SZ::value>(F1, f_scale(o), f_bias(o))))
-                    FOLDED_B(B_TRANSPOSE, (transpose_op_f<SF, S0, SZ::value>(F0, tile0, lane), transpose_op_f<SF, S0, SZ::value>(F1, tile1, lane)))
-                    FOLDED_B(B_STASH, (stash2(SZ{}, o)))
-                    FOLDED_B(B_UNSTASH, (unstash2(SZ{}, o)))
-                    FOLDED_B(B_ADD, (add2s(SZ{}, o)))
-                    FOLDED_B(B_RELU, (relu_fold(SZ{}, o)))
-                    case B_DENSE + 0: {
-                        FETCH(1);
-                        float t0[4], t1[4];
-                        dense_op_f<SF, S0 / 2>(F0, lane, f_scale(o), f_bias(o), t0);
-                        dense_op_f<SF, S0 / 2>(F1, lane, f_scale(o), f_bias(o), t1);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) { tot[e] = t0[e]; tot[4 + e] = t1[e]; }
-                        break;
-                    }
-                    case B_DENSE + 1: {
-                        FETCH(1);
-                        float t0[4], t1[4];
-                        dense_op_f<SF, S0 / 4>(F0, lane, f_scale(o), f_bias(o), t0);
-                        dense_op_f<SF, S0 / 4>(F1, lane, f_scale(o), f_bias(o), t1);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) { tot[e] = t0[e]; tot[4 + e] = t1[e]; }
-                        break;
-                    }
-                    case B_IDBLOCK + 0: {
-                        const int4 r1 = ops_s[k + 1], c1 = ops_s[k + 2], r2 = ops_s[k + 3], c2 = ops_s[k + 4], ad = ops_s[k + 5];
-                        FETCH(6);
-                        stash2(IS2{}, o); relu_fold(IS2{}, r1); conv2(IS2{}, IS2{}, I1{}, I1{}, c1);
-                        relu_fold(IS2{}, r2); conv2(IS2{}, IS2{}, I1{}, I1{}, c2); add2s(IS2{}, ad);
-                        break;
-                    }
-                    case B_IDBLOCK + 1: {
-                        const int4 r1 = ops_s[k + 1], c1 = ops_s[k + 2], r2 = ops_s[k + 3], c2 = ops_s[k + 4], ad = ops_s[k + 5];
-                        FETCH(6);
-                        stash2(IS4{}, o); relu_fold(IS4{}, r1); conv2(IS4{}, IS4{}, I1{}, I1{}, c1);
-                        relu_fold(IS4{}, r2); conv2(IS4{}, IS4{}, I1{}, I1{}, c2); add2s(IS4{}, ad);
-                        break;
-                    }
-                    default: FETCH(1); more = false; break;  // B_END
-                }
-#undef FOLDED_B
-                o = nxt;
-            }
-            // tensor memory of parity b is free for the heavy warps' tile n + 2
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(&handE[b * kHeavy + q]); mbar_arrive(&handE[b * kHeavy + q + 4]); }
-
-            for (bool more = true; more;) {  // tail: the eight scalars of the warp
-                int4 nxt;
-                switch (o.x & 0xff) {
-                    case T_CASE_AFFINE:
-                        FETCH(1);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) tot[e] = fmaf(tot[e], f_scale(o), f_bias(o));
-                        break;
-                    case T_CASE_RELU: {
-                        FETCH(1);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int i = min(i_base + (e >> 2) * 2 + ((e >> 1) & 1), p.N1 - 1), j = min(j_base + q * 2 + (e & 1), p.N2 - 1);
-                            const float vx = __ldg(p.aux_x + (long long)i * p.aux_stride + o.w);
-                            const float vy = __ldg(p.aux_z + (long long)j * p.aux_stride + o.w);
-                            tot[e] = relu_scalar(tot[e], vx, vy);
-                        }
-                        break;
-                    }
-                    default: more = false; break;  // T_END
-                }
-                if (more) o = nxt;
-            }
-#undef FETCH
-            if (lane < 8) {
-                const int wi = lane >> 2, a = (lane >> 1) & 1, bb = lane & 1;
-                const int i = i_base + wi * 2 + a, j = j_base + q * 2 + bb;
-                float v = tot[0];
-#pragma unroll
-                for (int e = 1; e < 8; ++e) v = lane == e ? tot[e] : v;
-                if (i < p.N1 && j < p.N2) {
-                    if (!p.symmetric) {
-                        p.out[(long long)i * p.ld_out + j] = v;
-                    } else if (j > i) {
-                        p.out[(long long)i * p.ld_out + j] = v;
-                        p.out[(long long)j * p.ld_out + i] = v;
-                    } else if (j == i) {
-                        p.out[(long long)i * p.ld_out + i] = p.kdiag ? p.kdiag[i] : v;
-                    }
-                }
-            }
-            if (p.row_done) {
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) atomicAdd(&p.row_done[ib / p.sti], 2u);  // two (tile, heavy warp) units
-            }
-        }
-    }
-
-    // all consumers are done with tensor memory before the allocating warp frees it
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    asm volatile("bar.sync 1, %0;" ::"n"((kHeavy + kLight) * 32) : "memory");
-    if (warp == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
-    }
-}
-
 }  // namespace
 
 // ---- host: translate the two-slot plan into the kernel's op list --------------------------------
@@ -1683,8 +1078,6 @@ struct FNetPlan {
     int n_relu = 0;           // staged ReLU layers in program order (the producer's list)
     int relu_aux[kMaxRelu], relu_half[kMaxRelu];
     int n_blocks = 0;         // residual blocks dispatched as one case
-    int k_phase_b = 0;        // index of the first phase-B descriptor
-    bool ws = false;          // the warp-specialised kernel covers the program (heavy / light warps)
     size_t smem = 0;
     int nst = 0;
     int fused_row_floats = 0;  // floats per image the Gram kernel reads (super-tile sizing)
@@ -2045,30 +1438,6 @@ bool build_kops(FNetPlan *fp, bool blocks) {
         k += len;
     }
     sentinel.code = A_END; push(sentinel);
-    fp->k_phase_b = nk;
-    {   // warp-specialised kernel: phase A is all full-size ops on tensor-memory slot 0 except folded skip
-        // maps stashed into slot 1 (strided projection blocks); phase B has at least one staged ReLU (the
-        // tile index reaches the light warps with its stage) and reads nothing but slot 1 from phase A
-        bool ok = end_a < first_tail;
-        for (int k = 0; k < end_a && ok; ++k) {
-            const NOp &o = fp->ops[k];
-            if (o.si == S0) {
-                if ((o.kind == N_STASH || o.kind == N_UNSTASH || o.kind == N_ADD) && o.slot != 0) ok = false;
-                if (o.kind == N_DENSE) ok = false;
-            } else if (!(o.kind == N_STASH && o.si == S0 / 2 && o.slot == 1)) {
-                ok = false;
-            }
-        }
-        bool written[2] = {false, false};
-        int n_relu_b = 0;
-        for (int k = end_a; k < first_tail && ok; ++k) {
-            const NOp &o = fp->ops[k];
-            if (o.kind == N_STASH) written[o.slot & 1] = true;
-            if ((o.kind == N_UNSTASH || o.kind == N_ADD) && !written[o.slot & 1] && o.slot != 1) ok = false;
-            n_relu_b += o.kind == N_RELU;
-        }
-        fp->ws = ok && n_relu_b > 0;
-    }
     for (int k = end_a; k < first_tail;) {
         const NOp *o = fp->ops + k;
         if (o->si == S0 || o->si == 1) return false;
@@ -2127,18 +1496,14 @@ FNetPlan *fnet_plan_create(const Plan *plan_const) {
     // twelve consumer warps when the second tensor-memory slot only ever holds folded maps of at most
     // half the edge (3 warps share a 512-column lane quadrant: 3 x 5 S0 columns)
     const bool twelve = tr.slot1_max <= S0 / 2 && !getenv("CNNGP_FNET_8WARPS");
-    if (S0 == 28 && twelve) { fp->nw = 12; fp->nst = 2; fp->smem = fnet_smem<28, 12, 2, 2>(); }
+    // three ring stages (1.5 layers of variance maps in flight): + 4 % over two on the straight-line kernel
+    const bool deep = getenv("CNNGP_FNET_NST2") == nullptr;
+    if (S0 == 28 && twelve && deep) { fp->nw = 12; fp->nst = 3; fp->smem = fnet_smem<28, 12, 3, 2>(); }
+    else if (S0 == 28 && twelve) { fp->nw = 12; fp->nst = 2; fp->smem = fnet_smem<28, 12, 2, 2>(); }
     else if (S0 == 28) { fp->nw = 8; fp->nst = 4; fp->smem = fnet_smem<28, 8, 4, 2>(); }
     // 32 x 32: the maps alone are 128 registers per thread, which leaves a 160-register warp nothing to
     // work with (measured: 21 M pairs/s with twelve spilling warps against 62 M with eight) -- eight warps
     else { fp->nw = 8; fp->nst = 3; fp->smem = fnet_smem<32, 8, 3, 2>(); }
-    if (fp->ws && !getenv("CNNGP_FNET_NOWS")) {  // heavy / light warp specialisation: 4 x 8-image tiles
-        fp->nw = 8;
-        if (S0 == 28) { fp->nst = 2; fp->smem = WsGeo<28, 2, 2, 3>::smem; }
-        else { fp->nst = 3; fp->smem = WsGeo<32, 4, 3, 2>::smem; }
-    } else {
-        fp->ws = false;
-    }
     for (const DevOp &o : plan->ops)
         if (o.opcode == CNNGP_OP_RELU) fp->fused_row_floats += 4 * o.aux_half;
     return fp;
@@ -2147,8 +1512,7 @@ FNetPlan *fnet_plan_create(const Plan *plan_const) {
 void fnet_plan_destroy(FNetPlan *fp) { delete fp; }
 
 std::string fnet_plan_describe(const FNetPlan *fp) {
-    std::string t = "fused_net S0=" + std::to_string(fp->S0) + " warps=" + std::to_string(fp->nw) + (fp->ws ? "+4 (heavy+light)" : "") +
-                    " stages=" + std::to_string(fp->nst) + " blocks=" + std::to_string(fp->n_blocks) + " :";
+    std::string t = "fused_net S0=" + std::to_string(fp->S0) + " warps=" + std::to_string(fp->nw) + " stages=" + std::to_string(fp->nst) + " blocks=" + std::to_string(fp->n_blocks) + " :";
     for (int k = 0; k < fp->n_ops; ++k) {
         const NOp &o = fp->ops[k];
         t += std::string(" ") + kNames[o.kind] + "(" + std::to_string(o.si);
@@ -2192,7 +1556,6 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
     memcpy(p.relu_aux, fp->relu_aux, sizeof(int) * fp->n_relu);
     memcpy(p.relu_half, fp->relu_half, sizeof(int) * fp->n_relu);
     p.n_relu = fp->n_relu;
-    p.k_phase_b = fp->k_phase_b;
     p.x = (const float *)d_x; p.z = (const float *)d_z;
     p.aux_x = (const float *)d_aux_x; p.aux_z = (const float *)d_aux_z;
     p.aux_stride = plan->aux_elems; p.aux_f_off = plan->aux_f_off;
@@ -2240,12 +1603,9 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);
     void (*kern)(const NParams) = fp->S0 == 32 ? fnet_kernel<32, 8, 3, 2>
-                                               : (fp->nw == 12 ? fnet_kernel<28, 12, 2, 2> : fnet_kernel<28, 8, 4, 2>);
-    unsigned threads = (fp->nw + 4) * 32;
-    if (fp->ws) {
-        kern = fp->S0 == 32 ? fnet_ws_kernel<32, 4, 3, 2> : fnet_ws_kernel<28, 2, 2, 3>;
-        threads = 512;
-    }
+                                               : (fp->nw == 12 ? (fp->nst == 3 ? fnet_kernel<28, 12, 3, 2> : fnet_kernel<28, 12, 2, 2>)
+                                                               : fnet_kernel<28, 8, 4, 2>);
+    const unsigned threads = (fp->nw + 4) * 32;
     unsigned long long *ctr = nullptr;
     cudaError_t e = cudaGetSymbolAddress((void **)&ctr, g_fnet_tile_ctr);
     const char *order = getenv("CNNGP_TILE_ORDER");  // "static": fixed stride instead of the counter

@@ -38,10 +38,15 @@ namespace {
 
 // Geometry of one kernel variant: NW consumer warps as 2 x NW/2 warps of 2 x 2 image pairs,
 // plus a fourth/third warpgroup that holds the producer warp and donates registers (setmaxnreg).
-template <int NW>
+// NG > 1: the consumer warps form NG independent groups, each with its own tile stream, staging ring
+// and producer warp -- like NG small CTAs sharing the SM.  Groups drift apart, so that one group's
+// ReLU (FP32 pipe) runs under another group's transposition (shared-memory pipe) instead of all
+// warps of the SM hitting the same pipe in the same phase.
+template <int NW, int NG = 1>
 struct Geo {
     static constexpr int kWarps = NW;
-    static constexpr int kTileI = 4, kTileJ = NW;        // images per CTA tile along i and j
+    static constexpr int kGroups = NG, kGW = NW / NG;     // consumer warps per group
+    static constexpr int kTileI = 4, kTileJ = NW / NG;    // images per group tile along i and j
     static constexpr int kImgs = kTileI + kTileJ;
     static constexpr int kPairs = kImgs / 2;              // image pairs whose interleaved variance maps are staged
     static constexpr int kThreads = (NW + 4) * 32;
@@ -157,10 +162,11 @@ __device__ __forceinline__ void tile_load_t(const u64 *tile, u64 (&a)[S], int lx
 //
 // Staging: a ring of NST stages.  A ReLU layer's pair-interleaved variance maps arrive in NSPLIT
 // row bands (one stage each), a channel of the tile's images in IMG_PARTS bands.
-template <int S, int LO, int HI, int NW, int NSPLIT, int NST>
-__global__ void __launch_bounds__(Geo<NW>::kThreads, 1) fused_kernel(const __grid_constant__ FParams p) {
-    using G = Geo<NW>;
+template <int S, int LO, int HI, int NW, int NSPLIT, int NST, int NG = 1>
+__global__ void __launch_bounds__(Geo<NW, NG>::kThreads, 1) fused_kernel(const __grid_constant__ FParams p) {
+    using G = Geo<NW, NG>;
     constexpr int kWarps = G::kWarps, kTileI = G::kTileI, kTileJ = G::kTileJ, kImgs = G::kImgs, kPairs = G::kPairs;
+    constexpr int kGW = G::kGW;
     constexpr int P = S * S;
     constexpr int PITCH = S + 1;
     constexpr int IMG_PARTS = NSPLIT == 4 ? 2 : 1;
@@ -170,10 +176,12 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) fused_kernel(const __gri
     static_assert(S % NSPLIT == 0 && (NSPLIT == 1 || NSPLIT == 2 || NSPLIT == 4), "band split");
     static_assert(kImgs * IBAND * 4 <= STAGE_F4 * 16, "an image band must fit a stage");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // [NST][kPairs][BAND] float4 stages | [kWarps][S*PITCH] u64 transpose tiles | barriers
-    float4 *stage = reinterpret_cast<float4 *>(smem_raw);
-    u64 *tiles = reinterpret_cast<u64 *>(stage + NST * STAGE_F4);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + kWarps * S * PITCH);
+    // [NG][NST][kPairs][BAND] float4 stages | [kWarps][S*PITCH] u64 transpose tiles | barriers
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = warp < kWarps ? warp / kGW : (warp - kWarps < NG ? warp - kWarps : 0);  // consumer group / the group a producer serves
+    float4 *stage = reinterpret_cast<float4 *>(smem_raw) + grp * NST * STAGE_F4;
+    u64 *tiles = reinterpret_cast<u64 *>(reinterpret_cast<float4 *>(smem_raw) + NG * NST * STAGE_F4);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + kWarps * S * PITCH) + grp * 3 * NST;
     uint64_t *full = bars, *empty = bars + NST;
     // tile index each stage belongs to (-1: no more tiles).  Tiles are handed out by a global
     // atomic counter, not by a fixed stride: all CTAs then work on consecutive tiles of one
@@ -182,10 +190,9 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) fused_kernel(const __gri
     // of the launch is balanced to one tile.
     long long *stage_tile = reinterpret_cast<long long *>(bars + 2 * NST);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int b = 0; b < NST; ++b) { mbar_init(&full[b], 1); mbar_init(&empty[b], kWarps); }
+        for (int g = 0; g < NG; ++g)
+            for (int b = 0; b < NST; ++b) { mbar_init(&full[g * 3 * NST + b], 1); mbar_init(&empty[g * 3 * NST + b], kGW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) fused_kernel(const __gri
     if (warp >= kWarps) {
         // last warpgroup: hand its registers to the consumers; only its first warp works
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::kRegsProducer));
-        if (warp != kWarps) return;
+        if (warp >= kWarps + NG) return;
         // ---- producer warp: stages, up to NST - 1 stages ahead, first the tile's images (per
         // channel) and then each ReLU layer's pair-interleaved (s_a, s_b, 1/s_a, 1/s_b) maps of the
         // tile's image pairs.  It runs on across tile boundaries, so the next tile's first stages
@@ -242,14 +249,15 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) fused_kernel(const __gri
                 if (lane == 0) v = (long long)atomicAdd(p.tile_ctr, 1ull);
                 return __shfl_sync(0xffffffffu, v, 0);
             };
-            long long t_raw = next_index((long long)blockIdx.x);
+            const long long stride = (long long)gridDim.x * NG;  // fixed-stride order: groups interleave
+            long long t_raw = next_index((long long)blockIdx.x * NG + grp);
             for (;;) {
                 int ib, jb;
                 t = t_raw;
-                while (t < p.n_tiles && !decode(t, ib, jb)) t = next_index(t + gridDim.x);
+                while (t < p.n_tiles && !decode(t, ib, jb)) t = next_index(t + stride);
                 if (t >= p.n_tiles) break;
                 // the next index is requested now and first looked at when this tile's stages are out
-                t_raw = next_index(t + gridDim.x);
+                t_raw = next_index(t + stride);
                 const int i_base = ib * kTileI, j_base = jb * kTileJ;
                 const float *img = nullptr, *var = nullptr;  // this lane's sources for the whole tile
                 if (lane < kImgs)
@@ -292,7 +300,7 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) fused_kernel(const __gri
 
     // ---- consumers ------------------------------------------------------------------------
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(G::kRegsConsumer));
-    const int wi = warp / (NW / 2), wj = warp % (NW / 2);
+    const int wi = (warp % kGW) / (kGW / 2), wj = (warp % kGW) % (kGW / 2);
     const int lx = lane < S ? lane : S - 1;  // clamped lane for loads
     u64 *tile = tiles + warp * S * PITCH;
     unsigned stage_l = 0;  // running stage counter, in step with the producer's
@@ -465,9 +473,9 @@ __global__ void __launch_bounds__(Geo<NW>::kThreads, 1) fused_kernel(const __gri
     }
 }
 
-template <int NW, int NSPLIT, int NST>
+template <int NW, int NSPLIT, int NST, int NG = 1>
 constexpr size_t fused_smem(int S) {
-    return (size_t)NST * (Geo<NW>::kPairs * S * S / NSPLIT) * 16 + (size_t)NW * S * (S + 1) * 8 + 3 * NST * 8;
+    return (size_t)NG * NST * (Geo<NW, NG>::kPairs * S * S / NSPLIT) * 16 + (size_t)NW * S * (S + 1) * 8 + (size_t)NG * 3 * NST * 8;
 }
 
 }  // namespace
@@ -606,9 +614,9 @@ std::atomic<unsigned> g_next_ctr{0};
 
 struct Variant { int nw, nsplit, nst; };
 
-template <int NW, int NSPLIT, int NST>
+template <int NW, int NSPLIT, int NST, int NG = 1>
 int launch_variant(const FusedPlan *fp, FParams &p, int64_t N1, int64_t N2, cudaStream_t stream, RowProgress *prog) {
-    using G = Geo<NW>;
+    using G = Geo<NW, NG>;
     p.nbi = (int)((N1 + G::kTileI - 1) / G::kTileI);
     p.nbj = (int)((N2 + G::kTileJ - 1) / G::kTileJ);
     long long n_super;
@@ -637,7 +645,7 @@ int launch_variant(const FusedPlan *fp, FParams &p, int64_t N1, int64_t N2, cuda
             long long jb_lo = (long long)si * p.stj;
             const long long need = ((long long)ib * G::kTileI - (G::kTileJ - 1) + G::kTileJ - 1) / G::kTileJ;
             if (need > jb_lo) jb_lo = need;
-            if (jb_lo < p.nbj) prog->expected[si] += (unsigned)((p.nbj - jb_lo) * NW);
+            if (jb_lo < p.nbj) prog->expected[si] += (unsigned)((p.nbj - jb_lo) * G::kGW);
         }
         p.row_done = prog->d_done;
     }
@@ -646,14 +654,14 @@ int launch_variant(const FusedPlan *fp, FParams &p, int64_t N1, int64_t N2, cuda
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);  // persistent: one CTA per SM
     void (*kern)(const FParams) = nullptr;
-    constexpr bool kDefault = NW == 12 && NSPLIT == 2 && NST == 2;
-    if (fp->lo == 3 && fp->hi == 3) kern = fused_kernel<28, 3, 3, NW, NSPLIT, NST>;
-    else if (kDefault && fp->lo == 1 && fp->hi == 1) kern = fused_kernel<28, 1, 1, 12, 2, 2>;
-    else if (kDefault && fp->lo == 1 && fp->hi == 2) kern = fused_kernel<28, 1, 2, 12, 2, 2>;
-    else if (kDefault && fp->lo == 2 && fp->hi == 2) kern = fused_kernel<28, 2, 2, 12, 2, 2>;
-    else if (kDefault) kern = fused_kernel<28, -1, -1, 12, 2, 2>;
+    constexpr bool kDefault = NW == 12 && NSPLIT == 2 && NST == 3 && NG == 1;
+    if (fp->lo == 3 && fp->hi == 3) kern = fused_kernel<28, 3, 3, NW, NSPLIT, NST, NG>;
+    else if (kDefault && fp->lo == 1 && fp->hi == 1) kern = fused_kernel<28, 1, 1, 12, 2, 3>;
+    else if (kDefault && fp->lo == 1 && fp->hi == 2) kern = fused_kernel<28, 1, 2, 12, 2, 3>;
+    else if (kDefault && fp->lo == 2 && fp->hi == 2) kern = fused_kernel<28, 2, 2, 12, 2, 3>;
+    else if (kDefault) kern = fused_kernel<28, -1, -1, 12, 2, 3>;
     else return -1;  // experimental variants exist for the 7x7 window only: caller falls back to the default
-    const size_t smem = fused_smem<NW, NSPLIT, NST>(28);
+    const size_t smem = fused_smem<NW, NSPLIT, NST, NG>(28);
     unsigned long long *ctr = nullptr;
     cudaError_t e = cudaGetSymbolAddress((void **)&ctr, g_tile_ctr);
     const char *order = getenv("CNNGP_TILE_ORDER");  // "static": fixed stride instead of the counter
@@ -694,10 +702,11 @@ int launch_fused_gram(const Plan *plan, const void *d_x, int64_t N1, const void 
     p.kdiag = (const float *)d_kdiag;
     p.inv_c = 1.0f / (float)C;
     // kernel variant: consumer warps, ReLU bands per layer, ring depth.  Default 12 warps (three
-    // per SM sub-partition at 160 registers), two bands per layer, two stages: measured 247 M
-    // pairs/s on the 10k x 10k headline job against 228 M for the 8-warp / 240-register variant.
+    // per SM sub-partition at 160 registers), two bands per layer, three stages (one and a half
+    // layers of variance maps in flight: 247.6 M pairs/s against 237.7 M with two stages on the same
+    // box; 228 M for the 8-warp / 240-register variant).
     // CNNGP_FUSED_VARIANT=nw,nsplit,nst selects the others (7x7 window only) for comparison.
-    Variant v{12, 2, 2};
+    Variant v{12, 2, 3};
     if (const char *e = getenv("CNNGP_FUSED_VARIANT")) sscanf(e, "%d,%d,%d", &v.nw, &v.nsplit, &v.nst);
     if (const char *e = getenv("CNNGP_FUSED_SKEW_NS")) p.skew_ns = (unsigned)atoi(e);
     int rc = -1;
@@ -706,7 +715,9 @@ int launch_fused_gram(const Plan *plan, const void *d_x, int64_t N1, const void 
     else if (v.nw == 8 && v.nsplit == 1 && v.nst == 2) rc = launch_variant<8, 1, 2>(fp, p, N1, N2, st, progress);
     else if (v.nw == 8 && v.nsplit == 2 && v.nst == 4) rc = launch_variant<8, 2, 4>(fp, p, N1, N2, st, progress);
     else if (v.nw == 12 && v.nsplit == 2 && v.nst == 3) rc = launch_variant<12, 2, 3>(fp, p, N1, N2, st, progress);
-    if (rc < 0) rc = launch_variant<12, 2, 2>(fp, p, N1, N2, st, progress);
+    else if (v.nw == 12 && v.nsplit == 2 && v.nst == 2) rc = launch_variant<12, 2, 2>(fp, p, N1, N2, st, progress);
+    else if (v.nw == 122) rc = launch_variant<12, 2, 2, 2>(fp, p, N1, N2, st, progress);  // two independent groups of six warps
+    if (rc < 0) rc = launch_variant<12, 2, 3>(fp, p, N1, N2, st, progress);
     return rc;
 }
 
