@@ -5,6 +5,7 @@ include/cnngp.h; torch is only used for device memory and streams.  There is no 
 CPU tensors raise.
 """
 import ctypes
+import weakref
 
 import torch
 
@@ -44,14 +45,25 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# compiled plans per model object.  Kept OUTSIDE the module (a plan holds a ctypes handle, which
+# copy.deepcopy / pickle / torch.save of the model must not meet) and keyed by everything the
+# program depends on, so that editing a layer's hyperparameters after the first call recompiles
+# (the reference reads them on every propagate, kernels.py:92-98).
+_PLANS = weakref.WeakKeyDictionary()
+
+
 def plan_for(model, H, W, dtype):
-    """Compiled plan for ``model`` on H x W maps, cached on the module."""
-    cache = model.__dict__.setdefault("_cnngp_plans", {})
-    key = (H, W, dtype, model._mixture_signature())
+    """Compiled plan for ``model`` on H x W maps, cached per model object and program signature."""
+    cache = _PLANS.get(model)
+    if cache is None:
+        cache = _PLANS[model] = {}
+    key = (H, W, dtype, model._program_signature())
     plan = cache.get(key)
     if plan is None:
         ops, n_slots = program.compile_model(model)
         plan = nat.Plan(ops, n_slots, H, W, _DTYPE_CODE[dtype])
+        if len(cache) >= 8:  # a model whose hyperparameters keep changing must not pile plans up
+            cache.clear()
         cache[key] = plan
     return plan
 
@@ -74,18 +86,25 @@ def variances(plan, x, z=None):
     return aux_x, aux_z, kdiag
 
 
-def gram_with_aux(plan, x, z, aux_x, aux_z, same, diag, symmetric, out=None, kdiag=None):
-    """One cnngp_gram launch on prepared operands; ``out`` may be a (strided-row) view."""
+def gram_with_aux(plan, x, z, aux_x, aux_z, same, diag, symmetric, out=None, kdiag=None, path=None):
+    """One cnngp_gram launch on prepared operands; ``out`` may be a (strided-row) view.
+    ``path`` overrides the module-wide kernel choice for this call."""
     N1, N2, C = x.shape[0], z.shape[0], x.shape[1]
     if out is None:
         out = torch.empty((N1,) if diag else (N1, N2), dtype=x.dtype, device=x.device)
+    # the kernels write elements of the plan's dtype: a buffer of another width would be overrun
+    for name, t in (("z", z), ("aux_x", aux_x), ("aux_z", aux_z), ("out", out), ("kdiag", kdiag)):
+        if t is not None and (t.dtype != x.dtype or t.device != x.device):
+            raise TypeError(f"cnn_gp (B200): {name} is {t.dtype} on {t.device}, the images are {x.dtype} on {x.device}")
+    if _DTYPE_CODE[x.dtype] != plan.dtype_code:
+        raise TypeError(f"cnn_gp (B200): plan compiled for dtype code {plan.dtype_code}, images are {x.dtype}")
     ld = 1 if diag else out.stride(0)
     if not diag:
         assert out.stride(1) == 1 and out.shape == (N1, N2)
     nat.check(nat.lib().cnngp_gram(
         plan.handle, x.data_ptr(), N1, z.data_ptr(), N2, C, aux_x.data_ptr(), aux_z.data_ptr(),
         kdiag.data_ptr() if kdiag is not None else None,
-        int(same), int(diag), int(symmetric), out.data_ptr(), ld, _PATH_CODE[_force_path], _stream()),
+        int(same), int(diag), int(symmetric), out.data_ptr(), ld, _PATH_CODE[path or _force_path], _stream()),
         "cnngp_gram")
     return out
 

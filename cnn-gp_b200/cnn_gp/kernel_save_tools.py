@@ -6,8 +6,10 @@ Layout contract (reference kernel_save_tools.py:7-23): dataset ``name`` has shap
 an unlimited leading dimension.  NaN therefore marks "block not computed by this worker", which
 is what the merge step relies on (exp_mnist_resnet/merge_h5_files.py:27-28).
 
-``f`` may be an ``h5py.File`` or a ``cnn_gp.block_store.NpyStore`` (same calls, ``.npy`` memmaps;
-h5py / libhdf5 are not part of this image).
+``f`` may be a ``cnn_gp.h5store.File`` (real HDF5 files written and read by this repository's own
+implementation of the format, csrc/h5store.cpp: h5py / libhdf5 are not part of this image), an
+``h5py.File`` where one is installed, or a ``cnn_gp.block_store.NpyStore`` (same calls, a directory
+of ``.npy`` memmaps); ``cnn_gp.block_store.open_store`` picks by path.
 """
 import numpy as np
 
@@ -104,7 +106,12 @@ def save_K_resident(f, model, name, X, X2, diag, batch_size, worker_rank=0, n_wo
         # (flat: every row segment is viewed as a CONTIGUOUS [rows, cols] matrix, so the device-to-host
         # copy is one plain async memcpy -- torch stages non-contiguous cross-device copies through
         # pageable memory and blocks)
-        dev_bufs = [torch.empty(batch_size * N2, dtype=torch.float32, device=device) for _ in range(2)]
+        # device rows in the images' dtype (a .double() dataset runs the float64 kernel); the store is
+        # float32 like the reference's (kernel_save_tools.py:21: the numpy tile is cast on assignment), so
+        # a float64 row is narrowed on the device before it leaves
+        dev_bufs = [torch.empty(batch_size * N2, dtype=x.dtype, device=device) for _ in range(2)]
+        narrow = x.dtype != torch.float32
+        dev32 = [torch.empty(batch_size * N2, dtype=torch.float32, device=device) for _ in range(2)] if narrow else None
         host_bufs = [torch.empty(batch_size * N2, dtype=torch.float32).pin_memory() for _ in range(2)]
         flags = torch.ones(2, dtype=torch.bool).pin_memory()  # per buffer: "every entry of the row is finite"
         pending = []  # (event, buffer index, host view, i0, i1, j0, j1)
@@ -140,10 +147,16 @@ def save_K_resident(f, model, name, X, X2, diag, batch_size, worker_rank=0, n_wo
                 js = c0 * batch_size
                 job.block_into(buf[:, js - j0:], i0, i1, js, j1, symmetric=False)
             finite = torch.isfinite(buf).all()  # stays on the device: no host sync in this loop
+            if narrow:
+                src = dev32[k % 2][:rows * cols].view(rows, cols)
+                src.copy_(buf)
+            else:
+                src = buf
             host = host_bufs[k % 2][:rows * cols].view(rows, cols)
             copy_stream.wait_stream(torch.cuda.current_stream())
+            finite.record_stream(copy_stream)  # read there: the allocator must not hand it out again before
             with torch.cuda.stream(copy_stream):
-                host.copy_(buf, non_blocking=True)
+                host.copy_(src, non_blocking=True)
                 flags[k % 2:k % 2 + 1].copy_(finite.reshape(1), non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)

@@ -51,12 +51,22 @@ class NNGPKernel(nn.Module):
     def propagate(self, kp):
         raise NotImplementedError
 
-    def _mixture_signature(self):
-        """Values the compiled program depends on besides the tree structure."""
+    def _program_signature(self):
+        """Everything the compiled program depends on: the module tree with each layer's
+        hyperparameters (read on every call, like the reference's propagate) and the Mixture weights."""
         sig = []
         for m in self.modules():
-            if isinstance(m, Mixture):
-                sig.append(tuple(F.softmax(m.logit.detach().double(), dim=0).tolist()))
+            if isinstance(m, Conv2d):
+                sig.append(("C", m.kernel_size, m.stride, m.padding, m.dilation, float(m.var_weight), float(m.var_bias),
+                            bool(m.kernel_has_row_of_zeros)))
+            elif isinstance(m, Mixture):
+                sig.append(("M", len(m.mods)) + tuple(F.softmax(m.logit.detach().double(), dim=0).tolist()))
+            elif isinstance(m, Sum):
+                sig.append(("S", len(m.mods)))
+            elif isinstance(m, Sequential):
+                sig.append(("Q", len(m.mods)))
+            else:
+                sig.append((type(m).__name__,))
         return tuple(sig)
 
 

@@ -32,18 +32,20 @@ class GramJob:
         self.launches = 1 if self.same else 2
 
     def block(self, out, i0, i1, j0, j1, symmetric):
-        """out[i0:i1, j0:j1] = K(X[i0:i1], X2[j0:j1]) (upper triangle mirrored when symmetric).
-        Block origins must be even: the fused kernel's variance maps interleave images 2k, 2k+1."""
+        """out[i0:i1, j0:j1] = K(X[i0:i1], X2[j0:j1]) (upper triangle mirrored when symmetric)."""
         self.block_into(out[i0:i1, j0:j1], i0, i1, j0, j1, symmetric)
 
     def block_into(self, view, i0, i1, j0, j1, symmetric):
         """view[...] = K(X[i0:i1], X2[j0:j1]); ``view`` is any [i1-i0, j1-j0] tensor with unit
-        column stride (e.g. a slice of a row buffer)."""
-        assert i0 % 2 == 0 and j0 % 2 == 0, "tile origins must be even (use an even batch_size)"
+        column stride (e.g. a slice of a row buffer) and the images' dtype.
+        The fused kernels' variance maps interleave images 2k and 2k+1, so a block whose origin is
+        odd (an odd ``batch_size``: the reference accepts any) goes to the generic kernel, which
+        reads the plain per-image rows."""
+        path = "generic" if (i0 % 2 or j0 % 2) else None
         with torch.cuda.device(self.X.device):
             engine.gram_with_aux(self.plan, self.X[i0:i1], self.X2[j0:j1], self.aux_x[i0:i1],
                                  self.aux_x2[j0:j1], same=symmetric, diag=False, symmetric=symmetric,
-                                 out=view, kdiag=self.kdiag[i0:i1] if symmetric else None)
+                                 out=view, kdiag=self.kdiag[i0:i1] if symmetric else None, path=path)
         self.launches += 1
 
 

@@ -1523,11 +1523,6 @@ std::string fnet_plan_describe(const FNetPlan *fp) {
     return t;
 }
 
-// tile counters of the launches in flight (one slot per launch, reused round-robin)
-constexpr int kCtrSlots = 64;
-__device__ unsigned long long g_fnet_tile_ctr[kCtrSlots];
-static std::atomic<unsigned> g_fnet_next_ctr{0};
-
 // one line per register-level op, every field, floats with nine significant digits (exact for float32)
 std::string fnet_plan_dump(const FNetPlan *fp) {
     std::string t = "fused_net S0=" + std::to_string(fp->S0) + "\n";
@@ -1606,13 +1601,13 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
                                                : (fp->nw == 12 ? (fp->nst == 3 ? fnet_kernel<28, 12, 3, 2> : fnet_kernel<28, 12, 2, 2>)
                                                                : fnet_kernel<28, 8, 4, 2>);
     const unsigned threads = (fp->nw + 4) * 32;
-    unsigned long long *ctr = nullptr;
-    cudaError_t e = cudaGetSymbolAddress((void **)&ctr, g_fnet_tile_ctr);
+    cudaError_t e = cudaSuccess;
     const char *order = getenv("CNNGP_TILE_ORDER");  // "static": fixed stride instead of the counter
     if (order && !strcmp(order, "static")) {
         p.tile_ctr = nullptr;
-    } else if (e == cudaSuccess) {
-        p.tile_ctr = ctr + g_fnet_next_ctr.fetch_add(1) % kCtrSlots;
+    } else {
+        p.tile_ctr = tile_counter_for(stream);
+        if (!p.tile_ctr) return 7;
         e = cudaMemsetAsync(p.tile_ctr, 0, sizeof(unsigned long long), (cudaStream_t)stream);
     }
     if (e != cudaSuccess) { set_error(std::string("fused-net tile counter: ") + cudaGetErrorString(e)); return 7; }

@@ -607,11 +607,6 @@ std::string fused_plan_dump(const FusedPlan *fp, const Plan *plan) {
 
 namespace {
 
-// tile counters of the launches in flight (one slot per launch, reused round-robin)
-constexpr int kCtrSlots = 64;
-__device__ unsigned long long g_tile_ctr[kCtrSlots];
-std::atomic<unsigned> g_next_ctr{0};
-
 struct Variant { int nw, nsplit, nst; };
 
 template <int NW, int NSPLIT, int NST, int NG = 1>
@@ -662,13 +657,13 @@ int launch_variant(const FusedPlan *fp, FParams &p, int64_t N1, int64_t N2, cuda
     else if (kDefault) kern = fused_kernel<28, -1, -1, 12, 2, 3>;
     else return -1;  // experimental variants exist for the 7x7 window only: caller falls back to the default
     const size_t smem = fused_smem<NW, NSPLIT, NST, NG>(28);
-    unsigned long long *ctr = nullptr;
-    cudaError_t e = cudaGetSymbolAddress((void **)&ctr, g_tile_ctr);
+    cudaError_t e = cudaSuccess;
     const char *order = getenv("CNNGP_TILE_ORDER");  // "static": fixed stride instead of the counter
     if (order && !strcmp(order, "static")) {
         p.tile_ctr = nullptr;
-    } else if (e == cudaSuccess) {
-        p.tile_ctr = ctr + g_next_ctr.fetch_add(1) % kCtrSlots;
+    } else {
+        p.tile_ctr = tile_counter_for(stream);
+        if (!p.tile_ctr) return 7;
         e = cudaMemsetAsync(p.tile_ctr, 0, sizeof(unsigned long long), stream);
     }
     if (e != cudaSuccess) { set_error(std::string("fused tile counter: ") + cudaGetErrorString(e)); return 7; }

@@ -5,6 +5,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "plan.h"
 
@@ -117,16 +120,30 @@ const DevOp *plan_device_ops(const Plan *plan) {
     std::lock_guard<std::mutex> lk(plan->mu);
     int dev = -1;
     if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed (no CUDA device?)"); return nullptr; }
-    if (plan->d_ops && plan->d_ops_device == dev) return plan->d_ops;
-    // a plan used on a second device gets a second copy; the first is kept alive (tiny)
+    for (const auto &e : plan->d_ops)
+        if (e.first == dev) return e.second;
     DevOp *d = nullptr;
     size_t bytes = std::max<size_t>(1, plan->ops.size()) * sizeof(DevOp);
     cudaError_t e = cudaMalloc(&d, bytes);
     if (e != cudaSuccess) { set_error(std::string("cudaMalloc(plan ops): ") + cudaGetErrorString(e)); return nullptr; }
     e = cudaMemcpy(d, plan->ops.data(), plan->ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { set_error(std::string("cudaMemcpy(plan ops): ") + cudaGetErrorString(e)); cudaFree(d); return nullptr; }
-    plan->d_ops = d;
-    plan->d_ops_device = dev;
+    plan->d_ops.emplace_back(dev, d);
+    return d;
+}
+
+unsigned long long *tile_counter_for(void *stream) {
+    static std::mutex mu;
+    static std::vector<std::pair<std::pair<int, void *>, unsigned long long *>> table;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed (no CUDA device?)"); return nullptr; }
+    std::lock_guard<std::mutex> lk(mu);
+    for (const auto &e : table)
+        if (e.first.first == dev && e.first.second == stream) return e.second;
+    unsigned long long *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(unsigned long long));
+    if (e != cudaSuccess) { set_error(std::string("cudaMalloc(tile counter): ") + cudaGetErrorString(e)); return nullptr; }
+    table.push_back({{dev, stream}, d});
     return d;
 }
 
@@ -173,7 +190,7 @@ int cnngp_plan_create(const cnngp_op *ops, int32_t n_ops, int32_t n_slots, int32
 void cnngp_plan_destroy(cnngp_plan *plan) {
     Plan *p = reinterpret_cast<Plan *>(plan);
     if (!p) return;
-    if (p->d_ops) cudaFree(p->d_ops);
+    for (const auto &e : p->d_ops) cudaFree(e.second);
     if (p->fused) fused_plan_destroy(p->fused);
     if (p->fnet) fnet_plan_destroy(p->fnet);
     delete p;

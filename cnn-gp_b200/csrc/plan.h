@@ -40,10 +40,9 @@ struct Plan {
     int32_t n_relu = 0;
     int32_t max_map = 0;      // largest map (or separable-conv intermediate) in elements
     int32_t final_slot = 0;
-    // lazily uploaded device copy of `ops` (per device the plan was first used on)
+    // lazily uploaded device copies of `ops`, one per device the plan has been used on
     mutable std::mutex mu;
-    mutable DevOp *d_ops = nullptr;
-    mutable int d_ops_device = -1;
+    mutable std::vector<std::pair<int, DevOp *>> d_ops;
     // fused-kernel description (nullptr when the program is outside the fused kernel's set)
     FusedPlan *fused = nullptr;
     // fused kernel for programs with Sum / stride / several map sizes (nullptr when not covered)
@@ -54,6 +53,10 @@ void set_error(const std::string &msg);
 int build_plan(const cnngp_op *ops, int32_t n_ops, int32_t n_slots, int32_t H, int32_t W,
                int32_t dtype, Plan **out);
 const DevOp *plan_device_ops(const Plan *plan);  // uploads on first use; nullptr on CUDA error
+// One tile counter per (device, stream) for the persistent Gram kernels: launches on one stream are
+// ordered, so zeroing the stream's counter on that stream ahead of each launch cannot disturb a
+// launch that is still running (a round-robin pool shared by all streams could).  nullptr on error.
+unsigned long long *tile_counter_for(void *stream);
 double plan_flops_per_pair(const Plan *plan, int32_t C);
 
 // gram_generic.cu

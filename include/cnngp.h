@@ -15,7 +15,8 @@
  * Conventions
  *   - plain C types only; every pointer named d_* is a DEVICE pointer owned by the caller
  *     (PyTorch allocates; pass tensor.data_ptr()).  The library allocates nothing that
- *     outlives a call except the small plan object.
+ *     outlives a call except the small plan object, its per-device copy of the op list and
+ *     one 8-byte tile counter per (device, stream) the persistent Gram kernels have run on.
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), on the current
  *     device; no hidden synchronisation.
  *   - return value 0 = success, non-zero = error; cnngp_last_error() returns a thread-local

@@ -561,3 +561,24 @@ def test_fused_translations_reevaluated_on_cpu(family):
         np.testing.assert_allclose(got, want, rtol=1e-6, atol=0, err_msg=f"{family} case {case}:\n{plan.describe()}")
     assert hits >= 25, hits
 
+
+
+# ---- plan cache (engine.plan_for) ------------------------------------------------------------------
+def test_plan_cache_follows_hyperparameters_and_survives_copies():
+    """The reference reads a layer's hyperparameters on every propagate (kernels.py:92-98); the compiled
+    plan is therefore keyed by them, and lives outside the module so that deepcopy / pickle of a model
+    that has been called keep working (a plan holds a ctypes handle)."""
+    import copy
+    import pickle
+    from cnn_gp import engine
+    model = Sequential(Conv2d(3, var_bias=0.5), ReLU(), Conv2d(28, padding=0))
+    p1 = engine.plan_for(model, 28, 28, torch.float32)
+    assert engine.plan_for(model, 28, 28, torch.float32) is p1
+    model.mods[0].var_bias = 2.0
+    p2 = engine.plan_for(model, 28, 28, torch.float32)
+    assert p2 is not p1
+    assert "2" in p2.dump() and p2.dump() != p1.dump()
+    clone = copy.deepcopy(model)
+    assert pickle.loads(pickle.dumps(model)).mods[0].var_bias == 2.0
+    assert engine.plan_for(clone, 28, 28, torch.float32) is not p2
+    assert not any(k.startswith("_cnngp") for k in model.__dict__)

@@ -225,6 +225,42 @@ def test_save_kernel_resident_equals_reference_loop_and_classify_matches_scipy(t
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("batch_size,double", [(63, False), (64, True), (45, True)])
+def test_resident_rows_with_odd_batch_size_and_float64_images(tmp_path, batch_size, double):
+    """The reference's save_K accepts any batch size and any image dtype (the numpy tile is cast into
+    the float32 dataset, kernel_save_tools.py:21,55-58).  The resident path must too: blocks with an
+    odd origin go to the generic kernel (the fused kernels' variance maps interleave image pairs), a
+    float64 dataset computes in float64 and is narrowed on the way out -- same bytes as the literal loop."""
+    from cnn_gp import save_K
+    from cnn_gp.block_store import open_store
+    from cnn_gp.kernel_save_tools import save_K_resident
+    cfg = _synthetic_config(150, 40, 50)
+    model = cfg.initial_model.cuda()
+    g = torch.Generator().manual_seed(5)
+    X = torch.rand(150, 1, 28, 28, generator=g)
+    X2 = torch.rand(70, 1, 28, 28, generator=g)
+    if double:
+        X, X2, model = X.double(), X2.double(), model.double()
+    ds, ds2 = torch.utils.data.TensorDataset(X, torch.zeros(150)), torch.utils.data.TensorDataset(X2, torch.zeros(70))
+
+    def kern(x, x2, same, diag):
+        with torch.no_grad():
+            return model(x.cuda(), x2.cuda(), same, diag).cpu().numpy()
+    try:
+        with open_store(str(tmp_path / "a.h5"), "w") as fa, open_store(str(tmp_path / "b.h5"), "w") as fb:
+            for name, A, B in (("Kxx", ds, None), ("Kx2x", ds2, ds)):
+                save_K_resident(fa, model, name, A, B, False, batch_size, 1, 2)
+                save_K(fb, kern, name, A, B, False, batch_size, 1, 2)
+                a, b = fa[name][...], fb[name][...]
+                assert a.dtype == np.float32 and a.shape == b.shape
+                np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+                assert np.isfinite(a).any()
+                np.testing.assert_allclose(a[~np.isnan(a)], b[~np.isnan(b)], rtol=1e-5 if not double else 0, atol=0)
+    finally:
+        model.float().cpu()
+
+
+@pytest.mark.gpu
 def test_classify_api_matches_reference_functions():
     """solve_system / diag_add / print_accuracy keep the reference's signatures and semantics."""
     from exp_mnist_resnet import classify_gp
