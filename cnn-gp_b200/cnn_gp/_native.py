@@ -55,6 +55,13 @@ _SIGNATURES = {
                                              ctypes.c_void_p]),
     "cnngp_potrf_panel_f64": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "cnngp_trsm_fwd_panel_f64": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                                ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p]),
+    "cnngp_trsm_bwd_diag_f64": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                               ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p]),
+    "cnngp_rows_update_f64": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
+                                             ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                             ctypes.c_int32, ctypes.c_void_p]),
     "cnngp_syrk_upper_f64": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p,
                                             ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                             ctypes.c_void_p]),

@@ -7,8 +7,13 @@ are computed once per dataset, and a worker's contiguous slice of the reference'
 (cnn_gp/data.py:11-29) is evaluated with at most two launches per block row: the diagonal tile
 (symmetric: only j >= i is computed) and the rectangle to its right.
 
-Tiles are independent, so workers never talk to each other while computing; `gather_blocks`
-is the single exchange step (the reference does it through files, merge_h5_files.py).
+Tiles are independent, so workers never talk to each other while computing.  The single exchange
+step (the reference does it through files, merge_h5_files.py) is `exchange_rows`: every worker
+keeps only the block rows its tiles touch (`RowShard`), and finished block rows travel from their
+owner(s) to whoever consumes them -- the block-cyclic rows of the distributed Cholesky, or one
+rank that writes the store -- by NCCL broadcasts of row panels over NVLink.  `gather_blocks` is the
+older whole-matrix form (NaN-marked N x N matrices on every rank, reduced), kept for small
+matrices and for the CPU (gloo) tests.
 """
 import torch
 
@@ -91,6 +96,85 @@ def compute_worker_blocks(job, out, batch_size, worker_rank=0, n_workers=1, bala
         if on_row is not None:
             on_row(i0, i1)
     return pairs
+
+
+class RowShard:
+    """The block rows of K(X, X2) that one worker's slice of the tile list touches: rows
+    [row_lo, row_hi) x all N2 columns, NaN where another worker owns the entry (or, for a symmetric
+    Gram, below the block diagonal).  A worker of an 8-way split of a 60 000^2 Gram holds 1.1 .. 3.6 GB
+    instead of the 14.4 GB a full NaN-marked matrix costs."""
+
+    def __init__(self, N, N2, batch_size, worker_rank, n_workers, same, device, dtype=torch.float32, balanced=True):
+        self.N, self.N2, self.bs, self.rank, self.world, self.same = N, N2, batch_size, worker_rank, n_workers, same
+        split = worker_tiles_balanced if balanced else worker_tiles
+        self.balanced = balanced
+        self.tiles = split(N, None if same else N2, batch_size, worker_rank, n_workers)
+        self.segments = row_segments(self.tiles)
+        rows = [r for r, _, _, _ in self.segments]
+        self.row_lo = min(rows) * batch_size if rows else 0
+        self.row_hi = min(N, (max(rows) + 1) * batch_size) if rows else 0
+        self.data = torch.full((self.row_hi - self.row_lo, N2), float("nan"), dtype=dtype, device=device)
+
+    def compute(self, job, on_row=None):
+        """Evaluate this worker's tiles into the shard; returns the number of unique pairs."""
+        pairs = 0
+        for r, has_diag, c0, c1 in self.segments:
+            i0, i1 = r * self.bs, min(self.N, (r + 1) * self.bs)
+            view = self.data[i0 - self.row_lo:i1 - self.row_lo]
+            if has_diag:
+                job.block_into(view[:, i0:i1], i0, i1, i0, i1, symmetric=True)
+                pairs += (i1 - i0) * (i1 - i0 + 1) // 2
+            if c0 is not None:
+                j0, j1 = c0 * self.bs, min(self.N2, c1 * self.bs)
+                job.block_into(view[:, j0:j1], i0, i1, j0, j1, symmetric=False)
+                pairs += (i1 - i0) * (j1 - j0)
+            if on_row is not None:
+                on_row(i0, i1)
+        return pairs
+
+
+def row_owners(N, N2, batch_size, n_workers, same, balanced=True):
+    """For every block row of the tile grid: [(worker, col_lo, col_hi)] -- who computed which columns
+    (a pure function of the split, identical on every rank; at most two workers share a row)."""
+    split = worker_tiles_balanced if balanced else worker_tiles
+    nbx = -(-N // batch_size)
+    owners = [[] for _ in range(nbx)]
+    N2 = N if (same or N2 is None) else N2
+    for w in range(n_workers):
+        for r, has_diag, c0, c1 in row_segments(split(N, None if same else N2, batch_size, w, n_workers)):
+            lo = r * batch_size if has_diag else c0 * batch_size
+            hi = min(N2, c1 * batch_size) if c0 is not None else min(N2, (r + 1) * batch_size)
+            owners[r].append((w, lo, hi))
+    return owners
+
+
+def exchange_rows(shard, consume, group=None, wanted=None):
+    """Send every finished block row from its owner(s) to all ranks, one row panel at a time, and call
+    ``consume(i0, i1, panel)`` with the [i1 - i0, N2] float32 panel (NaN where nobody computed: the
+    lower block triangle of a symmetric Gram) on every rank for which ``wanted(i0, i1)`` holds (default:
+    all).  The panel buffer is reused: consumers copy what they keep.  Broadcasts are ring collectives on
+    the communicator that already exists (no point-to-point channels to set up)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    owners = row_owners(shard.N, shard.N2, shard.bs, world, shard.same, shard.balanced) if world > 1 else None
+    dev, bs, N, N2 = shard.data.device, shard.bs, shard.N, shard.N2
+    panel = torch.empty((min(bs, N), N2), dtype=shard.data.dtype, device=dev)
+    for r in range(-(-N // bs)):
+        i0, i1 = r * bs, min(N, (r + 1) * bs)
+        buf = panel[:i1 - i0]
+        if world == 1:
+            buf.copy_(shard.data[i0 - shard.row_lo:i1 - shard.row_lo])
+        else:
+            buf.fill_(float("nan"))
+            for w, lo, hi in owners[r]:
+                piece = torch.empty((i1 - i0, hi - lo), dtype=buf.dtype, device=dev)
+                if w == rank:
+                    piece.copy_(shard.data[i0 - shard.row_lo:i1 - shard.row_lo, lo:hi])
+                dist.broadcast(piece, src=dist.get_global_rank(group, w) if group is not None else w, group=group)
+                buf[:, lo:hi].copy_(piece)
+        if wanted is None or wanted(i0, i1):
+            consume(i0, i1, buf)
 
 
 def gather_blocks(out, dst=0, group=None):

@@ -489,6 +489,186 @@ __global__ void __launch_bounds__(256) bwd_update_kernel(const double *U, long l
 
 constexpr size_t kBwdSmem = (size_t)(64 * DP + NB * NR) * sizeof(double);
 
+// ---- the two triangular sweeps as persistent dataflow kernels -------------------------------------
+// U^T y = b and U x = y with a few right-hand sides are chains of n / NB dependent block steps.  One
+// launch per step (the first version: a one-CTA substitution + an update launch per block, 1 024
+// launches at n = 32 768) is latency-bound: 39 ms for 8.6 GB of traffic.  Here ONE launch runs the
+// whole sweep: CTA c owns the right-hand-side blocks c, c + G, ... (G co-resident CTAs).  For its
+// block j it applies the updates of all earlier blocks k as their solutions are published
+// (flag[k], release / acquire through global memory), then solves with the diagonal block and
+// publishes flag[j].  Only "last update + substitution" of each block is on the critical path; all
+// other updates run ahead of it.  Each U block is read once, coalesced, staged through shared memory.
+constexpr int SW_THREADS = 512;
+constexpr int SW_NR = 16;   // right-hand sides per pass
+constexpr size_t kSweepSmem = (size_t)(NB * DP + SW_NR * DP + NB * SW_NR + NB) * sizeof(double);
+
+__device__ __forceinline__ void flag_wait(const int *f) {
+    if (threadIdx.x == 0) {
+        int v;
+        do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory"); } while (v == 0);
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void flag_set(int *f) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(1) : "memory");
+    }
+}
+
+// FWD: U^T y = b (blocks ascending, update with U[k-block rows, j-block columns]^T);
+// else U x = y (blocks descending, update with U[j-block rows, k-block columns]).
+// Thread (r, cg): row r of the block, right-hand sides 4 cg .. 4 cg + 3.
+template <bool FWD>
+__global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const double *__restrict__ U, long long lda, int n, double *B,
+                                                             long long ldb, int c0, int nr, int *flags) {
+    extern __shared__ __align__(16) double sw_smem[];
+    double *d = sw_smem;                    // [NB][DP]: a U block (updates: staged ahead of the flag; then the diagonal block)
+    double *bs = d + NB * DP;               // [SW_NR][DP]: this block's right-hand sides, bs[c * DP + r]
+    double *ys = bs + SW_NR * DP;           // [NB][SW_NR]: the published solution of block k
+    double *invd = ys + NB * SW_NR;         // [NB]
+    const int tid = threadIdx.x;
+    const int nblk = (n + NB - 1) / NB;
+    const int r = tid & (NB - 1), cg = tid >> 7;
+    for (int q = blockIdx.x; q < nblk; q += gridDim.x) {
+        const int j = FWD ? q : nblk - 1 - q;
+        const int jb = j * NB, nbj = n - jb < NB ? n - jb : NB;
+        double acc[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = cg * 4 + e;
+            acc[e] = (r < nbj && c < nr) ? B[(long long)(jb + r) * ldb + c0 + c] : 0.0;
+        }
+        // the diagonal block waits in registers (32 doubles per thread) until the substitution: its memory
+        // latency is paid here, under the update loop, not on the critical path
+        double dg[NB * NB / SW_THREADS];
+#pragma unroll
+        for (int u = 0; u < NB * NB / SW_THREADS; ++u) {
+            const int e = tid + u * SW_THREADS, i = e >> 7, t = e & (NB - 1);
+            dg[u] = (i < nbj && t < nbj && t >= i) ? __ldg(U + (long long)(jb + i) * lda + jb + t) : 0.0;
+        }
+        const int k_lo = FWD ? 0 : j + 1, k_hi = FWD ? j : nblk;
+        for (int kk = k_lo; kk < k_hi; ++kk) {
+            const int k = FWD ? kk : nblk - 1 - (kk - k_lo);  // backward: the last block first
+            const int kb = k * NB, nbk = n - kb < NB ? n - kb : NB;
+            // stage the U block BEFORE looking at the flag (it does not depend on it): all 32 loads of a
+            // thread are in flight together, and the DRAM latency hides under the wait for block k.
+            // FWD: rows kb.., columns jb..; else rows jb.., columns kb.. (both read along their rows: coalesced)
+            {
+                const long long row0 = FWD ? kb : jb, col0 = FWD ? jb : kb;
+                const int rows = FWD ? nbk : nbj, cols = FWD ? nbj : nbk;
+#pragma unroll 8
+                for (int e = tid; e < NB * NB; e += SW_THREADS) {
+                    const int i = e >> 7, t = e & (NB - 1);
+                    d[i * DP + t] = (i < rows && t < cols) ? __ldg(U + (row0 + i) * lda + col0 + t) : 0.0;
+                }
+            }
+            flag_wait(flags + k);
+            for (int e = tid; e < NB * SW_NR; e += SW_THREADS) {
+                const int t = e / SW_NR, c = e % SW_NR;
+                // published by another SM: read through L2
+                ys[e] = (t < nbk && c < nr) ? __ldcg(B + (long long)(kb + t) * ldb + c0 + c) : 0.0;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int t = 0; t < NB; ++t) {
+                // FWD: acc[r] -= sum_t U[kb + t][jb + r] y[t]; else acc[r] -= sum_t U[jb + r][kb + t] x[t]
+                const double v = FWD ? d[t * DP + r] : d[r * DP + t];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[e] -= v * ys[t * SW_NR + cg * 4 + e];
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int u = 0; u < NB * NB / SW_THREADS; ++u) {
+            const int e = tid + u * SW_THREADS;
+            d[(e >> 7) * DP + (e & (NB - 1))] = dg[u];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) bs[(cg * 4 + e) * DP + r] = acc[e];
+        __syncthreads();
+        if (tid < NB) invd[tid] = tid < nbj ? 1.0 / d[tid * DP + tid] : 0.0;
+        __syncthreads();
+        // substitution with the diagonal block in four 32-row steps: warp w owns right-hand side w of the
+        // 32 x 32 triangle (lane = row, the pivot's value travels by shuffle: no block barrier inside), then
+        // all threads apply the step to the rows outside it
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int s0 = FWD ? 0 : NB - 32; FWD ? s0 < NB : s0 >= 0; s0 += FWD ? 32 : -32) {
+            if (warp < SW_NR) {
+                double v = bs[warp * DP + s0 + lane];
+                if (FWD) {
+                    for (int t = 0; t < 32; ++t) {
+                        const double xt = __shfl_sync(0xffffffffu, v, t) * invd[s0 + t];
+                        if (lane > t) v -= d[(s0 + t) * DP + s0 + lane] * xt;
+                        if (lane == t) v = xt;
+                    }
+                } else {
+                    for (int t = 31; t >= 0; --t) {
+                        const double xt = __shfl_sync(0xffffffffu, v, t) * invd[s0 + t];
+                        if (lane < t) v -= d[(s0 + lane) * DP + s0 + t] * xt;
+                        if (lane == t) v = xt;
+                    }
+                }
+                bs[warp * DP + s0 + lane] = v;
+            }
+            __syncthreads();
+            // rows still to come: FWD r >= s0 + 32, else r < s0
+            const bool mine = FWD ? (r >= s0 + 32) : (r < s0);
+            if (mine) {
+                double a4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
+                for (int t = 0; t < 32; ++t) {
+                    const double v = FWD ? d[(s0 + t) * DP + r] : d[r * DP + s0 + t];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) a4[e] += v * bs[(cg * 4 + e) * DP + s0 + t];
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) bs[(cg * 4 + e) * DP + r] -= a4[e];
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = cg * 4 + e;
+            if (r < nbj && c < nr) B[(long long)(jb + r) * ldb + c0 + c] = bs[c * DP + r];
+        }
+        flag_set(flags + j);
+        __syncthreads();
+    }
+}
+
+// Y[i][:] -= sum_t U[i][t] X[t][:] for nrows stacked rows of a rank's block rows (distributed backward
+// sweep: X is the freshly broadcast solution block, U points at its columns): 64 rows per CTA, staged
+__global__ void __launch_bounds__(256) rows_update_kernel(const double *U, long long ldu, int nrows, int nb, const double *X,
+                                                          long long ldx, double *Y, long long ldy, int c0, int nr) {
+    extern __shared__ __align__(16) double bw_smem[];
+    double *us = bw_smem;             // [64][DP]
+    double *xs = bw_smem + 64 * DP;   // [NB][NR]
+    const int i0 = blockIdx.x * 64;
+    for (int e = threadIdx.x; e < 64 * nb; e += 256) {
+        const int i = e / nb, t = e % nb;
+        us[i * DP + t] = (i0 + i < nrows) ? U[(long long)(i0 + i) * ldu + t] : 0.0;
+    }
+    for (int e = threadIdx.x; e < nb * NR; e += 256) {
+        const int t = e / NR, c = e % NR;
+        xs[e] = c < nr ? X[(long long)t * ldx + c0 + c] : 0.0;
+    }
+    __syncthreads();
+    const int i = threadIdx.x & 63, cg = threadIdx.x >> 6;
+    if (i0 + i >= nrows) return;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int t = 0; t < nb; ++t) {
+        const double v = us[i * DP + t];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] += v * xs[t * NR + cg + 4 * q];
+    }
+    double *b = Y + (long long)(i0 + i) * ldy + c0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (cg + 4 * q < nr) b[cg + 4 * q] -= acc[q];
+}
+
 // ---- prediction: scores = K A (float32 K widened to float64), pred = argmax ------------------
 // A warp owns PR_ROWS rows of K; its lanes stride over the n training points, so K is read from
 // HBM exactly once, coalesced, and every weight row A[t, :] fetched (L1 / L2 resident: n x nrhs
@@ -729,39 +909,112 @@ int cnngp_potrf_upper_f64(double *d_A, int64_t n, int64_t lda, int32_t *d_info, 
     return check(cudaGetLastError(), "cnngp_potrf_upper_f64") ? 0 : 9;
 }
 
+static bool ensure_solve_attrs() {
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && attr_done[dev]) return true;
+    if (!check(cudaFuncSetAttribute(trsv_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsvSmem), "attr") ||
+        !check(cudaFuncSetAttribute(trsv_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsvSmem), "attr") ||
+        !check(cudaFuncSetAttribute(bwd_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem), "attr") ||
+        !check(cudaFuncSetAttribute(rows_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem), "attr") ||
+        !check(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem), "attr") ||
+        !check(cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmem), "attr"))
+        return false;
+    if (dev < 64) attr_done[dev] = true;
+    return true;
+}
+
 int cnngp_potrs_upper_f64(const double *d_U, int64_t n, int64_t lda, double *d_B, int32_t nrhs, int64_t ldb,
                           void *stream_) {
     if (!d_U || !d_B || n < 0 || lda < n || nrhs < 0 || ldb < nrhs) { set_error("cnngp_potrs_upper_f64: bad arguments"); return 1; }
     if (n == 0 || nrhs == 0) return 0;
+    if (n > 2000000000LL) { set_error("cnngp_potrs_upper_f64: n too large"); return 1; }
     cudaStream_t s = (cudaStream_t)stream_;
-    static bool attr_done[64] = {};
-    int dev = 0;
+    if (!ensure_solve_attrs()) return 7;
+    const int nblk = (int)((n + NB - 1) / NB);
+    int dev = 0, sms = 148;
     cudaGetDevice(&dev);
-    if (dev < 64 && !attr_done[dev]) {
-        if (!check(cudaFuncSetAttribute(trsv_block_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsvSmem), "attr") ||
-            !check(cudaFuncSetAttribute(trsv_block_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsvSmem), "attr") ||
-            !check(cudaFuncSetAttribute(bwd_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem), "attr"))
-            return 7;
-        attr_done[dev] = true;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // the sweep's CTAs wait for each other: all of them must be resident (one per SM: 150 KB of shared memory each)
+    const unsigned grid = (unsigned)(nblk < sms ? nblk : sms);
+    int *flags = nullptr;
+    if (!check(cudaMallocAsync((void **)&flags, sizeof(int) * nblk, s), "potrs flags")) return 6;
+    for (int c0 = 0; c0 < nrhs; c0 += SW_NR) {
+        const int nr = nrhs - c0 < SW_NR ? nrhs - c0 : SW_NR;
+        cudaMemsetAsync(flags, 0, sizeof(int) * nblk, s);
+        sweep_kernel<true><<<grid, SW_THREADS, kSweepSmem, s>>>(d_U, lda, (int)n, d_B, ldb, c0, nr, flags);  // U^T y = b
+        cudaMemsetAsync(flags, 0, sizeof(int) * nblk, s);
+        sweep_kernel<false><<<grid, SW_THREADS, kSweepSmem, s>>>(d_U, lda, (int)n, d_B, ldb, c0, nr, flags);  // U x = y
     }
+    cudaFreeAsync(flags, s);
+    return check(cudaGetLastError(), "cnngp_potrs_upper_f64") ? 0 : 9;
+}
+
+// ---- building blocks of the two sweeps for drivers that keep block rows of U on several GPUs --------
+// (cnn_gp/linalg_dist.py).  A "panel" is one block row of U as its owner stores it: d_P points at
+// the diagonal element, `rows` (<= 256) rows of `width` columns each.
+//
+// forward: the rows' right-hand sides d_B[0:rows] (already reduced over the ranks) become y; the
+// rank's accumulator d_B[rows:width] takes  -= U[panel rows, later columns]^T y.
+int cnngp_trsm_fwd_panel_f64(const double *d_P, int64_t ldp, int64_t rows, int64_t width, double *d_B, int32_t nrhs,
+                             int64_t ldb, void *stream_) {
+    if (!d_P || !d_B || rows < 1 || width < rows || ldp < width || nrhs < 1 || ldb < nrhs) {
+        set_error("cnngp_trsm_fwd_panel_f64: bad arguments");
+        return 1;
+    }
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (!ensure_solve_attrs()) return 7;
     for (int c0 = 0; c0 < nrhs; c0 += NR) {
         const int nr = nrhs - c0 < NR ? nrhs - c0 : NR;
-        for (int64_t kb = 0; kb < n; kb += NB) {  // U^T y = b
-            const int nb = (int)(n - kb < NB ? n - kb : NB);
-            trsv_block_kernel<true><<<1, 512, kTrsvSmem, s>>>(d_U, lda, (int)kb, nb, d_B, ldb, c0, nr);
-            const int64_t m = n - kb - nb;
+        for (int64_t kb = 0; kb < rows; kb += NB) {
+            const int nb = (int)(rows - kb < NB ? rows - kb : NB);
+            trsv_block_kernel<true><<<1, 512, kTrsvSmem, s>>>(d_P, ldp, (int)kb, nb, d_B, ldb, c0, nr);
+            const int64_t m = width - kb - nb;
             if (m > 0)
-                fwd_update_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(d_U, lda, (int)kb, nb, (int)n, d_B, ldb, c0, nr);
-        }
-        const int64_t last = ((n - 1) / NB) * NB;
-        for (int64_t kb = last; kb >= 0; kb -= NB) {  // U x = y
-            const int nb = (int)(n - kb < NB ? n - kb : NB);
-            trsv_block_kernel<false><<<1, 512, kTrsvSmem, s>>>(d_U, lda, (int)kb, nb, d_B, ldb, c0, nr);
-            if (kb > 0)
-                bwd_update_kernel<<<(unsigned)((kb + 63) / 64), 256, kBwdSmem, s>>>(d_U, lda, (int)kb, nb, d_B, ldb, c0, nr);
+                fwd_update_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(d_P, ldp, (int)kb, nb, (int)width, d_B, ldb, c0, nr);
         }
     }
-    return check(cudaGetLastError(), "cnngp_potrs_upper_f64") ? 0 : 9;
+    return check(cudaGetLastError(), "cnngp_trsm_fwd_panel_f64") ? 0 : 9;
+}
+
+// backward, the diagonal block only: d_B[0:rows] (y minus the updates of all later blocks) becomes x
+int cnngp_trsm_bwd_diag_f64(const double *d_P, int64_t ldp, int64_t rows, double *d_B, int32_t nrhs, int64_t ldb,
+                            void *stream_) {
+    if (!d_P || !d_B || rows < 1 || ldp < rows || nrhs < 1 || ldb < nrhs) { set_error("cnngp_trsm_bwd_diag_f64: bad arguments"); return 1; }
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (!ensure_solve_attrs()) return 7;
+    for (int c0 = 0; c0 < nrhs; c0 += NR) {
+        const int nr = nrhs - c0 < NR ? nrhs - c0 : NR;
+        const int64_t last = ((rows - 1) / NB) * NB;
+        for (int64_t kb = last; kb >= 0; kb -= NB) {
+            const int nb = (int)(rows - kb < NB ? rows - kb : NB);
+            trsv_block_kernel<false><<<1, 512, kTrsvSmem, s>>>(d_P, ldp, (int)kb, nb, d_B, ldb, c0, nr);
+            if (kb > 0)
+                bwd_update_kernel<<<(unsigned)((kb + 63) / 64), 256, kBwdSmem, s>>>(d_P, ldp, (int)kb, nb, d_B, ldb, c0, nr);
+        }
+    }
+    return check(cudaGetLastError(), "cnngp_trsm_bwd_diag_f64") ? 0 : 9;
+}
+
+// backward update of a rank's stacked rows: d_Y[i] -= d_U[i][0:nb] d_X for i < nrows (d_U points at the
+// solved block's columns inside the rank's local rows, d_X [nb, ldx] is the broadcast solution block)
+int cnngp_rows_update_f64(const double *d_U, int64_t ldu, int64_t nrows, int32_t nb, const double *d_X, int64_t ldx,
+                          double *d_Y, int64_t ldy, int32_t nrhs, void *stream_) {
+    if (!d_U || !d_X || !d_Y || nrows < 0 || nb < 1 || nb > 2 * NB || ldu < nb || nrhs < 1 || ldx < nrhs || ldy < nrhs) {
+        set_error("cnngp_rows_update_f64: bad arguments");
+        return 1;
+    }
+    if (nrows == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (!ensure_solve_attrs()) return 7;
+    for (int c0 = 0; c0 < nrhs; c0 += NR)
+        for (int t0 = 0; t0 < nb; t0 += NB) {  // the staged tile is NB columns wide
+            const int nbt = nb - t0 < NB ? nb - t0 : NB;
+            rows_update_kernel<<<(unsigned)((nrows + 63) / 64), 256, kBwdSmem, s>>>(
+                d_U + t0, ldu, (int)nrows, nbt, d_X + (int64_t)t0 * ldx, ldx, d_Y, ldy, c0, nrhs - c0 < NR ? nrhs - c0 : NR);
+        }
+    return check(cudaGetLastError(), "cnngp_rows_update_f64") ? 0 : 9;
 }
 
 int cnngp_predict_argmax(const float *d_K, int64_t R, int64_t n, int64_t ldk, const double *d_A, int32_t nrhs,

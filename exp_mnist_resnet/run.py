@@ -5,10 +5,13 @@ workers, wait, merge, classify) as a torchrun program.
         -m exp_mnist_resnet.run --config=synthetic --batch_size=200 [--out_path=DIR]
 
 Every rank holds the (small) datasets in HBM, evaluates its contiguous slice of the reference's
-tile lists (cnn_gp/data.py:11-29) with no communication, and the NaN-marked partial matrices
-meet on rank 0 in one NCCL reduction over NVLink (cnn_gp.tiles.gather_blocks) instead of through
-per-worker files; rank 0 then runs the float64 Cholesky solve and prints the accuracies.  With
-``--out_path`` rank 0 also writes the merged store in the save_K layout."""
+tile lists (cnn_gp/data.py:11-29) with no communication and keeps only the block rows its tiles
+touch (cnn_gp.tiles.RowShard).  Nothing is gathered to one GPU: finished block rows of Kxx travel
+from their owners straight into the block-cyclic rows of the distributed float64 Cholesky (NCCL
+broadcasts of row panels over NVLink), both triangular sweeps run on the distributed factor, and
+every rank scores the validation / test entries it computed itself (partial K* A summed by one
+small all-reduce).  With ``--out_path`` rank 0 additionally streams the merged matrices, row panel by
+row panel, into a store in the save_K layout -- the job of merge_h5_files.py."""
 import importlib
 import os
 import sys
@@ -25,19 +28,28 @@ from cnn_gp import DatasetFromConfig  # noqa: E402
 from cnn_gp import linalg, linalg_dist  # noqa: E402
 from cnn_gp.block_store import open_store  # noqa: E402
 from cnn_gp.kernel_save_tools import create_h5py_dataset  # noqa: E402
-from cnn_gp.tiles import GramJob, compute_worker_blocks, gather_blocks  # noqa: E402
+from cnn_gp.tiles import GramJob, RowShard, exchange_rows  # noqa: E402
 
 FLAGS = absl.app.flags.FLAGS
 
 
-def gram_sharded(model, X, X2, batch_size, rank, world):
-    """This rank's tiles of K(X, X2) gathered on rank 0 (None elsewhere)."""
+def gram_shard(model, X, X2, batch_size, rank, world):
+    """This rank's tiles of K(X, X2), in the block rows they touch."""
     N, N2 = X.shape[0], (X if X2 is None else X2).shape[0]
-    K = torch.full((N, N2), float("nan"), dtype=torch.float32, device=X.device)
-    compute_worker_blocks(GramJob(model, X, X2), K, batch_size, rank, world, balanced=True)
-    if world == 1:
-        return K
-    return gather_blocks(K, dst=0)
+    shard = RowShard(N, N2, batch_size, rank, world, X2 is None, X.device)
+    shard.compute(GramJob(model, X, X2))
+    return shard
+
+
+def partial_scores(shard, A):
+    """sum over the entries this rank computed of K*[i, j] A[j, :]  ->  [N*, classes] (classify_gp.py:40)."""
+    scores = torch.zeros((shard.N, A.shape[1]), dtype=torch.float64, device=A.device)
+    for r, has_diag, c0, c1 in shard.segments:
+        i0, i1 = r * shard.bs, min(shard.N, (r + 1) * shard.bs)
+        j0, j1 = c0 * shard.bs, min(shard.N2, c1 * shard.bs)
+        K = shard.data[i0 - shard.row_lo:i1 - shard.row_lo, j0:j1]
+        scores[i0:i1] += linalg.predict_argmax(K, A[j0:j1].contiguous(), return_scores=True)[1]
+    return scores
 
 
 def main(_):
@@ -54,38 +66,61 @@ def main(_):
     sets = {k: DatasetFromConfig.resident(getattr(dataset, k), dev) for k in ("train", "validation", "test")}
     t0 = time.perf_counter()
     with torch.no_grad():
-        Kxx = gram_sharded(model, sets["train"].images, None, FLAGS.batch_size, rank, world)
-        Kxvx = gram_sharded(model, sets["validation"].images, sets["train"].images, FLAGS.batch_size, rank, world)
-        Kxtx = gram_sharded(model, sets["test"].images, sets["train"].images, FLAGS.batch_size, rank, world)
+        Kxx = gram_shard(model, sets["train"].images, None, FLAGS.batch_size, rank, world)
+        Kxvx = gram_shard(model, sets["validation"].images, sets["train"].images, FLAGS.batch_size, rank, world)
+        Kxtx = gram_shard(model, sets["test"].images, sets["train"].images, FLAGS.batch_size, rank, world)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n = Kxx.N
     if rank == 0:
-        print(f"kernels: {time.perf_counter() - t0:.3f} s on {world} GPU(s)")
-        if FLAGS.out_path:
-            with open_store(FLAGS.out_path, "w") as f:
-                for name, K in (("Kxx", Kxx), ("Kxvx", Kxvx), ("Kxtx", Kxtx)):
-                    ds = create_h5py_dataset(f, FLAGS.batch_size, name, False, K.shape[0], K.shape[1])
-                    ds[0, :, :] = K.cpu().numpy()
+        print(f"kernels: {time.perf_counter() - t0:.3f} s on {world} GPU(s); rank 0 holds rows "
+              f"[{Kxx.row_lo}, {Kxx.row_hi}) of Kxx ({Kxx.data.numel() * 4 / 2**30:.2f} GiB of {n * n * 4 / 2**30:.2f})")
+    if FLAGS.out_path:
+        # the merge: row panels from their owners to rank 0, which writes them as they arrive
+        t2 = time.perf_counter()
+        store = open_store(FLAGS.out_path, "w") if rank == 0 else None
+        for name, sh in (("Kxx", Kxx), ("Kxvx", Kxvx), ("Kxtx", Kxtx)):
+            ds = create_h5py_dataset(store, FLAGS.batch_size, name, False, sh.N, sh.N2) if rank == 0 else None
+
+            def write(i0, i1, panel, ds=ds):
+                ds[0, i0:i1, :] = panel.cpu().numpy()
+            exchange_rows(sh, write, wanted=lambda i0, i1: rank == 0)
+        if rank == 0:
+            store.close()
+            print(f"store written: {time.perf_counter() - t2:.3f} s")
     Y = sets["train"].labels
     n_classes = int(Y.max()) + 1
     Y_1hot = torch.ones((len(Y), n_classes), dtype=torch.float64).neg_()
     Y_1hot[torch.arange(len(Y)), Y] = 1.
     t1 = time.perf_counter()
     if world > 1 and FLAGS.dist_solve:
-        # block rows of Kxx dealt out to all GPUs, panel broadcasts over NVLink (cnn_gp.linalg_dist)
-        if rank == 0 and FLAGS.jitter:
-            Kxx.diagonal().add_(FLAGS.jitter)
-        A = linalg_dist.solve_pos_upper_distributed(Kxx, Y_1hot.to(dev) if rank == 0 else None, len(Y), dev)
-    elif rank == 0:
-        K64 = Kxx.to(torch.float64)
-        K64.diagonal().add_(FLAGS.jitter)
-        A = linalg.solve_pos_upper(K64, Y_1hot.to(dev), overwrite_a=True)
-        del K64
+        # block rows of Kxx dealt out to all GPUs, panel broadcasts over NVLink; the jitter is added in
+        # float64 on the owners (classify_gp.py:64), the sweeps run on the distributed factor
+        A = linalg_dist.solve_pos_upper_distributed(
+            None, Y_1hot.to(dev) if rank == 0 else None, n, dev, jitter=FLAGS.jitter,
+            fill=lambda ch: exchange_rows(Kxx, ch.fill_rows, wanted=ch.wants_rows))
+    else:
+        K64 = torch.empty((n, n), dtype=torch.float64, device=dev) if rank == 0 else None
+        exchange_rows(Kxx, lambda i0, i1, panel: K64[i0:i1].copy_(panel), wanted=lambda i0, i1: rank == 0)
+        A = torch.empty((n, n_classes), dtype=torch.float64, device=dev)
+        if rank == 0:
+            K64.diagonal().add_(FLAGS.jitter)
+            A.copy_(linalg.solve_pos_upper(K64, Y_1hot.to(dev), overwrite_a=True))
+            del K64
+        if world > 1:
+            dist.broadcast(A, src=0)
+    torch.cuda.synchronize()
     if rank == 0:
-        torch.cuda.synchronize()
-        print(f"solve: {time.perf_counter() - t1:.3f} s (n = {len(Y)}, "
-              f"{'distributed over ' + str(world) + ' GPUs' if world > 1 and FLAGS.dist_solve else 'one GPU'})")
-        for key, K in (("validation", Kxvx), ("test", Kxtx)):
-            pred = linalg.predict_argmax(K, A).cpu()
+        print(f"solve: {time.perf_counter() - t1:.3f} s (n = {n}, "
+              f"{'distributed over ' + str(world) + ' GPUs' if world > 1 and FLAGS.dist_solve else 'one GPU'}); "
+              f"peak HBM on rank 0: {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB")
+    for key, sh in (("validation", Kxvx), ("test", Kxtx)):
+        scores = partial_scores(sh, A)
+        if world > 1:
+            dist.all_reduce(scores)
+        if rank == 0:
+            pred = scores.argmax(dim=1).cpu()
             acc = float((pred == sets[key].labels).double().mean())
             print(f"{key} accuracy: {acc*100}%")
     if world > 1:

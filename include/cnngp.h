@@ -178,6 +178,22 @@ int cnngp_syrk_upper_strided_f64(const double *d_X, int64_t ldx, int32_t K, doub
                                  void *stream);
 int cnngp_potrs_upper_f64(const double *d_U, int64_t n, int64_t lda, double *d_B, int32_t nrhs,
                           int64_t ldb, void *stream);
+/* The two triangular sweeps of potrs for drivers that keep block rows of U on several GPUs
+ * (linalg_dist.py: no rank ever holds all of U; classify_gp.py:17-27 on a matrix spread over GPUs).
+ * A panel is one block row of U as its owner stores it: d_P points at its diagonal element,
+ * rows <= 256, `width` columns to the end of the matrix.
+ * fwd_panel: d_B[0:rows] (right-hand sides with the updates of all earlier blocks, already summed
+ *            over the ranks) becomes y = U_kk^-T (.) in place, and the caller's accumulator rows
+ *            d_B[rows:width] take  -= U[panel rows, later columns]^T y.
+ * bwd_diag:  d_B[0:rows] (y minus the updates of all later blocks) becomes x = U_kk^-1 (.) in place.
+ * rows_update: d_Y[i] -= d_U[i][0:nb] d_X for the nrows stacked local rows above the solved block;
+ *            d_U points at that block's columns, d_X [nb, ldx] is its (broadcast) solution. */
+int cnngp_trsm_fwd_panel_f64(const double *d_P, int64_t ldp, int64_t rows, int64_t width, double *d_B,
+                             int32_t nrhs, int64_t ldb, void *stream);
+int cnngp_trsm_bwd_diag_f64(const double *d_P, int64_t ldp, int64_t rows, double *d_B, int32_t nrhs,
+                            int64_t ldb, void *stream);
+int cnngp_rows_update_f64(const double *d_U, int64_t ldu, int64_t nrows, int32_t nb, const double *d_X,
+                          int64_t ldx, double *d_Y, int64_t ldy, int32_t nrhs, void *stream);
 /* classify_gp.py:39-41: pred[r] = argmax_c (K[r,:] . A[:,c]); K row-major float32 [R, ldk]
  * (as stored by save_K), A row-major float64 [n, nrhs]; accumulates in float64. */
 int cnngp_predict_argmax(const float *d_K, int64_t R, int64_t n, int64_t ldk, const double *d_A,

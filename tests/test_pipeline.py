@@ -333,6 +333,23 @@ class _NumpyBackend:
         y = scipy.linalg.solve_triangular(u, B.numpy(), trans="T", lower=False)
         return torch.from_numpy(scipy.linalg.solve_triangular(u, y, lower=False))
 
+    # the distributed sweeps (cnngp_trsm_fwd_panel_f64 / cnngp_trsm_bwd_diag_f64 / cnngp_rows_update_f64)
+    def fwd_panel(self, rows, col0, n, acc):
+        import scipy.linalg
+        a, b = rows.numpy(), acc.numpy()
+        nb = a.shape[0]
+        b[:nb] = scipy.linalg.solve_triangular(np.triu(a[:, col0:col0 + nb]), b[:nb], trans="T", lower=False)
+        b[nb:] -= a[:, col0 + nb:n].T @ b[:nb]
+
+    def bwd_diag(self, rows, col0, yb):
+        import scipy.linalg
+        a, y = rows.numpy(), yb.numpy()
+        y[:] = scipy.linalg.solve_triangular(np.triu(a[:, col0:col0 + a.shape[0]]), y, lower=False)
+
+    def rows_update(self, local, nrows, col0, nb, xb, y_local):
+        if nrows > 0:
+            y_local.numpy()[:nrows] -= local.numpy()[:nrows, col0:col0 + nb] @ xb.numpy()
+
 
 def _dist_solve_worker(rank, world, port, n, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -348,11 +365,9 @@ def _dist_solve_worker(rank, world, port, n, ret):
         Y = torch.from_numpy(rng.standard_normal((n, 3)))
         K = torch.from_numpy(np.triu(Kfull) + np.tril(np.full((n, n), np.nan), -1))  # lower triangle never read
         ret["K"], ret["Y"] = Kfull, Y.numpy()
-    A = linalg_dist.solve_pos_upper_distributed(K, Y, n, torch.device("cpu"), backend=_NumpyBackend(), lookahead=False)
-    if rank == 0:
-        ret["A"] = A.numpy()
-    else:
-        assert A is None
+    A = linalg_dist.solve_pos_upper_distributed(K, Y, n, torch.device("cpu"), backend=_NumpyBackend(), lookahead=False,
+                                                jitter=0.25)
+    ret[f"A{rank}"] = A.numpy()  # the solution comes back on every rank; no rank ever held all of U
     dist.destroy_process_group()
 
 
@@ -370,5 +385,64 @@ def test_distributed_cholesky_orchestration_over_gloo(n, world):
     for p in procs:
         p.join(180)
         assert p.exitcode == 0
-    want = np.linalg.solve(ret["K"], ret["Y"])
-    np.testing.assert_allclose(ret["A"], want, rtol=0, atol=1e-9 * np.abs(want).max())
+    want = np.linalg.solve(ret["K"] + 0.25 * np.eye(n), ret["Y"])  # the jitter is added in float64 on the owners
+    for r in range(world):
+        np.testing.assert_allclose(ret[f"A{r}"], want, rtol=0, atol=1e-9 * np.abs(want).max())
+        np.testing.assert_array_equal(ret[f"A{r}"], ret["A0"])
+
+
+def _exchange_worker(rank, world, port, N, bs, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path[:0] = [os.path.join(ROOT, "cnn-gp_b200"), ROOT, os.path.join(ROOT, "tests")]
+    import torch.distributed as dist
+    from cnn_gp import linalg_dist
+    from cnn_gp.tiles import RowShard, exchange_rows
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(3)
+    B = rng.standard_normal((N, N + 10))
+    truth = (B @ B.T / N + 0.5 * np.eye(N)).astype(np.float32)
+    shard = RowShard(N, N, bs, rank, world, True, torch.device("cpu"))
+    for r, has_diag, c0, c1 in shard.segments:  # stand-in for shard.compute(job): this worker's tiles only
+        i0, i1 = r * bs, min(N, (r + 1) * bs)
+        if has_diag:
+            shard.data[i0 - shard.row_lo:i1 - shard.row_lo, i0:i1] = torch.from_numpy(truth[i0:i1, i0:i1])
+        if c0 is not None:
+            j0, j1 = c0 * bs, min(N, c1 * bs)
+            shard.data[i0 - shard.row_lo:i1 - shard.row_lo, j0:j1] = torch.from_numpy(truth[i0:i1, j0:j1])
+    ret[f"rows{rank}"] = (shard.row_lo, shard.row_hi)
+    Y = torch.from_numpy(rng.standard_normal((N, 2))) if rank == 0 else None
+    A = linalg_dist.solve_pos_upper_distributed(
+        None, Y, N, torch.device("cpu"), backend=_NumpyBackend(), lookahead=False,
+        fill=lambda ch: exchange_rows(shard, ch.fill_rows, wanted=ch.wants_rows))
+    full = torch.full((N, N), float("nan"))
+    exchange_rows(shard, lambda i0, i1, panel: full[i0:i1].copy_(panel))
+    if rank == 0:
+        ret["A"], ret["Y"], ret["truth"], ret["full"] = A.numpy(), Y.numpy(), truth, full.numpy()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("N,bs,world", [(600, 64, 3), (300, 50, 2)])
+def test_row_shards_feed_the_distributed_cholesky_without_a_gather(N, bs, world):
+    """Every worker keeps only the block rows its tiles touch (RowShard); exchange_rows moves finished
+    rows from their owners straight into the block-cyclic rows of the distributed Cholesky (the Gram
+    matrix never exists on one rank), or to a rank that wants the whole matrix: same NaN pattern as
+    merge_h5_files (strictly lower block triangle), same values."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, N, bs, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    truth = ret["truth"]
+    want = np.linalg.solve(truth.astype(np.float64), ret["Y"])
+    np.testing.assert_allclose(ret["A"], want, rtol=0, atol=1e-8 * np.abs(want).max())
+    bi = np.arange(N) // bs
+    owned = bi[None, :] >= bi[:, None]
+    np.testing.assert_array_equal(ret["full"][owned], truth[owned])
+    assert np.isnan(ret["full"][~owned]).all()
+    spans = [ret[f"rows{r}"] for r in range(world)]
+    assert max(hi - lo for lo, hi in spans) < N, "no worker holds every row"
