@@ -81,8 +81,8 @@ enum { N_CONV = 0, N_AFFINE, N_RELU, N_STASH, N_UNSTASH, N_ADD, N_TRANSPOSE, N_D
 // dispatch cases.  Phase A works on the full register set M[2][S0]: kind x size class (0: S0,
 // 1: S0/2, 2: S0/4; folded maps live in M[0]), convolutions by variant.  Phase B works on the
 // folded array F[S0/2] (size classes 1 and 2 only).  The tail works on the four scalars.
-enum { A_CONV = 0, A_AFFINE = 10, A_TRANSPOSE = 13, A_STASH = 16, A_UNSTASH = 19, A_ADD = 22, A_DENSE = 25, A_RELU = 28,
-       A_IDBLOCK = 31, A_RESBLOCK = 32, A_END = 33, A_CASES = 34 };
+enum { A_CONV = 0 /* + 10: 3 x 3 with dilation 2 at full size */, A_AFFINE = 11, A_TRANSPOSE = 14, A_STASH = 17, A_UNSTASH = 20,
+       A_ADD = 23, A_DENSE = 26, A_RELU = 29, A_IDBLOCK = 32, A_RESBLOCK = 33, A_END = 34, A_CASES = 35 };
 enum { B_CONV = 0 /* +0: S/2 s1, +1: S/2 -> S/4 k3 s2, +2: S/2 -> S/4 k1 s2, +3: S/4 s1 */, B_AFFINE = 4, B_TRANSPOSE = 6,
        B_STASH = 8, B_UNSTASH = 10, B_ADD = 12, B_DENSE = 14, B_RELU = 16, B_IDBLOCK = 18, B_END = 20, B_CASES = 21 };
 enum { T_CASE_AFFINE = 0, T_CASE_RELU = 1, T_END = 2 };
@@ -90,7 +90,8 @@ enum { T_CASE_AFFINE = 0, T_CASE_RELU = 1, T_END = 2 };
 struct NOp {
     int kind;
     short si, so;       // map edge before / after the op
-    short lo, hi, st;   // N_CONV: window offsets [-lo, +hi] and stride
+    short lo, hi, st;   // N_CONV: window offsets [-lo, +hi] (in taps) and stride
+    short dil;          // N_CONV: distance between taps (reference Conv2d(dilation=), kernels.py:61,95-96)
     short slot;         // N_STASH / N_UNSTASH / N_ADD: tensor-memory slot (0 or 1)
     float scale, bias;  // N_CONV / N_AFFINE / N_DENSE / T_AFFINE: explicit scale-and-bias pass (1, 0: none);
                         // N_ADD: factor applied to the stashed map, constant added
@@ -328,6 +329,24 @@ __device__ __forceinline__ void box_s1(u64 (&v)[NA], u64 B) {
     for (int y = 0; y < S; ++y) v[y] = o[y];
 }
 
+// dilated taps, stride 1, zero padding: out[y] = B + sum_{t=-LO..HI} v[y + t DIL] -- a direct sum (the taps of
+// neighbouring outputs do not overlap, so there is nothing to slide)
+template <int NA, int S, int LO, int HI, int DIL, bool BIAS>
+__device__ __forceinline__ void box_dil(u64 (&v)[NA], u64 B) {
+    u64 o[S];
+#pragma unroll
+    for (int y = 0; y < S; ++y) {
+        o[y] = BIAS ? add2(v[y], B) : v[y];
+#pragma unroll
+        for (int t = -LO; t <= HI; ++t) {
+            const int idx = y + t * DIL;
+            if (t != 0 && idx >= 0 && idx < S) o[y] = add2(o[y], v[idx]);
+        }
+    }
+#pragma unroll
+    for (int y = 0; y < S; ++y) v[y] = o[y];
+}
+
 // stride 2: out[y] = sum_{t=-LO..HI} v[2y+t], SI entries -> SO entries
 template <int NA, int SI, int SO, int LO, int HI>
 __device__ __forceinline__ void box_s2(u64 (&v)[NA]) {
@@ -375,16 +394,19 @@ __device__ __forceinline__ void affine_arr(u64 (&a)[NA], float scale, float bias
 // register layout), software-pipelined over the two packed arrays.  Stride 1: the second pass
 // carries `pre_bias`.  The explicit tap * sum + bias pass runs only when the translator asks for it
 // (scale != 1 or bias != 0: strided convolutions with a bias, and the rare reset of the carried factor).
-template <int S0, int SI, int SO, int LO, int HI, int ST>
+template <int S0, int SI, int SO, int LO, int HI, int ST, int DIL = 1>
 __device__ __forceinline__ void conv_op(u64 (&M)[2][S0], u64 *tile, int lane, float pre_bias, float scale, float bias) {
     static_assert(ST == 1 ? SI == SO : SI == 2 * SO, "conv geometry");
+    static_assert(DIL == 1 || ST == 1, "dilated windows are stride 1 here");
     const u64 PB = pk(pre_bias, pre_bias);
     auto pass1 = [](u64 (&v)[S0]) {
-        if (ST == 1) box_s1<S0, SI, LO, HI, false>(v, 0ull);
+        if (DIL > 1) box_dil<S0, SI, LO, HI, DIL, false>(v, 0ull);
+        else if (ST == 1) box_s1<S0, SI, LO, HI, false>(v, 0ull);
         else box_s2<S0, SI, SO, LO, HI>(v);
     };
     auto pass2 = [&](u64 (&v)[S0]) {
-        if (ST == 1) box_s1<S0, SI, LO, HI, true>(v, PB);
+        if (DIL > 1) box_dil<S0, SI, LO, HI, DIL, true>(v, PB);
+        else if (ST == 1) box_s1<S0, SI, LO, HI, true>(v, PB);
         else box_s2<S0, SI, SO, LO, HI>(v);
     };
     const int lx = lane < SO ? lane : SO - 1;
@@ -900,6 +922,7 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
                     case A_CONV + 7: FETCH(1); conv_op_f<S0, S0, S0 / 2, S0 / 4, 1, 1, 2>(M[0], tile, lane, 0.f, f_scale(o), f_bias(o)); break;
                     case A_CONV + 8: FETCH(1); conv_op_f<S0, S0, S0 / 2, S0 / 4, 0, 0, 2>(M[0], tile, lane, 0.f, f_scale(o), f_bias(o)); break;
                     case A_CONV + 9: FETCH(1); conv_op_f<S0, S0, S0 / 4, S0 / 4, 1, 1, 1>(M[0], tile, lane, f_pre(o), f_scale(o), f_bias(o)); break;
+                    case A_CONV + 10: FETCH(1); conv_op<S0, S0, S0, 1, 1, 1, 2>(M, tile, lane, f_pre(o), f_scale(o), f_bias(o)); break;
                     case A_AFFINE + 0: FETCH(1); affine_arr<S0, S0>(M[0], f_scale(o), f_bias(o)); affine_arr<S0, S0>(M[1], f_scale(o), f_bias(o)); break;
                     FOLDED_A(A_AFFINE, (affine_arr<S0, S>(M[0], f_scale(o), f_bias(o))))
                     case A_TRANSPOSE + 0: FETCH(1); transpose_op<S0, S0>(M, tile, lane); break;
@@ -1078,6 +1101,7 @@ struct FNetPlan {
     int n_relu = 0;           // staged ReLU layers in program order (the producer's list)
     int relu_aux[kMaxRelu], relu_half[kMaxRelu];
     int n_blocks = 0;         // residual blocks dispatched as one case
+    bool folded_phase = false;  // the program has ops on folded (half / quarter size) maps
     size_t smem = 0;
     int nst = 0;
     int fused_row_floats = 0;  // floats per image the Gram kernel reads (super-tile sizing)
@@ -1086,7 +1110,8 @@ struct FNetPlan {
 
 namespace {
 
-bool conv_supported(int S0, int si, int lo, int hi, int st) {
+bool conv_supported(int S0, int si, int lo, int hi, int st, int dil) {
+    if (dil != 1) return dil == 2 && si == S0 && st == 1 && lo == 1 && hi == 1;  // 3 x 3, dilation 2, "same"
     if (si == S0) {
         if (st == 1) return (lo == 1 && hi == 1) || (lo == 1 && hi == 2) || (lo == 2 && hi == 2) || (lo == 3 && hi == 3);
         return (lo == 1 && hi == 1) || (lo == 0 && hi == 0);
@@ -1138,6 +1163,7 @@ struct Translator {
     static NOp blank(int kind, int si, int so) {
         NOp n{};
         n.kind = kind; n.si = (short)si; n.so = (short)so; n.scale = 1.f; n.bias = 0.f; n.pre_bias = 0.f; n.aux_scale = 1.f;
+        n.dil = 1;
         return n;
     }
     void affine(int size, float scale, float bias) {
@@ -1296,9 +1322,12 @@ struct Translator {
                     break;
                 }
                 case CNNGP_OP_CONV: {
-                    if (o.dil != 1 || o.Hi != o.Wi || o.Ho != o.Wo || o.Hi != src.size) return false;
-                    const int lo = o.pad - o.t0, hi = o.ke - 1 - o.pad;
+                    if (o.Hi != o.Wi || o.Ho != o.Wo || o.Hi != src.size) return false;
+                    // taps t0 .. ke-1 at distance dil, the first at offset dil * t0 - pad: window [-lo, +hi] in taps
+                    if (o.dil < 1 || (o.pad - o.dil * o.t0) % o.dil != 0) return false;
+                    const int lo = (o.pad - o.dil * o.t0) / o.dil, hi = o.ke - 1 - o.t0 - lo;
                     if (lo < 0 || hi < 0) return false;
+                    if (o.dil != 1 && (src.size == 1 || (lo == 0 && hi == 0))) return false;
                     NOp n = blank(N_CONV, src.size, o.Ho);
                     // true_out = scale_f * box(true_in) + bias_f; stored_in = pend * true_in
                     const double np = (double)src.pend / (double)o.scale_f;  // carried: stored_out = box(stored_in) + bias_f * np
@@ -1306,7 +1335,7 @@ struct Translator {
                     if (src.size == 1) {
                         if (lo != 0 || hi != 0 || o.Ho != 1) return false;
                         n.kind = T_AFFINE;
-                    } else if (o.Ho == 1 && lo == 0 && hi == src.size - 1) {
+                    } else if (o.Ho == 1 && lo == 0 && hi == src.size - 1 && o.dil == 1) {
                         n.kind = N_DENSE;
                     } else if (lo == 0 && hi == 0 && o.stride == 1) {
                         n.kind = N_AFFINE;
@@ -1316,9 +1345,9 @@ struct Translator {
                         }
                     } else {
                         if (o.stride != 1 && o.stride != 2) return false;
-                        if (!conv_supported(S0, src.size, lo, hi, o.stride)) return false;
+                        if (!conv_supported(S0, src.size, lo, hi, o.stride, o.dil)) return false;
                         if (o.Ho != (o.stride == 1 ? src.size : src.size / 2)) return false;
-                        n.lo = (short)lo; n.hi = (short)hi; n.st = (short)o.stride;
+                        n.lo = (short)lo; n.hi = (short)hi; n.st = (short)o.stride; n.dil = (short)o.dil;
                         dst.orient = src.orient ^ 1;
                         if (carry && o.scale_f > 0.f && pend_ok(np)) {
                             carried = true;
@@ -1361,6 +1390,7 @@ int case_of(const NOp &n, int S0, bool phase_b) {
     if (!phase_b) {
         switch (n.kind) {
             case N_CONV: {
+                if (n.dil == 2) return A_CONV + 10;
                 const int v = n.st == 1 ? (n.lo == 1 && n.hi == 1 ? 0 : n.lo == 1 && n.hi == 2 ? 1 : n.lo == 2 ? 2 : 3)
                                         : (n.lo == 1 ? 4 : 5);
                 return A_CONV + (sc == 0 ? v : sc == 1 ? (n.st == 1 ? 6 : (n.lo == 1 ? 7 : 8)) : 9);
@@ -1400,7 +1430,7 @@ KOp make_kop(const NOp &n, int code) {
 bool is_idblock(const NOp *o, int n_left) {
     if (n_left < 6) return false;
     const int s = o[0].si;
-    auto conv33 = [&](const NOp &c) { return c.kind == N_CONV && c.si == s && c.so == s && c.st == 1 && c.lo == 1 && c.hi == 1; };
+    auto conv33 = [&](const NOp &c) { return c.kind == N_CONV && c.si == s && c.so == s && c.st == 1 && c.lo == 1 && c.hi == 1 && c.dil == 1; };
     return o[0].kind == N_STASH && o[1].kind == N_RELU && o[1].si == s && conv33(o[2]) && o[3].kind == N_RELU && o[3].si == s &&
            conv33(o[4]) && o[5].kind == N_ADD && o[5].si == s && o[5].slot == o[0].slot;
 }
@@ -1408,7 +1438,7 @@ bool is_idblock(const NOp *o, int n_left) {
 bool is_resblock(const NOp *o, int n_left, int S0) {
     if (n_left < 5) return false;
     return o[0].kind == N_STASH && o[0].si == S0 && o[1].kind == N_CONV && o[1].si == S0 && o[1].so == S0 && o[1].st == 1 &&
-           o[1].lo == 1 && o[1].hi == 2 && o[2].kind == N_RELU && o[2].si == S0 && o[3].kind == N_TRANSPOSE && o[3].si == S0 &&
+           o[1].lo == 1 && o[1].hi == 2 && o[1].dil == 1 && o[2].kind == N_RELU && o[2].si == S0 && o[3].kind == N_TRANSPOSE && o[3].si == S0 &&
            o[4].kind == N_ADD && o[4].si == S0 && o[4].slot == o[0].slot;
 }
 
@@ -1438,6 +1468,7 @@ bool build_kops(FNetPlan *fp, bool blocks) {
         k += len;
     }
     sentinel.code = A_END; push(sentinel);
+    fp->folded_phase = end_a < first_tail;
     for (int k = end_a; k < first_tail;) {
         const NOp *o = fp->ops + k;
         if (o->si == S0 || o->si == 1) return false;
@@ -1471,7 +1502,7 @@ FNetPlan *fnet_plan_create(const Plan *plan_const) {
     Plan *plan = const_cast<Plan *>(plan_const);
     if (plan->dtype != CNNGP_F32) return nullptr;
     if (plan->H != plan->W || (plan->H != 28 && plan->H != 32)) return nullptr;
-    if (plan->n_slots > 2) return nullptr;
+    if (plan->n_slots > 3) return nullptr;  // one map in registers + two tensor-memory slots
     const int S0 = plan->H;
     std::vector<DevOp> saved = plan->ops;
     // measurement aids: CNNGP_FNET_NOCARRY=1 applies every tap explicitly (one FMA pass per conv),
@@ -1495,7 +1526,10 @@ FNetPlan *fnet_plan_create(const Plan *plan_const) {
     }
     // twelve consumer warps when the second tensor-memory slot only ever holds folded maps of at most
     // half the edge (3 warps share a 512-column lane quadrant: 3 x 5 S0 columns)
-    const bool twelve = tr.slot1_max <= S0 / 2 && !getenv("CNNGP_FNET_8WARPS");
+    // ... and when the program has a folded phase: its short, latency-bound ops want three warps per
+    // scheduler (mnist_as_tf: 75.8 M pairs/s with twelve warps, 72.8 M with eight), whereas full-size layers
+    // alone run better on eight warps with 240 registers (mnist_paper_residual_cnn_gp: 123.8 M against 114.8 M)
+    const bool twelve = tr.slot1_max <= S0 / 2 && (fp->folded_phase || getenv("CNNGP_FNET_12WARPS")) && !getenv("CNNGP_FNET_8WARPS");
     // three ring stages (1.5 layers of variance maps in flight): + 4 % over two on the straight-line kernel
     const bool deep = getenv("CNNGP_FNET_NST2") == nullptr;
     if (S0 == 28 && twelve && deep) { fp->nw = 12; fp->nst = 3; fp->smem = fnet_smem<28, 12, 3, 2>(); }
@@ -1516,7 +1550,8 @@ std::string fnet_plan_describe(const FNetPlan *fp) {
     for (int k = 0; k < fp->n_ops; ++k) {
         const NOp &o = fp->ops[k];
         t += std::string(" ") + kNames[o.kind] + "(" + std::to_string(o.si);
-        if (o.kind == N_CONV) t += "," + std::to_string(o.lo) + "," + std::to_string(o.hi) + ",s" + std::to_string(o.st);
+        if (o.kind == N_CONV) t += "," + std::to_string(o.lo) + "," + std::to_string(o.hi) + ",s" + std::to_string(o.st) +
+                                   (o.dil != 1 ? ",d" + std::to_string(o.dil) : "");
         if (o.kind == N_STASH || o.kind == N_UNSTASH || o.kind == N_ADD) t += ",t" + std::to_string(o.slot);
         t += ")";
     }
@@ -1530,8 +1565,8 @@ std::string fnet_plan_dump(const FNetPlan *fp) {
     for (int k = 0; k < fp->n_ops; ++k) {
         const NOp &o = fp->ops[k];
         snprintf(line, sizeof line,
-                 "%s si=%d so=%d lo=%d hi=%d st=%d slot=%d scale=%.9g bias=%.9g pre_bias=%.9g aux_scale=%.9g aux=%d half=%d\n",
-                 kNames[o.kind], (int)o.si, (int)o.so, (int)o.lo, (int)o.hi, (int)o.st, (int)o.slot, (double)o.scale,
+                 "%s si=%d so=%d lo=%d hi=%d st=%d dil=%d slot=%d scale=%.9g bias=%.9g pre_bias=%.9g aux_scale=%.9g aux=%d half=%d\n",
+                 kNames[o.kind], (int)o.si, (int)o.so, (int)o.lo, (int)o.hi, (int)o.st, (int)o.dil, (int)o.slot, (double)o.scale,
                  (double)o.bias, (double)o.pre_bias, (double)o.aux_scale, o.aux, o.half);
         t += line;
     }

@@ -65,6 +65,25 @@ def edge2_models():
     }
 
 
+def edge3_models():
+    """The third batch (tests/golden/make_golden_f3.py): dilated windows and nested Sums at fused-net sizes."""
+    return {
+        "edge3_28_dilated": Sequential(
+            Conv2d(3, dilation=2, var_weight=1.3, var_bias=0.1), ReLU(), Conv2d(3), ReLU(),
+            Sum([Sequential(), Sequential(Conv2d(3, dilation=2, var_bias=0.05), ReLU(), Conv2d(3, var_weight=0.8))]),
+            ReLU(), Conv2d(28, padding=0, var_bias=0.02)),
+        "edge3_28_nested": Sequential(
+            Conv2d(3),
+            Sum([Sequential(), Sequential(ReLU(), Sum([Sequential(), Conv2d(3, var_weight=1.2)]), ReLU(), Conv2d(3))]),
+            Mixture([Conv2d(1), Sequential(ReLU(), Conv2d(5, var_bias=0.2))], logit_proportions=torch.tensor([0.3, -0.7])),
+            ReLU(), Conv2d(28, padding=0)),
+        "edge3_32_dilated_nested": Sequential(
+            Conv2d(3, var_bias=0.3),
+            Sum([Sequential(), Sequential(ReLU(), Sum([Sequential(), Conv2d(3, dilation=2)]), ReLU(), Conv2d(3))]),
+            ReLU(), Conv2d(3, stride=2), ReLU(), Conv2d(16, padding=0, var_bias=0.1)),
+    }
+
+
 def golden_models():
     """name -> model for every gram_<name>.npz fixture."""
     out = {"readme": readme_model()}
@@ -74,4 +93,5 @@ def golden_models():
         out[c + "_randn"] = m
     out.update(edge_models())
     out.update(edge2_models())
+    out.update(edge3_models())
     return out

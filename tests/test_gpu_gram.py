@@ -60,6 +60,25 @@ def test_golden_parity(name, tag, path):
         engine.set_path(prev)
 
 
+@pytest.mark.parametrize("name", ["edge3_28_dilated", "edge3_28_nested", "edge3_32_dilated_nested"])
+def test_dilation_and_nested_sums_run_on_the_fused_net_kernel(name):
+    """a dilated 3 x 3 window (Conv2d(dilation=2), reference kernels.py:61,95-96) and a Sum
+    inside a Sum (three live maps: registers + both tensor-memory slots) are inside the fused-net kernel's
+    set -- not left to the generic kernel -- and match the reference goldens."""
+    g = np.load(os.path.join(GOLD, f"gram_{name}.npz"))
+    model = MODELS[name].float().cuda()
+    X, Z = torch.from_numpy(g["X"]).cuda(), torch.from_numpy(g["Z"]).cuda()
+    Kxz = model(X, Z)
+    assert engine.last_path() == "fused_net"
+    assert rel_err(Kxz.cpu().numpy(), g["Kxz_f32"]) < 1e-5
+    Kxx = model(X)
+    assert engine.last_path() == "fused_net"
+    assert rel_err(Kxx.cpu().numpy(), g["Kxx_f32"]) < 1e-5
+    plan = engine.plan_for(model, X.shape[2], X.shape[3], torch.float32)
+    if "dilated" in name:
+        assert ",d2)" in plan.describe()
+
+
 def test_readme_calls():
     """The four calls of the reference README (README.md:33-46)."""
     g = np.load(os.path.join(GOLD, "gram_readme.npz"))

@@ -404,13 +404,13 @@ def test_compiled_program_equals_tree_walk_on_random_trees():
 
 
 # ---- the fused kernels' host translators, re-evaluated on the CPU --------------------------------
-def _box(R, lo, hi, st):
-    """out[y, x] = sum of in[st*y + dy, st*x + dx], dy, dx in [-lo, hi], zero padding (both fused kernels)."""
+def _box(R, lo, hi, st, dil=1):
+    """out[y, x] = sum of in[st*y + dil*dy, st*x + dil*dx], dy, dx in [-lo, hi], zero padding (both fused kernels)."""
     M, H, W = R.shape
-    P = np.zeros((M, H + lo + hi, W + lo + hi))
-    P[:, lo:lo + H, lo:lo + W] = R
+    P = np.zeros((M, H + dil * (lo + hi), W + dil * (lo + hi)))
+    P[:, dil * lo:dil * lo + H, dil * lo:dil * lo + W] = R
     k = lo + hi + 1
-    full = sum(P[:, dy:dy + H, dx:dx + W] for dy in range(k) for dx in range(k))
+    full = sum(P[:, dil * dy:dil * dy + H, dil * dx:dil * dx + W] for dy in range(k) for dx in range(k))
     return full[:, ::st, ::st]
 
 
@@ -456,7 +456,7 @@ def _simulate_translation(plan, xy0, relu_vars, N1, N2):
             continue
         if kind == "CONV":
             # the second sliding sum carries pre_bias (the folded conv bias); scale / bias are the explicit pass
-            R = (_box(R, f["lo"], f["hi"], f["st"]) + f["pre_bias"]) * f["scale"] + f["bias"]
+            R = (_box(R, f["lo"], f["hi"], f["st"], f["dil"]) + f["pre_bias"]) * f["scale"] + f["bias"]
             assert R.shape[1] == f["so"]
         elif kind == "AFFINE":
             R = R * f["scale"] + f["bias"]
@@ -507,7 +507,7 @@ def _random_resnet(rng, S0):
                       var_bias=rng.choice([0.0, 0.1, 1.0]), **kw)
     mods, size = [conv()], S0
     for _ in range(rng.randint(1, 5)):
-        kind = rng.choice(["identity", "projection", "strided", "sum", "mixture", "relu_conv"])
+        kind = rng.choice(["identity", "projection", "strided", "sum", "mixture", "relu_conv", "dilated", "nested"])
         if kind == "identity":
             mods.append(resnet_block(stride=1))
         elif kind == "projection":
@@ -518,6 +518,10 @@ def _random_resnet(rng, S0):
         elif kind == "sum":
             k = 3 if size < S0 else None
             mods.append(Sum([Sequential(), Sequential(ReLU(), conv(k), ReLU(), conv(k))]))
+        elif kind == "dilated" and size == S0:
+            mods += [ReLU(), Conv2d(3, dilation=2, var_weight=rng.uniform(0.5, 2.0), var_bias=rng.choice([0.0, 0.3]))]
+        elif kind == "nested" and size == S0:
+            mods.append(Sum([Sequential(), Sequential(ReLU(), Sum([Sequential(), conv(3)]), ReLU(), conv(3))]))
         elif kind == "mixture":
             k = 3 if size < S0 else None
             mods.append(Mixture([Sequential(), Sequential(ReLU(), conv(k))],
