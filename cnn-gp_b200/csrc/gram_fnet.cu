@@ -203,34 +203,17 @@ __device__ __forceinline__ void tmem_landed8(uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// one packed array (first S entries of a[NA]) -> S * 2 consecutive tensor-memory columns at `ta`:
-// entries move in groups of 8 (x16), then 4 (x8), 2 (x4), 1 (x2).  The caller waits (tmem_wait_st).
+// one packed array (first S entries of a[NA]) -> S * 2 consecutive tensor-memory columns at `ta`, one
+// tcgen05.st.x2 per entry: a packed map entry IS an aligned register pair, so nothing has to be
+// marshalled (the x16 form wants sixteen consecutive registers: 112 register moves per full-size
+// stash, which the profile showed as 15 % of all executed instructions).  The caller waits (tmem_wait_st).
 template <int NA, int S>
 __device__ __forceinline__ void stash_store_arr(uint32_t ta, const u64 (&a)[NA]) {
-    constexpr int G8 = S / 8, R8 = S % 8, B4 = G8 * 8, B2 = B4 + (R8 & 4), B1 = B2 + (R8 & 2);
 #pragma unroll
-    for (int c = 0; c < G8; ++c) {
-        uint32_t r[16];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) split64(a[c * 8 + q], r[2 * q], r[2 * q + 1]);
-        tmem_st16(ta + c * 16, r);
-    }
-    if (R8 & 4) {
-        uint32_t r[8];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) split64(a[(B4 + q) % NA], r[2 * q], r[2 * q + 1]);
-        tmem_st8(ta + 2 * B4, r);
-    }
-    if (R8 & 2) {
-        uint32_t r[4];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) split64(a[(B2 + q) % NA], r[2 * q], r[2 * q + 1]);
-        tmem_st4(ta + 2 * B2, r);
-    }
-    if (R8 & 1) {
+    for (int q = 0; q < S; ++q) {
         uint32_t r[2];
-        split64(a[B1 % NA], r[0], r[1]);
-        tmem_st2(ta + 2 * B1, r);
+        split64(a[q], r[0], r[1]);
+        tmem_st2(ta + 2 * q, r);
     }
 }
 
@@ -239,6 +222,18 @@ __device__ __forceinline__ void stash_store_arr(uint32_t ta, const u64 (&a)[NA])
 // registers with 112 of them holding the maps) or all of them (phase B: registers are plentiful)
 template <int NA, int S, bool ADD>
 __device__ __forceinline__ void stash_load_arr(uint32_t ta, u64 (&a)[NA], u64 alpha) {
+    if (!ADD) {  // plain reload: x2 loads land in the map's own register pairs, all in flight, one wait
+        uint32_t r[S][2];
+#pragma unroll
+        for (int q = 0; q < S; ++q) tmem_ld2(ta + 2 * q, r[q]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < S; ++q) {
+            asm volatile("" : "+r"(r[q][0]), "+r"(r[q][1]));  // first use stays below the wait
+            a[q] = join64(r[q][0], r[q][1]);
+        }
+        return;
+    }
     constexpr int G8 = S / 8, R8 = S % 8, B4 = G8 * 8, B2 = B4 + (R8 & 4), B1 = B2 + (R8 & 2);
     uint32_t t8[8], t4[4], t2[2];
     if (R8 & 4) tmem_ld8(ta + 2 * B4, t8);
@@ -303,6 +298,29 @@ __device__ __forceinline__ void add_const(u64 (&a)[NA], float beta_f) {
 template <int NA, int S, int LO, int HI, bool BIAS>
 __device__ __forceinline__ void box_s1(u64 (&v)[NA], u64 B) {
     if (LO == 0 && HI == 0) return;
+    if (LO == 1 && HI == 1) {
+        // 3 taps: the direct sum costs the same two adds per output as a sliding window, but every output is
+        // independent (no 14-step dependency chain from either end) and each input dies two outputs after it
+        // is first used (fewer register moves: the sliding form keeps the leaving element alive)
+        u64 prev = v[0];
+        v[0] = add2(v[0], v[1]);
+#pragma unroll
+        for (int y = 1; y < S; ++y) {
+            const u64 cur = v[y];
+            const u64 two = add2(prev, cur);
+            v[y] = y + 1 < S ? add2(two, v[y + 1]) : two;
+            prev = cur;
+        }
+        if (BIAS) {
+            float b0, b1;
+            upk(B, b0, b1);
+            if (b0 != 0.f) {  // uniform: the ResNet GPs have no bias
+#pragma unroll
+                for (int y = 0; y < S; ++y) v[y] = add2(v[y], B);
+            }
+        }
+        return;
+    }
     constexpr int MID = S / 2;
     u64 o[S];
     u64 top = v[0], bot = v[S - 1];
