@@ -87,7 +87,6 @@ struct FParams {
     unsigned long long *tile_ctr;  // zeroed before the launch: the next tile index to hand out
     unsigned *row_done;            // optional: finished (tile, warp) units per super-row (RowProgress)
     float inv_c;       // 1 / C
-    unsigned skew_ns;  // measurement aid: the warps of the second i-pair start this much later (phase offset)
 };
 
 using namespace fusedk;
@@ -304,7 +303,6 @@ __global__ void __launch_bounds__(Geo<NW, NG>::kThreads, 1) fused_kernel(const _
     const int lx = lane < S ? lane : S - 1;  // clamped lane for loads
     u64 *tile = tiles + warp * S * PITCH;
     unsigned stage_l = 0;  // running stage counter, in step with the producer's
-    if (p.skew_ns && wi == 1) __nanosleep(p.skew_ns);
     // 2*H(e), degree-5 minimax fit on [0,1]: |error| < 2.1e-7 relative (one float32 ulp is 1.2e-7)
     const u64 C5 = pk(1.678542030e-04f, 1.678542030e-04f), C4 = pk(-1.571319990e-05f, -1.571319990e-05f),
               C3 = pk(6.585370866e-04f, 6.585370866e-04f), C2 = pk(2.386197913e-03f, 2.386197913e-03f),
@@ -703,7 +701,6 @@ int launch_fused_gram(const Plan *plan, const void *d_x, int64_t N1, const void 
     // CNNGP_FUSED_VARIANT=nw,nsplit,nst selects the others (7x7 window only) for comparison.
     Variant v{12, 2, 3};
     if (const char *e = getenv("CNNGP_FUSED_VARIANT")) sscanf(e, "%d,%d,%d", &v.nw, &v.nsplit, &v.nst);
-    if (const char *e = getenv("CNNGP_FUSED_SKEW_NS")) p.skew_ns = (unsigned)atoi(e);
     int rc = -1;
     cudaStream_t st = (cudaStream_t)stream;
     if (v.nw == 12 && v.nsplit == 4 && v.nst == 4) rc = launch_variant<12, 4, 4>(fp, p, N1, N2, st, progress);
