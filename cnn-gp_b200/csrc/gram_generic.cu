@@ -41,6 +41,11 @@ __device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(
 __device__ __forceinline__ float acos_t(float a) { return acosf(a); }
 __device__ __forceinline__ double acos_t(double a) { return acos(a); }
 
+// idx / d for 0 <= idx < 2^22 and 1 <= d <= idx_max without an integer division (a runtime divisor costs
+// ~20 instructions, and the interpreter's loops did two to four of them per map element): (idx + 0.5) / d
+// is at least 0.5 / d away from an integer, far more than the float32 rounding of the product
+__device__ __forceinline__ int fdiv(int idx, float inv_d) { return (int)(((float)idx + 0.5f) * inv_d); }
+
 // kernels.py:146-152, one pixel.
 template <typename T>
 __device__ __forceinline__ T relu_literal(T c, T vx, T vy) {
@@ -118,8 +123,9 @@ __global__ void __launch_bounds__(kThreads) generic_kernel(GenericParams<T> p) {
     {
         const int P = p.H * p.W;
         const T cnt = (T)p.C;
+        const float inv_P = 1.0f / (float)P;
         for (int idx = tid; idx < G * P; idx += kThreads) {
-            const int g = idx / P, px = idx - g * P;
+            const int g = fdiv(idx, inv_P), px = idx - g * P;
             T s = (T)0;
             if (evalid[g]) {
                 const T *a, *b;
@@ -144,9 +150,10 @@ __global__ void __launch_bounds__(kThreads) generic_kernel(GenericParams<T> p) {
             case CNNGP_OP_CONV: {
                 // separable box sum: rows first (into scratch), then columns
                 const int n1 = o.Hi * o.Wo;
+                const float inv_n1 = 1.0f / (float)n1, inv_Wo = 1.0f / (float)o.Wo;
                 for (int idx = tid; idx < G * n1; idx += kThreads) {
-                    const int g = idx / n1, r = idx - g * n1;
-                    const int y = r / o.Wo, xo = r - y * o.Wo;
+                    const int g = fdiv(idx, inv_n1), r = idx - g * n1;
+                    const int y = fdiv(r, inv_Wo), xo = r - y * o.Wo;
                     const T *src = slot(o.src, g) + y * o.Wi;
                     T acc = (T)0;
                     int xi = xo * o.stride - o.pad + o.dil * o.t0;
@@ -158,9 +165,10 @@ __global__ void __launch_bounds__(kThreads) generic_kernel(GenericParams<T> p) {
                 const int n2 = o.Ho * o.Wo;
                 const T scale = sizeof(T) == 4 ? (T)o.scale_f : (T)o.scale_d;
                 const T bias = sizeof(T) == 4 ? (T)o.bias_f : (T)o.bias_d;
+                const float inv_n2 = 1.0f / (float)n2;
                 for (int idx = tid; idx < G * n2; idx += kThreads) {
-                    const int g = idx / n2, r = idx - g * n2;
-                    const int yo = r / o.Wo, xo = r - yo * o.Wo;
+                    const int g = fdiv(idx, inv_n2), r = idx - g * n2;
+                    const int yo = fdiv(r, inv_Wo), xo = r - yo * o.Wo;
                     const T *src = scratch0 + (size_t)g * MM + xo;
                     T acc = (T)0;
                     int yi = yo * o.stride - o.pad + o.dil * o.t0;
@@ -172,9 +180,10 @@ __global__ void __launch_bounds__(kThreads) generic_kernel(GenericParams<T> p) {
             }
             case CNNGP_OP_RELU: {
                 const int P = o.Hi * o.Wi;
+                const float inv_P = 1.0f / (float)P, inv_Wi = 1.0f / (float)o.Wi;
                 if (MODE == 0) {
                     for (int idx = tid; idx < G * P; idx += kThreads) {
-                        const int g = idx / P, px = idx - g * P;
+                        const int g = fdiv(idx, inv_P), px = idx - g * P;
                         T r = (T)0;
                         if (evalid[g]) {
                             const T c = slot(o.src, g)[px];
@@ -191,7 +200,7 @@ __global__ void __launch_bounds__(kThreads) generic_kernel(GenericParams<T> p) {
                 } else {
                     const int GE = G / p.NP;  // images in this CTA
                     for (int idx = tid; idx < GE * P; idx += kThreads) {
-                        const int ge = idx / P, px = idx - ge * P;
+                        const int ge = fdiv(idx, inv_P), px = idx - ge * P;
                         const int g0 = ge * p.NP;
                         if (!evalid[g0]) continue;
                         const size_t arow = (size_t)ei[g0] * p.aux_elems + o.aux_off + px;
@@ -203,7 +212,8 @@ __global__ void __launch_bounds__(kThreads) generic_kernel(GenericParams<T> p) {
                             // register layout that kernel is in at this layer, interleaved with the
                             // partner image of the pair (2k, 2k+1): float4 (s_2k, s_2k+1, 1/s_2k, 1/s_2k+1)
                             // per pixel, first half of the pixels in row 2k, second half in row 2k+1
-                            const int tp = o.aux_t ? (px % o.Wi) * o.Hi + px / o.Wi : px;
+                            const int py = fdiv(px, inv_Wi);
+                            const int tp = o.aux_t ? (px - py * o.Wi) * o.Hi + py : px;
                             const int half = o.aux_half;
                             const int hi = tp >= half ? 1 : 0;
                             const int64_t n = ei[g0];
@@ -227,7 +237,7 @@ __global__ void __launch_bounds__(kThreads) generic_kernel(GenericParams<T> p) {
             case CNNGP_OP_COPY: {
                 const int P = o.Hi * o.Wi;
                 for (int idx = tid; idx < G * P; idx += kThreads) {
-                    const int g = idx / P, px = idx - g * P;
+                    const int g = fdiv(idx, 1.0f / (float)P), px = idx - g * P;
                     slot(o.dst, g)[px] = slot(o.src, g)[px];
                 }
                 break;
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__(kThreads) generic_kernel(GenericParams<T> p) {
             case CNNGP_OP_ADD: {
                 const int P = o.Hi * o.Wi;
                 for (int idx = tid; idx < G * P; idx += kThreads) {
-                    const int g = idx / P, px = idx - g * P;
+                    const int g = fdiv(idx, 1.0f / (float)P), px = idx - g * P;
                     slot(o.dst, g)[px] = add_rn(slot(o.dst, g)[px], slot(o.src, g)[px]);
                 }
                 break;
@@ -244,7 +254,7 @@ __global__ void __launch_bounds__(kThreads) generic_kernel(GenericParams<T> p) {
                 const int P = o.Hi * o.Wi;
                 const T scale = sizeof(T) == 4 ? (T)o.scale_f : (T)o.scale_d;
                 for (int idx = tid; idx < G * P; idx += kThreads) {
-                    const int g = idx / P, px = idx - g * P;
+                    const int g = fdiv(idx, 1.0f / (float)P), px = idx - g * P;
                     slot(o.dst, g)[px] = mul_rn(slot(o.src, g)[px], scale);
                 }
                 break;
@@ -302,6 +312,25 @@ int launch(const Plan *plan, GenericParams<T> &gp, int NP, cudaStream_t st) {
     }
     G -= G % NP;
     if (G < NP) G = NP;
+    if (MODE == 1 && gp.Q > G) {
+        // variance rows (one launch per dataset, O(N) work): pick the entries per CTA that minimise
+        // waves x entries -- the time of the launch if a CTA's time is proportional to its entries.  With
+        // the largest G, 10 000 images are 625 CTAs on 296 resident ones: three waves, the last 11 % full.
+        int sms = 148, smem_sm = 228 * 1024;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        int best = G;
+        double best_cost = 1e300;
+        for (int g = G; g >= NP; g -= NP) {
+            int per_sm = (int)((size_t)smem_sm / (per_entry * g + 2048));
+            if (per_sm > 2048 / kThreads) per_sm = 2048 / kThreads;
+            if (per_sm < 1) continue;
+            const int64_t ctas = (gp.Q + g - 1) / g, resident = (int64_t)per_sm * sms;
+            const double cost = (double)((ctas + resident - 1) / resident) * g;
+            if (cost < best_cost - 1e-9) { best_cost = cost; best = g; }
+        }
+        G = best;
+    }
     gp.G = G;
     const size_t smem = per_entry * G;
     auto kern = generic_kernel<T, MODE>;
