@@ -73,6 +73,9 @@ _SIGNATURES = {
     "cnngp_predict_argmax": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                             ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
                                             ctypes.c_void_p]),
+    "cnngp_predict_argmax_f64": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                            ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

@@ -81,10 +81,12 @@ def solve_pos_upper(K, Y, overwrite_a=False):
 
 @torch.no_grad()
 def predict_argmax(K, A, return_scores=False):
-    """``(K.double() @ A).argmax(1)`` for a float32 kernel block ``K`` [R, n] as stored by
-    save_K and float64 weights ``A`` [n, classes]; accumulates in float64 without
-    materialising the widened ``K``."""
-    _check_matrix(K, "K", torch.float32)
+    """``(K.double() @ A).argmax(1)`` for a kernel block ``K`` [R, n] -- float32 as stored by save_K, or
+    float64 -- and float64 weights ``A`` [n, classes]; accumulates in float64 without materialising a
+    widened ``K``."""
+    if K.dtype not in (torch.float32, torch.float64):
+        raise TypeError(f"cnn_gp.linalg: K must be float32 or float64, got {K.dtype}")
+    _check_matrix(K, "K", K.dtype)
     _check_matrix(A, "A", torch.float64)
     A = A.contiguous()
     R, n = K.shape
@@ -92,7 +94,8 @@ def predict_argmax(K, A, return_scores=False):
     pred = torch.empty(R, dtype=torch.int64, device=K.device)
     scores = torch.empty((R, A.shape[1]), dtype=torch.float64, device=K.device) if return_scores else None
     with torch.cuda.device(K.device):
-        nat.check(nat.lib().cnngp_predict_argmax(K.data_ptr(), R, n, K.stride(0) if R > 1 else max(n, 1),
+        fn = nat.lib().cnngp_predict_argmax if K.dtype == torch.float32 else nat.lib().cnngp_predict_argmax_f64
+        nat.check(fn(K.data_ptr(), R, n, K.stride(0) if R > 1 else max(n, 1),
                                                  A.data_ptr(), A.shape[1], pred.data_ptr(),
                                                  scores.data_ptr() if scores is not None else None, _stream()),
                   "cnngp_predict_argmax")

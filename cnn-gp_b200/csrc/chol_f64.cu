@@ -676,8 +676,8 @@ __global__ void __launch_bounds__(256) rows_update_kernel(const double *U, long 
 // the load latency.
 constexpr int PR_ROWS = 4;
 
-template <int NC>
-__global__ void __launch_bounds__(128) predict_kernel(const float *K, long long R, long long n, long long ldk,
+template <int NC, typename KT>
+__global__ void __launch_bounds__(128) predict_kernel(const KT *K, long long R, long long n, long long ldk,
                                                       const double *A, int nrhs, int c0, long long *pred,
                                                       double *scores, double *best_val) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(128) predict_kernel(const float *K, long long 
     for (int q = 0; q < PR_ROWS; ++q)
 #pragma unroll
         for (int c = 0; c < NC; ++c) acc[q][c] = 0.0;
-    const float *k[PR_ROWS];
+    const KT *k[PR_ROWS];
 #pragma unroll
     for (int q = 0; q < PR_ROWS; ++q) k[q] = K + min(r0 + q, R - 1) * ldk;
 #pragma unroll 2
@@ -830,6 +830,22 @@ void launch_panel(double *P, int64_t ldp, int64_t width, double *W, int *info, i
 }  // namespace cnngp
 
 using namespace cnngp;
+
+template <typename KT>
+static int predict_any(const KT *d_K, int64_t R, int64_t n, int64_t ldk, const double *d_A, int32_t nrhs,
+                       int64_t *d_pred, double *d_scores, void *stream_, const char *who) {
+    if (!d_K || !d_A || !d_pred || R < 0 || n < 0 || ldk < n || nrhs < 1) { set_error(std::string(who) + ": bad arguments"); return 1; }
+    if (R == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream_;
+    double *best = nullptr;
+    if (nrhs > 10 && !check(cudaMallocAsync((void **)&best, sizeof(double) * R, s), "predict workspace")) return 6;
+    constexpr int PC = 10;  // right-hand sides per pass: the ten classes of the shipped configs
+    const unsigned grid = (unsigned)((R + 4 * PR_ROWS - 1) / (4 * PR_ROWS));
+    for (int c0 = 0; c0 < nrhs; c0 += PC)
+        predict_kernel<PC, KT><<<grid, 128, 0, s>>>(d_K, R, n, ldk, d_A, nrhs, c0, (long long *)d_pred, d_scores, best);
+    if (best) cudaFreeAsync(best, s);
+    return check(cudaGetLastError(), who) ? 0 : 9;
+}
 
 extern "C" {
 
@@ -1019,17 +1035,12 @@ int cnngp_rows_update_f64(const double *d_U, int64_t ldu, int64_t nrows, int32_t
 
 int cnngp_predict_argmax(const float *d_K, int64_t R, int64_t n, int64_t ldk, const double *d_A, int32_t nrhs,
                          int64_t *d_pred, double *d_scores, void *stream_) {
-    if (!d_K || !d_A || !d_pred || R < 0 || n < 0 || ldk < n || nrhs < 1) { set_error("cnngp_predict_argmax: bad arguments"); return 1; }
-    if (R == 0) return 0;
-    cudaStream_t s = (cudaStream_t)stream_;
-    double *best = nullptr;
-    if (nrhs > 10 && !check(cudaMallocAsync((void **)&best, sizeof(double) * R, s), "predict workspace")) return 6;
-    constexpr int PC = 10;  // right-hand sides per pass: the ten classes of the shipped configs
-    const unsigned grid = (unsigned)((R + 4 * PR_ROWS - 1) / (4 * PR_ROWS));
-    for (int c0 = 0; c0 < nrhs; c0 += PC)
-        predict_kernel<PC><<<grid, 128, 0, s>>>(d_K, R, n, ldk, d_A, nrhs, c0, (long long *)d_pred, d_scores, best);
-    if (best) cudaFreeAsync(best, s);
-    return check(cudaGetLastError(), "cnngp_predict_argmax") ? 0 : 9;
+    return predict_any<float>(d_K, R, n, ldk, d_A, nrhs, d_pred, d_scores, stream_, "cnngp_predict_argmax");
+}
+
+int cnngp_predict_argmax_f64(const double *d_K, int64_t R, int64_t n, int64_t ldk, const double *d_A, int32_t nrhs,
+                             int64_t *d_pred, double *d_scores, void *stream_) {
+    return predict_any<double>(d_K, R, n, ldk, d_A, nrhs, d_pred, d_scores, stream_, "cnngp_predict_argmax_f64");
 }
 
 }  // extern "C"

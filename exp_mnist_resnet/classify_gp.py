@@ -50,15 +50,11 @@ def diag_add(K, diag):
 
 
 def predict(A, Kxvx):
-    """argmax_c (Kxvx @ A)[:, c] accumulated in float64; ``Kxvx`` float32 (as stored) or float64."""
+    """argmax_c (Kxvx @ A)[:, c] accumulated in float64 (classify_gp.py:40); ``Kxvx`` float32 (as stored)
+    or float64 -- both go through the library's prediction kernel, never through a library matmul."""
     K = Kxvx.to(DEVICE)
-    if K.dtype == torch.float64:
-        K32 = K.to(torch.float32)
-        # kernels are stored in float32 (kernel_save_tools.py:14): widening and narrowing is exact;
-        # anything else keeps the float64 product
-        if not torch.equal(K32.to(torch.float64), K):
-            return (K @ A.to(DEVICE)).argmax(dim=1).cpu()
-        K = K32
+    if K.dtype not in (torch.float32, torch.float64):
+        K = K.to(torch.float64)
     return linalg.predict_argmax(K.contiguous(), A.to(DEVICE)).cpu()
 
 

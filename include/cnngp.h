@@ -198,6 +198,10 @@ int cnngp_rows_update_f64(const double *d_U, int64_t ldu, int64_t nrows, int32_t
  * (as stored by save_K), A row-major float64 [n, nrhs]; accumulates in float64. */
 int cnngp_predict_argmax(const float *d_K, int64_t R, int64_t n, int64_t ldk, const double *d_A,
                          int32_t nrhs, int64_t *d_pred, double *d_scores, void *stream);
+/* the same for a kernel block that is genuinely float64 (classify_gp.py:63 widens what it loads; a caller
+ * may also hand over float64 kernels it computed itself) */
+int cnngp_predict_argmax_f64(const double *d_K, int64_t R, int64_t n, int64_t ldk, const double *d_A,
+                             int32_t nrhs, int64_t *d_pred, double *d_scores, void *stream);
 
 #ifdef __cplusplus
 }

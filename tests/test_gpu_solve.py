@@ -104,6 +104,11 @@ def test_predict_argmax(R, n, c):
     pred, scores = linalg.predict_argmax(torch.from_numpy(K).cuda(), torch.from_numpy(A).cuda(), return_scores=True)
     np.testing.assert_allclose(scores.cpu().numpy(), want, rtol=0, atol=1e-12 * np.abs(want).max() * np.sqrt(n))
     np.testing.assert_array_equal(pred.cpu().numpy(), want.argmax(1))
+    # a genuinely float64 kernel block goes through the same kernel (no library matmul anywhere on this path)
+    K64 = K.astype(np.float64) + 1e-9 * rng.standard_normal(K.shape)
+    pred64, scores64 = linalg.predict_argmax(torch.from_numpy(K64).cuda(), torch.from_numpy(A).cuda(), return_scores=True)
+    np.testing.assert_allclose(scores64.cpu().numpy(), K64 @ A, rtol=0, atol=1e-12 * np.abs(K64 @ A).max() * np.sqrt(n))
+    np.testing.assert_array_equal(pred64.cpu().numpy(), (K64 @ A).argmax(1))
     np.testing.assert_array_equal(linalg.predict_argmax(torch.from_numpy(K).cuda(), torch.from_numpy(A).cuda()).cpu().numpy(),
                                   want.argmax(1))
 
