@@ -956,14 +956,24 @@ int cnngp_potrs_upper_f64(const double *d_U, int64_t n, int64_t lda, double *d_B
     const unsigned grid = (unsigned)(nblk < sms ? nblk : sms);
     int *flags = nullptr;
     if (!check(cudaMallocAsync((void **)&flags, sizeof(int) * nblk, s), "potrs flags")) return 6;
-    for (int c0 = 0; c0 < nrhs; c0 += SW_NR) {
-        const int nr = nrhs - c0 < SW_NR ? nrhs - c0 : SW_NR;
+    // cooperative launches: the runtime guarantees that all CTAs are resident together (or fails the launch),
+    // which the flag dataflow relies on
+    long long lda_ = lda, ldb_ = ldb;
+    int n_ = (int)n;
+    bool ok = true;
+    for (int c0 = 0; c0 < nrhs && ok; c0 += SW_NR) {
+        int nr = nrhs - c0 < SW_NR ? nrhs - c0 : SW_NR, c0_ = c0;
+        void *args[] = {(void *)&d_U, (void *)&lda_, (void *)&n_, (void *)&d_B, (void *)&ldb_, (void *)&c0_, (void *)&nr, (void *)&flags};
         cudaMemsetAsync(flags, 0, sizeof(int) * nblk, s);
-        sweep_kernel<true><<<grid, SW_THREADS, kSweepSmem, s>>>(d_U, lda, (int)n, d_B, ldb, c0, nr, flags);  // U^T y = b
+        ok = check(cudaLaunchCooperativeKernel((const void *)sweep_kernel<true>, dim3(grid), dim3(SW_THREADS), args, kSweepSmem, s),
+                   "cnngp_potrs_upper_f64 (forward sweep)");  // U^T y = b
+        if (!ok) break;
         cudaMemsetAsync(flags, 0, sizeof(int) * nblk, s);
-        sweep_kernel<false><<<grid, SW_THREADS, kSweepSmem, s>>>(d_U, lda, (int)n, d_B, ldb, c0, nr, flags);  // U x = y
+        ok = check(cudaLaunchCooperativeKernel((const void *)sweep_kernel<false>, dim3(grid), dim3(SW_THREADS), args, kSweepSmem, s),
+                   "cnngp_potrs_upper_f64 (backward sweep)");  // U x = y
     }
     cudaFreeAsync(flags, s);
+    if (!ok) return 9;
     return check(cudaGetLastError(), "cnngp_potrs_upper_f64") ? 0 : 9;
 }
 
