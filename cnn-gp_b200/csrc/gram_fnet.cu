@@ -667,8 +667,11 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
     // tensor-memory window of a warp: 8 warps: 256 columns, slots at 0 / 128 with 64 columns per
     // array; 12 warps (three per lane quadrant): 5 S0 columns, slot 0 (full size) at 0 with 2 S0
     // per array, slot 1 (a folded map of at most half the edge: one array of S0 columns) at 4 S0
-    constexpr int TM_WARP = NW == 8 ? 256 : 5 * S0, TM_SLOT1 = NW == 8 ? 128 : 4 * S0;
-    constexpr int TM_A0 = NW == 8 ? 64 : 2 * S0, TM_A1 = NW == 8 ? 64 : S0;
+    // (12 warps, aligned: 160 columns, the two arrays of slot 0 at 0 and 64, slot 1 at 128 -- every x16 group
+    // then starts at a multiple of 16 columns)
+    constexpr int TM_WARP = NW == 8 ? 256 : 160, TM_SLOT1 = 128;
+    constexpr int TM_A0 = 64, TM_A1 = NW == 8 ? 64 : 32;
+    static_assert(2 * S0 <= 64 && (NW == 8 || S0 <= 32), "a packed array of S0 entries takes 2 S0 columns");
     static_assert((NW / 4) * TM_WARP <= kTmemCols, "tensor-memory budget");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *stage = smem_raw;
