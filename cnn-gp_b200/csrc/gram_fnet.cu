@@ -67,8 +67,10 @@ struct NGeo {
     static constexpr int kImgs = kTileI + kTileJ;
     static constexpr int kPairs = kImgs / 2;
     static constexpr int kThreads = (NW + 4) * 32;
-    static constexpr int kRegsProducer = NW == 8 ? 24 : 32;  // what the pool holds: launch registers x threads
-    static constexpr int kRegsConsumer = NW == 8 ? 240 : 160;
+    static constexpr int kRegsProducer = NW == 12 ? 32 : 24;  // what the pool holds: launch registers x threads
+    // setmaxnreg moves registers inside the CTA's launch allocation (ptxas' count x threads): 16 + 4 warps are
+    // launched with 96 registers, 20 x 32 x 96 = 16 x 32 x 112 + 4 x 32 x 24 (asking for more blocks forever)
+    static constexpr int kRegsConsumer = NW == 8 ? 240 : (NW == 12 ? 160 : 112);
 };
 constexpr int kMaxNOps = 192;   // register-level ops of a translated program
 constexpr int kMaxKOps = 224;   // descriptors the kernel sees (ops + phase sentinels)
@@ -122,6 +124,15 @@ struct NParams {
     int nbi, nbj, sti, stj, nst_j, nst;
     long long n_tiles;
     unsigned long long *tile_ctr;  // zeroed before the launch: the next tile index to hand out
+    // split launches (phase A and phase B as two kernels, see fnet_kernel): this launch covers tiles
+    // [t_begin, n_tiles); phase A leaves every 2 x 2 block's folded map and tensor-memory slot 1 in
+    // `handoff` (one record of 2 x S0/2 x 32 packed entries per block, `rec_per_st` records per
+    // super-tile, `rec_ld` per block row; super-tile `st_begin` is the first of the buffer)
+    long long t_begin;
+    unsigned long long *handoff;
+    int st_begin, rec_ld, rec_per_st;
+    int n_relu_a;  // staged ReLU layers that belong to phase A
+    int k_b;       // first descriptor of phase B
     unsigned *row_done;            // optional: finished (tile, warp) units per super-row (RowProgress, plan.h)
     float inv_c;
 };
@@ -652,7 +663,13 @@ __device__ __forceinline__ void dense_op_f(const u64 (&a)[NA], int lane, float s
 
 // NSPLIT: row bands (= stages) a full-size ReLU layer's variance maps arrive in (2 or 4); a channel
 // of the tile's images arrives in NSPLIT / 2 bands.
-template <int S0, int NW, int NST, int NSPLIT>
+// PH: 3 = the whole program in one launch.  1 / 2 = the program split at the end of phase A into two
+// launches with their own geometry: phase A needs the full register set (eight warps x 240
+// registers: the maps alone are 112 / 128), phase B keeps S0 / 2 registers per thread and is bound by
+// dependency latency, so it wants many warps per scheduler (sixteen x 120 registers).  Launch 1 ends
+// every tile by writing each 2 x 2 block's folded map and tensor-memory slot 1 to global memory
+// (7 / 8 KB per block, coalesced), launch 2 starts from there (other tile shape, same block grid).
+template <int S0, int NW, int NST, int NSPLIT, int PH = 3>
 __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __grid_constant__ NParams p) {
     using G = NGeo<NW>;
     constexpr int kWarps = G::kWarps, kTileI = G::kTileI, kTileJ = G::kTileJ, kImgs = G::kImgs, kPairs = G::kPairs;
@@ -661,22 +678,27 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
     constexpr int SF = S0 / 2;                                     // registers of a folded map
     constexpr int IMG_PARTS = NSPLIT / 2, IBAND = P0 / IMG_PARTS;  // pixels of one image band
     constexpr int BAND = P0 / NSPLIT;                              // pixels of one full-size ReLU band
-    constexpr int STAGE = kImgs * IBAND * 4;  // bytes: one image band of kImgs images == kPairs ReLU bands of float4
+    // bytes of a stage: one image band of kImgs images == kPairs ReLU bands of float4; phase B alone: one folded layer
+    constexpr int STAGE = PH == 2 ? kPairs * ((SF * SF + 1) / 2) * 32 : kImgs * IBAND * 4;
+    constexpr int TILE_ELEMS = PH == 2 ? SF * PITCH : S0 * PITCH;  // transposition tile of a warp (folded maps: SF rows)
+    constexpr int REC = 2 * SF * 32;                               // packed entries of a hand-off record
     static_assert(NSPLIT == 2 || NSPLIT == 4, "band split");
-    static_assert(kPairs * BAND * 16 == STAGE && S0 % NSPLIT == 0, "stage geometry");
+    static_assert(PH == 2 || (kPairs * BAND * 16 == STAGE && S0 % NSPLIT == 0), "stage geometry");
+    static_assert(PH >= 1 && PH <= 3 && (NW != 16 || PH == 2), "sixteen warps: phase B only");
     // tensor-memory window of a warp: 8 warps: 256 columns, slots at 0 / 128 with 64 columns per
     // array; 12 warps (three per lane quadrant): 5 S0 columns, slot 0 (full size) at 0 with 2 S0
     // per array, slot 1 (a folded map of at most half the edge: one array of S0 columns) at 4 S0
     // (12 warps, aligned: 160 columns, the two arrays of slot 0 at 0 and 64, slot 1 at 128 -- every x16 group
     // then starts at a multiple of 16 columns)
-    constexpr int TM_WARP = NW == 8 ? 256 : 160, TM_SLOT1 = 128;
+    // (16 warps, folded maps only: 128 columns, slots at 0 / 64)
+    constexpr int TM_WARP = NW == 8 ? 256 : (NW == 12 ? 160 : 128), TM_SLOT1 = NW == 16 ? 64 : 128;
     constexpr int TM_A0 = 64, TM_A1 = NW == 8 ? 64 : 32;
     static_assert(2 * S0 <= 64 && (NW == 8 || S0 <= 32), "a packed array of S0 entries takes 2 S0 columns");
     static_assert((NW / 4) * TM_WARP <= kTmemCols, "tensor-memory budget");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *stage = smem_raw;
     u64 *tiles = reinterpret_cast<u64 *>(smem_raw + (size_t)NST * STAGE);
-    int4 *ops_s = reinterpret_cast<int4 *>(tiles + kWarps * S0 * PITCH);
+    int4 *ops_s = reinterpret_cast<int4 *>(tiles + kWarps * TILE_ELEMS);
     uint64_t *bars = reinterpret_cast<uint64_t *>(ops_s + kMaxKOps);
     uint64_t *full = bars, *empty = bars + NST;
     // tile index each stage belongs to (-1: no more tiles); tiles are handed out by a global atomic
@@ -707,8 +729,10 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
     const uint32_t tmem_base = *tmem_word;
 
     const int per_st = p.sti * p.stj;
+    int dec_st = 0, dec_w = 0;  // super-tile and position inside it of the last decoded tile
     auto decode = [&](long long t, int &ib, int &jb) -> bool {
         const int st = (int)(t / per_st), w_in = (int)(t - (long long)st * per_st);
+        dec_st = st; dec_w = w_in;
         int si, sj;
         if (p.symmetric) {
             int r = 0, rem = st;
@@ -753,10 +777,11 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
             auto next_index = [&](long long stat) -> long long {
                 if (!dyn) return stat;
                 long long v = 0;
-                if (lane == 0) v = (long long)atomicAdd(p.tile_ctr, 1ull);
+                if (lane == 0) v = p.t_begin + (long long)atomicAdd(p.tile_ctr, 1ull);
                 return __shfl_sync(0xffffffffu, v, 0);
             };
-            long long t_raw = next_index((long long)blockIdx.x);
+            long long t_raw = next_index(p.t_begin + (long long)blockIdx.x);
+            const int relu_lo = PH == 2 ? p.n_relu_a : 0, relu_hi = PH == 1 ? p.n_relu_a : p.n_relu;
             for (;;) {
                 int ib, jb;
                 t = t_raw;
@@ -776,17 +801,17 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
                                                          : min((j_base >> 1) + vs - kTileI / 2, last_pj);
                     var = (vs < kTileI / 2 ? p.aux_x : p.aux_z) + (2 * pr + vh) * p.aux_stride + p.aux_f_off;
                 }
-                for (int c = 0; c < p.C; ++c) {
+                for (int c = 0; c < (PH == 2 ? 0 : p.C); ++c) {
                     for (int ip = 0; ip < IMG_PARTS; ++ip) {
                         float *dst = reinterpret_cast<float *>(acquire(kImgs * IBAND * 4));
                         if (lane < kImgs) bulk_g2s(dst + lane * IBAND, img + (long long)c * P0 + ip * IBAND, IBAND * 4, &full[l % NST]);
                         ++l;
                     }
                 }
-                for (int k = 0; k < p.n_relu; ++k) {
+                for (int k = relu_lo; k < relu_hi; ++k) {
                     const int off = p.relu_aux[k];
                     const int half = p.relu_half[k] & 0xffff;
-                    if (p.relu_half[k] >> 30) {  // full-size layers: NSPLIT row bands, one stage each
+                    if (PH != 2 && (p.relu_half[k] >> 30)) {  // full-size layers: NSPLIT row bands, one stage each
                         for (int part = 0; part < NSPLIT; ++part) {
                             float4 *dst = reinterpret_cast<float4 *>(acquire((unsigned)(kPairs * BAND * 16)));
                             // band `part`: pixels [part * BAND, +BAND); the first half of the pixels is in row 2k
@@ -810,7 +835,7 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
     // ---- consumers ------------------------------------------------------------------------
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(G::kRegsConsumer));
     const int wi = warp / (NW / 2), wj = warp % (NW / 2);
-    u64 *tile = tiles + warp * S0 * PITCH;
+    u64 *tile = tiles + warp * TILE_ELEMS;
     // this warp's tensor-memory window: lanes of quadrant warp % 4
     const uint32_t tm_warp = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * TM_WARP);
     unsigned stage_l = 0;
@@ -833,9 +858,14 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
 
         float tot[4] = {0.f, 0.f, 0.f, 0.f};
         u64 F[SF];
-        int k = 0;
-        int4 o = ops_s[0];
-        {   // ================= phase A: the full register set =================================
+        int k = PH == 2 ? p.k_b : 0;
+        int4 o = ops_s[k];
+        // this warp's hand-off record (split launches): block row / column inside the super-tile
+        u64 *rec = nullptr;
+        if (PH != 3)
+            rec = p.handoff + ((size_t)(dec_st - p.st_begin) * p.rec_per_st + (size_t)(dec_w / p.stj * (kTileI / 2) + wi) * p.rec_ld +
+                               (size_t)(dec_w % p.stj) * (kTileJ / 2) + wj) * REC + lane;
+        if constexpr (PH != 2) {   // ================= phase A: the full register set =================================
             u64 M[2][S0];
             {   // init, kernels.py:43-49
                 const int lx = lane < S0 ? lane : S0 - 1;
@@ -988,9 +1018,61 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
             }
 #pragma unroll
             for (int r = 0; r < SF; ++r) F[r] = M[0][r];
+            if constexpr (PH == 1) {  // hand the folded map and tensor-memory slot 1 over to the phase-B launch
+                u64 K[SF];
+                stash_load_arr<SF, SF, false>(tm_warp + TM_SLOT1, K, 0ull);
+#pragma unroll
+                for (int r = 0; r < SF; ++r) {
+                    rec[r * 32] = F[r];
+                    rec[(SF + r) * 32] = K[r];
+                }
+                continue;
+            }
         }
 
-        {   // ================= phase B: folded maps, S0 / 2 live registers ====================
+        if constexpr (PH != 1) {   // ================= phase B: folded maps, S0 / 2 live registers ====================
+            // tensor-memory slot 1 lives in registers here (K): phase B has them to spare, and its
+            // residual blocks then never touch tensor memory
+            u64 K[SF];
+            if constexpr (PH == 2) {
+#pragma unroll
+                for (int r = 0; r < SF; ++r) {
+                    F[r] = rec[r * 32];
+                    K[r] = rec[(SF + r) * 32];
+                }
+            } else {
+                stash_load_arr<SF, SF, false>(tm_warp + TM_SLOT1, K, 0ull);
+            }
+            auto b_stash = [&](auto SZ, const int4 &d) {
+                constexpr int S = decltype(SZ)::value;
+                if (f_slot(d)) {
+#pragma unroll
+                    for (int r = 0; r < S; ++r) K[r] = F[r];
+                } else {
+                    stash_store_arr<SF, S>(tm_warp, F);
+                    tmem_wait_st();
+                }
+            };
+            auto b_unstash = [&](auto SZ, const int4 &d) {
+                constexpr int S = decltype(SZ)::value;
+                if (f_slot(d)) {
+#pragma unroll
+                    for (int r = 0; r < S; ++r) F[r] = K[r];
+                } else {
+                    stash_load_arr<SF, S, false>(tm_warp, F, 0ull);
+                }
+            };
+            auto b_add = [&](auto SZ, const int4 &d) {
+                constexpr int S = decltype(SZ)::value;
+                const u64 alpha = pk(f_scale(d), f_scale(d));
+                if (f_slot(d)) {
+#pragma unroll
+                    for (int r = 0; r < S; ++r) F[r] = fma2(K[r], alpha, F[r]);
+                } else {
+                    stash_load_arr<SF, S, true>(tm_warp, F, alpha);
+                }
+                add_const<SF, S>(F, f_bias(d));
+            };
             auto relu_fold = [&](auto SZ, const int4 &d) {
                 constexpr int S = decltype(SZ)::value;
                 const unsigned buf = stage_l % NST;
@@ -1005,14 +1087,12 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
             };
             auto idblock = [&](auto SZ, const int4 &st, const int4 &r1, const int4 &c1, const int4 &r2, const int4 &c2, const int4 &ad) {
                 constexpr int S = decltype(SZ)::value;
-                stash_store_arr<SF, S>(tm_warp + f_slot(st) * TM_SLOT1, F);
-                tmem_wait_st();
+                b_stash(SZ, st);
                 relu_fold(SZ, r1);
                 conv_op_f<SF, S0, S, S, 1, 1, 1>(F, tile, lane, f_pre(c1), f_scale(c1), f_bias(c1));
                 relu_fold(SZ, r2);
                 conv_op_f<SF, S0, S, S, 1, 1, 1>(F, tile, lane, f_pre(c2), f_scale(c2), f_bias(c2));
-                stash_load_arr<SF, S, true>(tm_warp + f_slot(ad) * TM_SLOT1, F, pk(f_scale(ad), f_scale(ad)));
-                add_const<SF, S>(F, f_bias(ad));
+                b_add(SZ, ad);
             };
             for (bool more = true; more;) {
                 int4 nxt;
@@ -1026,10 +1106,9 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
                     case B_CONV + 3: FETCH(1); conv_op_f<SF, S0, S0 / 4, S0 / 4, 1, 1, 1>(F, tile, lane, f_pre(o), f_scale(o), f_bias(o)); break;
                     FOLDED_B(B_AFFINE, (affine_arr<SF, S>(F, f_scale(o), f_bias(o))))
                     FOLDED_B(B_TRANSPOSE, (transpose_op_f<SF, S0, S>(F, tile, lane)))
-                    FOLDED_B(B_STASH, (stash_store_arr<SF, S>(tm_warp + f_slot(o) * TM_SLOT1, F), tmem_wait_st()))
-                    FOLDED_B(B_UNSTASH, (stash_load_arr<SF, S, false>(tm_warp + f_slot(o) * TM_SLOT1, F, 0ull)))
-                    FOLDED_B(B_ADD, (stash_load_arr<SF, S, true>(tm_warp + f_slot(o) * TM_SLOT1, F, pk(f_scale(o), f_scale(o))),
-                                     add_const<SF, S>(F, f_bias(o))))
+                    FOLDED_B(B_STASH, (b_stash(std::integral_constant<int, S>{}, o)))
+                    FOLDED_B(B_UNSTASH, (b_unstash(std::integral_constant<int, S>{}, o)))
+                    FOLDED_B(B_ADD, (b_add(std::integral_constant<int, S>{}, o)))
                     FOLDED_B(B_DENSE, (dense_op_f<SF, S>(F, lane, f_scale(o), f_bias(o), tot)))
                     case B_RELU + 0: FETCH(1); relu_fold(std::integral_constant<int, S0 / 2>{}, o); break;
                     case B_RELU + 1: FETCH(1); relu_fold(std::integral_constant<int, S0 / 4>{}, o); break;
@@ -1127,6 +1206,11 @@ struct FNetPlan {
     int nst = 0;
     int fused_row_floats = 0;  // floats per image the Gram kernel reads (super-tile sizing)
     int nw = 8;                // consumer warps of the kernel variant
+    // split launches: phase A (8 warps) and phase B (16 warps) as two kernels with a global hand-off
+    bool split = false;
+    int n_relu_a = 0;          // staged ReLU layers consumed by phase A
+    int k_b = 0;               // first kernel descriptor of phase B
+    size_t smem_a = 0, smem_b = 0;
 };
 
 namespace {
@@ -1397,10 +1481,12 @@ struct Translator {
     }
 };
 
-template <int S0, int NW, int NST, int NSPLIT>
+template <int S0, int NW, int NST, int NSPLIT, int PH = 3>
 constexpr size_t fnet_smem() {
-    return (size_t)NST * NGeo<NW>::kImgs * S0 * S0 * 4 / (NSPLIT / 2) + (size_t)NW * S0 * (S0 + 1) * 8 + (size_t)kMaxKOps * 16 +
-           (size_t)3 * NST * 8 + 16;
+    constexpr int SF = S0 / 2;
+    return (PH == 2 ? (size_t)NST * NGeo<NW>::kPairs * ((SF * SF + 1) / 2) * 32 + (size_t)NW * SF * (S0 + 1) * 8
+                    : (size_t)NST * NGeo<NW>::kImgs * S0 * S0 * 4 / (NSPLIT / 2) + (size_t)NW * S0 * (S0 + 1) * 8) +
+           (size_t)kMaxKOps * 16 + (size_t)3 * NST * 8 + 16;
 }
 
 const char *kNames[] = {"CONV", "AFFINE", "RELU", "STASH", "UNSTASH", "ADD", "TRANSPOSE", "DENSE", "T_RELU", "T_AFFINE"};
@@ -1489,7 +1575,22 @@ bool build_kops(FNetPlan *fp, bool blocks) {
         k += len;
     }
     sentinel.code = A_END; push(sentinel);
+    fp->k_b = nk;
     fp->folded_phase = end_a < first_tail;
+    {   // can the program be cut at the end of phase A?  Phase B must stage at least one ReLU layer (a tile's
+        // index travels with its first stage) and only tensor-memory slot 1 may carry a map across the cut
+        int relu_b = 0;
+        fp->n_relu_a = 0;
+        for (int k = 0; k < first_tail; ++k)
+            if (fp->ops[k].kind == N_RELU) (k < end_a ? fp->n_relu_a : relu_b) += 1;
+        bool slot0_live = false;
+        for (int k = end_a; k < first_tail; ++k) {
+            const NOp &o = fp->ops[k];
+            if ((o.kind == N_UNSTASH || o.kind == N_ADD) && o.slot == 0) { slot0_live = true; break; }
+            if (o.kind == N_STASH && o.slot == 0) break;
+        }
+        fp->split = fp->folded_phase && relu_b > 0 && !slot0_live && end_a > 0;
+    }
     for (int k = end_a; k < first_tail;) {
         const NOp *o = fp->ops + k;
         if (o->si == S0 || o->si == 1) return false;
@@ -1559,6 +1660,13 @@ FNetPlan *fnet_plan_create(const Plan *plan_const) {
     // 32 x 32: the maps alone are 128 registers per thread, which leaves a 160-register warp nothing to
     // work with (measured: 21 M pairs/s with twelve spilling warps against 62 M with eight) -- eight warps
     else { fp->nw = 8; fp->nst = 3; fp->smem = fnet_smem<32, 8, 3, 2>(); }
+    // programs with a folded phase run as two launches (phase A on eight warps, phase B on sixteen) unless
+    // CNNGP_FNET_NOSPLIT=1 asks for the single-launch kernels above
+    if (getenv("CNNGP_FNET_NOSPLIT")) fp->split = false;
+    if (fp->split) {
+        fp->smem_a = S0 == 28 ? fnet_smem<28, 8, 4, 2, 1>() : fnet_smem<32, 8, 3, 2, 1>();
+        fp->smem_b = S0 == 28 ? fnet_smem<28, 16, 4, 2, 2>() : fnet_smem<32, 16, 3, 2, 2>();
+    }
     for (const DevOp &o : plan->ops)
         if (o.opcode == CNNGP_OP_RELU) fp->fused_row_floats += 4 * o.aux_half;
     return fp;
@@ -1567,7 +1675,9 @@ FNetPlan *fnet_plan_create(const Plan *plan_const) {
 void fnet_plan_destroy(FNetPlan *fp) { delete fp; }
 
 std::string fnet_plan_describe(const FNetPlan *fp) {
-    std::string t = "fused_net S0=" + std::to_string(fp->S0) + " warps=" + std::to_string(fp->nw) + " stages=" + std::to_string(fp->nst) + " blocks=" + std::to_string(fp->n_blocks) + " :";
+    std::string t = "fused_net S0=" + std::to_string(fp->S0) +
+                    (fp->split ? std::string(" warps=8+16 (two launches)") : " warps=" + std::to_string(fp->nw) + " stages=" + std::to_string(fp->nst)) +
+                    " blocks=" + std::to_string(fp->n_blocks) + " :";
     for (int k = 0; k < fp->n_ops; ++k) {
         const NOp &o = fp->ops[k];
         t += std::string(" ") + kNames[o.kind] + "(" + std::to_string(o.si);
@@ -1594,10 +1704,75 @@ std::string fnet_plan_dump(const FNetPlan *fp) {
     return t;
 }
 
+namespace {
+
+// tile grid of one kernel geometry (tiles of 4 x tile_j images, super-tiles of `edge` images)
+void fnet_geometry(NParams &p, int64_t N1, int64_t N2, int tile_j, int edge, long long *n_super) {
+    const int kTileI = 4;
+    p.nbi = (int)((N1 + kTileI - 1) / kTileI);
+    p.nbj = (int)((N2 + tile_j - 1) / tile_j);
+    const int super_i = edge / kTileI, super_j = edge / tile_j;
+    if (p.nbi <= super_i && p.nbj <= super_j) {
+        p.sti = p.nbi; p.stj = p.nbj; p.nst_j = 1; p.nst = 1;
+        *n_super = 1;
+    } else {
+        p.sti = super_i; p.stj = super_j;
+        const int nsi = (p.nbi + super_i - 1) / super_i, nsj = (p.nbj + super_j - 1) / super_j;
+        p.nst_j = nsj;
+        p.nst = nsi > nsj ? nsi : nsj;
+        *n_super = p.symmetric ? (long long)p.nst * (p.nst + 1) / 2 : (long long)nsi * nsj;
+    }
+}
+
+// what the kernel will count per super-row: valid tiles x consumer warps (see gram_fused.cu)
+int fnet_progress(NParams &p, RowProgress *prog, int tile_j, int nw) {
+    const int kTileI = 4;
+    prog->n_super_rows = (p.nbi + p.sti - 1) / p.sti;
+    prog->rows_per_super = (int64_t)p.sti * kTileI;
+    if (!p.symmetric || prog->n_super_rows > prog->capacity) { set_error("fused-net kernel: progress counters too few"); return 8; }
+    prog->expected.assign(prog->n_super_rows, 0u);
+    for (int ib = 0; ib < p.nbi; ++ib) {
+        const int si = ib / p.sti;
+        long long jb_lo = (long long)si * p.stj;
+        const long long need = ((long long)ib * kTileI) / tile_j;  // first tile that reaches the diagonal
+        if (need > jb_lo) jb_lo = need;
+        if (jb_lo < p.nbj) prog->expected[si] += (unsigned)((p.nbj - jb_lo) * nw);
+    }
+    p.row_done = prog->d_done;
+    return 0;
+}
+
+int fnet_launch_one(void (*kern)(const NParams), NParams &p, unsigned threads, size_t smem, cudaStream_t stream) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long todo = p.n_tiles - p.t_begin;
+    const unsigned grid = (unsigned)(todo < sms ? todo : sms);
+    cudaError_t e = cudaSuccess;
+    const char *order = getenv("CNNGP_TILE_ORDER");  // "static": fixed stride instead of the counter
+    if (order && !strcmp(order, "static")) {
+        p.tile_ctr = nullptr;
+    } else {
+        p.tile_ctr = tile_counter_for(stream);
+        if (!p.tile_ctr) return 7;
+        e = cudaMemsetAsync(p.tile_ctr, 0, sizeof(unsigned long long), stream);
+    }
+    if (e != cudaSuccess) { set_error(std::string("fused-net tile counter: ") + cudaGetErrorString(e)); return 7; }
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error(std::string("fused-net cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 7; }
+    kern<<<grid, threads, smem, stream>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error(std::string("fused-net kernel launch: ") + cudaGetErrorString(e)); return 9; }
+    return 0;
+}
+
+}  // namespace
+
 int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2, int32_t C,
                      const void *d_aux_x, const void *d_aux_z, int32_t symmetric, const void *d_kdiag,
-                     void *d_out, int64_t ld_out, void *stream, RowProgress *prog) {
+                     void *d_out, int64_t ld_out, void *stream_, RowProgress *prog) {
     const FNetPlan *fp = plan->fnet;
+    cudaStream_t stream = (cudaStream_t)stream_;
     if (!fp) { set_error("fused-net kernel: unsupported call"); return 4; }
     if (N1 > 2000000000LL || N2 > 2000000000LL) { set_error("fused-net kernel: too many images"); return 8; }
     NParams p;  // ~4.5 KB, passed by value at launch
@@ -1607,6 +1782,8 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
     memcpy(p.relu_aux, fp->relu_aux, sizeof(int) * fp->n_relu);
     memcpy(p.relu_half, fp->relu_half, sizeof(int) * fp->n_relu);
     p.n_relu = fp->n_relu;
+    p.n_relu_a = fp->n_relu_a;
+    p.k_b = fp->k_b;
     p.x = (const float *)d_x; p.z = (const float *)d_z;
     p.aux_x = (const float *)d_aux_x; p.aux_z = (const float *)d_aux_z;
     p.aux_stride = plan->aux_elems; p.aux_f_off = plan->aux_f_off;
@@ -1614,65 +1791,60 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
     p.out = (float *)d_out; p.ld_out = ld_out;
     p.symmetric = symmetric ? 1 : 0;
     p.kdiag = (const float *)d_kdiag;
-    const int kTileI = 4, kTileJ = fp->nw;
-    p.nbi = (int)((N1 + kTileI - 1) / kTileI);
-    p.nbj = (int)((N2 + kTileJ - 1) / kTileJ);
-    // super-tiles of side `edge` images: the 2 * edge variance rows a wave of CTAs shares stay in L2
-    int edge = 504;  // divisible by 4, 8 and 12
-    while (edge > 72 && (size_t)2 * edge * fp->fused_row_floats * 4 > ((size_t)72 << 20)) edge = edge / 2 / 24 * 24;
-    if (const char *e = getenv("CNNGP_SUPER_EDGE")) { const int v = atoi(e); if (v >= 24 && v % 24 == 0) edge = v; }
-    const int super_i = edge / kTileI, super_j = edge / kTileJ;
-    long long n_super;
-    if (p.nbi <= super_i && p.nbj <= super_j) {
-        p.sti = p.nbi; p.stj = p.nbj; p.nst_j = 1; p.nst = 1;
-        n_super = 1;
-    } else {
-        p.sti = super_i; p.stj = super_j;
-        const int nsi = (p.nbi + super_i - 1) / super_i, nsj = (p.nbj + super_j - 1) / super_j;
-        p.nst_j = nsj;
-        p.nst = nsi > nsj ? nsi : nsj;
-        n_super = p.symmetric ? (long long)p.nst * (p.nst + 1) / 2 : (long long)nsi * nsj;
-    }
-    p.n_tiles = n_super * p.sti * p.stj;
-    if (prog) {  // what the kernel will count per super-row: valid tiles x consumer warps (see gram_fused.cu)
-        prog->n_super_rows = (p.nbi + p.sti - 1) / p.sti;
-        prog->rows_per_super = (int64_t)p.sti * kTileI;
-        if (!p.symmetric || prog->n_super_rows > prog->capacity) { set_error("fused-net kernel: progress counters too few"); return 8; }
-        prog->expected.assign(prog->n_super_rows, 0u);
-        for (int ib = 0; ib < p.nbi; ++ib) {
-            const int si = ib / p.sti;
-            long long jb_lo = (long long)si * p.stj;
-            const long long need = ((long long)ib * kTileI) / kTileJ;  // first tile that reaches the diagonal
-            if (need > jb_lo) jb_lo = need;
-            if (jb_lo < p.nbj) prog->expected[si] += (unsigned)((p.nbj - jb_lo) * fp->nw);
-        }
-        p.row_done = prog->d_done;
-    }
     p.inv_c = 1.0f / (float)C;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);
-    void (*kern)(const NParams) = fp->S0 == 32 ? fnet_kernel<32, 8, 3, 2>
-                                               : (fp->nw == 12 ? (fp->nst == 3 ? fnet_kernel<28, 12, 3, 2> : fnet_kernel<28, 12, 2, 2>)
-                                                               : fnet_kernel<28, 8, 4, 2>);
-    const unsigned threads = (fp->nw + 4) * 32;
-    cudaError_t e = cudaSuccess;
-    const char *order = getenv("CNNGP_TILE_ORDER");  // "static": fixed stride instead of the counter
-    if (order && !strcmp(order, "static")) {
-        p.tile_ctr = nullptr;
-    } else {
-        p.tile_ctr = tile_counter_for(stream);
-        if (!p.tile_ctr) return 7;
-        e = cudaMemsetAsync(p.tile_ctr, 0, sizeof(unsigned long long), (cudaStream_t)stream);
+    const size_t row_bytes = (size_t)fp->fused_row_floats * 4;
+    if (!fp->split) {
+        // super-tiles of side `edge` images: the 2 * edge variance rows a wave of CTAs shares stay in L2
+        int edge = 504;  // divisible by 4, 8 and 12
+        while (edge > 72 && (size_t)2 * edge * row_bytes > ((size_t)72 << 20)) edge = edge / 2 / 24 * 24;
+        if (const char *e = getenv("CNNGP_SUPER_EDGE")) { const int v = atoi(e); if (v >= 24 && v % 24 == 0) edge = v; }
+        long long n_super;
+        fnet_geometry(p, N1, N2, fp->nw, edge, &n_super);
+        p.n_tiles = n_super * p.sti * p.stj;
+        if (prog) { const int rc = fnet_progress(p, prog, fp->nw, fp->nw); if (rc) return rc; }
+        void (*kern)(const NParams) = fp->S0 == 32 ? fnet_kernel<32, 8, 3, 2>
+                                                   : (fp->nw == 12 ? (fp->nst == 3 ? fnet_kernel<28, 12, 3, 2> : fnet_kernel<28, 12, 2, 2>)
+                                                                   : fnet_kernel<28, 8, 4, 2>);
+        return fnet_launch_one(kern, p, (fp->nw + 4) * 32, fp->smem, stream);
     }
-    if (e != cudaSuccess) { set_error(std::string("fused-net tile counter: ") + cudaGetErrorString(e)); return 7; }
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp->smem);
-    if (e != cudaSuccess) { set_error(std::string("fused-net cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return 7; }
-    kern<<<grid, threads, fp->smem, (cudaStream_t)stream>>>(p);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) { set_error(std::string("fused-net kernel launch: ") + cudaGetErrorString(e)); return 9; }
-    return 0;
+    // ---- two launches per chunk of super-tiles: phase A (4 x 8 tiles, eight warps), phase B (4 x 16, sixteen) ----
+    int edge = 480;  // divisible by 4, 8 and 16; both launches see the same super-tiles and 2 x 2 blocks
+    while (edge > 48 && (size_t)2 * edge * row_bytes > ((size_t)72 << 20)) edge = edge > 96 ? edge / 2 / 48 * 48 : 48;
+    if (const char *e = getenv("CNNGP_SUPER_EDGE")) { const int v = atoi(e); if (v >= 48 && v % 48 == 0) edge = v; }
+    NParams pa = p, pb = p;
+    long long n_super = 0, n_super_b = 0;
+    fnet_geometry(pa, N1, N2, 8, edge, &n_super);
+    fnet_geometry(pb, N1, N2, 16, edge, &n_super_b);
+    if (n_super != n_super_b) { set_error("fused-net kernel: the two launches disagree on the super-tiles"); return 9; }
+    if (prog) { const int rc = fnet_progress(pb, prog, 16, 16); if (rc) return rc; }
+    const int blocks_i = pa.sti * 2, blocks_j = pa.stj * 4 > pb.stj * 8 ? pa.stj * 4 : pb.stj * 8;
+    const size_t rec_bytes = (size_t)2 * (fp->S0 / 2) * 32 * 8;
+    const size_t st_bytes = (size_t)blocks_i * blocks_j * rec_bytes;
+    size_t budget = (size_t)1 << 30;  // hand-off buffer per chunk
+    if (const char *e = getenv("CNNGP_FNET_HANDOFF_MB")) { const long v = atol(e); if (v > 0) budget = (size_t)v << 20; }
+    long long per_chunk = (long long)(budget / st_bytes);
+    if (per_chunk < 1) per_chunk = 1;
+    if (per_chunk > n_super) per_chunk = n_super;
+    void *handoff = nullptr;
+    cudaError_t e = cudaMallocAsync(&handoff, (size_t)per_chunk * st_bytes, stream);
+    if (e != cudaSuccess) { set_error(std::string("fused-net hand-off buffer: ") + cudaGetErrorString(e)); return 7; }
+    pa.handoff = pb.handoff = (unsigned long long *)handoff;
+    pa.rec_ld = pb.rec_ld = blocks_j;
+    pa.rec_per_st = pb.rec_per_st = blocks_i * blocks_j;
+    pa.row_done = nullptr;
+    void (*kern_a)(const NParams) = fp->S0 == 32 ? fnet_kernel<32, 8, 3, 2, 1> : fnet_kernel<28, 8, 4, 2, 1>;
+    void (*kern_b)(const NParams) = fp->S0 == 32 ? fnet_kernel<32, 16, 3, 2, 2> : fnet_kernel<28, 16, 4, 2, 2>;
+    int rc = 0;
+    for (long long s0 = 0; s0 < n_super && !rc; s0 += per_chunk) {
+        const long long s1 = s0 + per_chunk < n_super ? s0 + per_chunk : n_super;
+        pa.st_begin = pb.st_begin = (int)s0;
+        pa.t_begin = s0 * pa.sti * pa.stj; pa.n_tiles = s1 * pa.sti * pa.stj;
+        pb.t_begin = s0 * pb.sti * pb.stj; pb.n_tiles = s1 * pb.sti * pb.stj;
+        rc = fnet_launch_one(kern_a, pa, (8 + 4) * 32, fp->smem_a, stream);
+        if (!rc) rc = fnet_launch_one(kern_b, pb, (16 + 4) * 32, fp->smem_b, stream);
+    }
+    cudaFreeAsync(handoff, stream);
+    return rc;
 }
 
 }  // namespace cnngp

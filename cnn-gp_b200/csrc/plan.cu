@@ -102,7 +102,8 @@ int build_plan(const cnngp_op *ops, int32_t n_ops, int32_t n_slots, int32_t H, i
             d.aux_foff = foff;
             foff += 4 * d.aux_half;
         }
-        p->fused = fused_plan_create(p);
+        // CNNGP_NO_FUSED=1 (measurement aid): straight-line programs run on the fused-net kernel too
+        p->fused = getenv("CNNGP_NO_FUSED") ? nullptr : fused_plan_create(p);
         if (!p->fused) {
             for (DevOp &d : p->ops) { d.aux_t = 0; d.aux_scale = 1.f; }  // whatever a partial translation left
             p->fnet = fnet_plan_create(p);

@@ -359,6 +359,32 @@ def test_tile_order_is_invisible(name, C, S, n, monkeypatch):
         assert torch.equal(g, w)
 
 
+@pytest.mark.parametrize("name,C,S,n", [("mnist_as_tf", 1, 28, 210), ("cifar10", 3, 32, 130), ("mnist", 1, 28, 75)])
+def test_split_launches_match_the_single_launch(name, C, S, n, monkeypatch):
+    """Programs with a folded phase run as two launches per chunk of super-tiles (phase A on eight
+    warps, phase B on sixteen, 2 x 2 blocks handed over through global memory).  Same arithmetic per
+    entry as the single-launch kernel: bit-identical, with many one-super-tile chunks, ragged edges,
+    symmetric and rectangular calls."""
+    model = MODELS[name].float().cuda()
+    gen = torch.Generator().manual_seed(23)
+    X = torch.rand(n, C, S, S, generator=gen).cuda()
+    Z = torch.rand(n // 2 + 5, C, S, S, generator=gen).cuda()
+    monkeypatch.setenv("CNNGP_SUPER_EDGE", "48")
+    monkeypatch.setenv("CNNGP_FNET_HANDOFF_MB", "1")
+    try:
+        engine._PLANS.pop(model, None)
+        got = (model(X), model(X, Z))
+        assert "two launches" in engine.plan_for(model, S, S, torch.float32).describe()
+        monkeypatch.setenv("CNNGP_FNET_NOSPLIT", "1")
+        engine._PLANS.pop(model, None)
+        want = (model(X), model(X, Z))
+        assert "two launches" not in engine.plan_for(model, S, S, torch.float32).describe()
+    finally:
+        engine._PLANS.pop(model, None)
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
+
+
 @pytest.mark.parametrize("n", [2, 505, 1100])
 def test_host_call_streams_the_same_bytes(n):
     """model(x_host) on a GPU-resident model: host in, host out (the per-tile round trip of
