@@ -27,6 +27,7 @@ _SIGNATURES = {
     "cnngp_abi_version": (ctypes.c_int, []),
     "cnngp_last_error": (ctypes.c_char_p, []),
     "cnngp_last_path": (ctypes.c_int, []),
+    "cnngp_last_launches": (ctypes.c_int, []),
     "cnngp_plan_create": (ctypes.c_int, [ctypes.POINTER(Op), ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                          ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]),
     "cnngp_plan_destroy": (None, [ctypes.c_void_p]),

@@ -32,6 +32,12 @@ def last_path():
     return {0: "none", 1: "generic", 2: "fused", 3: "fused_net"}[nat.lib().cnngp_last_path()]
 
 
+def last_launches():
+    """Kernels the last Gram call of this thread launched (two per chunk of super-tiles for programs with a
+    folded phase, one otherwise)."""
+    return nat.lib().cnngp_last_launches()
+
+
 def _require_cuda(t, what):
     if not t.is_cuda:
         raise RuntimeError(

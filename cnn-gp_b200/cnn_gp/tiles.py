@@ -51,7 +51,7 @@ class GramJob:
             engine.gram_with_aux(self.plan, self.X[i0:i1], self.X2[j0:j1], self.aux_x[i0:i1],
                                  self.aux_x2[j0:j1], same=symmetric, diag=False, symmetric=symmetric,
                                  out=view, kdiag=self.kdiag[i0:i1] if symmetric else None, path=path)
-        self.launches += 1
+        self.launches += engine.last_launches()
 
 
 def row_segments(tiles):

@@ -559,7 +559,8 @@ __device__ __forceinline__ void relu_rows(u64 (&M)[2][S0], const float4 *ai, con
             upk(M[h][r], c0, c1);
             const u64 NC = pk(neg_abs(c0), neg_abs(c1));
             const u64 D = fma2(SA, SB, NC);             // s - |c|
-            const u64 E = fma2(NC, mul2(RA, RB), ONE);  // e = 1 - |c|/s
+            const u64 RR = mul2(RA, RB);
+            const u64 E = fma2(NC, RR, ONE);  // e = 1 - |c|/s
             float e0, e1;
             upk(E, e0, e1);
             const u64 W = mul2(D, pk(sqrt_approx(fabsf(e0)), sqrt_approx(fabsf(e1))));
@@ -1211,6 +1212,7 @@ struct FNetPlan {
     int n_relu_a = 0;          // staged ReLU layers consumed by phase A
     int k_b = 0;               // first kernel descriptor of phase B
     size_t smem_a = 0, smem_b = 0;
+    int nw_a = 8;              // consumer warps of the phase-A launch (8 or 12)
 };
 
 namespace {
@@ -1550,7 +1552,7 @@ bool is_resblock(const NOp *o, int n_left, int S0) {
 }
 
 // register-level ops -> kernel descriptors: phase split, block grouping, sentinels, producer list
-bool build_kops(FNetPlan *fp, bool blocks) {
+bool build_kops(FNetPlan *fp, bool blocks, bool blocks_a = true) {
     const int S0 = fp->S0, n = fp->n_ops;
     int first_tail = n;
     for (int k = 0; k < n; ++k)
@@ -1567,8 +1569,8 @@ bool build_kops(FNetPlan *fp, bool blocks) {
     for (int k = 0; k < end_a;) {
         const NOp *o = fp->ops + k;
         int len = 1, code = case_of(*o, S0, false);
-        if (blocks && o->si == S0 && is_idblock(o, end_a - k)) { len = 6; code = A_IDBLOCK; }
-        else if (blocks && is_resblock(o, end_a - k, S0)) { len = 5; code = A_RESBLOCK; }
+        if (blocks && blocks_a && o->si == S0 && is_idblock(o, end_a - k)) { len = 6; code = A_IDBLOCK; }
+        else if (blocks && blocks_a && is_resblock(o, end_a - k, S0)) { len = 5; code = A_RESBLOCK; }
         if (len > 1) ++fp->n_blocks;
         push(make_kop(o[0], code));
         for (int q = 1; q < len; ++q) push(make_kop(o[q], case_of(o[q], S0, false)));
@@ -1664,7 +1666,17 @@ FNetPlan *fnet_plan_create(const Plan *plan_const) {
     // CNNGP_FNET_NOSPLIT=1 asks for the single-launch kernels above
     if (getenv("CNNGP_FNET_NOSPLIT")) fp->split = false;
     if (fp->split) {
-        fp->smem_a = S0 == 28 ? fnet_smem<28, 8, 4, 2, 1>() : fnet_smem<32, 8, 3, 2, 1>();
+        // phase A of 28 x 28 programs on twelve warps (without the phase-B code and the output bookkeeping the
+        // 160-register warps hardly spill: 207 ms against 214 ms on eight warps, mnist_as_tf at 6 000 images;
+        // CNNGP_FNET_A8=1 asks for eight), full-size ops dispatched one by one (the block cases cost registers a
+        // 160-register warp does not have: 1.35 against 1.23 ns per pair and block)
+        if (S0 == 28 && tr.slot1_max <= S0 / 2 && !getenv("CNNGP_FNET_A8")) {
+            fp->nw_a = 12;
+            fp->n_blocks = 0;
+            if (!build_kops(fp, getenv("CNNGP_FNET_NOBLOCKS") == nullptr, false)) { delete fp; plan->ops = saved; return nullptr; }
+            fp->split = true;
+        }
+        fp->smem_a = S0 == 28 ? (fp->nw_a == 12 ? fnet_smem<28, 12, 3, 2, 1>() : fnet_smem<28, 8, 4, 2, 1>()) : fnet_smem<32, 8, 3, 2, 1>();
         fp->smem_b = S0 == 28 ? fnet_smem<28, 16, 4, 2, 2>() : fnet_smem<32, 16, 3, 2, 2>();
     }
     for (const DevOp &o : plan->ops)
@@ -1676,7 +1688,7 @@ void fnet_plan_destroy(FNetPlan *fp) { delete fp; }
 
 std::string fnet_plan_describe(const FNetPlan *fp) {
     std::string t = "fused_net S0=" + std::to_string(fp->S0) +
-                    (fp->split ? std::string(" warps=8+16 (two launches)") : " warps=" + std::to_string(fp->nw) + " stages=" + std::to_string(fp->nst)) +
+                    (fp->split ? " warps=" + std::to_string(fp->nw_a) + "+16 (two launches)" : " warps=" + std::to_string(fp->nw) + " stages=" + std::to_string(fp->nst)) +
                     " blocks=" + std::to_string(fp->n_blocks) + " :";
     for (int k = 0; k < fp->n_ops; ++k) {
         const NOp &o = fp->ops[k];
@@ -1813,26 +1825,41 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
     if (const char *e = getenv("CNNGP_SUPER_EDGE")) { const int v = atoi(e); if (v >= 48 && v % 48 == 0) edge = v; }
     NParams pa = p, pb = p;
     long long n_super = 0, n_super_b = 0;
-    fnet_geometry(pa, N1, N2, 8, edge, &n_super);
+    const int nw_a = fp->nw_a;
+    fnet_geometry(pa, N1, N2, nw_a, edge, &n_super);
     fnet_geometry(pb, N1, N2, 16, edge, &n_super_b);
     if (n_super != n_super_b) { set_error("fused-net kernel: the two launches disagree on the super-tiles"); return 9; }
     if (prog) { const int rc = fnet_progress(pb, prog, 16, 16); if (rc) return rc; }
-    const int blocks_i = pa.sti * 2, blocks_j = pa.stj * 4 > pb.stj * 8 ? pa.stj * 4 : pb.stj * 8;
+    const int blocks_i = pa.sti * 2, blocks_j = pa.stj * (nw_a / 2) > pb.stj * 8 ? pa.stj * (nw_a / 2) : pb.stj * 8;
     const size_t rec_bytes = (size_t)2 * (fp->S0 / 2) * 32 * 8;
     const size_t st_bytes = (size_t)blocks_i * blocks_j * rec_bytes;
-    size_t budget = (size_t)1 << 30;  // hand-off buffer per chunk
+    size_t budget = (size_t)2 << 30;  // hand-off buffer per chunk (1 GB: 201.4 ms, 2 GB: 200.3 ms, 128 MB: 230 ms per 6000 x 6000 mnist_as_tf Gram)
     if (const char *e = getenv("CNNGP_FNET_HANDOFF_MB")) { const long v = atol(e); if (v > 0) budget = (size_t)v << 20; }
     long long per_chunk = (long long)(budget / st_bytes);
     if (per_chunk < 1) per_chunk = 1;
     if (per_chunk > n_super) per_chunk = n_super;
     void *handoff = nullptr;
+    {   // stream-ordered allocation; the pool keeps what it is given back (default: released at the next
+        // synchronisation, i.e. a gigabyte mapped and unmapped per call)
+        static std::atomic<unsigned> pool_set{0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 32 && !(pool_set.fetch_or(1u << dev) & (1u << dev))) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = (unsigned long long)budget;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+        }
+    }
     cudaError_t e = cudaMallocAsync(&handoff, (size_t)per_chunk * st_bytes, stream);
     if (e != cudaSuccess) { set_error(std::string("fused-net hand-off buffer: ") + cudaGetErrorString(e)); return 7; }
     pa.handoff = pb.handoff = (unsigned long long *)handoff;
     pa.rec_ld = pb.rec_ld = blocks_j;
     pa.rec_per_st = pb.rec_per_st = blocks_i * blocks_j;
     pa.row_done = nullptr;
-    void (*kern_a)(const NParams) = fp->S0 == 32 ? fnet_kernel<32, 8, 3, 2, 1> : fnet_kernel<28, 8, 4, 2, 1>;
+    void (*kern_a)(const NParams) = fp->S0 == 32 ? fnet_kernel<32, 8, 3, 2, 1>
+                                                 : (nw_a == 12 ? fnet_kernel<28, 12, 3, 2, 1> : fnet_kernel<28, 8, 4, 2, 1>);
     void (*kern_b)(const NParams) = fp->S0 == 32 ? fnet_kernel<32, 16, 3, 2, 2> : fnet_kernel<28, 16, 4, 2, 2>;
     int rc = 0;
     for (long long s0 = 0; s0 < n_super && !rc; s0 += per_chunk) {
@@ -1840,10 +1867,11 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
         pa.st_begin = pb.st_begin = (int)s0;
         pa.t_begin = s0 * pa.sti * pa.stj; pa.n_tiles = s1 * pa.sti * pa.stj;
         pb.t_begin = s0 * pb.sti * pb.stj; pb.n_tiles = s1 * pb.sti * pb.stj;
-        rc = fnet_launch_one(kern_a, pa, (8 + 4) * 32, fp->smem_a, stream);
+        rc = fnet_launch_one(kern_a, pa, (nw_a + 4) * 32, fp->smem_a, stream);
         if (!rc) rc = fnet_launch_one(kern_b, pb, (16 + 4) * 32, fp->smem_b, stream);
     }
     cudaFreeAsync(handoff, stream);
+    note_launches((int)(2 * ((n_super + per_chunk - 1) / per_chunk)));
     return rc;
 }
 

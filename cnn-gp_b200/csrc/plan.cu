@@ -15,6 +15,7 @@ namespace cnngp {
 
 static thread_local std::string g_err;
 static thread_local int g_last_path = CNNGP_PATH_NONE;
+static thread_local int g_last_launches = 0;
 
 void set_error(const std::string &msg) { g_err = msg; }
 
@@ -24,6 +25,8 @@ static int conv_out(int n, int ke, int stride, int pad, int dil) {
     if (num < 0) return 0;
     return num / stride + 1;
 }
+void note_launches(int n) { g_last_launches = n; }
+
 
 int build_plan(const cnngp_op *ops, int32_t n_ops, int32_t n_slots, int32_t H, int32_t W,
                int32_t dtype, Plan **out) {
@@ -177,6 +180,7 @@ extern "C" {
 int cnngp_abi_version(void) { return CNNGP_ABI_VERSION; }
 const char *cnngp_last_error(void) { return g_err.c_str(); }
 int cnngp_last_path(void) { return g_last_path; }
+int cnngp_last_launches(void) { return g_last_launches; }
 
 int cnngp_plan_create(const cnngp_op *ops, int32_t n_ops, int32_t n_slots, int32_t H, int32_t W,
                       int32_t dtype, cnngp_plan **out) {
@@ -272,6 +276,7 @@ int cnngp_gram(const cnngp_plan *plan, const void *d_x, int64_t N1, const void *
     }
     if (use_fused && diag) use_fused = false;  // O(N) work: generic is enough
     g_last_path = !use_fused ? CNNGP_PATH_GENERIC : (p->fused ? CNNGP_PATH_FUSED : CNNGP_PATH_FUSED_NET);
+    g_last_launches = 1;
     if (use_fused && p->fused)
         return launch_fused_gram(p, d_x, N1, d_z, N2, C, d_aux_x, d_aux_z, same, diag, symmetric, d_kdiag, d_out, ld_out, stream);
     if (use_fused)
@@ -315,6 +320,7 @@ int cnngp_gram_symmetric_to_host(const cnngp_plan *plan, const void *d_x, int64_
     if (ev) cudaEventDestroy(ev);
     if (e != cudaSuccess) { set_error(std::string("cnngp_gram_symmetric_to_host: ") + cudaGetErrorString(e)); return 7; }
     g_last_path = p->fused ? CNNGP_PATH_FUSED : CNNGP_PATH_FUSED_NET;
+    g_last_launches = 1;
     int rc = p->fused ? launch_fused_gram(p, d_x, N, d_x, N, C, d_aux, d_aux, 1, 0, 1, d_kdiag, d_out, ld_out, stream, &prog)
                       : launch_fnet_gram(p, d_x, N, d_x, N, C, d_aux, d_aux, 1, d_kdiag, d_out, ld_out, stream, &prog);
     if (rc) return rc;  // nothing was queued on the copy stream yet: it cannot wait for a launch that never ran

@@ -50,6 +50,7 @@ struct Plan {
 };
 
 void set_error(const std::string &msg);
+void note_launches(int n);  // kernels launched by the current Gram call (cnngp_last_launches)
 int build_plan(const cnngp_op *ops, int32_t n_ops, int32_t n_slots, int32_t H, int32_t W,
                int32_t dtype, Plan **out);
 const DevOp *plan_device_ops(const Plan *plan);  // uploads on first use; nullptr on CUDA error

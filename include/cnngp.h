@@ -128,6 +128,9 @@ int cnngp_gram(const cnngp_plan *plan, const void *d_x, int64_t N1, const void *
                int32_t C, const void *d_aux_x, const void *d_aux_z, const void *d_kdiag, int32_t same,
                int32_t diag, int32_t symmetric, void *d_out, int64_t ld_out, int32_t path, void *stream);
 int cnngp_last_path(void);
+/* kernels the last cnngp_gram / cnngp_gram_symmetric_to_host call of this thread launched (programs with a
+ * folded phase run as two launches per chunk of super-tiles, everything else as one) */
+int cnngp_last_launches(void);
 
 /* model(X) for a caller that wants the result in HOST memory (what save_kernel's `kern` does with
  * .cpu(), exp_mnist_resnet/save_kernel.py:21-24): the symmetric Gram of d_x is computed into
