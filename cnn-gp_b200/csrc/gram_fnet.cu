@@ -1032,21 +1032,34 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
         }
 
         if constexpr (PH != 1) {   // ================= phase B: folded maps, S0 / 2 live registers ====================
-            // tensor-memory slot 1 lives in registers here (K): phase B has them to spare, and its
-            // residual blocks then never touch tensor memory
-            u64 K[SF];
+            // single launch: tensor-memory slot 1 lives in registers here (K): phase B has them to spare at 160 / 240
+            // registers per thread, and its residual blocks then never touch tensor memory
+            // (the phase-B launch keeps it in tensor memory: its sixteen warps run at 112 registers, where the 28 / 32
+            // registers of K were spilled -- 193 against 200 ms per 6 000 x 6 000 mnist_as_tf Gram)
+            constexpr bool KREGS = PH != 2;
+            u64 K[KREGS ? SF : 1];
             if constexpr (PH == 2) {
 #pragma unroll
-                for (int r = 0; r < SF; ++r) {
-                    F[r] = rec[r * 32];
-                    K[r] = rec[(SF + r) * 32];
+                for (int r = 0; r < SF; ++r) F[r] = rec[r * 32];
+                if constexpr (KREGS) {
+#pragma unroll
+                    for (int r = 0; r < SF; ++r) K[r] = rec[(SF + r) * 32];
+                } else {
+                    u64 T[SF];
+#pragma unroll
+                    for (int r = 0; r < SF; ++r) T[r] = rec[(SF + r) * 32];
+                    stash_store_arr<SF, SF>(tm_warp + TM_SLOT1, T);
+                    tmem_wait_st();
                 }
-            } else {
+            } else if constexpr (KREGS) {
                 stash_load_arr<SF, SF, false>(tm_warp + TM_SLOT1, K, 0ull);
             }
             auto b_stash = [&](auto SZ, const int4 &d) {
                 constexpr int S = decltype(SZ)::value;
-                if (f_slot(d)) {
+                if constexpr (!KREGS) {
+                    stash_store_arr<SF, S>(tm_warp + f_slot(d) * TM_SLOT1, F);
+                    tmem_wait_st();
+                } else if (f_slot(d)) {
 #pragma unroll
                     for (int r = 0; r < S; ++r) K[r] = F[r];
                 } else {
@@ -1056,7 +1069,9 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
             };
             auto b_unstash = [&](auto SZ, const int4 &d) {
                 constexpr int S = decltype(SZ)::value;
-                if (f_slot(d)) {
+                if constexpr (!KREGS) {
+                    stash_load_arr<SF, S, false>(tm_warp + f_slot(d) * TM_SLOT1, F, 0ull);
+                } else if (f_slot(d)) {
 #pragma unroll
                     for (int r = 0; r < S; ++r) F[r] = K[r];
                 } else {
@@ -1066,7 +1081,9 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
             auto b_add = [&](auto SZ, const int4 &d) {
                 constexpr int S = decltype(SZ)::value;
                 const u64 alpha = pk(f_scale(d), f_scale(d));
-                if (f_slot(d)) {
+                if constexpr (!KREGS) {
+                    stash_load_arr<SF, S, true>(tm_warp + f_slot(d) * TM_SLOT1, F, alpha);
+                } else if (f_slot(d)) {
 #pragma unroll
                     for (int r = 0; r < S; ++r) F[r] = fma2(K[r], alpha, F[r]);
                 } else {

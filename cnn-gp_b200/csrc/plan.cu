@@ -18,6 +18,7 @@ static thread_local int g_last_path = CNNGP_PATH_NONE;
 static thread_local int g_last_launches = 0;
 
 void set_error(const std::string &msg) { g_err = msg; }
+void note_launches(int n) { g_last_launches = n; }
 
 static int conv_out(int n, int ke, int stride, int pad, int dil) {
     // torch: floor((n + 2 pad - dil (ke-1) - 1) / stride) + 1, empty when the numerator < 0
@@ -25,7 +26,6 @@ static int conv_out(int n, int ke, int stride, int pad, int dil) {
     if (num < 0) return 0;
     return num / stride + 1;
 }
-void note_launches(int n) { g_last_launches = n; }
 
 
 int build_plan(const cnngp_op *ops, int32_t n_ops, int32_t n_slots, int32_t H, int32_t W,
