@@ -231,7 +231,7 @@ __device__ __forceinline__ void stash_store_arr(uint32_t ta, const u64 (&a)[NA])
 // a = stash (ADD == false) or a = stash * alpha + a (ADD == true); the loads of the array are in
 // flight together, two 16-register groups at a time (LIGHT: the 12-warp variant runs phase A at 160
 // registers with 112 of them holding the maps) or all of them (phase B: registers are plentiful)
-template <int NA, int S, bool ADD>
+template <int NA, int S, bool ADD, bool ONE_GROUP = false>
 __device__ __forceinline__ void stash_load_arr(uint32_t ta, u64 (&a)[NA], u64 alpha) {
     if (!ADD) {  // plain reload: x2 loads land in the map's own register pairs, all in flight, one wait
         uint32_t r[S][2];
@@ -246,6 +246,41 @@ __device__ __forceinline__ void stash_load_arr(uint32_t ta, u64 (&a)[NA], u64 al
         return;
     }
     constexpr int G8 = S / 8, R8 = S % 8, B4 = G8 * 8, B2 = B4 + (R8 & 4), B1 = B2 + (R8 & 2);
+    if (ONE_GROUP) {
+        // one 16-register group at a time: with twelve warps reading (three per lane quadrant) the loads of the
+        // other warps keep tensor memory busy anyway (scripts/tmem_probe.cu: 7 x (ld16 + wait) = 205 cycles
+        // against 203 with all seven in flight), and the 40 staging registers of the deeper form do not
+        // exist next to a full-size map set in a 160-register warp
+#pragma unroll
+        for (int c = 0; c < G8; ++c) {
+            uint32_t t[16];
+            tmem_ld16(ta + c * 16, t);
+            tmem_landed16(t);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a[c * 8 + q] = fma2(join64(t[2 * q], t[2 * q + 1]), alpha, a[c * 8 + q]);
+        }
+        if (R8 & 4) {
+            uint32_t t[8];
+            tmem_ld8(ta + 2 * B4, t);
+            tmem_landed8(t);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[(B4 + q) % NA] = fma2(join64(t[2 * q], t[2 * q + 1]), alpha, a[(B4 + q) % NA]);
+        }
+        if (R8 & 2) {
+            uint32_t t[4];
+            tmem_ld4(ta + 2 * B2, t);
+            tmem_landed4(t);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) a[(B2 + q) % NA] = fma2(join64(t[2 * q], t[2 * q + 1]), alpha, a[(B2 + q) % NA]);
+        }
+        if (R8 & 1) {
+            uint32_t t[2];
+            tmem_ld2(ta + 2 * B1, t);
+            tmem_landed2(t);
+            a[B1 % NA] = fma2(join64(t[0], t[1]), alpha, a[B1 % NA]);
+        }
+        return;
+    }
     uint32_t t8[8], t4[4], t2[2];
     if (R8 & 4) tmem_ld8(ta + 2 * B4, t8);
     if (R8 & 2) tmem_ld4(ta + 2 * B2, t4);
@@ -950,8 +985,8 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
                 const uint32_t ta = tm_warp + s * TM_SLOT1;
                 const float al = f_scale(d);
                 const u64 alpha = pk(al, al);
-                stash_load_arr<S0, S0, true>(ta, M[0], alpha);
-                stash_load_arr<S0, S0, true>(ta + (s ? TM_A1 : TM_A0), M[1], alpha);
+                stash_load_arr<S0, S0, true, NW == 12>(ta, M[0], alpha);
+                stash_load_arr<S0, S0, true, NW == 12>(ta + (s ? TM_A1 : TM_A0), M[1], alpha);
                 add_const<S0, S0>(M[0], f_bias(d));
                 add_const<S0, S0>(M[1], f_bias(d));
             };
@@ -1015,7 +1050,8 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
                     default: FETCH(1); more = false; break;  // A_END
                 }
 #undef FOLDED_A
-                o = nxt;
+                // twelve warps: the next descriptor is fetched now, not one op ahead (four registers less across the op)
+                o = NW == 12 ? ops_s[k] : nxt;
             }
 #pragma unroll
             for (int r = 0; r < SF; ++r) F[r] = M[0][r];
