@@ -530,11 +530,12 @@ __device__ __forceinline__ void fold_op(u64 (&M)[2][S0], int lane) {
 template <int NA, int S0, int R, int L>
 __device__ __forceinline__ void tstore_f(u64 *tile, const u64 (&a)[NA], int lane) {
     constexpr int PITCH = S0 + 1;
+    static_assert(2 * L <= S0, "the pad column must be free");
     const int b = lane >> 4, l = lane & 15;
-    if (l < L) {
+    // lanes that hold nothing write the pad column S0, which is never read (no divergent region around the stores)
+    const int col = l < L ? b * L + l : S0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) tile[r * PITCH + b * L + l] = a[r];
-    }
+    for (int r = 0; r < R; ++r) tile[r * PITCH + col] = a[r];
 }
 template <int NA, int S0, int R, int NEWL>
 __device__ __forceinline__ void tload_f(const u64 *tile, u64 (&a)[NA], int lane) {

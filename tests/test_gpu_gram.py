@@ -375,10 +375,12 @@ def test_split_launches_match_the_single_launch(name, C, S, n, monkeypatch):
         engine._PLANS.pop(model, None)
         got = (model(X), model(X, Z))
         assert "two launches" in engine.plan_for(model, S, S, torch.float32).describe()
+        assert engine.last_launches() >= 4 and engine.last_launches() % 2 == 0  # two per chunk, several chunks
         monkeypatch.setenv("CNNGP_FNET_NOSPLIT", "1")
         engine._PLANS.pop(model, None)
         want = (model(X), model(X, Z))
         assert "two launches" not in engine.plan_for(model, S, S, torch.float32).describe()
+        assert engine.last_launches() == 1
     finally:
         engine._PLANS.pop(model, None)
     for g, w in zip(got, want):
