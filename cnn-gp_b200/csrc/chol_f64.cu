@@ -245,6 +245,61 @@ constexpr int POTF2_THREADS = 512;
 // are small products spread over all 512 threads.
 constexpr int QB = 32;
 
+// W = U^{-1} in place for the upper-triangular NB x NB block s[NB][DP] (identity-padded), rinv = reciprocals of its
+// diagonal, tmp = [QB][QB + 1] scratch; all POTF2_THREADS threads of the CTA call it, a barrier has ordered s and rinv.
+__device__ __forceinline__ void tri_inverse_inplace(double *s, const double *rinv, double *tmp, int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp < NB / QB) {  // diagonal blocks: lane j solves U w = e_j for column j of the inverse, in registers
+        const int o = warp * QB;
+        double w[QB];
+#pragma unroll
+        for (int i = QB - 1; i >= 0; --i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int t = i + 1; t < QB; ++t) acc += s[(o + i) * DP + o + t] * (t <= lane ? w[t] : 0.0);
+            w[i] = i == lane ? rinv[o + i] : (i < lane ? -acc * rinv[o + i] : 0.0);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < QB; ++i)
+            if (lane >= i) s[(o + i) * DP + o + lane] = w[i];
+    }
+    __syncthreads();
+    // off-diagonal blocks: W_ij = -W_ii * sum_{k=i+1..j} U_ik W_kj, block columns right to left (the
+    // U_ik of the columns left of j are still intact), block rows bottom to top
+    for (int bj = NB / QB - 1; bj >= 1; --bj) {
+        for (int bi = bj - 1; bi >= 0; --bi) {
+            double t2[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int e = tid + q * POTF2_THREADS, r = e / QB, c = e % QB;
+                double acc = 0.0;
+                for (int k = (bi + 1) * QB; k < (bj + 1) * QB; ++k) acc += s[(bi * QB + r) * DP + k] * s[k * DP + bj * QB + c];
+                t2[q] = acc;
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int e = tid + q * POTF2_THREADS;
+                tmp[(e / QB) * (QB + 1) + e % QB] = t2[q];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int e = tid + q * POTF2_THREADS, r = e / QB, c = e % QB;
+                double acc = 0.0;
+                for (int t = r; t < QB; ++t) acc += s[(bi * QB + r) * DP + bi * QB + t] * tmp[t * (QB + 1) + c];
+                t2[q] = -acc;
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int e = tid + q * POTF2_THREADS;
+                s[(bi * QB + e / QB) * DP + bj * QB + e % QB] = t2[q];
+            }
+            __syncthreads();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_inv_kernel(double *A, long long lda, int kb, int nb,
                                                                      double *W, int *info, long long info_base) {
     extern __shared__ __align__(16) double ps_smem[];
@@ -320,55 +375,7 @@ __global__ void __launch_bounds__(POTF2_THREADS, 1) potf2_inv_kernel(double *A, 
     __syncthreads();
 
     // ---- W = U^{-1} in place --------------------------------------------------------------------
-    if (warp < NB / QB) {  // diagonal blocks: lane j solves U w = e_j for column j of the inverse, in registers
-        const int o = warp * QB;
-        double w[QB];
-#pragma unroll
-        for (int i = QB - 1; i >= 0; --i) {
-            double acc = 0.0;
-#pragma unroll
-            for (int t = i + 1; t < QB; ++t) acc += s[(o + i) * DP + o + t] * (t <= lane ? w[t] : 0.0);
-            w[i] = i == lane ? rinv[o + i] : (i < lane ? -acc * rinv[o + i] : 0.0);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < QB; ++i)
-            if (lane >= i) s[(o + i) * DP + o + lane] = w[i];
-    }
-    __syncthreads();
-    // off-diagonal blocks: W_ij = -W_ii * sum_{k=i+1..j} U_ik W_kj, block columns right to left (the
-    // U_ik of the columns left of j are still intact), block rows bottom to top
-    for (int bj = NB / QB - 1; bj >= 1; --bj) {
-        for (int bi = bj - 1; bi >= 0; --bi) {
-            double t2[2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int e = tid + q * POTF2_THREADS, r = e / QB, c = e % QB;
-                double acc = 0.0;
-                for (int k = (bi + 1) * QB; k < (bj + 1) * QB; ++k) acc += s[(bi * QB + r) * DP + k] * s[k * DP + bj * QB + c];
-                t2[q] = acc;
-            }
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int e = tid + q * POTF2_THREADS;
-                tmp[(e / QB) * (QB + 1) + e % QB] = t2[q];
-            }
-            __syncthreads();
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int e = tid + q * POTF2_THREADS, r = e / QB, c = e % QB;
-                double acc = 0.0;
-                for (int t = r; t < QB; ++t) acc += s[(bi * QB + r) * DP + bi * QB + t] * tmp[t * (QB + 1) + c];
-                t2[q] = -acc;
-            }
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int e = tid + q * POTF2_THREADS;
-                s[(bi * QB + e / QB) * DP + bj * QB + e % QB] = t2[q];
-            }
-            __syncthreads();
-        }
-    }
+    tri_inverse_inplace(s, rinv, tmp, tid);
     for (int e = tid; e < NB * NB; e += POTF2_THREADS) {
         const int i = e / NB, j = e % NB;
         W[e] = (i < nb && j < nb && j >= i) ? s[i * DP + j] : 0.0;
@@ -500,7 +507,11 @@ constexpr size_t kBwdSmem = (size_t)(64 * DP + NB * NR) * sizeof(double);
 // other updates run ahead of it.  Each U block is read once, coalesced, staged through shared memory.
 constexpr int SW_THREADS = 512;
 constexpr int SW_NR = 16;   // right-hand sides per pass
-constexpr size_t kSweepSmem = (size_t)(NB * DP + SW_NR * DP + NB * SW_NR + NB) * sizeof(double);
+// pitches of the update stage: a staged U block and the published solution are read as mma.m8n8k4 fragments
+// (lane = 4 x fragment row + k): a pitch of 4 mod 16 doubles puts the sixteen lanes of a half-warp on sixteen bank pairs
+constexpr int SW_UP = NB + 4;     // staged U block (the diagonal block reuses the buffer at pitch DP, see below)
+constexpr int SW_YP = SW_NR + 4;  // published solution of block k
+constexpr size_t kSweepSmem = (size_t)(NB * SW_UP + SW_NR * DP + NB * SW_YP + NB) * sizeof(double);
 
 __device__ __forceinline__ void flag_wait(const int *f) {
     if (threadIdx.x == 0) {
@@ -524,30 +535,48 @@ template <bool FWD>
 __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const double *__restrict__ U, long long lda, int n, double *B,
                                                              long long ldb, int c0, int nr, int *flags) {
     extern __shared__ __align__(16) double sw_smem[];
-    double *d = sw_smem;                    // [NB][DP]: a U block (updates: staged ahead of the flag; then the diagonal block)
-    double *bs = d + NB * DP;               // [SW_NR][DP]: this block's right-hand sides, bs[c * DP + r]
-    double *ys = bs + SW_NR * DP;           // [NB][SW_NR]: the published solution of block k
-    double *invd = ys + NB * SW_NR;         // [NB]
+    double *d = sw_smem;                    // [NB][SW_UP]: a U block (updates: staged ahead of the flag); then [NB][DP]: the diagonal block
+    double *bs = d + NB * SW_UP;            // [SW_NR][DP]: this block's right-hand sides, bs[c * DP + r]
+    double *ys = bs + SW_NR * DP;           // [NB][SW_YP]: the published solution of block k
+    double *invd = ys + NB * SW_YP;         // [NB]
     const int tid = threadIdx.x;
     const int nblk = (n + NB - 1) / NB;
-    const int r = tid & (NB - 1), cg = tid >> 7;
+    // the updates run on the FP64 tensor pipe (mma.m8n8k4: 4.4 x the DFMA rate of one SM, and the last update
+    // of a block is on the critical path of the whole sweep): warp w owns rows 8 w .. 8 w + 7 of the block and
+    // all sixteen right-hand sides = two 8 x 8 accumulator fragments, element (row lr, columns 8 nt + 2 lk + {0, 1})
+    const int wq = tid >> 5, lr = (tid & 31) >> 2, lk = tid & 3;
     for (int q = blockIdx.x; q < nblk; q += gridDim.x) {
         const int j = FWD ? q : nblk - 1 - q;
         const int jb = j * NB, nbj = n - jb < NB ? n - jb : NB;
-        double acc[4];
+        double acc[2][2];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int c = cg * 4 + e;
-            acc[e] = (r < nbj && c < nr) ? B[(long long)(jb + r) * ldb + c0 + c] : 0.0;
-        }
-        // the diagonal block waits in registers (32 doubles per thread) until the substitution: its memory
-        // latency is paid here, under the update loop, not on the critical path
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int rr = 8 * wq + lr, c = nt * 8 + 2 * lk + e;
+                acc[nt][e] = (rr < nbj && c < nr) ? B[(long long)(jb + rr) * ldb + c0 + c] : 0.0;
+            }
+        // W = inverse of the diagonal block, computed HERE -- before the updates, i.e. while the blocks this one
+        // depends on are still being solved (only the first blocks of a sweep have no such slack) -- and kept in
+        // registers (32 doubles per thread) under the update loop: the solve with the diagonal block is then one
+        // more tensor-pipe product on the critical path instead of 128 dependent substitution steps
         double dg[NB * NB / SW_THREADS];
+#pragma unroll 8
+        for (int e = tid; e < NB * NB; e += SW_THREADS) {
+            const int i = e >> 7, t = e & (NB - 1);
+            d[i * DP + t] = (i < nbj && t < nbj && t >= i) ? __ldg(U + (long long)(jb + i) * lda + jb + t) : (i == t ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        if (tid < NB) invd[tid] = 1.0 / d[tid * DP + tid];
+        __syncthreads();
+        tri_inverse_inplace(d, invd, bs, tid);
+        __syncthreads();
 #pragma unroll
         for (int u = 0; u < NB * NB / SW_THREADS; ++u) {
             const int e = tid + u * SW_THREADS, i = e >> 7, t = e & (NB - 1);
-            dg[u] = (i < nbj && t < nbj && t >= i) ? __ldg(U + (long long)(jb + i) * lda + jb + t) : 0.0;
+            dg[u] = t >= i ? d[i * DP + t] : 0.0;
         }
+        __syncthreads();
         const int k_lo = FWD ? 0 : j + 1, k_hi = FWD ? j : nblk;
         for (int kk = k_lo; kk < k_hi; ++kk) {
             const int k = FWD ? kk : nblk - 1 - (kk - k_lo);  // backward: the last block first
@@ -561,77 +590,61 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(const double *__re
 #pragma unroll 8
                 for (int e = tid; e < NB * NB; e += SW_THREADS) {
                     const int i = e >> 7, t = e & (NB - 1);
-                    d[i * DP + t] = (i < rows && t < cols) ? __ldg(U + (row0 + i) * lda + col0 + t) : 0.0;
+                    d[i * SW_UP + t] = (i < rows && t < cols) ? __ldg(U + (row0 + i) * lda + col0 + t) : 0.0;
                 }
             }
             flag_wait(flags + k);
             for (int e = tid; e < NB * SW_NR; e += SW_THREADS) {
                 const int t = e / SW_NR, c = e % SW_NR;
                 // published by another SM: read through L2
-                ys[e] = (t < nbk && c < nr) ? __ldcg(B + (long long)(kb + t) * ldb + c0 + c) : 0.0;
+                ys[t * SW_YP + c] = (t < nbk && c < nr) ? __ldcg(B + (long long)(kb + t) * ldb + c0 + c) : 0.0;
             }
             __syncthreads();
+            {   // FWD: acc[r] -= sum_t U[kb + t][jb + r] y[t]; else acc[r] -= sum_t U[jb + r][kb + t] x[t]
+                const double *pa = FWD ? d + lk * SW_UP + 8 * wq + lr : d + (8 * wq + lr) * SW_UP + lk;
+                const double *pb = ys + lk * SW_YP + lr;
 #pragma unroll 8
-            for (int t = 0; t < NB; ++t) {
-                // FWD: acc[r] -= sum_t U[kb + t][jb + r] y[t]; else acc[r] -= sum_t U[jb + r][kb + t] x[t]
-                const double v = FWD ? d[t * DP + r] : d[r * DP + t];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) acc[e] -= v * ys[t * SW_NR + cg * 4 + e];
+                for (int k4 = 0; k4 < NB / 4; ++k4) {
+                    const double a = -(FWD ? pa[k4 * 4 * SW_UP] : pa[k4 * 4]);
+                    const double b0 = pb[k4 * 4 * SW_YP], b1 = pb[k4 * 4 * SW_YP + 8];
+                    dmma(acc[0][0], acc[0][1], a, b0);
+                    dmma(acc[1][0], acc[1][1], a, b1);
+                }
             }
             __syncthreads();
         }
+        // y_j = W^T b (FWD) / x_j = W y (else): W into the fragment-friendly buffer, the updated right-hand sides
+        // into the B-operand buffer, one product over the non-zero half of the k range
 #pragma unroll
         for (int u = 0; u < NB * NB / SW_THREADS; ++u) {
             const int e = tid + u * SW_THREADS;
-            d[(e >> 7) * DP + (e & (NB - 1))] = dg[u];
+            d[(e >> 7) * SW_UP + (e & (NB - 1))] = dg[u];
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) bs[(cg * 4 + e) * DP + r] = acc[e];
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) ys[(8 * wq + lr) * SW_YP + nt * 8 + 2 * lk + e] = acc[nt][e];
         __syncthreads();
-        if (tid < NB) invd[tid] = tid < nbj ? 1.0 / d[tid * DP + tid] : 0.0;
-        __syncthreads();
-        // substitution with the diagonal block in four 32-row steps: warp w owns right-hand side w of the
-        // 32 x 32 triangle (lane = row, the pivot's value travels by shuffle: no block barrier inside), then
-        // all threads apply the step to the rows outside it
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int s0 = FWD ? 0 : NB - 32; FWD ? s0 < NB : s0 >= 0; s0 += FWD ? 32 : -32) {
-            if (warp < SW_NR) {
-                double v = bs[warp * DP + s0 + lane];
-                if (FWD) {
-                    for (int t = 0; t < 32; ++t) {
-                        const double xt = __shfl_sync(0xffffffffu, v, t) * invd[s0 + t];
-                        if (lane > t) v -= d[(s0 + t) * DP + s0 + lane] * xt;
-                        if (lane == t) v = xt;
-                    }
-                } else {
-                    for (int t = 31; t >= 0; --t) {
-                        const double xt = __shfl_sync(0xffffffffu, v, t) * invd[s0 + t];
-                        if (lane < t) v -= d[(s0 + lane) * DP + s0 + t] * xt;
-                        if (lane == t) v = xt;
-                    }
-                }
-                bs[warp * DP + s0 + lane] = v;
+        {
+            double out[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            const double *pa = FWD ? d + lk * SW_UP + 8 * wq + lr : d + (8 * wq + lr) * SW_UP + lk;
+            const double *pb = ys + lk * SW_YP + lr;
+            // W is upper triangular: FWD uses W[t][r], t <= r; else W[r][t], t >= r (rows 8 wq .. 8 wq + 7 of this warp)
+            const int k4_lo = FWD ? 0 : 2 * wq, k4_hi = FWD ? 2 * wq + 2 : NB / 4;
+#pragma unroll 4
+            for (int k4 = k4_lo; k4 < k4_hi; ++k4) {
+                const double a = FWD ? pa[k4 * 4 * SW_UP] : pa[k4 * 4];
+                const double b0 = pb[k4 * 4 * SW_YP], b1 = pb[k4 * 4 * SW_YP + 8];
+                dmma(out[0][0], out[0][1], a, b0);
+                dmma(out[1][0], out[1][1], a, b1);
             }
-            __syncthreads();
-            // rows still to come: FWD r >= s0 + 32, else r < s0
-            const bool mine = FWD ? (r >= s0 + 32) : (r < s0);
-            if (mine) {
-                double a4[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 8
-                for (int t = 0; t < 32; ++t) {
-                    const double v = FWD ? d[(s0 + t) * DP + r] : d[r * DP + s0 + t];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) a4[e] += v * bs[(cg * 4 + e) * DP + s0 + t];
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int rr = 8 * wq + lr, c = nt * 8 + 2 * lk + e;
+                    if (rr < nbj && c < nr) B[(long long)(jb + rr) * ldb + c0 + c] = out[nt][e];
                 }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) bs[(cg * 4 + e) * DP + r] -= a4[e];
-            }
-            __syncthreads();
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int c = cg * 4 + e;
-            if (r < nbj && c < nr) B[(long long)(jb + r) * ldb + c0 + c] = bs[c * DP + r];
         }
         flag_set(flags + j);
         __syncthreads();
