@@ -683,68 +683,117 @@ __global__ void __launch_bounds__(256) rows_update_kernel(const double *U, long 
 }
 
 // ---- prediction: scores = K A (float32 K widened to float64), pred = argmax ------------------
-// A warp owns PR_ROWS rows of K; its lanes stride over the n training points, so K is read from
-// HBM exactly once, coalesced, and every weight row A[t, :] fetched (L1 / L2 resident: n x nrhs
-// doubles) serves PR_ROWS rows.  No shared memory, no block barriers: many warps in flight hide
-// the load latency.
-constexpr int PR_ROWS = 4;
+// classify_gp.py:39-41.  The product is skinny ([R, n] x [n, <= 16]) and its arithmetic is float64: on the
+// plain FP64 pipe it is compute-bound at 4 x the time HBM needs for K (1.3 G DFMA at n = 32 768, R = 4 096), so
+// it runs on the FP64 tensor pipe.  A warp owns 32 rows of K (four 8-row mma.m8n8k4 fragments that share every
+// B fragment) and one chunk of the n training points; lane (lr, lk) reads four consecutive entries of its
+// rows per 16 points (one 16-byte load where the row is aligned) and feeds them to four mma steps, the
+// B fragments take the matching rows of A (L2-resident) -- the order of k inside a step is free as long as
+// both operands agree.  Partial scores per chunk go to a scratch buffer and are summed in chunk order by
+// predict_reduce_kernel (deterministic), which also takes the argmax.
+constexpr int PD_ROWS = 32;  // rows of K per warp
+constexpr int PD_NC = 16;    // right-hand sides per pass (two 8-column fragments)
 
-template <int NC, typename KT>
-__global__ void __launch_bounds__(128) predict_kernel(const KT *K, long long R, long long n, long long ldk,
-                                                      const double *A, int nrhs, int c0, long long *pred,
-                                                      double *scores, double *best_val) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long r0 = ((long long)blockIdx.x * 4 + warp) * PR_ROWS;
-    if (r0 >= R) return;
-    const int nc = min(NC, nrhs - c0);
-    double acc[PR_ROWS][NC];
+__device__ __forceinline__ void load4(const float *p, bool vec, long long left, double (&a)[4]) {
+    if (vec && left >= 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+        a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+    } else {
 #pragma unroll
-    for (int q = 0; q < PR_ROWS; ++q)
+        for (int j = 0; j < 4; ++j) a[j] = j < left ? (double)__ldg(p + j) : 0.0;
+    }
+}
+__device__ __forceinline__ void load4(const double *p, bool vec, long long left, double (&a)[4]) {
+    if (vec && left >= 4) {
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(p)), w = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+        a[0] = v.x; a[1] = v.y; a[2] = w.x; a[3] = w.y;
+    } else {
 #pragma unroll
-        for (int c = 0; c < NC; ++c) acc[q][c] = 0.0;
-    const KT *k[PR_ROWS];
+        for (int j = 0; j < 4; ++j) a[j] = j < left ? __ldg(p + j) : 0.0;
+    }
+}
+
+constexpr int PD_KT = 128;         // training points per shared-memory tile of A
+constexpr int PD_PB = PD_NC + 1;   // its pitch: odd, so that the B fragments (lane = 4 x column + k) are conflict-free
+
+template <typename KT>
+__global__ void __launch_bounds__(128) predict_dmma_kernel(const KT *K, long long R, long long n, long long ldk,
+                                                           const double *A, int nrhs, int c0, long long kc, int nchunks,
+                                                           double *part, int vec) {
+    __shared__ double sB[PD_KT * PD_PB];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lk = lane & 3;
+    const long long groups = (R + 4 * PD_ROWS - 1) / (4 * PD_ROWS);  // a CTA: 4 warps x 32 rows, one chunk
+    const long long rg = blockIdx.x % groups, ch = blockIdx.x / groups;
+    const long long r0 = rg * 4 * PD_ROWS + warp * PD_ROWS, k_begin = ch * kc, k_end = k_begin + kc < n ? k_begin + kc : n;
+    const int nc = nrhs - c0 < PD_NC ? nrhs - c0 : PD_NC;
+    double acc[4][2][2];
 #pragma unroll
-    for (int q = 0; q < PR_ROWS; ++q) k[q] = K + min(r0 + q, R - 1) * ldk;
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) acc[m][nt][0] = acc[m][nt][1] = 0.0;
+    const KT *rowp[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const long long r = r0 + 8 * m + lr;
+        rowp[m] = K + (r < R ? r : R - 1) * ldk;
+    }
+    for (int e = tid; e < PD_KT * PD_PB; e += 128) sB[e] = 0.0;  // columns >= nc stay zero
+    for (long long kt = k_begin; kt < k_end; kt += PD_KT) {
+        __syncthreads();
+        const int rows = (int)(k_end - kt < PD_KT ? k_end - kt : PD_KT);
+        for (int e = tid; e < PD_KT * nc; e += 128) {  // rows of A are contiguous when nc == nrhs: coalesced
+            const int k = e / nc, c = e - k * nc;
+            sB[k * PD_PB + c] = k < rows ? __ldg(A + (kt + k) * nrhs + c0 + c) : 0.0;
+        }
+        __syncthreads();
+        if (r0 >= R) continue;
 #pragma unroll 2
-    for (long long t = lane; t < n; t += 32) {
-        double kv[PR_ROWS];
+        for (int k16 = 0; k16 < PD_KT; k16 += 16) {
+            if (k16 >= rows) break;
+            const long long kk = kt + k16 + 4 * lk, left = k_end - kk;  // this lane's four points
+            double a[4][4];
 #pragma unroll
-        for (int q = 0; q < PR_ROWS; ++q) kv[q] = (double)__ldg(k[q] + t);
-        const double *a = A + t * nrhs + c0;
+            for (int m = 0; m < 4; ++m) load4(rowp[m] + kk, vec != 0, left, a[m]);
+            const double *pb = sB + (k16 + 4 * lk) * PD_PB + lr;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            if (c < nc) {
-                const double av = __ldg(a + c);
+            for (int j = 0; j < 4; ++j) {
+                const double b0 = pb[j * PD_PB], b1 = pb[j * PD_PB + 8];
 #pragma unroll
-                for (int q = 0; q < PR_ROWS; ++q) acc[q][c] += kv[q] * av;
+                for (int m = 0; m < 4; ++m) {
+                    dmma(acc[m][0][0], acc[m][0][1], a[m][j], b0);
+                    dmma(acc[m][1][0], acc[m][1][1], a[m][j], b1);
+                }
             }
         }
     }
 #pragma unroll
-    for (int q = 0; q < PR_ROWS; ++q)
+    for (int m = 0; m < 4; ++m) {
+        const long long r = r0 + 8 * m + lr;
+        if (r >= R) continue;
+        double *o = part + (ch * R + r) * PD_NC + 2 * lk;
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) acc[q][c] += __shfl_xor_sync(0xffffffffu, acc[q][c], d);
-    if (lane == 0) {
-#pragma unroll
-        for (int q = 0; q < PR_ROWS; ++q) {
-            const long long r = r0 + q;
-            if (r >= R) break;
-            double bv = c0 == 0 ? -INFINITY : best_val[r];
-            long long bi = c0 == 0 ? 0 : pred[r];
-            bool any = c0 != 0;
-#pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                if (c >= nc) break;
-                if (scores) scores[r * nrhs + c0 + c] = acc[q][c];
-                // first maximum wins, NaN propagates like torch.argmax (a NaN score is the maximum)
-                if (!any || acc[q][c] > bv || (acc[q][c] != acc[q][c] && bv == bv)) { bv = acc[q][c]; bi = c0 + c; any = true; }
-            }
-            pred[r] = bi;
-            if (best_val) best_val[r] = bv;
-        }
+        for (int nt = 0; nt < 2; ++nt) *reinterpret_cast<double2 *>(o + 8 * nt) = make_double2(acc[m][nt][0], acc[m][nt][1]);
     }
+}
+
+// one thread per row: partial scores summed in chunk order, then the running argmax over the column passes
+__global__ void __launch_bounds__(128) predict_reduce_kernel(const double *part, long long R, int nrhs, int c0, int nchunks,
+                                                             long long *pred, double *scores, double *best_val) {
+    const long long r = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (r >= R) return;
+    const int nc = nrhs - c0 < PD_NC ? nrhs - c0 : PD_NC;
+    double bv = c0 == 0 ? -INFINITY : best_val[r];
+    long long bi = c0 == 0 ? 0 : pred[r];
+    bool any = c0 != 0;
+    for (int c = 0; c < nc; ++c) {
+        double v = 0.0;
+        for (int ch = 0; ch < nchunks; ++ch) v += part[((long long)ch * R + r) * PD_NC + c];
+        if (scores) scores[r * nrhs + c0 + c] = v;
+        // first maximum wins, NaN propagates like torch.argmax (a NaN score is the maximum)
+        if (!any || v > bv || (v != v && bv == bv)) { bv = v; bi = c0 + c; any = true; }
+    }
+    pred[r] = bi;
+    if (best_val) best_val[r] = bv;
 }
 
 bool check(cudaError_t e, const char *what) {
@@ -850,12 +899,29 @@ static int predict_any(const KT *d_K, int64_t R, int64_t n, int64_t ldk, const d
     if (!d_K || !d_A || !d_pred || R < 0 || n < 0 || ldk < n || nrhs < 1) { set_error(std::string(who) + ": bad arguments"); return 1; }
     if (R == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream_;
-    double *best = nullptr;
-    if (nrhs > 10 && !check(cudaMallocAsync((void **)&best, sizeof(double) * R, s), "predict workspace")) return 6;
-    constexpr int PC = 10;  // right-hand sides per pass: the ten classes of the shipped configs
-    const unsigned grid = (unsigned)((R + 4 * PR_ROWS - 1) / (4 * PR_ROWS));
-    for (int c0 = 0; c0 < nrhs; c0 += PC)
-        predict_kernel<PC, KT><<<grid, 128, 0, s>>>(d_K, R, n, ldk, d_A, nrhs, c0, (long long *)d_pred, d_scores, best);
+    double *best = nullptr, *part = nullptr;
+    if (nrhs > PD_NC && !check(cudaMallocAsync((void **)&best, sizeof(double) * R, s), "predict workspace")) return 6;
+    // enough (128-row group, chunk) CTAs for every SM to hold four; chunks of whole shared-memory tiles
+    const long long groups = (R + 4 * PD_ROWS - 1) / (4 * PD_ROWS);
+    long long nchunks = (2368 + groups - 1) / groups, max_chunks = (n + 4 * PD_KT - 1) / (4 * PD_KT);  // ~4 waves of 4 CTAs per SM
+    if (nchunks > max_chunks) nchunks = max_chunks;
+    if (nchunks < 1) nchunks = 1;
+    long long kc = ((n + nchunks - 1) / nchunks + PD_KT - 1) / PD_KT * PD_KT;
+    nchunks = (n + kc - 1) / kc;
+    if (nchunks < 1) nchunks = 1;
+    pool_keep((size_t)64 << 20);
+    if (!check(cudaMallocAsync((void **)&part, sizeof(double) * nchunks * R * PD_NC, s), "predict workspace")) {
+        if (best) cudaFreeAsync(best, s);
+        return 6;
+    }
+    // 16-byte loads of four consecutive entries need aligned rows
+    const int vec = ((uintptr_t)d_K % 16 == 0) && (ldk * sizeof(KT)) % 16 == 0;
+    const unsigned grid = (unsigned)(groups * nchunks), rgrid = (unsigned)((R + 127) / 128);
+    for (int c0 = 0; c0 < nrhs; c0 += PD_NC) {
+        predict_dmma_kernel<KT><<<grid, 128, 0, s>>>(d_K, R, n, ldk, d_A, nrhs, c0, kc, (int)nchunks, part, vec);
+        predict_reduce_kernel<<<rgrid, 128, 0, s>>>(part, R, nrhs, c0, (int)nchunks, (long long *)d_pred, d_scores, best);
+    }
+    cudaFreeAsync(part, s);
     if (best) cudaFreeAsync(best, s);
     return check(cudaGetLastError(), who) ? 0 : 9;
 }

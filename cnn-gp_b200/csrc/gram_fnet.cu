@@ -1893,19 +1893,7 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
     if (per_chunk < 1) per_chunk = 1;
     if (per_chunk > n_super) per_chunk = n_super;
     void *handoff = nullptr;
-    {   // stream-ordered allocation; the pool keeps what it is given back (default: released at the next
-        // synchronisation, i.e. a gigabyte mapped and unmapped per call)
-        static std::atomic<unsigned> pool_set{0};
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev >= 0 && dev < 32 && !(pool_set.fetch_or(1u << dev) & (1u << dev))) {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                unsigned long long keep = (unsigned long long)budget;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-        }
-    }
+    pool_keep(budget);  // the hand-off buffer stays mapped between calls
     cudaError_t e = cudaMallocAsync(&handoff, (size_t)per_chunk * st_bytes, stream);
     if (e != cudaSuccess) { set_error(std::string("fused-net hand-off buffer: ") + cudaGetErrorString(e)); return 7; }
     pa.handoff = pb.handoff = (unsigned long long *)handoff;

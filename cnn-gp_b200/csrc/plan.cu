@@ -19,6 +19,18 @@ static thread_local int g_last_launches = 0;
 
 void set_error(const std::string &msg) { g_err = msg; }
 void note_launches(int n) { g_last_launches = n; }
+void pool_keep(size_t bytes) {
+    static std::mutex mu;
+    static unsigned long long kept[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    std::lock_guard<std::mutex> lk(mu);
+    if (kept[dev] >= bytes) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return;
+    unsigned long long keep = (unsigned long long)bytes;
+    if (cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess) kept[dev] = keep;
+}
 
 static int conv_out(int n, int ke, int stride, int pad, int dil) {
     // torch: floor((n + 2 pad - dil (ke-1) - 1) / stride) + 1, empty when the numerator < 0

@@ -50,6 +50,9 @@ struct Plan {
 };
 
 void set_error(const std::string &msg);
+// stream-ordered scratch (cudaMallocAsync): let the device's default pool keep at least `bytes` between calls
+// (its default gives everything back at the next synchronisation: a map / unmap per call)
+void pool_keep(size_t bytes);
 void note_launches(int n);  // kernels launched by the current Gram call (cnngp_last_launches)
 int build_plan(const cnngp_op *ops, int32_t n_ops, int32_t n_slots, int32_t H, int32_t W,
                int32_t dtype, Plan **out);
