@@ -901,13 +901,23 @@ static int predict_any(const KT *d_K, int64_t R, int64_t n, int64_t ldk, const d
     cudaStream_t s = (cudaStream_t)stream_;
     double *best = nullptr, *part = nullptr;
     if (nrhs > PD_NC && !check(cudaMallocAsync((void **)&best, sizeof(double) * R, s), "predict workspace")) return 6;
-    // enough (128-row group, chunk) CTAs for every SM to hold four; chunks of whole shared-memory tiles
     const long long groups = (R + 4 * PD_ROWS - 1) / (4 * PD_ROWS);
-    long long nchunks = (2368 + groups - 1) / groups, max_chunks = (n + 4 * PD_KT - 1) / (4 * PD_KT);  // ~4 waves of 4 CTAs per SM
-    if (nchunks > max_chunks) nchunks = max_chunks;
-    if (nchunks < 1) nchunks = 1;
-    long long kc = ((n + nchunks - 1) / nchunks + PD_KT - 1) / PD_KT * PD_KT;
-    nchunks = (n + kc - 1) / kc;
+    // chunks of whole shared-memory tiles, chosen so that the CTAs fill whole waves (four resident per SM): the cost of
+    // a split is waves x (points per chunk + a fixed per-CTA share)
+    long long nchunks = 1, kc = (n + PD_KT - 1) / PD_KT * PD_KT;
+    {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long resident = 4LL * sms, max_chunks = (n + 2 * PD_KT - 1) / (2 * PD_KT);
+        double best = 1e300;
+        for (long long c = 1; c <= max_chunks && c <= 512; ++c) {
+            const long long k = ((n + c - 1) / c + PD_KT - 1) / PD_KT * PD_KT, ch = (n + k - 1) / k;
+            const long long waves = (groups * ch + resident - 1) / resident;
+            const double cost = (double)waves * (double)(k + 2 * PD_KT);
+            if (cost < best) { best = cost; kc = k; nchunks = ch; }
+        }
+    }
     if (nchunks < 1) nchunks = 1;
     pool_keep((size_t)64 << 20);
     if (!check(cudaMallocAsync((void **)&part, sizeof(double) * nchunks * R * PD_NC, s), "predict workspace")) {
