@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libcnngp.so")
-SOURCES = ["plan.cu", "gram_generic.cu", "gram_fused.cu", "gram_fnet.cu", "chol_f64.cu"]
+SOURCES = ["plan.cu", "gram_generic.cu", "gram_variance.cu", "gram_fused.cu", "gram_fnet.cu", "chol_f64.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-ccbin", "/usr/bin/g++"]

@@ -259,6 +259,10 @@ int cnngp_variances(const cnngp_plan *plan, const void *d_x, const void *d_z, in
     if (p->aux_elems > 0 && !d_aux_x) { set_error("cnngp_variances: d_aux_x is NULL"); return 1; }
     if (d_z && p->aux_elems > 0 && !d_aux_z) { set_error("cnngp_variances: d_aux_z is NULL"); return 1; }
     if (N == 0) return 0;
+    if (!d_z) {  // straight-line 28 x 28 programs: the streaming kernel (bit-identical to the interpreter)
+        const int rc = launch_fused_variances(p, d_x, N, C, d_aux_x, d_kdiag, stream);
+        if (rc >= 0) return rc;
+    }
     return launch_generic_variances(p, d_x, d_z, N, C, d_aux_x, d_aux_z, d_kdiag, stream);
 }
 

@@ -74,6 +74,11 @@ int launch_conv_maps(const void *d_in, int64_t M, int32_t Hi, int32_t Wi, const 
 int launch_relu_maps(void *d_xy, const void *d_xx, const void *d_yy, int64_t Nx, int64_t Ny, int64_t P,
                      int32_t same, int32_t diag, int32_t dtype, void *stream);
 
+// gram_variance.cu: variance rows of the straight-line fused kernel's programs, one warp per image pair;
+// -1 when the program is not covered (the caller falls back to launch_generic_variances)
+int launch_fused_variances(const Plan *plan, const void *d_x, int64_t N, int32_t C, void *d_aux_x,
+                           void *d_kdiag, void *stream);
+
 // Optional progress reporting of a symmetric fused launch, for streaming the result out while the
 // launch is still running: the kernel counts finished (tile, warp) units per SUPER-ROW (a band of
 // `rows_per_super` image rows, enumerated first to last); band b of the output is final -- mirrored

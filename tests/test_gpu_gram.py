@@ -302,6 +302,62 @@ def test_fused_matches_generic_and_oracle(k):
     assert rel_err(Kf.cpu().numpy(), want) < 1e-5
 
 
+def _variance_models():
+    from cnn_gp import Conv2d, ReLU, Sequential
+    dense = lambda: Conv2d(28, padding=0, var_weight=0.7, var_bias=0.1)
+    return {
+        "headline": MODELS["mnist_paper_convnet_gp"],
+        "k3": _fused_model(3), "k4": _fused_model(4), "k5": _fused_model(5), "k1": _fused_model(1),
+        # mixed windows, a pointwise conv between windows, conv -> conv, a ReLU as the first op
+        "mixed": Sequential(Conv2d(3, var_bias=0.2), ReLU(), Conv2d(1, var_weight=2.0), Conv2d(5), ReLU(),
+                            Conv2d(4, var_bias=0.4), Conv2d(7), ReLU(), dense()),
+        "relu_first": Sequential(ReLU(), Conv2d(3, var_bias=0.5), ReLU(), dense()),
+        "conv_dense": Sequential(Conv2d(7, var_bias=0.05), ReLU(), Conv2d(3), dense()),
+    }
+
+
+@pytest.mark.parametrize("name", sorted(_variance_models()))
+@pytest.mark.parametrize("n,C", [(1, 1), (2, 3), (37, 1), (300, 3), (1201, 1)])
+def test_variance_kernel_is_bit_identical_to_the_interpreter(name, n, C, monkeypatch):
+    """cnngp_variances: the one-warp-per-image-pair kernel (gram_variance.cu) writes the same bytes as the
+    generic interpreter (gram_generic.cu, MODE 1) -- the plain xx maps, the fused kernel's
+    (s, s', 1/s, 1/s') operands in either layout, and the diagonal values -- for every window shape of the
+    fused kernel's set, odd image counts and several channels (kernels.py:48-49, :98, :154-158)."""
+    model = _variance_models()[name].float().cuda()
+    gen = torch.Generator().manual_seed(7 * n + C)
+    X = torch.rand(n, C, 28, 28, generator=gen).cuda()
+    if n > 2:
+        X[1] = 0.0  # an all-zero image: s = sqrt(tiny) stand-in, 1/s finite
+    plan = engine.plan_for(model, 28, 28, torch.float32)
+    assert plan.fused_kind == 2
+    aux, _, kdiag = engine.variances(plan, X)
+    monkeypatch.setenv("CNNGP_VARIANCE_GENERIC", "1")
+    aux_g, _, kdiag_g = engine.variances(plan, X)
+    monkeypatch.delenv("CNNGP_VARIANCE_GENERIC")
+    torch.cuda.synchronize()
+    assert torch.equal(kdiag.view(torch.int32), kdiag_g.view(torch.int32))
+    # rows of existing images, bit for bit; the partner half of an odd last pair is unspecified
+    full = n - (n & 1)
+    assert torch.equal(aux[:full].view(torch.int32), aux_g[:full].view(torch.int32))
+    if n & 1:
+        # compare the slots image n-1 owns: its plain maps and elements 0 / 2 of every operand float4
+        plain = slice(0, plan_relu_elems(plan))
+        assert torch.equal(aux[n - 1, plain].view(torch.int32), aux_g[n - 1, plain].view(torch.int32))
+        a = aux[n - 1:n + 1, plan_relu_elems_aligned(plan):].reshape(2, -1, 4)
+        b = aux_g[n - 1:n + 1, plan_relu_elems_aligned(plan):].reshape(2, -1, 4)
+        assert torch.equal(a[:, :, 0::2].contiguous().view(torch.int32), b[:, :, 0::2].contiguous().view(torch.int32))
+    assert torch.isfinite(aux[:full]).all()
+
+
+def plan_relu_elems(plan):
+    """floats of the plain xx section of a variance row: every ReLU of these programs sees a 28 x 28 map"""
+    return plan.describe().count("RELU") * 28 * 28
+
+
+def plan_relu_elems_aligned(plan):
+    return (plan_relu_elems(plan) + 3) // 4 * 4
+
+
 def test_fused_headline_program_large():
     """mnist_paper_convnet_gp through the fused kernel on a tile spanning several super-tiles'
     worth of CTA tiles; checked against the generic kernel on a sample of rows."""
