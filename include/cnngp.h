@@ -103,7 +103,8 @@ int64_t cnngp_plan_dump(const cnngp_plan *plan, char *buf, int64_t cap);
  *   d_x        [N, C, H, W] images
  *   d_z        NULL, or [N, C, H, W] partner images for the literal same=True-with-different-
  *              data semantics (after each ReLU yy := xx, kernels.py:155-156)
- *   d_aux_x    [N, aux_elems] out: xx at the input of every ReLU
+ *   d_aux_x    [N rounded up to even, aux_elems] out: xx at the input of every ReLU (+ the fused kernels'
+ *              operands, which interleave images 2k and 2k+1 over rows 2k and 2k+1)
  *   d_aux_z    [N, aux_elems] out (only when d_z != NULL): yy at the input of every ReLU
  *   d_kdiag    [N] out, may be NULL: the final 1x1 value of the xx recursion, i.e.
  *              model(x, diag=True) (kernels.py:155-158) */
