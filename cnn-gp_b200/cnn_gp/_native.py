@@ -43,6 +43,9 @@ _SIGNATURES = {
                                   ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                   ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
                                   ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p]),
+    "cnngp_gram_band": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
+                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                       ctypes.c_void_p]),
     "cnngp_gram_symmetric_to_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
                                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                                     ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,

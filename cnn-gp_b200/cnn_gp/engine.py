@@ -115,6 +115,20 @@ def gram_with_aux(plan, x, z, aux_x, aux_z, same, diag, symmetric, out=None, kdi
     return out
 
 
+def gram_band(plan, x, n_rows, aux, kdiag, block, out):
+    """Rows [0, n_rows) x all columns of model(x) in one launch (cnngp_gram_band): entries j >= i, mirrored inside
+    the diagonal blocks of ``block`` rows -- the reference's tiles (i, j >= i) of these block rows.  ``out``:
+    [n_rows, len(x)] view with unit column stride; what lies below the diagonal blocks is left untouched."""
+    N2, C = x.shape[0], x.shape[1]
+    for name, t in (("aux", aux), ("out", out), ("kdiag", kdiag)):
+        if t.dtype != x.dtype or t.device != x.device:
+            raise TypeError(f"cnn_gp (B200): {name} is {t.dtype} on {t.device}, the images are {x.dtype} on {x.device}")
+    assert out.stride(1) == 1 and out.shape == (n_rows, N2) and x.is_contiguous()
+    nat.check(nat.lib().cnngp_gram_band(plan.handle, x.data_ptr(), n_rows, N2, C, aux.data_ptr(), kdiag.data_ptr(),
+                                        int(block), out.data_ptr(), out.stride(0), _stream()), "cnngp_gram_band")
+    return out
+
+
 @torch.no_grad()
 def gram(model, x, y, same, diag):
     """model(x, y, same, diag) -- reference kernels.py:18-57."""

@@ -4,8 +4,9 @@ The reference computes one 200 x 200 tile per Python iteration, copying both ima
 the device and the result back every time (exp_mnist_resnet/save_kernel.py:21-24,
 cnn_gp/kernel_save_tools.py:49-58).  Here the images stay in HBM, the per-image variance maps
 are computed once per dataset, and a worker's contiguous slice of the reference's tile list
-(cnn_gp/data.py:11-29) is evaluated with at most two launches per block row: the diagonal tile
-(symmetric: only j >= i is computed) and the rectangle to its right.
+(cnn_gp/data.py:11-29) is evaluated with ONE launch for every run of whole block rows (a band of the
+symmetric Gram, `cnngp_gram_band`: the diagonal tiles and everything to their right) and at most two launches --
+the diagonal tile and the rectangle to its right -- for the partial block rows at either end of the slice.
 
 Tiles are independent, so workers never talk to each other while computing.  The single exchange
 step (the reference does it through files, merge_h5_files.py) is `exchange_rows`: every worker
@@ -53,6 +54,44 @@ class GramJob:
                                  out=view, kdiag=self.kdiag[i0:i1] if symmetric else None, path=path)
         self.launches += engine.last_launches()
 
+    def can_band(self, i0):
+        """Whole block rows starting at image i0 can go out as ONE launch (cnngp_gram_band): a symmetric job on a
+        program a fused kernel covers, float32, even origin, kernel family not pinned to the generic one."""
+        return (self.same and self.plan.fused_kind in (2, 3) and self.X.dtype == torch.float32 and i0 % 2 == 0
+                and engine._force_path != "generic")
+
+    def band_into(self, view, i0, i1, block):
+        """view[...] = rows [i0, i1) x columns [i0, N) of K(X, X): entries j >= i, mirrored inside the diagonal
+        blocks of ``block`` rows (the reference's same=True tiles); the block triangle below them is not touched."""
+        with torch.cuda.device(self.X.device):
+            engine.gram_band(self.plan, self.X[i0:], i1 - i0, self.aux_x[i0:], self.kdiag[i0:], block, view)
+        self.launches += engine.last_launches()
+
+
+def launch_groups(segments, n_block_rows, max_rows=None):
+    """Group the block-row segments of a worker into launches: runs of WHOLE block rows of a symmetric Gram (the
+    diagonal tile and everything to its right) become ("band", first_row, last_row) -- one launch each, at most
+    ``max_rows`` block rows --, everything else stays ("row", segment) with its one or two launches."""
+    groups, run = [], []
+
+    def flush():
+        if run:
+            groups.append(("band", run[0], run[-1]))
+            run.clear()
+    for seg in segments:
+        r, has_diag, c0, c1 = seg
+        whole = has_diag and ((c0 == r + 1 and c1 == n_block_rows) or (c0 is None and r == n_block_rows - 1))
+        if whole and (not run or (run[-1] == r - 1 and (max_rows is None or len(run) < max_rows))):
+            run.append(r)
+        elif whole:
+            flush()
+            run.append(r)
+        else:
+            flush()
+            groups.append(("row", seg))
+    flush()
+    return groups
+
 
 def row_segments(tiles):
     """Group a contiguous slice of the reference tile list by block row:
@@ -74,27 +113,61 @@ def row_segments(tiles):
     return [(i, rows[i][0], rows[i][1], rows[i][2]) for i in order]
 
 
-def compute_worker_blocks(job, out, batch_size, worker_rank=0, n_workers=1, balanced=False, on_row=None):
+def compute_worker_blocks(job, out, batch_size, worker_rank=0, n_workers=1, balanced=False, on_row=None,
+                          rows_per_launch=None):
     """Fill ``out`` ([N, N2], any float dtype matching the job) with this worker's tiles; entries
     owned by other workers are left untouched.  Returns the number of unique pairs computed.
     ``balanced`` cuts the reference's tile list by pair count instead of tile count.
-    ``on_row(i0, i1)`` is called after the launches of each block row have been queued (e.g. to
-    record an event and start copying the row out on another stream)."""
+    ``on_row(i0, i1)`` is called after the launches of each block row (or band of block rows, see
+    ``rows_per_launch`` / ``_compute_segments``) have been queued (e.g. to record an event and start copying
+    the rows out on another stream)."""
     N, N2 = job.X.shape[0], job.X2.shape[0]
     split = worker_tiles_balanced if balanced else worker_tiles
     tiles = split(N, None if job.same else N2, batch_size, worker_rank, n_workers)
+    return _compute_segments(job, row_segments(tiles), batch_size, lambda i0, i1: out[i0:i1], on_row, rows_per_launch)
+
+
+def _band_pairs(N, bs, i0, i1):
+    """unique pairs of the whole block rows [i0, i1): per block row its diagonal tile's triangle + the rectangle"""
     pairs = 0
-    for r, has_diag, c0, c1 in row_segments(tiles):
-        i0, i1 = r * batch_size, min(N, (r + 1) * batch_size)
-        if has_diag:
-            job.block(out, i0, i1, i0, i1, symmetric=True)
-            pairs += (i1 - i0) * (i1 - i0 + 1) // 2
-        if c0 is not None:
-            j0, j1 = c0 * batch_size, min(N2, c1 * batch_size)
-            job.block(out, i0, i1, j0, j1, symmetric=False)
-            pairs += (i1 - i0) * (j1 - j0)
-        if on_row is not None:
-            on_row(i0, i1)
+    for a in range(i0, i1, bs):
+        h = min(N, a + bs) - a
+        pairs += h * (h + 1) // 2 + h * (N - a - h)
+    return pairs
+
+
+def _compute_segments(job, segments, bs, rows_of, on_row, rows_per_launch):
+    """Evaluate block-row segments into ``rows_of(i0, i1)`` ([i1 - i0, N2] views).  Runs of whole block rows go out
+    as one band launch each (``rows_per_launch`` block rows at most; default: all of them when nobody waits for
+    rows via ``on_row``, one otherwise), so a worker needs a handful of launches instead of two per block row."""
+    N, N2 = job.X.shape[0], job.X2.shape[0]
+    if rows_per_launch is None:
+        rows_per_launch = 1 if on_row is not None else 1 << 30
+    nbx = -(-N // bs)
+    groups = launch_groups(segments, nbx, rows_per_launch) if job.same and rows_per_launch > 1 else [("row", s) for s in segments]
+    pairs = 0
+    for g in groups:
+        if g[0] == "band" and job.can_band(g[1] * bs) and bs % 2 == 0:
+            i0, i1 = g[1] * bs, min(N, (g[2] + 1) * bs)
+            job.band_into(rows_of(i0, i1)[:, i0:], i0, i1, bs)
+            pairs += _band_pairs(N, bs, i0, i1)
+            if on_row is not None:
+                on_row(i0, i1)
+            continue
+        segs = [g[1]] if g[0] == "row" else [(r, True, r + 1 if r + 1 < nbx else None, nbx if r + 1 < nbx else None)
+                                             for r in range(g[1], g[2] + 1)]
+        for r, has_diag, c0, c1 in segs:
+            i0, i1 = r * bs, min(N, (r + 1) * bs)
+            view = rows_of(i0, i1)
+            if has_diag:
+                job.block_into(view[:, i0:i1], i0, i1, i0, i1, symmetric=True)
+                pairs += (i1 - i0) * (i1 - i0 + 1) // 2
+            if c0 is not None:
+                j0, j1 = c0 * bs, min(N2, c1 * bs)
+                job.block_into(view[:, j0:j1], i0, i1, j0, j1, symmetric=False)
+                pairs += (i1 - i0) * (j1 - j0)
+            if on_row is not None:
+                on_row(i0, i1)
     return pairs
 
 
@@ -115,22 +188,10 @@ class RowShard:
         self.row_hi = min(N, (max(rows) + 1) * batch_size) if rows else 0
         self.data = torch.full((self.row_hi - self.row_lo, N2), float("nan"), dtype=dtype, device=device)
 
-    def compute(self, job, on_row=None):
+    def compute(self, job, on_row=None, rows_per_launch=None):
         """Evaluate this worker's tiles into the shard; returns the number of unique pairs."""
-        pairs = 0
-        for r, has_diag, c0, c1 in self.segments:
-            i0, i1 = r * self.bs, min(self.N, (r + 1) * self.bs)
-            view = self.data[i0 - self.row_lo:i1 - self.row_lo]
-            if has_diag:
-                job.block_into(view[:, i0:i1], i0, i1, i0, i1, symmetric=True)
-                pairs += (i1 - i0) * (i1 - i0 + 1) // 2
-            if c0 is not None:
-                j0, j1 = c0 * self.bs, min(self.N2, c1 * self.bs)
-                job.block_into(view[:, j0:j1], i0, i1, j0, j1, symmetric=False)
-                pairs += (i1 - i0) * (j1 - j0)
-            if on_row is not None:
-                on_row(i0, i1)
-        return pairs
+        return _compute_segments(job, self.segments, self.bs,
+                                 lambda i0, i1: self.data[i0 - self.row_lo:i1 - self.row_lo], on_row, rows_per_launch)
 
 
 def row_owners(N, N2, batch_size, n_workers, same, balanced=True):

@@ -120,6 +120,7 @@ struct NParams {
     float *out;
     long long ld_out;
     int symmetric;
+    int mirror_bs;  // symmetric with N2 > N1 (a band of block rows): mirror only inside diagonal blocks of this many rows
     const float *kdiag;
     int nbi, nbj, sti, stj, nst_j, nst;
     long long n_tiles;
@@ -1221,7 +1222,9 @@ __global__ void __launch_bounds__(NGeo<NW>::kThreads, 1) fnet_kernel(const __gri
                     p.out[(long long)i * p.ld_out + j] = v;
                 } else if (j > i) {
                     p.out[(long long)i * p.ld_out + j] = v;
-                    p.out[(long long)j * p.ld_out + i] = v;
+                    // a band of block rows (N2 > N1): the mirror image stays inside the diagonal block (gram_fused.cu)
+                    if (j < p.N1 && (p.mirror_bs == 0 || j / p.mirror_bs == i / p.mirror_bs))
+                        p.out[(long long)j * p.ld_out + i] = v;
                 } else if (j == i) {
                     // i == j follows the variance recursion (kernels.py:155-162)
                     p.out[(long long)i * p.ld_out + i] = p.kdiag ? p.kdiag[i] : v;
@@ -1785,8 +1788,10 @@ void fnet_geometry(NParams &p, int64_t N1, int64_t N2, int tile_j, int edge, lon
         p.sti = super_i; p.stj = super_j;
         const int nsi = (p.nbi + super_i - 1) / super_i, nsj = (p.nbj + super_j - 1) / super_j;
         p.nst_j = nsj;
-        p.nst = nsi > nsj ? nsi : nsj;
-        *n_super = p.symmetric ? (long long)p.nst * (p.nst + 1) / 2 : (long long)nsi * nsj;
+        // symmetric: super-row r holds the super-tiles (r, r .. nsj - 1); a band of block rows (N2 > N1) has fewer
+        // super-rows than super-columns
+        p.nst = p.symmetric ? nsj : (nsi > nsj ? nsi : nsj);
+        *n_super = p.symmetric ? (long long)nsi * nsj - (long long)nsi * (nsi - 1) / 2 : (long long)nsi * nsj;
     }
 }
 
@@ -1795,7 +1800,7 @@ int fnet_progress(NParams &p, RowProgress *prog, int tile_j, int nw) {
     const int kTileI = 4;
     prog->n_super_rows = (p.nbi + p.sti - 1) / p.sti;
     prog->rows_per_super = (int64_t)p.sti * kTileI;
-    if (!p.symmetric || prog->n_super_rows > prog->capacity) { set_error("fused-net kernel: progress counters too few"); return 8; }
+    if (!p.symmetric || p.N1 != p.N2 || prog->n_super_rows > prog->capacity) { set_error("fused-net kernel: progress counters too few"); return 8; }
     prog->expected.assign(prog->n_super_rows, 0u);
     for (int ib = 0; ib < p.nbi; ++ib) {
         const int si = ib / p.sti;
@@ -1836,7 +1841,7 @@ int fnet_launch_one(void (*kern)(const NParams), NParams &p, unsigned threads, s
 
 int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2, int32_t C,
                      const void *d_aux_x, const void *d_aux_z, int32_t symmetric, const void *d_kdiag,
-                     void *d_out, int64_t ld_out, void *stream_, RowProgress *prog) {
+                     void *d_out, int64_t ld_out, void *stream_, RowProgress *prog, int64_t mirror_block) {
     const FNetPlan *fp = plan->fnet;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!fp) { set_error("fused-net kernel: unsupported call"); return 4; }
@@ -1856,6 +1861,8 @@ int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *
     p.N1 = (int)N1; p.N2 = (int)N2; p.C = C;
     p.out = (float *)d_out; p.ld_out = ld_out;
     p.symmetric = symmetric ? 1 : 0;
+    if (symmetric && N2 < N1) { set_error("fused-net kernel: a symmetric band needs N2 >= N1"); return 4; }
+    p.mirror_bs = (int)mirror_block;
     p.kdiag = (const float *)d_kdiag;
     p.inv_c = 1.0f / (float)C;
     const size_t row_bytes = (size_t)fp->fused_row_floats * 4;

@@ -78,6 +78,7 @@ struct FParams {
     float *out;
     long long ld_out;
     int symmetric;
+    int mirror_bs;     // symmetric with N2 > N1 (a band of block rows): mirror only inside diagonal blocks of this many rows
     const float *kdiag;
     int nbi, nbj;      // CTA tiles along i / j
     int sti, stj;      // super-tile size in CTA tiles
@@ -454,7 +455,10 @@ __global__ void __launch_bounds__(Geo<NW, NG>::kThreads, 1) fused_kernel(const _
                             p.out[(long long)i * p.ld_out + j] = v;
                         } else if (j > i) {
                             p.out[(long long)i * p.ld_out + j] = v;
-                            p.out[(long long)j * p.ld_out + i] = v;
+                            // a band of block rows (N2 > N1): the mirror image stays inside the diagonal block, as in
+                            // the reference's same=True tile; rows below the band belong to other launches
+                            if (j < p.N1 && (p.mirror_bs == 0 || j / p.mirror_bs == i / p.mirror_bs))
+                                p.out[(long long)j * p.ld_out + i] = v;
                         } else if (j == i) {
                             // i == j follows the variance recursion (kernels.py:155-162)
                             p.out[(long long)i * p.ld_out + i] = p.kdiag ? p.kdiag[i] : v;
@@ -623,14 +627,16 @@ int launch_variant(const FusedPlan *fp, FParams &p, int64_t N1, int64_t N2, cuda
         p.sti = super_i; p.stj = super_j;
         const int nsi = (p.nbi + super_i - 1) / super_i, nsj = (p.nbj + super_j - 1) / super_j;
         p.nst_j = nsj;
-        p.nst = nsi > nsj ? nsi : nsj;
-        n_super = p.symmetric ? (long long)p.nst * (p.nst + 1) / 2 : (long long)nsi * nsj;
+        // symmetric: super-row r holds the super-tiles (r, r .. nsj - 1); N2 > N1 (a band of block rows) has
+        // fewer super-rows than super-columns
+        p.nst = p.symmetric ? nsj : (nsi > nsj ? nsi : nsj);
+        n_super = p.symmetric ? (long long)nsi * nsj - (long long)nsi * (nsi - 1) / 2 : (long long)nsi * nsj;
     }
     p.n_tiles = n_super * p.sti * p.stj;
     if (prog) {  // what the kernel will count per super-row: valid tiles x consumer warps (decode() below)
         prog->n_super_rows = (p.nbi + p.sti - 1) / p.sti;
         prog->rows_per_super = (int64_t)p.sti * G::kTileI;
-        if (!p.symmetric || prog->n_super_rows > prog->capacity) { set_error("fused kernel: progress counters too few"); return 8; }
+        if (!p.symmetric || N1 != N2 || prog->n_super_rows > prog->capacity) { set_error("fused kernel: progress counters too few"); return 8; }
         prog->expected.assign(prog->n_super_rows, 0u);
         for (int ib = 0; ib < p.nbi; ++ib) {
             const int si = ib / p.sti;
@@ -678,7 +684,7 @@ int launch_variant(const FusedPlan *fp, FParams &p, int64_t N1, int64_t N2, cuda
 int launch_fused_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2,
                       int32_t C, const void *d_aux_x, const void *d_aux_z, int32_t same, int32_t diag,
                       int32_t symmetric, const void *d_kdiag, void *d_out, int64_t ld_out, void *stream,
-                      RowProgress *progress) {
+                      RowProgress *progress, int64_t mirror_block) {
     (void)same;
     const FusedPlan *fp = plan->fused;
     if (!fp || diag) { set_error("fused kernel: unsupported call"); return 4; }
@@ -692,6 +698,8 @@ int launch_fused_gram(const Plan *plan, const void *d_x, int64_t N1, const void 
     p.N1 = (int)N1; p.N2 = (int)N2; p.C = C;
     p.out = (float *)d_out; p.ld_out = ld_out;
     p.symmetric = symmetric ? 1 : 0;
+    if (symmetric && N2 < N1) { set_error("fused kernel: a symmetric band needs N2 >= N1"); return 4; }
+    p.mirror_bs = (int)mirror_block;
     p.kdiag = (const float *)d_kdiag;
     p.inv_c = 1.0f / (float)C;
     // kernel variant: consumer warps, ReLU bands per layer, ring depth.  Default 12 warps (three

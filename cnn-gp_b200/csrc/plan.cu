@@ -300,6 +300,22 @@ int cnngp_gram(const cnngp_plan *plan, const void *d_x, int64_t N1, const void *
     return launch_generic_gram(p, d_x, N1, d_z, N2, C, d_aux_x, d_aux_z, same, diag, symmetric, d_out, ld_out, stream);
 }
 
+// A band of block rows of model(X) in one launch (see cnngp.h).
+int cnngp_gram_band(const cnngp_plan *plan, const void *d_x, int64_t N1, int64_t N2, int32_t C, const void *d_aux,
+                    const void *d_kdiag, int64_t block, void *d_out, int64_t ld_out, void *stream) {
+    const Plan *p = reinterpret_cast<const Plan *>(plan);
+    if (!p || !d_x || !d_aux || !d_out || N1 < 0 || N2 < N1 || C < 1 || block < 0 || ld_out < N2) {
+        set_error("cnngp_gram_band: bad arguments");
+        return 1;
+    }
+    if (!p->fused && !p->fnet) { set_error("cnngp_gram_band: only the fused kernels evaluate bands"); return 4; }
+    if (N1 == 0) return 0;
+    g_last_path = p->fused ? CNNGP_PATH_FUSED : CNNGP_PATH_FUSED_NET;
+    g_last_launches = 1;
+    return p->fused ? launch_fused_gram(p, d_x, N1, d_x, N2, C, d_aux, d_aux, 1, 0, 1, d_kdiag, d_out, ld_out, stream, nullptr, block)
+                    : launch_fnet_gram(p, d_x, N1, d_x, N2, C, d_aux, d_aux, 1, d_kdiag, d_out, ld_out, stream, nullptr, block);
+}
+
 // model(X) with the result streamed to host memory while the launch is still running: the kernel
 // counts finished tiles per band of rows (RowProgress), the copy stream waits on each band's counter
 // with a stream memory operation (cuStreamWaitValue32) and copies the band out -- mirrored entries

@@ -99,7 +99,7 @@ std::string fused_plan_dump(const FusedPlan *fp, const Plan *plan);
 int launch_fused_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2,
                       int32_t C, const void *d_aux_x, const void *d_aux_z, int32_t same, int32_t diag,
                       int32_t symmetric, const void *d_kdiag, void *d_out, int64_t ld_out, void *stream,
-                      RowProgress *progress = nullptr);
+                      RowProgress *progress = nullptr, int64_t mirror_block = 0);
 
 // gram_fnet.cu
 FNetPlan *fnet_plan_create(const Plan *plan);  // nullptr if not covered
@@ -108,6 +108,6 @@ std::string fnet_plan_describe(const FNetPlan *fp);
 std::string fnet_plan_dump(const FNetPlan *fp);
 int launch_fnet_gram(const Plan *plan, const void *d_x, int64_t N1, const void *d_z, int64_t N2, int32_t C,
                      const void *d_aux_x, const void *d_aux_z, int32_t symmetric, const void *d_kdiag,
-                     void *d_out, int64_t ld_out, void *stream, RowProgress *progress = nullptr);
+                     void *d_out, int64_t ld_out, void *stream, RowProgress *progress = nullptr, int64_t mirror_block = 0);
 
 }  // namespace cnngp

@@ -133,6 +133,17 @@ int cnngp_last_path(void);
  * folded phase run as two launches per chunk of super-tiles, everything else as one) */
 int cnngp_last_launches(void);
 
+/* A band of block rows of model(X) in ONE launch: rows [0, N1) x columns [0, N2) of the symmetric Gram of the N2
+ * images at d_x (N1 <= N2; d_aux / d_kdiag are the variance rows / diagonal values of the same images, from
+ * cnngp_variances).  This is what a worker's slice of the reference's tile list (cnn_gp/data.py:11-29) amounts to for
+ * whole block rows: the same=True tile on the diagonal and every tile to its right (kernel_save_tools.py:49-58).
+ * Entries with j >= i are computed; inside each diagonal block of `block` rows (0: everywhere, i.e. N1 == N2
+ * gives model(X)) they are mirrored, so that out holds exactly what the reference's tiles (i, j >= i) of these block
+ * rows hold; entries below the diagonal blocks are left untouched (the reference leaves them NaN).  d_x must start at an
+ * even image index of the array cnngp_variances saw.  Fused kernels only (error 4 otherwise). */
+int cnngp_gram_band(const cnngp_plan *plan, const void *d_x, int64_t N1, int64_t N2, int32_t C, const void *d_aux,
+                    const void *d_kdiag, int64_t block, void *d_out, int64_t ld_out, void *stream);
+
 /* model(X) for a caller that wants the result in HOST memory (what save_kernel's `kern` does with
  * .cpu(), exp_mnist_resnet/save_kernel.py:21-24): the symmetric Gram of d_x is computed into
  * d_out [N, ld_out] as by cnngp_gram(symmetric = 1), and bands of finished rows are copied to the

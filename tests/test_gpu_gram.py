@@ -358,6 +358,46 @@ def plan_relu_elems_aligned(plan):
     return (plan_relu_elems(plan) + 3) // 4 * 4
 
 
+@pytest.mark.parametrize("name,C,S,n,bs", [("mnist_paper_convnet_gp", 1, 28, 1300, 200), ("mnist_paper_convnet_gp", 1, 28, 230, 48),
+                                          ("mnist_as_tf", 1, 28, 610, 100), ("mnist_paper_residual_cnn_gp", 1, 28, 540, 60),
+                                          ("cifar10", 3, 32, 170, 24)])
+@pytest.mark.parametrize("world", [1, 3])
+def test_band_launches_write_the_same_bytes_as_per_row_launches(name, C, S, n, bs, world):
+    """cnngp_gram_band: a worker's whole block rows as ONE launch (the reference's tiles (i, j >= i) of those block
+    rows, data.py:11-29 / kernel_save_tools.py:49-58) against the diagonal-tile + rectangle launches per block row:
+    identical bytes, including the NaN marks below the diagonal blocks that no launch may touch."""
+    from cnn_gp.tiles import GramJob, compute_worker_blocks, launch_groups, row_segments
+    from cnn_gp.data import worker_tiles_balanced
+    model = MODELS[name].float().cuda()
+    X = torch.rand(n, C, S, S, generator=torch.Generator().manual_seed(n + world)).cuda()
+    job = GramJob(model, X)
+    banded = 0
+    for rank in range(world):
+        a = torch.full((n, n), float("nan"), device="cuda")
+        b = torch.full((n, n), float("nan"), device="cuda")
+        l0 = job.launches
+        pa = compute_worker_blocks(job, a, bs, rank, world, balanced=True)
+        l1 = job.launches
+        pb = compute_worker_blocks(job, b, bs, rank, world, balanced=True, rows_per_launch=1)
+        l2 = job.launches
+        assert pa == pb
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32)), (name, rank)
+        groups = launch_groups(row_segments(worker_tiles_balanced(n, None, bs, rank, world)), -(-n // bs))
+        banded += sum(g[0] == "band" for g in groups)
+        if any(g[0] == "band" and g[2] > g[1] for g in groups) and engine.last_launches() == 1:
+            assert l1 - l0 < l2 - l1  # fewer launches (programs with split launches count their chunks)
+    assert banded > 0
+    # one worker: the band launch of all block rows holds the reference's tile layout of model(X)
+    if world == 1:
+        K = model(X)
+        owned = ~torch.isnan(a)
+        assert torch.equal(a[owned], K[owned])
+        nb = -(-n // bs)
+        for r in range(nb):  # block (r, c < r) untouched, block (r, c >= r) complete
+            assert torch.isnan(a[r * bs:(r + 1) * bs, :r * bs]).all()
+            assert owned[r * bs:(r + 1) * bs, r * bs:].all()
+
+
 def test_fused_headline_program_large():
     """mnist_paper_convnet_gp through the fused kernel on a tile spanning several super-tiles'
     worth of CTA tiles; checked against the generic kernel on a sample of rows."""
