@@ -162,7 +162,10 @@ __device__ __forceinline__ void tile_load_t(const u64 *tile, u64 (&a)[S], int lx
 //
 // Staging: a ring of NST stages.  A ReLU layer's pair-interleaved variance maps arrive in NSPLIT
 // row bands (one stage each), a channel of the tile's images in IMG_PARTS bands.
-template <int S, int LO, int HI, int NW, int NSPLIT, int NST, int NG = 1>
+// PROG: the launch reports finished tiles per super-row (RowProgress).  A separate instantiation: the consumer
+// warps run at the register limit, and even the few instructions of the reporting path cost the plain launch
+// 0.7 % through a different register allocation.
+template <int S, int LO, int HI, int NW, int NSPLIT, int NST, int NG = 1, bool PROG = false>
 __global__ void __launch_bounds__(Geo<NW, NG>::kThreads, 1) fused_kernel(const __grid_constant__ FParams p) {
     using G = Geo<NW, NG>;
     constexpr int kWarps = G::kWarps, kTileI = G::kTileI, kTileJ = G::kTileJ, kImgs = G::kImgs, kPairs = G::kPairs;
@@ -189,12 +192,20 @@ __global__ void __launch_bounds__(Geo<NW, NG>::kThreads, 1) fused_kernel(const _
     // enumeration, and the variance rows of several super-tiles competed for L2), and the tail
     // of the launch is balanced to one tile.
     long long *stage_tile = reinterpret_cast<long long *>(bars + 2 * NST);
+    // RowProgress: the consumers arrive on done[k & 1] after writing the entries of their k-th tile; the producer
+    // lane -- which has the time and the registers -- makes them visible device-wide and moves the counter, one
+    // fence per CTA tile.  (A fence + atomic per tile in every consumer warp cost 1.8 % of the launch: 197.8 ms
+    // against 194.3 ms without counters.)
+    uint64_t *done = reinterpret_cast<uint64_t *>(tiles + kWarps * S * PITCH) + NG * 3 * NST + grp * 2;
 
     if (threadIdx.x == 0) {
-        for (int g = 0; g < NG; ++g)
+        for (int g = 0; g < NG; ++g) {
             for (int b = 0; b < NST; ++b) { mbar_init(&full[g * 3 * NST + b], 1); mbar_init(&empty[g * 3 * NST + b], kGW); }
+            for (int b = 0; b < 2; ++b) mbar_init(&done[(g - grp) * 2 + b], kGW);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (PROG && threadIdx.x < kWarps) reinterpret_cast<unsigned *>(done + (NG - grp) * 2)[threadIdx.x] = 0u;  // tiles per consumer warp
     __syncthreads();
 
     const int per_st = p.sti * p.stj;
@@ -251,11 +262,29 @@ __global__ void __launch_bounds__(Geo<NW, NG>::kThreads, 1) fused_kernel(const _
             };
             const long long stride = (long long)gridDim.x * NG;  // fixed-stride order: groups interleave
             long long t_raw = next_index((long long)blockIdx.x * NG + grp);
+            // RowProgress: tile k of this group is complete when all consumer warps have arrived on done[k & 1]
+            // (phase k >> 1).  When the ring lets tile k + 2 start, every consumer is deep inside tile k + 1, so
+            // the wait for tile k returns at once; only the last two tiles are really waited for.
+            unsigned seq = 0;            // tiles of this group so far
+            int row_a = 0, row_b = 0;    // super-rows of tiles seq - 2 and seq - 1
+            auto report = [&](unsigned k, int row) {
+                if (lane == 0) {
+                    mbar_wait_relaxed(&done[k & 1], (k >> 1) & 1);
+                    __threadfence();  // cumulative: the consumers' entries, observed through the barrier
+                    atomicAdd(&p.row_done[row], (unsigned)kGW);
+                }
+            };
             for (;;) {
                 int ib, jb;
                 t = t_raw;
                 while (t < p.n_tiles && !decode(t, ib, jb)) t = next_index(t + stride);
                 if (t >= p.n_tiles) break;
+                // the report of tile seq - 2 waits until this tile's first layers are staged: at a tile boundary the
+                // ring is at its tightest (the image stage is consumed in no time), later the producer only waits
+                bool owe = PROG && seq >= 2;
+                const int row_old = row_a;
+                if (PROG) { row_a = row_b; row_b = ib / p.sti; }
+                ++seq;
                 // the next index is requested now and first looked at when this tile's stages are out
                 t_raw = next_index(t + stride);
                 const int i_base = ib * kTileI, j_base = jb * kTileJ;
@@ -290,10 +319,16 @@ __global__ void __launch_bounds__(Geo<NW, NG>::kThreads, 1) fused_kernel(const _
                         }
                         ++l;
                     }
+                    if (owe) { report(seq - 3, row_old); owe = false; }
                 }
+                if (owe) report(seq - 3, row_old);
             }
             t = -1;  // end marker: one empty stage
             acquire(0);
+            if (PROG) {
+                if (seq >= 2) report(seq - 2, row_a);
+                if (seq >= 1) report(seq - 1, row_b);
+            }
         }
         return;
     }
@@ -465,10 +500,16 @@ __global__ void __launch_bounds__(Geo<NW, NG>::kThreads, 1) fused_kernel(const _
                         }
                     }
                 }
-                if (p.row_done) {  // the entries above are visible device-wide before the count moves
-                    __threadfence();
+                // this warp's entries of its k-th tile are written (release at CTA scope; the producer lane reports)
+                // (the tile count lives in shared memory: the consumers have no register to spare across a tile)
+                if (PROG) {
                     __syncwarp();
-                    if (lane == 0) atomicAdd(&p.row_done[ib / p.sti], 1u);
+                    if (lane == 0) {
+                        unsigned *kw = reinterpret_cast<unsigned *>(done + (NG - grp) * 2) + warp;
+                        const unsigned k = *kw;
+                        mbar_arrive(&done[k & 1]);
+                        *kw = k + 1;
+                    }
                 }
             }
         }
@@ -477,7 +518,8 @@ __global__ void __launch_bounds__(Geo<NW, NG>::kThreads, 1) fused_kernel(const _
 
 template <int NW, int NSPLIT, int NST, int NG = 1>
 constexpr size_t fused_smem(int S) {
-    return (size_t)NG * NST * (Geo<NW, NG>::kPairs * S * S / NSPLIT) * 16 + (size_t)NW * S * (S + 1) * 8 + (size_t)NG * 3 * NST * 8;
+    return (size_t)NG * NST * (Geo<NW, NG>::kPairs * S * S / NSPLIT) * 16 + (size_t)NW * S * (S + 1) * 8 + (size_t)NG * 3 * NST * 8 +
+           (size_t)NG * 2 * 8 + (size_t)NW * 4;  // + the two tile-done barriers of every group, a tile count per consumer warp
 }
 
 }  // namespace
@@ -654,7 +696,15 @@ int launch_variant(const FusedPlan *fp, FParams &p, int64_t N1, int64_t N2, cuda
     const unsigned grid = (unsigned)(p.n_tiles < sms ? p.n_tiles : sms);  // persistent: one CTA per SM
     void (*kern)(const FParams) = nullptr;
     constexpr bool kDefault = NW == 12 && NSPLIT == 2 && NST == 3 && NG == 1;
-    if (fp->lo == 3 && fp->hi == 3) kern = fused_kernel<28, 3, 3, NW, NSPLIT, NST, NG>;
+    if (prog) {  // the reporting instantiations exist for the default variant only
+        if (!kDefault) return -1;
+        if (fp->lo == 3 && fp->hi == 3) kern = fused_kernel<28, 3, 3, 12, 2, 3, 1, true>;
+        else if (fp->lo == 1 && fp->hi == 1) kern = fused_kernel<28, 1, 1, 12, 2, 3, 1, true>;
+        else if (fp->lo == 1 && fp->hi == 2) kern = fused_kernel<28, 1, 2, 12, 2, 3, 1, true>;
+        else if (fp->lo == 2 && fp->hi == 2) kern = fused_kernel<28, 2, 2, 12, 2, 3, 1, true>;
+        else kern = fused_kernel<28, -1, -1, 12, 2, 3, 1, true>;
+    }
+    else if (fp->lo == 3 && fp->hi == 3) kern = fused_kernel<28, 3, 3, NW, NSPLIT, NST, NG>;
     else if (kDefault && fp->lo == 1 && fp->hi == 1) kern = fused_kernel<28, 1, 1, 12, 2, 3>;
     else if (kDefault && fp->lo == 1 && fp->hi == 2) kern = fused_kernel<28, 1, 2, 12, 2, 3>;
     else if (kDefault && fp->lo == 2 && fp->hi == 2) kern = fused_kernel<28, 2, 2, 12, 2, 3>;

@@ -362,6 +362,8 @@ int cnngp_gram_symmetric_to_host(const cnngp_plan *plan, const void *d_x, int64_
     e = cudaMemsetAsync(d_scratch, 0x7F, (size_t)scratch_bytes, st);
     if (e != cudaSuccess) { set_error(std::string("cnngp_gram_symmetric_to_host: ") + cudaGetErrorString(e)); return 7; }
     const size_t esz = sizeof(float);
+    const char *dbg = getenv("CNNGP_E2E_DEBUG");  // measurement aid: "nowait" = counters only, "nocopy" = waits without copies
+    if (dbg && !strcmp(dbg, "nowait")) return 0;
     for (int b = 0; b < prog.n_super_rows; ++b) {
         const int64_t r0 = (int64_t)b * prog.rows_per_super;
         const int64_t rows = std::min<int64_t>(prog.rows_per_super, N - r0);
@@ -369,6 +371,7 @@ int cnngp_gram_symmetric_to_host(const cnngp_plan *plan, const void *d_x, int64_
         // CU_STREAM_WAIT_VALUE_GEQ = 0: waits until (int32_t)(*addr - value) >= 0
         const int wr = wait_value(cs, (unsigned long long)(uintptr_t)(prog.d_done + b), prog.expected[b], 0u);
         if (wr != 0) { set_error("cnngp_gram_symmetric_to_host: cuStreamWaitValue32 failed (" + std::to_string(wr) + ")"); return 7; }
+        if (dbg && !strcmp(dbg, "nocopy")) continue;
         e = cudaMemcpy2DAsync((char *)h_out + (size_t)r0 * ld_host * esz, (size_t)ld_host * esz,
                               (const char *)d_out + (size_t)r0 * ld_out * esz, (size_t)ld_out * esz, (size_t)N * esz,
                               (size_t)rows, cudaMemcpyDeviceToHost, cs);
