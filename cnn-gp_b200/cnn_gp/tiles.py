@@ -145,6 +145,15 @@ def _compute_segments(job, segments, bs, rows_of, on_row, rows_per_launch):
         rows_per_launch = 1 if on_row is not None else 1 << 30
     nbx = -(-N // bs)
     groups = launch_groups(segments, nbx, rows_per_launch) if job.same and rows_per_launch > 1 else [("row", s) for s in segments]
+    if on_row is not None and rows_per_launch > 1 and job.same:
+        # somebody streams whole block rows out while later ones are computed.  A block row costs the same to copy
+        # wherever it lies, but the rows at the bottom of the triangle are short and cheap to compute: they go
+        # FIRST, so that every band's copy hides behind the longer rows that follow, and the top row goes last
+        # and alone -- what is left to copy when the last launch ends is one block row.
+        groups = groups[::-1]
+        if groups and groups[-1][0] == "band" and groups[-1][2] > groups[-1][1]:
+            _, a, b = groups.pop()
+            groups += [("band", a + 1, b), ("band", a, a)]
     pairs = 0
     for g in groups:
         if g[0] == "band" and job.can_band(g[1] * bs) and bs % 2 == 0:

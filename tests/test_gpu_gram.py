@@ -387,6 +387,19 @@ def test_band_launches_write_the_same_bytes_as_per_row_launches(name, C, S, n, b
         if any(g[0] == "band" and g[2] > g[1] for g in groups) and engine.last_launches() == 1:
             assert l1 - l0 < l2 - l1  # fewer launches (programs with split launches count their chunks)
     assert banded > 0
+    # streamed form (rows handed to `on_row` as their launches are queued, bands of three block rows, short rows
+    # first, the top row alone at the end): same bytes, every block row handed over exactly once
+    for rank in range(world):
+        b = torch.full((n, n), float("nan"), device="cuda")
+        c = torch.full((n, n), float("nan"), device="cuda")
+        seen = []
+        compute_worker_blocks(job, b, bs, rank, world, balanced=True, rows_per_launch=1)
+        compute_worker_blocks(job, c, bs, rank, world, balanced=True, rows_per_launch=3,
+                              on_row=lambda i0, i1: seen.append((i0, i1)))
+        assert torch.equal(b.view(torch.int32), c.view(torch.int32)), (name, rank)
+        rows = sorted(r for i0, i1 in seen for r in range(i0 // bs, -(-i1 // bs)))
+        mine = sorted({t[1] for t in worker_tiles_balanced(n, None, bs, rank, world)})
+        assert rows == mine
     # one worker: the band launch of all block rows holds the reference's tile layout of model(X)
     if world == 1:
         K = model(X)
