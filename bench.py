@@ -503,10 +503,10 @@ def run_ours(args):
             copy_stream.wait_event(done)
             with torch.cuda.stream(copy_stream):
                 K_host[i0 - row_lo:i1 - row_lo].copy_(K_dev[i0:i1], non_blocking=True)
-        # bands of up to eight block rows per launch (the last block row alone): few launches, and each band's rows
-        # leave while the next band is computed
+        # bands of up to four block rows per launch, short rows first, the longest whole block row alone at the end
+        # (tiles._streaming_order): few launches, and each band's rows leave while the next band is computed
         compute_worker_blocks(GramJob(model, x), K_dev, args.tile, rank, world, balanced=True, on_row=copy_row_out,
-                              rows_per_launch=8)
+                              rows_per_launch=4)
         torch.cuda.synchronize()
 
     step_e2e()

@@ -136,6 +136,21 @@ def _band_pairs(N, bs, i0, i1):
     return pairs
 
 
+def _streaming_order(groups):
+    """Launch order when somebody streams whole block rows out while later ones are computed.  A block row costs
+    the same to copy wherever it lies, but the rows at the bottom of the triangle are short and cheap to compute:
+    they go FIRST, so that every band's copy hides behind the longer rows that follow; the partial row at the top
+    of the slice comes next, and the topmost whole block row -- the longest launch of the slice -- goes last and
+    alone: its compute time hides every copy before it, and what is left to copy when it ends is one block row."""
+    groups = groups[::-1]
+    bands = [k for k, g in enumerate(groups) if g[0] == "band"]
+    if bands:
+        k = bands[-1]
+        _, a, b = groups[k]
+        groups = groups[:k] + ([("band", a + 1, b)] if b > a else []) + groups[k + 1:] + [("band", a, a)]
+    return groups
+
+
 def _compute_segments(job, segments, bs, rows_of, on_row, rows_per_launch):
     """Evaluate block-row segments into ``rows_of(i0, i1)`` ([i1 - i0, N2] views).  Runs of whole block rows go out
     as one band launch each (``rows_per_launch`` block rows at most; default: all of them when nobody waits for
@@ -146,14 +161,7 @@ def _compute_segments(job, segments, bs, rows_of, on_row, rows_per_launch):
     nbx = -(-N // bs)
     groups = launch_groups(segments, nbx, rows_per_launch) if job.same and rows_per_launch > 1 else [("row", s) for s in segments]
     if on_row is not None and rows_per_launch > 1 and job.same:
-        # somebody streams whole block rows out while later ones are computed.  A block row costs the same to copy
-        # wherever it lies, but the rows at the bottom of the triangle are short and cheap to compute: they go
-        # FIRST, so that every band's copy hides behind the longer rows that follow, and the top row goes last
-        # and alone -- what is left to copy when the last launch ends is one block row.
-        groups = groups[::-1]
-        if groups and groups[-1][0] == "band" and groups[-1][2] > groups[-1][1]:
-            _, a, b = groups.pop()
-            groups += [("band", a + 1, b), ("band", a, a)]
+        groups = _streaming_order(groups)
     pairs = 0
     for g in groups:
         if g[0] == "band" and job.can_band(g[1] * bs) and bs % 2 == 0:
