@@ -295,6 +295,47 @@ def test_balanced_split_is_a_contiguous_partition_with_even_pair_counts(N, N2, b
     assert max(cost) - sum(cost) / n <= biggest
 
 
+@pytest.mark.parametrize("N,bs,world", [(28284, 500, 8), (14142, 500, 2), (1000, 200, 1), (1100, 200, 3), (333, 50, 4), (64, 64, 2)])
+@pytest.mark.parametrize("max_rows", [None, 1, 3])
+def test_launch_groups_cover_a_workers_tiles_once(N, bs, world, max_rows):
+    """tiles.launch_groups / _streaming_order (host logic of the band launches, cnngp_gram_band): every tile of a
+    worker's slice of the reference tile list (data.py:11-29) lands in exactly one launch group; bands hold whole
+    block rows only and at most ``max_rows`` of them; the streaming order keeps the groups, puts the bottom rows
+    first and ends with one whole block row -- the topmost one of the slice."""
+    from cnn_gp.data import worker_tiles_balanced
+    from cnn_gp.tiles import launch_groups, row_segments, _streaming_order, _band_pairs
+    nbx = -(-N // bs)
+    total = 0
+    for rank in range(world):
+        tiles = worker_tiles_balanced(N, None, bs, rank, world)
+        groups = launch_groups(row_segments(tiles), nbx, max_rows)
+        covered = []
+        for g in groups:
+            if g[0] == "band":
+                assert max_rows is None or g[2] - g[1] + 1 <= max_rows
+                for r in range(g[1], g[2] + 1):
+                    covered += [(True, r, r)] + [(False, r, c) for c in range(r + 1, nbx)]
+                total += _band_pairs(N, bs, g[1] * bs, min(N, (g[2] + 1) * bs))
+            else:
+                r, has_diag, c0, c1 = g[1]
+                i0, i1 = r * bs, min(N, (r + 1) * bs)
+                if has_diag:
+                    covered.append((True, r, r))
+                    total += (i1 - i0) * (i1 - i0 + 1) // 2
+                if c0 is not None:
+                    covered += [(False, r, c) for c in range(c0, c1)]
+                    total += (i1 - i0) * (min(N, c1 * bs) - c0 * bs)
+        assert sorted(covered) == sorted(tiles)
+        order = _streaming_order(groups)
+        rows = lambda gs: sorted(r for g in gs for r in (range(g[1], g[2] + 1) if g[0] == "band" else [g[1][0]]))
+        assert rows(order) == rows(groups)
+        whole = [g for g in groups if g[0] == "band"]
+        if whole:
+            top = min(g[1] for g in whole)
+            assert order[-1] == ("band", top, top)
+    assert total == N * (N + 1) // 2
+
+
 # ----------------------------------------------------- distributed Cholesky orchestration (gloo, CPU)
 class _NumpyBackend:
     """The two compute calls of cnn_gp.linalg_dist restated with numpy / scipy (test-only), so that
