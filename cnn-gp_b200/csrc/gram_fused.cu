@@ -11,6 +11,12 @@
 // last layer is a register sum plus a warp-shuffle reduction.  Nothing but the final kernel
 // entry is written to HBM.
 //
+// Call forms: rectangular K(X, Z); symmetric model(X) (only j >= i computed, mirrored); a BAND of block rows
+// of model(X) -- rows [0, N1) x columns [0, N2 >= N1), mirrored inside the diagonal blocks only, which is a
+// worker's run of whole block rows of the reference's tile list (cnngp_gram_band) --; and the symmetric
+// call with progress counters per band of rows (template parameter PROG), behind which a copy stream
+// moves finished bands to host memory while the launch runs (cnngp_gram_symmetric_to_host).
+//
 // Reference semantics (paths relative to /root/reference):
 //   init   cnn_gp/kernels.py:43-49     conv  cnn_gp/kernels.py:92-98
 //   relu   cnn_gp/kernels.py:146-152 rewritten as
