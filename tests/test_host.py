@@ -149,6 +149,27 @@ def test_plan_rejects_bad_programs():
         nat.Plan(bad, 2, 1, 1, nat.F32)
 
 
+def test_band_call_validates_its_arguments_before_touching_the_gpu():
+    """cnngp_gram_band (include/cnngp.h): argument errors come back as codes with a message, no CUDA call made --
+    more rows than columns, a leading dimension shorter than the band, a program no fused kernel covers."""
+    import ctypes
+    L = nat.lib()
+    ops, ns = program.compile_model(golden_models()["mnist_paper_convnet_gp"])
+    plan = nat.Plan(ops, ns, 28, 28, nat.F32)
+    assert plan.fused_kind == 2
+    one = ctypes.c_void_p(16)  # never dereferenced: validation fails first
+    assert L.cnngp_gram_band(plan.handle, one, 8, 4, 1, one, one, 2, one, 8, None) == 1
+    assert b"bad arguments" in L.cnngp_last_error()
+    assert L.cnngp_gram_band(plan.handle, one, 4, 8, 1, one, one, 2, one, 7, None) == 1
+    assert L.cnngp_gram_band(plan.handle, None, 4, 8, 1, one, one, 2, one, 8, None) == 1
+    assert L.cnngp_gram_band(plan.handle, one, 0, 8, 1, one, one, 2, one, 8, None) == 0  # nothing to do
+    ops64, ns64 = program.compile_model(golden_models()["mnist_paper_convnet_gp"])
+    plan64 = nat.Plan(ops64, ns64, 28, 28, nat.F64)  # float64 runs on the generic kernel only
+    assert plan64.fused_kind == 0
+    assert L.cnngp_gram_band(plan64.handle, one, 4, 8, 1, one, one, 2, one, 8, None) == 4
+    assert b"fused" in L.cnngp_last_error()
+
+
 def test_cpu_tensors_are_refused():
     m = readme_model()
     with pytest.raises(RuntimeError, match="no CPU path"):
